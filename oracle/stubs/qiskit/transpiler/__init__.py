@@ -1,0 +1,2 @@
+from _stub_common import module_getattr
+__getattr__ = module_getattr("qiskit.transpiler")
