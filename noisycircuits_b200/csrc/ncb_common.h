@@ -1,0 +1,438 @@
+// Shared host/device definitions of the B200 noisy-circuit engine: packed program format, Philox draws, the
+// shared-memory tile layout and the per-thread executors.  Everything marked NCB_HD compiles both as CUDA device
+// code (the product) and as plain C++ (tests/emu: a thread-by-thread emulation used only to test the host planner
+// and the index maps on machines without a GPU).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NCB_HD __host__ __device__ __forceinline__
+#define NCB_D __device__ __forceinline__
+#if defined(__CUDA_ARCH__)
+// keeps the compiler from hoisting a whole operator matrix into registers across amplitude groups
+#define NCB_NO_HOIST() asm volatile("" ::: "memory")
+#endif
+#else
+#define NCB_HD inline
+#define NCB_D inline
+#endif
+
+#ifndef NCB_NO_HOIST
+#define NCB_NO_HOIST() ((void)0)
+#endif
+
+namespace ncb {
+
+constexpr int MAX_TILE_BITS = 13;   // 2^13 amplitudes * 16 B = 128 KB of shared memory
+constexpr int MAX_REG_BITS = 4;     // 2^4 amplitudes per thread
+constexpr int MAX_QUBITS = 30;
+
+struct alignas(16) cplx {
+    double x, y;
+};
+NCB_HD cplx cmul(cplx a, cplx b) { return cplx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+NCB_HD cplx cadd(cplx a, cplx b) { return cplx{a.x + b.x, a.y + b.y}; }
+NCB_HD cplx cfma(cplx a, cplx b, cplx c) {   // a*b + c
+    return cplx{a.x * b.x - a.y * b.y + c.x, a.x * b.y + a.y * b.x + c.y};
+}
+NCB_HD double cnorm2(cplx a) { return a.x * a.x + a.y * a.y; }
+
+// ------------------------------------------------------------------------------------------------------------
+// Program format
+// ------------------------------------------------------------------------------------------------------------
+enum OpKind : uint8_t {
+    OPK_DIAG = 0,     // diagonal on nb (1..4) tile-local bit positions pos[0..nb); table of 2^nb phases
+    OPK_DENSE1 = 1,   // 2x2 on register bit rb[0]
+    OPK_DENSE2 = 2,   // 4x4 on register bits rb[0] (matrix bit 0), rb[1] (matrix bit 1)
+    OPK_DENSE4 = 3,   // 16x16 on register bits rb[0..3]  (density-matrix superoperators, 3-4 qubit unitaries)
+    OPK_PERM1 = 4,    // X-like: anti-diagonal 2x2 on register bit rb[0]: out0 = m01*in1, out1 = m10*in0
+};
+
+// One executable step inside a pass.  `mat`/`mat_bare` are offsets (in doubles) into the matrix pool: `mat` is the
+// gate merged with the channel's base Kraus operator, `mat_bare` the gate alone (used for the last instruction of a
+// range that ends in a quantum-jump event, where the operator to apply is only known afterwards).
+struct Op {
+    uint32_t kind_nb;  // kind | nb << 8  (nb = number of bits the op acts on)
+    uint32_t rbs;      // 4 x 8 bit: DENSE*/PERM1: register-bit indices; DIAG: tile-local bit positions
+    int32_t instr;     // index of the instruction this op came from
+    int32_t mat;
+    int32_t mat_bare;
+    int32_t pad;
+};
+NCB_HD int op_kind(const Op& o) { return (int)(o.kind_nb & 0xff); }
+NCB_HD int op_nb(const Op& o) { return (int)((o.kind_nb >> 8) & 0xff); }
+NCB_HD int op_rb(const Op& o, int b) { return (int)((o.rbs >> (8 * b)) & 0xff); }
+
+// A pass: every thread pulls 2^R amplitudes out of the tile (the register bits select which), applies the ops whose
+// bits are register bits (or diagonal), and writes them back.
+struct Pass {
+    uint8_t regpos[MAX_REG_BITS];                      // tile-local position of register bit b
+    uint8_t tpos[MAX_TILE_BITS];                       // tile-local position of thread-index bit i
+    uint8_t pad[3];
+    uint16_t regoff[1 << MAX_REG_BITS];                // tile-local index offset of register slot m
+    uint16_t regoff_swz[1 << MAX_REG_BITS];            // swz(regoff[m]) (swz is XOR-linear)
+    int32_t op_begin, op_end;                          // ops of this pass
+    int32_t instr_lo, instr_hi;                        // instruction range covered: [lo, hi)
+};
+
+// A segment: a run of consecutive instructions whose qubits all live in one tile (K of the n state bits).
+struct Segment {
+    uint8_t tile_q[MAX_TILE_BITS];   // state bit of tile-local position p, ascending
+    uint8_t pad[3];
+    int32_t pass_begin, pass_end;
+    int32_t instr_lo, instr_hi;
+};
+
+// Static description of one noise channel (a Kraus list) for the event planner.
+struct Channel {
+    int32_t dim;          // 2 or 4
+    int32_t count;        // number of Kraus operators
+    int32_t kraus;        // offset (doubles) of the scaled operators in the matrix pool (count * dim*dim complex)
+    int32_t mk;           // offset (doubles) of M_k = K_k^+ K_k, UNSCALED (count * dim*dim complex)
+    int32_t bounds;       // offset (doubles) of lo[count-1], hi[count-1]
+    int32_t base;         // outcome merged into the gate
+    int32_t scale;        // offset (doubles) of the per-operator static scale (count doubles)
+    int32_t pad;
+};
+
+// Per-instruction static data.
+struct Instr {
+    int32_t channel;      // -1: no noise step
+    int32_t q0, q1;       // state bits the channel acts on (q1 = -1 for one-qubit channels)
+    int32_t seg;          // segment that executes it
+};
+
+// One unit of work of a tile-kernel launch: run the ops of `seg` whose instruction index is in [instr_lo, instr_hi)
+// on state slot `slot`.
+enum WorkFlags : int32_t {
+    WF_BARE_LAST = 1,      // instruction instr_hi-1 ends in a jump event: apply the bare gate (no base Kraus operator)
+    WF_PRO_STATIC = 2,     // first apply Kraus operator ev_k of instruction ev_instr (branch known from u alone)
+    WF_PRO_DYNAMIC = 4,    // first apply the operator the decide kernel chose for this slot
+    WF_REDUCE = 8,         // finally accumulate the reduced density matrix of instruction red_instr's qubits
+    WF_INIT = 16,          // the state is |0...0>: do not read it
+    WF_NORM = 32,          // finally accumulate the squared norm
+};
+struct Work {
+    int32_t slot, seg, instr_lo, instr_hi;
+    int32_t flags, ev_instr, ev_k, red_instr;
+};
+struct DecideItem {
+    int32_t slot, instr;
+    double u;
+};
+struct Decision {
+    double scale;
+    int32_t k, pad;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter = (instruction, traj_lo, traj_hi, stream), key = seed
+// ------------------------------------------------------------------------------------------------------------
+NCB_HD void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// Uniform in [0,1) with 53 random bits for (seed, trajectory, instruction).
+NCB_HD double philox_uniform(uint64_t seed, uint64_t traj, uint32_t instr) {
+    uint32_t c[4] = {instr, (uint32_t)traj, (uint32_t)(traj >> 32), 0x6e636232u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint64_t bits = ((uint64_t)c[0] << 21) ^ ((uint64_t)c[1] >> 11);
+    return (double)(bits & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Event classification: which Kraus branch does uniform u select?
+// cp[k](psi) = <C_k>/<C_total> lies in [lo[k], hi[k]] for every state; the reference picks the first k with
+// cp[k] >= u (std::discrete_distribution / lower_bound).  Returns kmin (branch >= kmin for sure) and kmax (branch
+// <= kmax for sure); kmin == kmax means the branch is known without looking at the state.
+// ------------------------------------------------------------------------------------------------------------
+constexpr double EVENT_MARGIN = 1e-9;
+NCB_HD void classify_uniform(const double* lo, const double* hi, int count, double u, int* kmin, int* kmax) {
+    int a = 0;
+    while (a < count - 1 && hi[a] < u - EVENT_MARGIN) ++a;          // boundaries certainly below u
+    int b = a;
+    while (b < count - 1 && !(lo[b] >= u + EVENT_MARGIN)) ++b;       // first boundary certainly >= u
+    *kmin = a; *kmax = b;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Tile layout in shared memory: amplitude with tile-local index j lives at slot swz(j).  The XOR fold makes the
+// 8 lanes of a quarter-warp hit 8 different 16-byte bank groups for (almost) every choice of register bits.
+// ------------------------------------------------------------------------------------------------------------
+NCB_HD int swz(int j) { return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9) ^ (j >> 12)) & 7); }
+
+// deposit the low bits of v at the positions listed in pos[0..nbits)
+NCB_HD int deposit(int v, const uint8_t* pos, int nbits) {
+    int r = 0;
+    for (int i = 0; i < nbits; ++i) r |= ((v >> i) & 1) << pos[i];
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Register-blocked pass executor (one thread's share)
+// ------------------------------------------------------------------------------------------------------------
+template <int R, int B>
+NCB_HD void dense1_bit(cplx* a, const cplx* __restrict__ M) {
+    const cplx m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        const int i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cfma(m01, y, cmul(m00, x));
+        a[i1] = cfma(m11, y, cmul(m10, x));
+    }
+}
+template <int R, int B>
+NCB_HD void perm1_bit(cplx* a, const cplx* __restrict__ M) {
+    const cplx m01 = M[1], m10 = M[2];
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        const int i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cmul(m01, y);
+        a[i1] = cmul(m10, x);
+    }
+}
+template <int R>
+NCB_HD void dense1(cplx* a, int b, const cplx* __restrict__ M) {
+    switch (b) {
+    case 0: dense1_bit<R, 0>(a, M); break;
+    case 1: if (R > 1) dense1_bit<R, (R > 1 ? 1 : 0)>(a, M); break;
+    case 2: if (R > 2) dense1_bit<R, (R > 2 ? 2 : 0)>(a, M); break;
+    case 3: if (R > 3) dense1_bit<R, (R > 3 ? 3 : 0)>(a, M); break;
+    }
+}
+template <int R>
+NCB_HD void perm1(cplx* a, int b, const cplx* __restrict__ M) {
+    switch (b) {
+    case 0: perm1_bit<R, 0>(a, M); break;
+    case 1: if (R > 1) perm1_bit<R, (R > 1 ? 1 : 0)>(a, M); break;
+    case 2: if (R > 2) perm1_bit<R, (R > 2 ? 2 : 0)>(a, M); break;
+    case 3: if (R > 3) perm1_bit<R, (R > 3 ? 3 : 0)>(a, M); break;
+    }
+}
+// 4x4 on register bits (B0 = matrix bit 0, B1 = matrix bit 1), B0 != B1
+template <int R, int B0, int B1>
+NCB_HD void dense2_bits(cplx* a, const cplx* __restrict__ M) {
+    constexpr int LO = B0 < B1 ? B0 : B1, HI = B0 < B1 ? B1 : B0;
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 2)); ++g) {
+        int base = ((g >> LO) << (LO + 1)) | (g & ((1 << LO) - 1));
+        base = ((base >> HI) << (HI + 1)) | (base & ((1 << HI) - 1));
+        const int idx[4] = {base, base | (1 << B0), base | (1 << B1), base | (1 << B0) | (1 << B1)};
+        const cplx s0 = a[idx[0]], s1 = a[idx[1]], s2 = a[idx[2]], s3 = a[idx[3]];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            cplx v = cmul(M[4 * r], s0);
+            v = cfma(M[4 * r + 1], s1, v);
+            v = cfma(M[4 * r + 2], s2, v);
+            v = cfma(M[4 * r + 3], s3, v);
+            a[idx[r]] = v;
+        }
+        NCB_NO_HOIST();
+    }
+}
+template <int R>
+NCB_HD void dense2(cplx* a, int b0, int b1, const cplx* __restrict__ M) {
+    if (R < 2) return;
+    switch (b0 * 4 + b1) {
+#define NCB_CASE(X, Y) case X * 4 + Y: if (R > X && R > Y) dense2_bits<R, (R > X ? X : 0), (R > Y ? Y : 1)>(a, M); break;
+        NCB_CASE(0, 1) NCB_CASE(0, 2) NCB_CASE(0, 3) NCB_CASE(1, 0) NCB_CASE(1, 2) NCB_CASE(1, 3)
+        NCB_CASE(2, 0) NCB_CASE(2, 1) NCB_CASE(2, 3) NCB_CASE(3, 0) NCB_CASE(3, 1) NCB_CASE(3, 2)
+#undef NCB_CASE
+    }
+}
+// 16x16 on all four register bits; register index bit b <-> matrix bit perm[b] was resolved on the host
+// (the matrix is stored already permuted so that matrix bit b == register bit b).
+template <int R>
+NCB_HD void dense4(cplx* a, const cplx* __restrict__ M) {
+    if (R < 4) return;
+    constexpr int MASK = (1 << R) - 1;   // keeps the R < 4 instantiations (never executed) in bounds
+    cplx out[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        cplx v = cmul(M[16 * r], a[0]);
+#pragma unroll
+        for (int c = 1; c < 16; ++c) v = cfma(M[16 * r + c], a[c & MASK], v);
+        out[r] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) a[r & MASK] = out[r];
+}
+
+// Executes the ops of `ps` whose instruction index is in [lo, hi) on this thread's 2^R amplitudes.
+// bare_last: the op(s) of instruction hi-1 use the bare gate matrix.
+template <int R, bool D4>
+NCB_HD void run_pass_thread(cplx* sm, int K, int tid, const Pass& ps, const Op* __restrict__ ops,
+                            const double* __restrict__ pool, int lo, int hi, bool bare_last) {
+    constexpr int NA = 1 << R;
+    const int jb = deposit(tid, ps.tpos, K - R);
+    const int jbs = swz(jb);
+    cplx a[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) a[m] = sm[jbs ^ ps.regoff_swz[m]];
+    for (int o = ps.op_begin; o < ps.op_end; ++o) {
+        const Op op = ops[o];
+        if (op.instr < lo || op.instr >= hi) continue;
+        const cplx* M = reinterpret_cast<const cplx*>(pool + ((bare_last && op.instr == hi - 1) ? op.mat_bare : op.mat));
+        const int nb = op_nb(op);
+        switch (op_kind(op)) {
+        case OPK_DIAG:
+#pragma unroll
+            for (int m = 0; m < NA; ++m) {
+                const int j = jb | ps.regoff[m];
+                int idx = 0;
+                for (int b = 0; b < nb; ++b) idx |= ((j >> op_rb(op, b)) & 1) << b;
+                a[m] = cmul(a[m], M[idx]);
+            }
+            break;
+        case OPK_DENSE1: dense1<R>(a, op_rb(op, 0), M); break;
+        case OPK_PERM1: perm1<R>(a, op_rb(op, 0), M); break;
+        case OPK_DENSE2: dense2<R>(a, op_rb(op, 0), op_rb(op, 1), M); break;
+        case OPK_DENSE4: if (D4) dense4<R>(a, M); break;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NA; ++m) sm[jbs ^ ps.regoff_swz[m]] = a[m];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Simple (non register-blocked) tile loops used by the rare jump events
+// ------------------------------------------------------------------------------------------------------------
+// Applies a dim x dim (dim = 2 or 4) operator, scaled by `scale`, on tile-local bits p0 (matrix bit 0) and p1.
+NCB_HD void tile_apply_dense(cplx* sm, int K, int tid, int nthreads, int dim, int p0, int p1,
+                             const cplx* __restrict__ M, double scale) {
+    if (dim == 2) {
+        for (int g = tid; g < (1 << (K - 1)); g += nthreads) {
+            const int i0 = ((g >> p0) << (p0 + 1)) | (g & ((1 << p0) - 1)), i1 = i0 | (1 << p0);
+            const cplx x = sm[swz(i0)], y = sm[swz(i1)];
+            cplx u = cfma(M[1], y, cmul(M[0], x)), v = cfma(M[3], y, cmul(M[2], x));
+            u.x *= scale; u.y *= scale; v.x *= scale; v.y *= scale;
+            sm[swz(i0)] = u; sm[swz(i1)] = v;
+        }
+    } else {
+        const int lo = p0 < p1 ? p0 : p1, hi = p0 < p1 ? p1 : p0;
+        for (int g = tid; g < (1 << (K - 2)); g += nthreads) {
+            int base = ((g >> lo) << (lo + 1)) | (g & ((1 << lo) - 1));
+            base = ((base >> hi) << (hi + 1)) | (base & ((1 << hi) - 1));
+            const int idx[4] = {base, base | (1 << p0), base | (1 << p1), base | (1 << p0) | (1 << p1)};
+            const cplx s0 = sm[swz(idx[0])], s1 = sm[swz(idx[1])], s2 = sm[swz(idx[2])], s3 = sm[swz(idx[3])];
+            for (int r = 0; r < 4; ++r) {
+                cplx v = cmul(M[4 * r], s0);
+                v = cfma(M[4 * r + 1], s1, v);
+                v = cfma(M[4 * r + 2], s2, v);
+                v = cfma(M[4 * r + 3], s3, v);
+                v.x *= scale; v.y *= scale;
+                sm[swz(idx[r])] = v;
+            }
+        }
+    }
+}
+
+// This thread's contribution to the LOWER TRIANGLE of the reduced density matrix of tile positions p0 (index bit 0)
+// and p1 (index bit 1; unused for D = 2): acc[2*(r*D+c)], acc[2*(r*D+c)+1] += psi_r conj(psi_c) for r >= c.
+template <int D>
+NCB_HD void reduce_rho_thread(const cplx* sm, int K, int tid, int nthreads, int p0, int p1, double* acc) {
+    if (D == 2) {
+        for (int g = tid; g < (1 << (K - 1)); g += nthreads) {
+            const int i0 = ((g >> p0) << (p0 + 1)) | (g & ((1 << p0) - 1)), i1 = i0 | (1 << p0);
+            const cplx s[2] = {sm[swz(i0)], sm[swz(i1)]};
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) {
+                    acc[2 * (r * 2 + c)] += s[r].x * s[c].x + s[r].y * s[c].y;
+                    acc[2 * (r * 2 + c) + 1] += s[r].y * s[c].x - s[r].x * s[c].y;
+                }
+        }
+    } else {
+        const int lo = p0 < p1 ? p0 : p1, hi = p0 < p1 ? p1 : p0;
+        for (int g = tid; g < (1 << (K - 2)); g += nthreads) {
+            int base = ((g >> lo) << (lo + 1)) | (g & ((1 << lo) - 1));
+            base = ((base >> hi) << (hi + 1)) | (base & ((1 << hi) - 1));
+            const cplx s[4] = {sm[swz(base)], sm[swz(base | (1 << p0))], sm[swz(base | (1 << p1))],
+                               sm[swz(base | (1 << p0) | (1 << p1))]};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) {
+                    acc[2 * (r * 4 + c)] += s[r].x * s[c].x + s[r].y * s[c].y;
+                    acc[2 * (r * 4 + c) + 1] += s[r].y * s[c].x - s[r].x * s[c].y;
+                }
+        }
+    }
+}
+
+// rho (lower triangle, dimension d) -> full Hermitian matrix in place
+NCB_HD void mirror_rho(double* rho, int d) {
+    for (int r = 0; r < d; ++r)
+        for (int c = r + 1; c < d; ++c) {
+            rho[2 * (r * d + c)] = rho[2 * (c * d + r)];
+            rho[2 * (r * d + c) + 1] = -rho[2 * (c * d + r) + 1];
+        }
+}
+
+// Tile geometry.  base: the tile index o deposited into the state bits that are NOT tile bits (ascending).
+NCB_HD long long tile_base(const Segment& sg, int K, int nbits, int o) {
+    long long base = 0;
+    int src = o, p = 0;
+    for (int b = 0; b < nbits; ++b) {
+        while (p < K && sg.tile_q[p] < b) ++p;
+        if (p < K && sg.tile_q[p] == b) continue;
+        base |= (long long)(src & 1) << b;
+        src >>= 1;
+    }
+    return base;
+}
+// position of state bit q inside the tile
+NCB_HD int tile_pos(const Segment& sg, int K, int q) {
+    for (int p = 0; p < K; ++p)
+        if (sg.tile_q[p] == q) return p;
+    return -1;
+}
+
+// Branch decision from a reduced density matrix (rho[2*(r*dim+c)] layout as above, any normalisation):
+// p_k = Re tr(M_k rho); picks the first k with cumsum(p/sum)[k] >= u (std::discrete_distribution semantics) and
+// returns the scale 1/sqrt(p_k) that renormalises K_k psi.  `kraus_scale[k]` is the static scale the stored
+// operator already carries.
+NCB_HD int decide_branch(const double* rho, const Channel& ch, const double* __restrict__ pool, double u, double* scale_out) {
+    const int d = ch.dim, dd = d * d;
+    const double* mk = pool + ch.mk;
+    double sum = 0.0;
+    for (int k = 0; k < ch.count; ++k) {
+        double p = 0.0;
+        for (int r = 0; r < d; ++r)
+            for (int c = 0; c < d; ++c)   // tr(M rho) = sum_{r,c} M[r][c] rho[c][r]
+                p += mk[2 * (k * dd + r * d + c)] * rho[2 * (c * d + r)] - mk[2 * (k * dd + r * d + c) + 1] * rho[2 * (c * d + r) + 1];
+        sum += p > 0.0 ? p : 0.0;
+    }
+    int pick = ch.count - 1;
+    double cp = 0.0, ppick = 0.0;
+    for (int k = 0; k < ch.count; ++k) {
+        double p = 0.0;
+        for (int r = 0; r < d; ++r)
+            for (int c = 0; c < d; ++c)
+                p += mk[2 * (k * dd + r * d + c)] * rho[2 * (c * d + r)] - mk[2 * (k * dd + r * d + c) + 1] * rho[2 * (c * d + r) + 1];
+        if (p < 0.0) p = 0.0;
+        cp += p / sum;
+        ppick = p;
+        if (k == ch.count - 1 || !(cp < u)) { pick = k; break; }
+    }
+    // stored operator = static_scale * K_k; we want K_k psi / sqrt(p_k)
+    const double st = pool[ch.scale + pick];
+    *scale_out = ppick > 0.0 ? 1.0 / (st * sqrt(ppick)) : 0.0;
+    return pick;
+}
+
+}  // namespace ncb

@@ -1,0 +1,516 @@
+// Host-side compiler of the B200 noisy-circuit engine (see ncb_compile.h).
+#include "ncb_compile.h"
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+
+namespace ncb {
+namespace {
+
+using cd = std::complex<double>;
+using cmat = std::vector<cd>;   // row-major square matrix
+
+cmat matmul(const cmat& a, const cmat& b, int d) {
+    cmat r(d * d, cd(0, 0));
+    for (int i = 0; i < d; ++i)
+        for (int k = 0; k < d; ++k) {
+            const cd x = a[i * d + k];
+            if (x == cd(0, 0)) continue;
+            for (int j = 0; j < d; ++j) r[i * d + j] += x * b[k * d + j];
+        }
+    return r;
+}
+cmat adjoint_times(const cmat& a, int d) {   // a^+ a
+    cmat r(d * d, cd(0, 0));
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) {
+            cd s(0, 0);
+            for (int k = 0; k < d; ++k) s += std::conj(a[k * d + i]) * a[k * d + j];
+            r[i * d + j] = s;
+        }
+    return r;
+}
+double max_abs(const cmat& a) {
+    double m = 0;
+    for (const cd& x : a) m = std::max(m, std::abs(x));
+    return m;
+}
+bool is_diagonal(const cmat& a, int d) {
+    const double tol = 1e-17 * std::max(1.0, max_abs(a));
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j)
+            if (i != j && std::abs(a[i * d + j]) > tol) return false;
+    return true;
+}
+bool is_antidiagonal2(const cmat& a) {
+    const double tol = 1e-17 * std::max(1.0, max_abs(a));
+    return std::abs(a[0]) <= tol && std::abs(a[3]) <= tol;
+}
+
+// Extreme eigenvalues of a Hermitian d x d matrix (d <= 4): cyclic Jacobi on the real symmetric embedding
+// [[A, -B], [B, A]] of H = A + iB (its spectrum is that of H, doubled).
+void herm_eig_minmax(const cmat& h, int d, double* emin, double* emax) {
+    const int n = 2 * d;
+    double s[8][8];
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) {
+            const cd x = 0.5 * (h[i * d + j] + std::conj(h[j * d + i]));
+            s[i][j] = x.real(); s[i + d][j + d] = x.real();
+            s[i][j + d] = -x.imag(); s[i + d][j] = x.imag();
+        }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) off += s[p][q] * s[p][q];
+        if (off < 1e-40) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                if (std::fabs(s[p][q]) < 1e-300) continue;
+                const double theta = (s[q][q] - s[p][p]) / (2.0 * s[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double a = s[k][p], b = s[k][q];
+                    s[k][p] = c * a - sn * b; s[k][q] = sn * a + c * b;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double a = s[p][k], b = s[q][k];
+                    s[p][k] = c * a - sn * b; s[q][k] = sn * a + c * b;
+                }
+            }
+    }
+    double lo = s[0][0], hi = s[0][0];
+    for (int i = 1; i < n; ++i) { lo = std::min(lo, s[i][i]); hi = std::max(hi, s[i][i]); }
+    *emin = lo; *emax = hi;
+}
+
+struct PoolBuilder {
+    std::vector<double>& pool;
+    int add_complex(const cmat& m) {
+        if (pool.size() & 1) pool.push_back(0.0);
+        const int off = (int)pool.size();
+        for (const cd& x : m) { pool.push_back(x.real()); pool.push_back(x.imag()); }
+        return off;
+    }
+    int add_doubles(const std::vector<double>& v) {
+        if (pool.size() & 1) pool.push_back(0.0);
+        const int off = (int)pool.size();
+        pool.insert(pool.end(), v.begin(), v.end());
+        if (pool.size() & 1) pool.push_back(0.0);
+        return off;
+    }
+};
+
+cmat read_complex(const double* p, int count) {
+    cmat m(count);
+    for (int i = 0; i < count; ++i) m[i] = cd(p[2 * i], p[2 * i + 1]);
+    return m;
+}
+std::vector<double> flatten(const cmat& m) {
+    std::vector<double> v;
+    v.reserve(2 * m.size());
+    for (const cd& x : m) { v.push_back(x.real()); v.push_back(x.imag()); }
+    return v;
+}
+cmat diag_of(const cmat& m, int d) {
+    cmat v(d);
+    for (int i = 0; i < d; ++i) v[i] = m[i * d + i];
+    return v;
+}
+
+struct ChannelInfo {
+    std::vector<cmat> raw;      // K_k
+    std::vector<cmat> scaled;   // s_k K_k
+    std::vector<double> scale;  // s_k
+    std::vector<bool> unitary_like;
+    bool certain_nonunitary = false;
+};
+
+}  // namespace
+
+void gate_matrix(int opcode, double theta, double* out, int* dim) {
+    const double c = std::cos(0.5 * theta), s = std::sin(0.5 * theta);
+    const double r2 = 0.70710678118654752440;
+    const cd I(0, 1);
+    cmat m;
+    switch (opcode) {
+    case G_X: m = {0, 1, 1, 0}; break;
+    case G_SX: m = {cd(0.5, 0.5), cd(0.5, -0.5), cd(0.5, -0.5), cd(0.5, 0.5)}; break;
+    case G_RZ: m = {cd(c, -s), 0, 0, cd(c, s)}; break;
+    case G_RX: m = {c, -I * s, -I * s, c}; break;
+    case G_RY: m = {c, -s, s, c}; break;
+    case G_H: m = {r2, r2, r2, -r2}; break;
+    case G_P: m = {1, 0, 0, cd(std::cos(theta), std::sin(theta))}; break;   // QuantumGates.hpp:689-698
+    case G_CZ: m = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1}; break;
+    case G_RZZ: m = {cd(c, -s), 0, 0, 0, 0, cd(c, s), 0, 0, 0, 0, cd(c, s), 0, 0, 0, 0, cd(c, -s)}; break;
+    case G_ECR: m = {0, r2, 0, I * r2, r2, 0, -I * r2, 0, 0, I * r2, 0, r2, -I * r2, 0, r2, 0}; break;
+    case G_CX: m = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0}; break;      // control = first listed qubit
+    case G_SWAP: m = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1}; break;
+    default: throw std::runtime_error("gate_matrix: unknown opcode " + std::to_string(opcode));
+    }
+    *dim = m.size() == 4 ? 2 : 4;
+    for (size_t i = 0; i < m.size(); ++i) { out[2 * i] = m[i].real(); out[2 * i + 1] = m[i].imag(); }
+}
+
+namespace {
+
+// Kraus list -> Channel record (+ pool data) and ChannelInfo for merging.
+Channel analyse_channel(const CircuitView& c, int ch, PoolBuilder& pb, ChannelInfo& info) {
+    const int d = c.channel_dim[ch], count = c.channel_count[ch], dd = d * d;
+    if (d != 2 && d != 4) throw std::runtime_error("channel " + std::to_string(ch) + ": operator dimension must be 2 or 4");
+    if (count < 1) throw std::runtime_error("channel " + std::to_string(ch) + ": empty Kraus list");
+    const double* src = c.kraus_pool + 2 * c.channel_offset[ch];
+    std::vector<cmat> mk(count);
+    std::vector<double> wmin(count), wmax(count);
+    info.raw.resize(count); info.scaled.resize(count); info.scale.resize(count); info.unitary_like.resize(count);
+    for (int k = 0; k < count; ++k) {
+        info.raw[k] = read_complex(src + 2 * (size_t)k * dd, dd);
+        mk[k] = adjoint_times(info.raw[k], d);
+        herm_eig_minmax(mk[k], d, &wmin[k], &wmax[k]);
+        const double w = 0.5 * (wmin[k] + wmax[k]);
+        info.unitary_like[k] = (wmax[k] - wmin[k]) <= 1e-13 * std::max(wmax[k], 1e-300) && wmax[k] > 0;
+        const double ref = info.unitary_like[k] ? w : wmax[k];
+        info.scale[k] = ref > 0 ? 1.0 / std::sqrt(ref) : 1.0;
+        info.scaled[k] = info.raw[k];
+        for (cd& x : info.scaled[k]) x *= info.scale[k];
+    }
+    // cumulative sums and state-independent bounds of cp[k] = <C_k>/<C_total>
+    std::vector<double> lo(std::max(count - 1, 1), 1.0), hi(std::max(count - 1, 1), 1.0);
+    cmat total(dd, cd(0, 0));
+    for (int k = 0; k < count; ++k)
+        for (int i = 0; i < dd; ++i) total[i] += mk[k][i];
+    double tmin, tmax;
+    herm_eig_minmax(total, d, &tmin, &tmax);
+    if (!(tmax > 0)) throw std::runtime_error("channel " + std::to_string(ch) + ": all Kraus operators are zero");
+    cmat cum(dd, cd(0, 0));
+    for (int k = 0; k + 1 < count; ++k) {
+        for (int i = 0; i < dd; ++i) cum[i] += mk[k][i];
+        double cmin, cmax;
+        herm_eig_minmax(cum, d, &cmin, &cmax);
+        cmin = std::max(cmin, 0.0); cmax = std::max(cmax, 0.0);
+        lo[k] = std::min(1.0, cmin / tmax);
+        hi[k] = tmin > 0 ? std::min(1.0, cmax / tmin) : 1.0;
+        if (k > 0) { lo[k] = std::max(lo[k], lo[k - 1]); hi[k] = std::max(hi[k], hi[k - 1]); }
+    }
+    // base branch = widest state-independent interval
+    int base = 0;
+    double best = -1;
+    for (int k = 0; k < count; ++k) {
+        const double left = k == 0 ? 0.0 : hi[k - 1], right = k == count - 1 ? 1.0 : lo[k];
+        const double w = right - left;
+        if (w > 2 * EVENT_MARGIN && !info.unitary_like[k]) info.certain_nonunitary = true;
+        if (w > best) { best = w; base = k; }
+    }
+    if (count == 1 && !info.unitary_like[0]) info.certain_nonunitary = true;
+    Channel out;
+    std::memset(&out, 0, sizeof(out));
+    out.dim = d; out.count = count; out.base = base;
+    cmat all_scaled, all_mk;
+    for (int k = 0; k < count; ++k) {
+        all_scaled.insert(all_scaled.end(), info.scaled[k].begin(), info.scaled[k].end());
+        all_mk.insert(all_mk.end(), mk[k].begin(), mk[k].end());
+    }
+    out.kraus = pb.add_complex(all_scaled);
+    out.mk = pb.add_complex(all_mk);
+    std::vector<double> bounds(lo.begin(), lo.begin() + std::max(count - 1, 0));
+    bounds.insert(bounds.end(), hi.begin(), hi.begin() + std::max(count - 1, 0));
+    if (bounds.empty()) bounds.push_back(1.0);
+    out.bounds = pb.add_doubles(bounds);
+    out.scale = pb.add_doubles(info.scale);
+    return out;
+}
+
+// superoperator sum_k A_k (x) conj(A_k) with vectorised index = row + d*col
+cmat superop(const std::vector<cmat>& A, int d) {
+    const int D = d * d;
+    cmat s(D * D, cd(0, 0));
+    for (const cmat& a : A) {
+        if (max_abs(a) == 0) continue;
+        for (int r2 = 0; r2 < d; ++r2)
+            for (int c2 = 0; c2 < d; ++c2)
+                for (int r = 0; r < d; ++r)
+                    for (int c = 0; c < d; ++c) s[(r2 + d * c2) * D + (r + d * c)] += a[r2 * d + r] * std::conj(a[c2 * d + c]);
+    }
+    return s;
+}
+
+LogicalOp make_lop(int instr, const std::vector<int>& bits, const cmat& merged, const cmat& bare) {
+    LogicalOp l;
+    l.instr = instr;
+    l.nb = (int)bits.size();
+    for (int i = 0; i < 4; ++i) l.bits[i] = i < l.nb ? bits[i] : -1;
+    const int d = 1 << l.nb;
+    l.diag = is_diagonal(merged, d) && is_diagonal(bare, d);
+    if (l.diag) { l.mat = flatten(diag_of(merged, d)); l.bare = flatten(diag_of(bare, d)); }
+    else { l.mat = flatten(merged); l.bare = flatten(bare); }
+    return l;
+}
+
+cmat conj_of(const cmat& a) {
+    cmat r(a);
+    for (cd& x : r) x = std::conj(x);
+    return r;
+}
+
+struct PassBuild {
+    std::vector<int> regset;            // tile-local positions
+    std::vector<const LogicalOp*> lops;
+};
+
+}  // namespace
+
+void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, Program& P) {
+    P = Program();
+    P.mode = mode; P.opt = opt;
+    P.nq = c.num_qubits; P.G = c.num_instructions;
+    if (P.nq < 1 || P.nq > MAX_QUBITS) throw std::runtime_error("num_qubits out of range");
+    P.nbits = mode == MODE_DENSITY ? 2 * P.nq : P.nq;
+    if (P.nbits > MAX_QUBITS) throw std::runtime_error("state too large: " + std::to_string(P.nbits) + " state bits");
+    P.R = std::min(std::max(opt.reg_bits, 1), MAX_REG_BITS);
+    const int kmin = P.R + 5;
+    P.K = std::min(std::max({opt.tile_bits, kmin}), MAX_TILE_BITS);
+    if (P.nbits <= P.K) P.K = std::max(P.nbits, kmin);          // whole state in one tile (extra bits are virtual)
+    const int K = P.K, R = P.R;
+    const int L = std::min(std::max(opt.low_bits, 0), std::min(K - 4, P.nbits));
+    PoolBuilder pb{P.pool};
+
+    // ---- channels -------------------------------------------------------------------------------------------
+    std::vector<ChannelInfo> cinfo(std::max(c.num_channels, 0));
+    const bool use_noise = mode != MODE_PURE;
+    if (use_noise)
+        for (int ch = 0; ch < c.num_channels; ++ch) P.chans.push_back(analyse_channel(c, ch, pb, cinfo[ch]));
+
+    // ---- logical ops ----------------------------------------------------------------------------------------
+    std::vector<LogicalOp> lops;
+    P.instrs.resize(P.G);
+    P.draw_pos.assign(P.G, -1);
+    for (int g = 0; g < P.G; ++g) {
+        const int opc = c.opcode[g];
+        Instr& in = P.instrs[g];
+        in.channel = -1; in.q0 = c.q0[g]; in.q1 = -1; in.seg = -1;
+        std::vector<int> qb;
+        cmat U;
+        if (opc == G_UNITARY) {
+            const int k = c.unitary_nq[g];
+            if (k < 1 || k > 4) throw std::runtime_error("instruction " + std::to_string(g) + ": unitary on " + std::to_string(k) + " qubits is not supported (1..4)");
+            for (int b = 0; b < k; ++b) qb.push_back(c.unitary_qubits[8 * g + b]);
+            U = read_complex(c.unitary_pool + 2 * c.unitary_offset[g], (1 << k) * (1 << k));
+        } else {
+            if (opc < 0 || opc >= G_UNITARY) throw std::runtime_error("instruction " + std::to_string(g) + ": unknown opcode " + std::to_string(opc));
+            double buf[32]; int d;
+            gate_matrix(opc, c.theta[g], buf, &d);
+            U = read_complex(buf, d * d);
+            qb.push_back(c.q0[g]);
+            if (d == 4) { qb.push_back(c.q1[g]); in.q1 = c.q1[g]; }
+        }
+        for (size_t a = 0; a < qb.size(); ++a) {
+            if (qb[a] < 0 || qb[a] >= P.nq) throw std::runtime_error("instruction " + std::to_string(g) + ": qubit out of range");
+            for (size_t b = a + 1; b < qb.size(); ++b)
+                if (qb[a] == qb[b]) throw std::runtime_error("instruction " + std::to_string(g) + ": repeated qubit");
+        }
+        const int d = 1 << qb.size();
+        int ch = (use_noise && opc != G_UNITARY && c.channel) ? c.channel[g] : -1;
+        if (ch >= c.num_channels) throw std::runtime_error("instruction " + std::to_string(g) + ": channel id out of range");
+        if (ch >= 0 && P.chans[ch].dim != d) throw std::runtime_error("instruction " + std::to_string(g) + ": channel dimension does not match the gate");
+        if (mode == MODE_DENSITY) {
+            std::vector<int> cb;
+            for (int q : qb) cb.push_back(q + P.nq);
+            if (ch >= 0) {
+                std::vector<cmat> A;
+                for (const cmat& k : cinfo[ch].raw) A.push_back(matmul(k, U, d));
+                std::vector<int> bits(qb);
+                bits.insert(bits.end(), cb.begin(), cb.end());
+                const cmat S = superop(A, d);
+                lops.push_back(make_lop(g, bits, S, S));
+            } else {
+                lops.push_back(make_lop(g, qb, U, U));
+                const cmat Uc = conj_of(U);
+                lops.push_back(make_lop(g, cb, Uc, Uc));
+            }
+            continue;
+        }
+        cmat merged = U;
+        if (ch >= 0) {
+            in.channel = ch;
+            merged = matmul(cinfo[ch].scaled[P.chans[ch].base], U, d);
+            if (cinfo[ch].certain_nonunitary) P.norm_preserving = false;
+            if (P.chans[ch].count >= 2) { P.draw_pos[g] = P.num_draws++; P.noisy_instrs.push_back(g); }
+        }
+        lops.push_back(make_lop(g, qb, merged, U));
+    }
+
+    // ---- segmentation: maximal runs of consecutive logical ops whose bits fit one tile --------------------------
+    struct SegBuild { std::vector<int> tile; size_t lop_begin, lop_end; };
+    std::vector<SegBuild> sb;
+    auto fresh_tile = [&]() { std::vector<int> t; for (int b = 0; b < L; ++b) t.push_back(b); return t; };
+    auto tile_union = [&](std::vector<int> t, const LogicalOp& l) {
+        for (int i = 0; i < l.nb; ++i)
+            if (std::find(t.begin(), t.end(), l.bits[i]) == t.end()) t.push_back(l.bits[i]);
+        return t;
+    };
+    const int kfit = std::min(K, P.nbits);
+    {
+        SegBuild cur{fresh_tile(), 0, 0};
+        for (size_t i = 0; i < lops.size(); ++i) {
+            std::vector<int> t = tile_union(cur.tile, lops[i]);
+            const bool new_instr = i == 0 || lops[i].instr != lops[i - 1].instr;
+            const bool force_split = !opt.fuse && new_instr && cur.lop_end > cur.lop_begin;
+            if ((int)t.size() > kfit || force_split) {
+                if (cur.lop_end == cur.lop_begin) throw std::runtime_error("an operation does not fit a tile; increase tile_bits");
+                sb.push_back(cur);
+                cur = SegBuild{fresh_tile(), i, i};
+                t = tile_union(cur.tile, lops[i]);
+                if ((int)t.size() > kfit) throw std::runtime_error("an operation does not fit a tile; increase tile_bits");
+            }
+            cur.tile = t; cur.lop_end = i + 1;
+        }
+        if (cur.lop_end > cur.lop_begin || sb.empty()) sb.push_back(cur);
+    }
+
+    // ---- passes and ops -----------------------------------------------------------------------------------------
+    for (SegBuild& s : sb) {
+        // complete the tile: lowest unused state bits first, then virtual bits
+        for (int b = 0; (int)s.tile.size() < kfit && b < P.nbits; ++b)
+            if (std::find(s.tile.begin(), s.tile.end(), b) == s.tile.end()) s.tile.push_back(b);
+        std::sort(s.tile.begin(), s.tile.end());
+        for (int b = P.nbits; (int)s.tile.size() < K; ++b) s.tile.push_back(b);
+        Segment seg;
+        std::memset(&seg, 0, sizeof(seg));
+        int local_of[64];
+        for (int i = 0; i < 64; ++i) local_of[i] = -1;
+        for (int p = 0; p < K; ++p) { seg.tile_q[p] = (uint8_t)s.tile[p]; local_of[s.tile[p]] = p; }
+        seg.pass_begin = (int)P.passes.size();
+        seg.instr_lo = s.lop_end > s.lop_begin ? lops[s.lop_begin].instr : 0;
+        seg.instr_hi = s.lop_end > s.lop_begin ? lops[s.lop_end - 1].instr + 1 : 0;
+        const int seg_id = (int)P.segs.size();
+
+        std::vector<PassBuild> pbs(1);
+        for (size_t i = s.lop_begin; i < s.lop_end; ++i) {
+            const LogicalOp& l = lops[i];
+            P.instrs[l.instr].seg = seg_id;
+            if (!l.diag) {
+                if (l.nb > R) throw std::runtime_error("instruction " + std::to_string(l.instr) + ": dense operator on " + std::to_string(l.nb) + " bits needs reg_bits >= " + std::to_string(l.nb));
+                std::vector<int> u = pbs.back().regset;
+                for (int b = 0; b < l.nb; ++b) {
+                    const int p = local_of[l.bits[b]];
+                    if (std::find(u.begin(), u.end(), p) == u.end()) u.push_back(p);
+                }
+                const bool need4 = l.nb >= 3;
+                if ((int)u.size() > R) {
+                    pbs.emplace_back();
+                    u.clear();
+                    for (int b = 0; b < l.nb; ++b) u.push_back(local_of[l.bits[b]]);
+                }
+                pbs.back().regset = u;
+                (void)need4;
+            }
+            pbs.back().lops.push_back(&l);
+        }
+        for (PassBuild& b : pbs) {
+            if (b.lops.empty() && P.G > 0 && pbs.size() > 1) continue;
+            Pass ps;
+            std::memset(&ps, 0, sizeof(ps));
+            // register bits: requested positions, padded with the highest unused tile positions
+            std::vector<int> reg = b.regset;
+            for (int p = K - 1; (int)reg.size() < R && p >= 0; --p)
+                if (std::find(reg.begin(), reg.end(), p) == reg.end()) reg.push_back(p);
+            std::sort(reg.begin(), reg.end());
+            int reg_of[MAX_TILE_BITS];
+            for (int p = 0; p < MAX_TILE_BITS; ++p) reg_of[p] = -1;
+            for (int r = 0; r < R; ++r) { ps.regpos[r] = (uint8_t)reg[r]; reg_of[reg[r]] = r; }
+            // thread bits: first three with distinct (position mod 3) so a quarter-warp touches 8 bank groups
+            std::vector<int> rest;
+            for (int p = 0; p < K; ++p)
+                if (reg_of[p] < 0) rest.push_back(p);
+            std::vector<int> order;
+            bool used_res[3] = {false, false, false};
+            std::vector<bool> taken(rest.size(), false);
+            for (size_t i = 0; i < rest.size() && order.size() < 3; ++i)
+                if (!used_res[rest[i] % 3]) { used_res[rest[i] % 3] = true; taken[i] = true; order.push_back(rest[i]); }
+            for (size_t i = 0; i < rest.size(); ++i)
+                if (!taken[i]) order.push_back(rest[i]);
+            for (int i = 0; i < K - R; ++i) ps.tpos[i] = (uint8_t)order[i];
+            for (int m = 0; m < (1 << R); ++m) {
+                const int off = deposit(m, ps.regpos, R);
+                ps.regoff[m] = (uint16_t)off;
+                ps.regoff_swz[m] = (uint16_t)swz(off);
+            }
+            ps.op_begin = (int)P.ops.size();
+            ps.instr_lo = b.lops.empty() ? 0 : b.lops.front()->instr;
+            ps.instr_hi = b.lops.empty() ? 0 : b.lops.back()->instr + 1;
+            for (const LogicalOp* lp : b.lops) {
+                const LogicalOp& l = *lp;
+                Op op;
+                std::memset(&op, 0, sizeof(op));
+                op.instr = l.instr;
+                int kind = OPK_DIAG;
+                uint32_t rb[4] = {0, 0, 0, 0};
+                const int d = 1 << l.nb;
+                if (l.diag) {
+                    kind = OPK_DIAG;
+                    for (int i = 0; i < l.nb; ++i) rb[i] = (uint32_t)local_of[l.bits[i]];
+                    op.mat = pb.add_doubles(l.mat);
+                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
+                } else if (l.nb <= 2) {
+                    for (int i = 0; i < l.nb; ++i) rb[i] = (uint32_t)reg_of[local_of[l.bits[i]]];
+                    const cmat m = read_complex(l.mat.data(), d * d), mb = read_complex(l.bare.data(), d * d);
+                    kind = l.nb == 2 ? OPK_DENSE2 : (is_antidiagonal2(m) && is_antidiagonal2(mb) ? OPK_PERM1 : OPK_DENSE1);
+                    op.mat = pb.add_doubles(l.mat);
+                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
+                } else {
+                    // 3- or 4-bit dense operator: re-index to the pass's four register bits
+                    if (R < 4) throw std::runtime_error("dense operators on 3-4 bits need reg_bits = 4");
+                    kind = OPK_DENSE4;
+                    P.has_dense4 = true;
+                    int rbit[4];
+                    for (int i = 0; i < l.nb; ++i) rbit[i] = reg_of[local_of[l.bits[i]]];
+                    auto remap = [&](const std::vector<double>& src) {
+                        const cmat m = read_complex(src.data(), d * d);
+                        cmat big(256, cd(0, 0));
+                        int spect_mask = 15;
+                        for (int i = 0; i < l.nb; ++i) spect_mask &= ~(1 << rbit[i]);
+                        for (int ro = 0; ro < 16; ++ro)
+                            for (int ri = 0; ri < 16; ++ri) {
+                                if ((ro & spect_mask) != (ri & spect_mask)) continue;
+                                int mo = 0, mi = 0;
+                                for (int i = 0; i < l.nb; ++i) { mo |= ((ro >> rbit[i]) & 1) << i; mi |= ((ri >> rbit[i]) & 1) << i; }
+                                big[ro * 16 + ri] = m[mo * d + mi];
+                            }
+                        return flatten(big);
+                    };
+                    for (int i = 0; i < 4; ++i) rb[i] = (uint32_t)i;
+                    op.mat = pb.add_doubles(remap(l.mat));
+                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(remap(l.bare));
+                }
+                op.kind_nb = (uint32_t)kind | ((uint32_t)l.nb << 8);
+                op.rbs = rb[0] | (rb[1] << 8) | (rb[2] << 16) | (rb[3] << 24);
+                P.ops.push_back(op);
+            }
+            ps.op_end = (int)P.ops.size();
+            P.passes.push_back(ps);
+        }
+        seg.pass_end = (int)P.passes.size();
+        P.segs.push_back(seg);
+    }
+}
+
+std::string describe_program(const Program& P) {
+    std::ostringstream o;
+    o << "mode=" << P.mode << " nq=" << P.nq << " nbits=" << P.nbits << " K=" << P.K << " R=" << P.R << " G=" << P.G
+      << " segments=" << P.segs.size() << " passes=" << P.passes.size() << " ops=" << P.ops.size()
+      << " channels=" << P.chans.size() << " noisy=" << P.noisy_instrs.size() << " draws=" << P.num_draws
+      << " norm_preserving=" << P.norm_preserving << " dense4=" << P.has_dense4 << " pool=" << P.pool.size() << "\n";
+    for (size_t s = 0; s < P.segs.size(); ++s) {
+        const Segment& g = P.segs[s];
+        o << "seg " << s << " instr[" << g.instr_lo << "," << g.instr_hi << ") tile{";
+        for (int p = 0; p < P.K; ++p) o << (p ? "," : "") << (int)g.tile_q[p];
+        o << "} passes " << g.pass_end - g.pass_begin << "\n";
+    }
+    return o.str();
+}
+
+}  // namespace ncb

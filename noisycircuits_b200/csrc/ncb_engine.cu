@@ -1,0 +1,687 @@
+// Runtime + C ABI of the B200 noisy-circuit engine (include/ncb200.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ncb200.h"
+#include "ncb_compile.h"
+#include "ncb_kernels.cuh"
+#include "ncb_schedule.h"
+
+namespace ncb {
+
+static thread_local std::string g_error;
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess)                                                                                     \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, n * sizeof(T)));
+        cap = n;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFreeHost(p));
+        p = nullptr; cap = 0;
+        CK(cudaMallocHost(&p, n * sizeof(T)));
+        cap = n;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Engine {
+    Program P;
+    int device = -1;
+    bool uploaded = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    DevProgram d{};
+    DevBuf<Op> d_ops; DevBuf<Pass> d_passes; DevBuf<Segment> d_segs; DevBuf<Instr> d_instrs; DevBuf<Channel> d_chans;
+    DevBuf<double> d_pool; DevBuf<int32_t> d_noisy;
+    DevBuf<cplx> d_states;
+    DevBuf<double> d_red, d_norm, d_invnorm, d_probs, d_partial, d_uniforms;
+    DevBuf<Decision> d_dec;
+    DevBuf<unsigned long long> d_counters;
+    DevBuf<Work> d_works[2];
+    DevBuf<DecideItem> d_decides[2];
+    PinnedBuf<Work> h_works[2];
+    PinnedBuf<DecideItem> h_decides[2];
+    cudaEvent_t buf_free[2] = {nullptr, nullptr};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+
+    ~Engine() {
+        d_ops.release(); d_passes.release(); d_segs.release(); d_instrs.release(); d_chans.release(); d_pool.release();
+        d_noisy.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_probs.release();
+        d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release();
+        for (int i = 0; i < 2; ++i) {
+            d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
+            if (buf_free[i]) cudaEventDestroy(buf_free[i]);
+        }
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
+    }
+
+    bool resident() const { return P.nbits <= P.K; }
+    size_t tile_smem() const { return ((size_t)1 << P.K) * sizeof(cplx); }
+    size_t resident_smem() const {
+        return tile_smem() + ((size_t)1 << P.nbits) * sizeof(double) + (((size_t)P.G + 31) / 32 + 1) * sizeof(unsigned);
+    }
+
+    template <class T>
+    static void upload(DevBuf<T>& b, const std::vector<T>& v) {
+        b.reserve(std::max<size_t>(v.size(), 1));
+        if (!v.empty()) CK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+
+    void ensure_device() {
+        if (uploaded) return;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw CudaError(std::string("no usable CUDA device (") + cudaGetErrorString(e) + "): this engine has no CPU fallback");
+        if (device >= 0) CK(cudaSetDevice(device));
+        CK(cudaGetDevice(&device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        sm_count = prop.multiProcessorCount;
+        smem_optin = prop.sharedMemPerBlockOptin;
+        upload(d_ops, P.ops); upload(d_passes, P.passes); upload(d_segs, P.segs); upload(d_instrs, P.instrs);
+        upload(d_chans, P.chans); upload(d_pool, P.pool); upload(d_noisy, P.noisy_instrs);
+        d.ops = d_ops.p; d.passes = d_passes.p; d.segs = d_segs.p; d.instrs = d_instrs.p; d.chans = d_chans.p;
+        d.pool = d_pool.p; d.noisy = d_noisy.p; d.n_noisy = (int)P.noisy_instrs.size(); d.G = P.G; d.nbits = P.nbits;
+        d.K = P.K; d.R = P.R; d.nseg = (int)P.segs.size();
+        const size_t need = resident() ? resident_smem() : tile_smem();
+        if (need + 6 * 1024 > smem_optin)
+            throw std::runtime_error("tile does not fit shared memory: need " + std::to_string(need) + " B, device offers " + std::to_string(smem_optin));
+        for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&buf_free[i], cudaEventDisableTiming));
+        CK(cudaEventCreate(&t0));
+        CK(cudaEventCreate(&t1));
+        d_counters.reserve(4);
+        uploaded = true;
+    }
+
+    // ---- kernel dispatch on (R, dense4) ----------------------------------------------------------------------
+    template <int R, bool D4>
+    void launch_tile_t(int grid, int threads, cudaStream_t s, const Work* works, int tile_shift) {
+        static thread_local bool configured = false;
+        if (!configured) {
+            CK(cudaFuncSetAttribute(tile_kernel<R, D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 8 * 1024));
+            configured = true;
+        }
+        tile_kernel<R, D4><<<grid, threads, tile_smem(), s>>>(d, works, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p);
+        CK(cudaGetLastError());
+    }
+    void launch_tile(int nworks, cudaStream_t s, const Work* works) {
+        const int tile_shift = P.nbits > P.K ? P.nbits - P.K : 0;
+        const int threads = 1 << (P.K - P.R);
+        const long long grid = (long long)nworks << tile_shift;
+        if (grid > 0x7fffffffLL) throw std::runtime_error("launch too large");
+        if (P.R == 4 && P.has_dense4) launch_tile_t<4, true>((int)grid, threads, s, works, tile_shift);
+        else if (P.R == 4) launch_tile_t<4, false>((int)grid, threads, s, works, tile_shift);
+        else if (P.R == 3) launch_tile_t<3, false>((int)grid, threads, s, works, tile_shift);
+        else throw std::runtime_error("unsupported reg_bits (3 or 4)");
+    }
+    template <int R, bool D4>
+    void launch_resident_t(int grid, int threads, cudaStream_t s, const ResidentArgs& a) {
+        static thread_local bool configured = false;
+        if (!configured) {
+            CK(cudaFuncSetAttribute(resident_kernel<R, D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 8 * 1024));
+            configured = true;
+        }
+        resident_kernel<R, D4><<<grid, threads, resident_smem(), s>>>(d, a);
+        CK(cudaGetLastError());
+    }
+    void launch_resident(int grid, cudaStream_t s, const ResidentArgs& a) {
+        const int threads = 1 << (P.K - P.R);
+        if (P.R == 4 && P.has_dense4) launch_resident_t<4, true>(grid, threads, s, a);
+        else if (P.R == 4) launch_resident_t<4, false>(grid, threads, s, a);
+        else if (P.R == 3) launch_resident_t<3, false>(grid, threads, s, a);
+        else throw std::runtime_error("unsupported reg_bits (3 or 4)");
+    }
+    int resident_ctas_per_sm() const {
+        const size_t per = resident_smem() + 8 * 1024;
+        int by_smem = (int)std::max<size_t>(1, (size_t)227 * 1024 / per);
+        int by_threads = std::max(1, 1536 / (1 << (P.K - P.R)));
+        return std::max(1, std::min({by_smem, by_threads, 8}));
+    }
+
+    // uniform(t_local, instr) for the host planner
+    struct UniformSource {
+        int rng; uint64_t seed; long long traj_begin; const double* table; int G;
+        std::vector<double> mt;         // [count][num_draws]
+        int num_draws = 0;
+        const int32_t* draw_pos = nullptr;
+        double get(long long tl, int i) const {
+            if (rng == NCB_RNG_PHILOX) return philox_uniform(seed, (uint64_t)(traj_begin + tl), (uint32_t)i);
+            if (rng == NCB_RNG_EXPLICIT) return table[tl * G + i];
+            return mt[(size_t)tl * num_draws + draw_pos[i]];
+        }
+    };
+
+    static double mt_canonical(std::mt19937_64& g) {
+        // what std::discrete_distribution draws: std::generate_canonical<double, 53>(g)
+        return std::generate_canonical<double, 53>(g);
+    }
+
+    void fill_mt(UniformSource& us, long long begin, long long count) {
+        us.num_draws = P.num_draws; us.draw_pos = P.draw_pos.data();
+        us.mt.resize((size_t)count * std::max(P.num_draws, 1));
+#pragma omp parallel for schedule(static)
+        for (long long t = 0; t < count; ++t) {
+            std::mt19937_64 g((unsigned int)(us.seed + (uint64_t)(us.traj_begin + begin + t)));   // Simulator.cpp:124: cuint seed
+            for (int k = 0; k < P.num_draws; ++k) us.mt[(size_t)t * P.num_draws + k] = mt_canonical(g);
+        }
+    }
+
+    // dense per-instruction uniform table [count][G] (resident path with MT / explicit rng)
+    void dense_table(const UniformSource& us, long long begin, long long count, std::vector<double>& out) {
+        out.assign((size_t)count * P.G, 0.5);
+#pragma omp parallel for schedule(static)
+        for (long long t = 0; t < count; ++t)
+            for (int32_t i : P.noisy_instrs) out[(size_t)t * P.G + i] = us.get(begin + t, i);
+    }
+
+    int auto_batch(long long count) const {
+        const long long tiles = 1ll << std::max(P.nbits - P.K, 0);
+        long long b = (148ll * 256 + tiles - 1) / tiles;
+        b = ((b + 36) / 37) * 37;
+        const long long mem_cap = std::max<long long>(1, (6ll << 30) / ((long long)sizeof(cplx) << P.nbits));
+        b = std::min(b, mem_cap);
+        return (int)std::max<long long>(1, std::min(b, count));
+    }
+
+    void mcwf_run(ncb_run_params* rp);
+    void mcwf_resident(ncb_run_params* rp, cudaStream_t s);
+    void mcwf_tiled(ncb_run_params* rp, cudaStream_t s);
+    void run_deterministic(cudaStream_t s);       // one slot, no events (pure / density modes); leaves the state in d_states
+};
+
+static void grid_1d(long long n, int* grid, int* block) {
+    *block = 256;
+    *grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    if (*grid < 1) *grid = 1;
+}
+
+void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
+    const long long dim = 1ll << P.nbits, count = rp->traj_count;
+    const int grid = (int)std::min<long long>(count, (long long)sm_count * resident_ctas_per_sm());
+    UniformSource us{rp->rng, rp->seed, rp->traj_begin, rp->uniforms, P.G};
+    ResidentArgs a{};
+    a.traj_begin = rp->traj_begin; a.traj_count = count; a.seed = rp->seed; a.normalize = P.norm_preserving ? 0 : 1;
+    a.uniforms = nullptr;
+    if (rp->rng != NCB_RNG_PHILOX) {
+        std::vector<double> table;
+        if (rp->rng == NCB_RNG_MT19937_REFERENCE) fill_mt(us, 0, count);
+        dense_table(us, 0, count, table);
+        d_uniforms.reserve(table.size());
+        CK(cudaMemcpyAsync(d_uniforms.p, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        a.uniforms = d_uniforms.p;
+    }
+    d_partial.reserve((size_t)grid * dim);
+    a.partial_probs = d_partial.p;
+    if (rp->states) { d_states.reserve((size_t)count * dim); a.states_out = d_states.p; }
+    CK(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(unsigned long long), s));
+    a.counters = d_counters.p;
+    launch_resident(grid, s, a);
+    int g, b;
+    grid_1d(dim, &g, &b);
+    sum_partials_kernel<<<g, b, 0, s>>>(d_probs.p, d_partial.p, dim, grid);
+    CK(cudaGetLastError());
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(cnt, d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    if (rp->states)
+        CK(cudaMemcpyAsync(rp->states, d_states.p, (size_t)count * dim * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    rp->out_events += (int64_t)cnt[0];
+    rp->out_hard_events += (int64_t)cnt[1];
+    rp->out_launches += 2;
+    rp->out_sweeps += 0;
+}
+
+void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
+    const long long dim = 1ll << P.nbits, count = rp->traj_count;
+    const int ntiles = 1 << (P.nbits - P.K);
+    const int B = rp->batch > 0 ? (int)std::min<long long>(rp->batch, count) : auto_batch(count);
+    d_states.reserve((size_t)B * dim);
+    d_red.reserve((size_t)B * ntiles * RED_VALUES);
+    d_norm.reserve((size_t)B * ntiles);
+    d_invnorm.reserve(B);
+    d_dec.reserve(B);
+    UniformSource us{rp->rng, rp->seed, rp->traj_begin, rp->uniforms, P.G};
+    std::vector<std::vector<Event>> events;
+    BatchPlan plan;
+    std::vector<cplx> host_states;
+    int buf = 0;
+    const bool want_norm = !P.norm_preserving;
+    CK(cudaMemsetAsync(d_red.p, 0, (size_t)B * ntiles * RED_VALUES * sizeof(double), s));
+    for (long long b0 = 0; b0 < count; b0 += B) {
+        const int nb = (int)std::min<long long>(B, count - b0);
+        if (rp->rng == NCB_RNG_MT19937_REFERENCE) {
+            UniformSource tmp = us;
+            fill_mt(tmp, b0, nb);
+            us.mt.swap(tmp.mt); us.num_draws = tmp.num_draws; us.draw_pos = tmp.draw_pos;
+        }
+        events.assign(nb, {});
+        const bool mt = rp->rng == NCB_RNG_MT19937_REFERENCE;
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int b = 0; b < nb; ++b) {
+            const long long tl = mt ? b : b0 + b;
+            plan_events(P, [&](int i) { return us.get(tl, i); }, events[b]);
+        }
+        schedule_batch(P, events, true, want_norm, plan);
+        for (int b = 0; b < nb; ++b) {
+            rp->out_events += (int64_t)events[b].size();
+            for (const Event& e : events[b]) rp->out_hard_events += e.kmin != e.kmax;
+        }
+        rp->out_sweeps += plan.sweeps;
+        // upload the batch's work lists (double-buffered so planning overlaps the previous batch's kernels)
+        CK(cudaEventSynchronize(buf_free[buf]));
+        h_works[buf].reserve(plan.works.size() + 1); d_works[buf].reserve(plan.works.size() + 1);
+        h_decides[buf].reserve(plan.decides.size() + 1); d_decides[buf].reserve(plan.decides.size() + 1);
+        std::memcpy(h_works[buf].p, plan.works.data(), plan.works.size() * sizeof(Work));
+        CK(cudaMemcpyAsync(d_works[buf].p, h_works[buf].p, plan.works.size() * sizeof(Work), cudaMemcpyHostToDevice, s));
+        if (!plan.decides.empty()) {
+            std::memcpy(h_decides[buf].p, plan.decides.data(), plan.decides.size() * sizeof(DecideItem));
+            CK(cudaMemcpyAsync(d_decides[buf].p, h_decides[buf].p, plan.decides.size() * sizeof(DecideItem), cudaMemcpyHostToDevice, s));
+        }
+        for (const LaunchStep& st : plan.steps) {
+            if (st.kind == 0) launch_tile(st.count, s, d_works[buf].p + st.begin);
+            else {
+                decide_kernel<<<st.count, 32, 0, s>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
+                CK(cudaGetLastError());
+            }
+            ++rp->out_launches;
+        }
+        CK(cudaEventRecord(buf_free[buf], s));
+        if (want_norm) {
+            norm_finalize_kernel<<<(nb + 7) / 8, 256, 0, s>>>(d_norm.p, ntiles, nb, d_invnorm.p);
+            CK(cudaGetLastError());
+        }
+        int g, bl;
+        grid_1d(dim, &g, &bl);
+        accumulate_kernel<<<g, bl, 0, s>>>(d_probs.p, d_states.p, P.nbits, nb, want_norm ? d_invnorm.p : nullptr);
+        CK(cudaGetLastError());
+        rp->out_launches += want_norm ? 2 : 1;
+        if (rp->states) {
+            host_states.resize((size_t)nb * dim);
+            CK(cudaMemcpyAsync(host_states.data(), d_states.p, (size_t)nb * dim * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            for (int b = 0; b < nb; ++b) {
+                double n2 = 0;
+                for (long long j = 0; j < dim; ++j) n2 += cnorm2(host_states[(size_t)b * dim + j]);
+                const double f = 1.0 / std::sqrt(n2);
+                for (long long j = 0; j < dim; ++j) {
+                    rp->states[2 * ((size_t)(b0 + b) * dim + j)] = host_states[(size_t)b * dim + j].x * f;
+                    rp->states[2 * ((size_t)(b0 + b) * dim + j) + 1] = host_states[(size_t)b * dim + j].y * f;
+                }
+            }
+        }
+        buf ^= 1;
+    }
+    CK(cudaStreamSynchronize(s));
+}
+
+void Engine::mcwf_run(ncb_run_params* rp) {
+    if (P.mode != MODE_MCWF) throw std::runtime_error("program was not compiled in MCWF mode");
+    if (rp->traj_count < 0) throw std::runtime_error("traj_count must be >= 0");
+    if (rp->rng == NCB_RNG_EXPLICIT && !rp->uniforms) throw std::runtime_error("rng = EXPLICIT needs uniforms");
+    if (!rp->probs) throw std::runtime_error("probs must not be NULL");
+    ensure_device();
+    cudaStream_t s = (cudaStream_t)rp->stream;
+    const long long dim = 1ll << P.nbits;
+    d_probs.reserve(dim);
+    CK(cudaMemsetAsync(d_probs.p, 0, dim * sizeof(double), s));
+    rp->out_sweeps = rp->out_events = rp->out_hard_events = rp->out_launches = 0;
+    rp->out_kernel_ms = 0.0;
+    CK(cudaEventRecord(t0, s));
+    if (rp->traj_count > 0) {
+        if (resident()) {
+            // chunk so the optional tables / states stay bounded
+            const long long chunk = rp->states || rp->rng != NCB_RNG_PHILOX ? std::max<long long>(1, (1ll << 28) / std::max<long long>(dim * 2, (long long)P.G)) : rp->traj_count;
+            ncb_run_params sub = *rp;
+            for (long long b0 = 0; b0 < rp->traj_count; b0 += chunk) {
+                sub.traj_begin = rp->traj_begin + b0;
+                sub.traj_count = std::min(chunk, rp->traj_count - b0);
+                sub.uniforms = rp->uniforms ? rp->uniforms + b0 * P.G : nullptr;
+                sub.states = rp->states ? rp->states + 2 * b0 * dim : nullptr;
+                mcwf_resident(&sub, s);
+            }
+            rp->out_sweeps = sub.out_sweeps; rp->out_events = sub.out_events; rp->out_hard_events = sub.out_hard_events;
+            rp->out_launches = sub.out_launches;
+        } else {
+            mcwf_tiled(rp, s);
+        }
+    }
+    CK(cudaEventRecord(t1, s));
+    CK(cudaEventSynchronize(t1));
+    {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, t0, t1));
+        rp->out_kernel_ms = ms;
+    }
+    // deliver
+    if (rp->probs_on_device) {
+        if (rp->accumulate) {
+            // probs += d_probs
+            int g, b;
+            grid_1d(dim, &g, &b);
+            sum_partials_kernel<<<g, b, 0, s>>>(rp->probs, d_probs.p, dim, 1);
+            CK(cudaGetLastError());
+        } else {
+            CK(cudaMemcpyAsync(rp->probs, d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        }
+        CK(cudaStreamSynchronize(s));
+    } else {
+        std::vector<double> tmp(dim);
+        CK(cudaMemcpyAsync(tmp.data(), d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (rp->accumulate) for (long long j = 0; j < dim; ++j) rp->probs[j] += tmp[j];
+        else std::memcpy(rp->probs, tmp.data(), dim * sizeof(double));
+    }
+}
+
+void Engine::run_deterministic(cudaStream_t s) {
+    ensure_device();
+    const long long dim = 1ll << P.nbits;
+    d_states.reserve(dim);
+    if (resident()) {
+        ResidentArgs a{};
+        a.traj_begin = 0; a.traj_count = 1; a.seed = 0; a.uniforms = nullptr; a.partial_probs = nullptr;
+        a.states_out = d_states.p; a.normalize = 0; a.counters = nullptr;
+        launch_resident(1, s, a);
+    } else {
+        d_red.reserve(RED_VALUES); d_norm.reserve((size_t)1 << (P.nbits - P.K)); d_dec.reserve(1);
+        std::vector<std::vector<Event>> events(1);
+        BatchPlan plan;
+        schedule_batch(P, events, true, false, plan);
+        d_works[0].reserve(plan.works.size() + 1);
+        CK(cudaMemcpyAsync(d_works[0].p, plan.works.data(), plan.works.size() * sizeof(Work), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        for (const LaunchStep& st : plan.steps) launch_tile(st.count, s, d_works[0].p + st.begin);
+    }
+}
+
+}  // namespace ncb
+
+// ==================================================================================================================
+// C ABI
+// ==================================================================================================================
+using namespace ncb;
+
+struct ncb_program {
+    Engine eng;
+};
+
+static int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+#define NCB_TRY try {
+#define NCB_CATCH                                                           \
+    }                                                                       \
+    catch (const CudaError& e) { return fail(NCB_E_CUDA, e.what()); }       \
+    catch (const std::bad_alloc&) { return fail(NCB_E_NOMEM, "out of host memory"); } \
+    catch (const std::exception& e) { return fail(NCB_E_INVALID, e.what()); }
+
+extern "C" {
+
+const char* ncb_last_error(void) { return g_error.c_str(); }
+int ncb_version(void) { return NCB_VERSION; }
+
+static CircuitView view_of(const ncb_circuit* c) {
+    CircuitView v;
+    v.num_qubits = c->num_qubits; v.num_instructions = c->num_instructions;
+    v.opcode = c->opcode; v.q0 = c->q0; v.q1 = c->q1; v.theta = c->theta; v.channel = c->channel;
+    v.unitary_offset = c->unitary_offset; v.unitary_nq = c->unitary_nq; v.unitary_qubits = c->unitary_qubits;
+    v.unitary_pool = c->unitary_pool; v.num_channels = c->num_channels; v.channel_offset = c->channel_offset;
+    v.channel_count = c->channel_count; v.channel_dim = c->channel_dim; v.kraus_pool = c->kraus_pool;
+    return v;
+}
+
+int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* options, ncb_program** out) {
+    if (!circuit || !out) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    CompileOptions opt;
+    int device = -1;
+    if (options) {
+        if (options->tile_bits > 0) opt.tile_bits = options->tile_bits;
+        if (options->reg_bits > 0) opt.reg_bits = options->reg_bits;
+        if (options->low_bits >= 0) opt.low_bits = options->low_bits;
+        opt.fuse = options->fuse;
+        device = options->device;
+    }
+    if (const char* e = getenv("NCB_TILE_BITS")) opt.tile_bits = atoi(e);
+    if (const char* e = getenv("NCB_REG_BITS")) opt.reg_bits = atoi(e);
+    if (const char* e = getenv("NCB_LOW_BITS")) opt.low_bits = atoi(e);
+    if (const char* e = getenv("NCB_FUSE")) opt.fuse = atoi(e);
+    if (opt.reg_bits != 3 && opt.reg_bits != 4) return fail(NCB_E_INVALID, "reg_bits must be 3 or 4");
+    opt.tile_bits = std::min(opt.tile_bits, opt.reg_bits == 4 ? 12 : 12);   // <= 256 threads (R = 4) / 512 threads (R = 3)
+    ncb_program* p = new ncb_program();
+    try {
+        compile_program(view_of(circuit), mode, opt, p->eng.P);
+    } catch (...) { delete p; throw; }
+    p->eng.device = device;
+    *out = p;
+    return NCB_OK;
+    NCB_CATCH
+}
+
+void ncb_program_destroy(ncb_program* program) { delete program; }
+
+int64_t ncb_program_describe(const ncb_program* program, char* buf, int64_t len) {
+    if (!program) return 0;
+    const std::string s = describe_program(program->eng.P);
+    if (buf && len > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)len - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+int64_t ncb_program_query(const ncb_program* program, int what) {
+    if (!program) return -1;
+    const Program& P = program->eng.P;
+    switch (what) {
+    case NCB_Q_NUM_QUBITS: return P.nq;
+    case NCB_Q_STATE_BITS: return P.nbits;
+    case NCB_Q_TILE_BITS: return P.K;
+    case NCB_Q_REG_BITS: return P.R;
+    case NCB_Q_NUM_SEGMENTS: return (int64_t)P.segs.size();
+    case NCB_Q_NUM_PASSES: return (int64_t)P.passes.size();
+    case NCB_Q_NUM_OPS: return (int64_t)P.ops.size();
+    case NCB_Q_NUM_DRAWS: return P.num_draws;
+    case NCB_Q_NORM_PRESERVING: return P.norm_preserving;
+    case NCB_Q_NUM_INSTRUCTIONS: return P.G;
+    case NCB_Q_RESIDENT: return program->eng.resident();
+    }
+    return -1;
+}
+
+int64_t ncb_program_events(const ncb_program* program, const double* uniforms, int32_t* out, int64_t cap) {
+    if (!program || !uniforms) return -1;
+    std::vector<Event> ev;
+    plan_events(program->eng.P, [&](int i) { return uniforms[i]; }, ev);
+    for (size_t i = 0; i < ev.size() && (int64_t)i < cap; ++i) {
+        out[3 * i] = ev[i].instr; out[3 * i + 1] = ev[i].kmin; out[3 * i + 2] = ev[i].kmax;
+    }
+    return (int64_t)ev.size();
+}
+
+int ncb_program_reference_uniforms(const ncb_program* program, uint64_t seed, double* uniforms) {
+    if (!program || !uniforms) return fail(NCB_E_INVALID, "null argument");
+    const Program& P = program->eng.P;
+    std::mt19937_64 g((unsigned int)seed);
+    for (int i = 0; i < P.G; ++i) uniforms[i] = P.draw_pos[i] >= 0 ? Engine::mt_canonical(g) : 0.5;
+    return NCB_OK;
+}
+
+int ncb_mcwf_run(ncb_program* program, ncb_run_params* params) {
+    if (!program || !params) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    program->eng.mcwf_run(params);
+    return NCB_OK;
+    NCB_CATCH
+}
+
+int ncb_pure_run(ncb_program* program, double* state, double* probs, void* stream) {
+    if (!program) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    Engine& E = program->eng;
+    if (E.P.mode != MODE_PURE) throw std::runtime_error("program was not compiled in PURE mode");
+    cudaStream_t s = (cudaStream_t)stream;
+    E.run_deterministic(s);
+    const long long dim = 1ll << E.P.nbits;
+    if (state) CK(cudaMemcpyAsync(state, E.d_states.p, dim * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    if (probs) {
+        E.d_probs.reserve(dim);
+        int g, b;
+        grid_1d(dim, &g, &b);
+        abs2_kernel<<<g, b, 0, s>>>(E.d_probs.p, E.d_states.p, dim);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(probs, E.d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return NCB_OK;
+    NCB_CATCH
+}
+
+int ncb_density_run(ncb_program* program, double* probs, void* stream) {
+    if (!program || !probs) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    Engine& E = program->eng;
+    if (E.P.mode != MODE_DENSITY) throw std::runtime_error("program was not compiled in DENSITY mode");
+    cudaStream_t s = (cudaStream_t)stream;
+    E.run_deterministic(s);
+    const long long dim = 1ll << E.P.nq;
+    E.d_probs.reserve(dim);
+    int g, b;
+    grid_1d(dim, &g, &b);
+    diag_kernel<<<g, b, 0, s>>>(E.d_probs.p, E.d_states.p, E.P.nq);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(probs, E.d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return NCB_OK;
+    NCB_CATCH
+}
+
+int ncb_apply_measurement_error_device(double* probabilities_device, const double* mats, const int32_t* qubits,
+                                       int32_t nq, int32_t num_qubits, void* stream) {
+    if (!probabilities_device || !mats || !qubits) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    if (num_qubits < 1 || num_qubits > MAX_QUBITS) throw std::runtime_error("num_qubits out of range");
+    const long long half = (1ll << num_qubits) >> 1;
+    int g, b;
+    grid_1d(half, &g, &b);
+    for (int k = 0; k < nq; ++k) {
+        if (qubits[k] < 0 || qubits[k] >= num_qubits) throw std::runtime_error("measured qubit out of range");
+        measurement_error_kernel<<<g, b, 0, (cudaStream_t)stream>>>(probabilities_device, half, qubits[k], mats[4 * k],
+                                                                     mats[4 * k + 1], mats[4 * k + 2], mats[4 * k + 3]);
+        CK(cudaGetLastError());
+    }
+    return NCB_OK;
+    NCB_CATCH
+}
+
+int ncb_apply_measurement_error(double* probabilities, const double* mats, const int32_t* qubits, int32_t nq,
+                                int32_t num_qubits, uint32_t num_threads) {
+    (void)num_threads;
+    if (!probabilities) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    if (num_qubits < 1 || num_qubits > MAX_QUBITS) throw std::runtime_error("num_qubits out of range");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) throw CudaError(std::string("no usable CUDA device (") + cudaGetErrorString(e) + ")");
+    const size_t bytes = sizeof(double) << num_qubits;
+    double* d = nullptr;
+    CK(cudaMalloc(&d, bytes));
+    int rc = NCB_OK;
+    try {
+        CK(cudaMemcpy(d, probabilities, bytes, cudaMemcpyHostToDevice));
+        rc = ncb_apply_measurement_error_device(d, mats, qubits, nq, num_qubits, nullptr);
+        if (rc == NCB_OK) CK(cudaMemcpy(probabilities, d, bytes, cudaMemcpyDeviceToHost));
+    } catch (...) { cudaFree(d); throw; }
+    cudaFree(d);
+    return rc;
+    NCB_CATCH
+}
+
+int ncb_simulate_circuit(const ncb_circuit* circuit, double* statevector, int noisy, uint32_t num_trajectories,
+                         int return_state, uint32_t thread_count) {
+    (void)thread_count;
+    if (!circuit || !statevector) return fail(NCB_E_INVALID, "null argument");
+    ncb_program* p = nullptr;
+    int rc = ncb_program_create(circuit, noisy ? NCB_MODE_MCWF : NCB_MODE_PURE, nullptr, &p);
+    if (rc != NCB_OK) return rc;
+    const long long dim = 1ll << circuit->num_qubits;
+    if (noisy) {
+        std::vector<double> probs(dim, 0.0);
+        ncb_run_params rp;
+        std::memset(&rp, 0, sizeof(rp));
+        rp.traj_begin = 0; rp.traj_count = num_trajectories; rp.rng = NCB_RNG_MT19937_REFERENCE; rp.seed = 42;
+        rp.probs = probs.data();
+        rc = ncb_mcwf_run(p, &rp);
+        if (rc == NCB_OK) {
+            const double inv = 1.0 / (double)num_trajectories;            // Simulator.cpp:121, 129
+            for (long long j = 0; j < dim; ++j) statevector[2 * j] += probs[j] * inv;
+        }
+    } else if (return_state) {
+        rc = ncb_pure_run(p, statevector, nullptr, nullptr);
+    } else {
+        std::vector<double> probs(dim);
+        rc = ncb_pure_run(p, nullptr, probs.data(), nullptr);
+        if (rc == NCB_OK)
+            for (long long j = 0; j < dim; ++j) { statevector[2 * j] = probs[j]; statevector[2 * j + 1] = 0.0; }
+    }
+    ncb_program_destroy(p);
+    return rc;
+}
+
+int ncb_run_trajectory(const ncb_circuit* circuit, double* statevector, uint32_t seed, uint32_t thread_count) {
+    (void)thread_count;
+    if (!circuit || !statevector) return fail(NCB_E_INVALID, "null argument");
+    ncb_program* p = nullptr;
+    int rc = ncb_program_create(circuit, NCB_MODE_MCWF, nullptr, &p);
+    if (rc != NCB_OK) return rc;
+    const long long dim = 1ll << circuit->num_qubits;
+    std::vector<double> probs(dim, 0.0);
+    ncb_run_params rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.traj_begin = 0; rp.traj_count = 1; rp.rng = NCB_RNG_MT19937_REFERENCE; rp.seed = seed;
+    rp.probs = probs.data();
+    rc = ncb_mcwf_run(p, &rp);
+    if (rc == NCB_OK)
+        for (long long j = 0; j < dim; ++j) { statevector[2 * j] = probs[j]; statevector[2 * j + 1] = 0.0; }
+    ncb_program_destroy(p);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,431 @@
+// sm_100a kernels of the B200 noisy-circuit engine.
+//
+//   tile_kernel      one CTA = one 2^K-amplitude tile of one trajectory, staged in shared memory: load (cp.async,
+//                    128-bit, runs of >= 2^low_bits amplitudes), optional jump operator, the segment's register-blocked
+//                    passes, optional reduced-density-matrix / norm reduction, store.  One launch sweeps the state of
+//                    every trajectory of the batch once (one HBM read + one HBM write per amplitude), whatever the
+//                    number of fused instructions.
+//   resident_kernel  states of <= 2^K amplitudes: the whole trajectory lives in one CTA's shared memory; persistent
+//                    CTAs loop over trajectories, plan their jump events with Philox draws, handle them inline and
+//                    accumulate |psi|^2 on chip.  HBM is touched only for the final probabilities.
+//   decide_kernel    branch decision of the state-dependent jump events from the reduced density matrices.
+//   accumulate / norm / diag / measurement-error kernels: the tail of the path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ncb_common.h"
+
+namespace ncb {
+
+struct DevProgram {
+    const Op* ops;
+    const Pass* passes;
+    const Segment* segs;
+    const Instr* instrs;
+    const Channel* chans;
+    const double* pool;
+    const int32_t* noisy;   // instructions with a channel of >= 2 operators
+    int n_noisy, G, nbits, K, R, nseg;
+};
+
+constexpr int RED_VALUES = 32;   // doubles per reduced-density-matrix partial
+
+// ---------------------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ void st_stream(cplx* p, cplx v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reduction of NV per-thread values: fixed shuffle tree inside a warp, warps summed in order.
+// s_buf: [32 warps][NV] doubles of shared memory.  Result valid in out[0..NV) on threads < NV after the call.
+template <int NV>
+__device__ __forceinline__ void block_reduce(const double* vals, double* s_buf, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const double s = warp_sum(vals[v]);
+        if (lane == 0) s_buf[warp * NV + v] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += s_buf[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// Runs the ops with instruction index in [lo, hi) of the passes [*pcur, pend) on the tile in shared memory.
+// *pcur is advanced past the passes that are entirely below hi.
+template <int R, bool D4>
+__device__ __forceinline__ void run_range(cplx* sm, const DevProgram& P, int* pcur, int pend, int lo, int hi, bool bare_last) {
+    int p = *pcur;
+    for (; p < pend; ++p) {
+        const Pass* ps = P.passes + p;
+        const int plo = ps->instr_lo, phi = ps->instr_hi;
+        if (plo >= hi) break;
+        if (phi > lo && ps->op_end > ps->op_begin) {
+            run_pass_thread<R, D4>(sm, P.K, threadIdx.x, *ps, P.ops, P.pool, lo, hi, bare_last);
+            __syncthreads();
+        }
+        if (phi > hi) break;      // this pass also holds later instructions: revisit it
+    }
+    *pcur = p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <int R, bool D4>
+__global__ void __launch_bounds__((D4 || R == 4) ? 256 : 512)
+tile_kernel(DevProgram P, const Work* __restrict__ works, cplx* __restrict__ states, int tile_shift,
+            double* __restrict__ red_part, double* __restrict__ norm_part, const Decision* __restrict__ decisions) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw);
+    __shared__ double s_buf[32 * 20];
+    __shared__ double s_out[20];
+    const int K = P.K, tid = threadIdx.x, nthreads = blockDim.x;
+    const int ntiles = 1 << tile_shift;
+    const int wi = blockIdx.x >> tile_shift, o = blockIdx.x & (ntiles - 1);
+    const Work w = works[wi];
+    const Segment* sg = P.segs + w.seg;
+
+    // tile geometry: base = tile index o deposited into the state bits that are not tile bits
+    const long long base = tile_base(*sg, K, P.nbits, o);
+    const int offA = deposit(tid, sg->tile_q, K - R);
+    cplx* st = states + ((long long)w.slot << P.nbits) + base;
+    const int limit = 1 << P.nbits;
+
+    // ---- load ----
+    if (w.flags & WF_INIT) {
+#pragma unroll 4
+        for (int it = 0; it < (1 << R); ++it) sm[swz(tid + (it << (K - R)))] = cplx{0.0, 0.0};
+        if (o == 0 && tid == 0) sm[swz(0)] = cplx{1.0, 0.0};
+    } else {
+#pragma unroll 4
+        for (int it = 0; it < (1 << R); ++it) {
+            const int off = offA | deposit(it, sg->tile_q + (K - R), R);
+            cplx* dst = sm + swz(tid + (it << (K - R)));
+            if (off < limit) cp_async16(dst, st + off);
+            else *dst = cplx{0.0, 0.0};
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+
+    // ---- jump operator of the event that ended the previous piece ----
+    if (w.flags & (WF_PRO_STATIC | WF_PRO_DYNAMIC)) {
+        const Instr in = P.instrs[w.ev_instr];
+        const Channel ch = P.chans[in.channel];
+        int k = w.ev_k;
+        double scale = 1.0;
+        if (w.flags & WF_PRO_DYNAMIC) { k = decisions[w.slot].k; scale = decisions[w.slot].scale; }
+        const cplx* M = reinterpret_cast<const cplx*>(P.pool + ch.kraus) + k * ch.dim * ch.dim;
+        const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;
+        tile_apply_dense(sm, K, tid, nthreads, ch.dim, p0, p1, M, scale);
+        __syncthreads();
+    }
+
+    // ---- the segment's passes ----
+    int pcur = sg->pass_begin;
+    run_range<R, D4>(sm, P, &pcur, sg->pass_end, w.instr_lo, w.instr_hi, (w.flags & WF_BARE_LAST) != 0);
+
+    // ---- reductions ----
+    if (w.flags & WF_REDUCE) {
+        const Instr in = P.instrs[w.red_instr];
+        const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;
+        double* dst = red_part + ((long long)w.slot * ntiles + o) * RED_VALUES;
+        if (p1 < 0) {
+            double acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+            reduce_rho_thread<2>(sm, K, tid, nthreads, p0, -1, acc);
+            double v[6] = {acc[0], acc[1], acc[4], acc[5], acc[6], acc[7]};   // (0,0) (1,0) (1,1)
+            block_reduce<6>(v, s_buf, s_out);
+            if (tid == 0) {
+                dst[0] = s_out[0]; dst[1] = s_out[1]; dst[4] = s_out[2]; dst[5] = s_out[3]; dst[6] = s_out[4]; dst[7] = s_out[5];
+            }
+        } else {
+            double acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+            reduce_rho_thread<4>(sm, K, tid, nthreads, p0, p1, acc);
+            double v[20];
+            int n = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) { v[n++] = acc[2 * (r * 4 + c)]; v[n++] = acc[2 * (r * 4 + c) + 1]; }
+            block_reduce<20>(v, s_buf, s_out);
+            if (tid == 0) {
+                int m = 0;
+                for (int r = 0; r < 4; ++r)
+                    for (int c = 0; c <= r; ++c) { dst[2 * (r * 4 + c)] = s_out[m++]; dst[2 * (r * 4 + c) + 1] = s_out[m++]; }
+            }
+        }
+    }
+    if (w.flags & WF_NORM) {
+        double v[1] = {0.0};
+        for (int i = tid; i < (1 << K); i += nthreads) v[0] += cnorm2(sm[i]);
+        block_reduce<1>(v, s_buf, s_out);
+        if (tid == 0) norm_part[(long long)w.slot * ntiles + o] = s_out[0];
+    }
+
+    // ---- store ----
+#pragma unroll 4
+    for (int it = 0; it < (1 << R); ++it) {
+        const int off = offA | deposit(it, sg->tile_q + (K - R), R);
+        if (off < limit) st_stream(st + off, sm[swz(tid + (it << (K - R)))]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// decide kernel: one warp per state-dependent event
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void decide_kernel(DevProgram P, const DecideItem* __restrict__ items, int nitems, const double* __restrict__ red_part,
+                              int ntiles, Decision* __restrict__ decisions) {
+    __shared__ double rho[RED_VALUES];
+    const int it = blockIdx.x;
+    if (it >= nitems) return;
+    const DecideItem d = items[it];
+    const double* src = red_part + (long long)d.slot * ntiles * RED_VALUES;
+    double s = 0.0;
+    for (int o = 0; o < ntiles; ++o) s += src[(long long)o * RED_VALUES + threadIdx.x];
+    rho[threadIdx.x] = s;
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        const Channel ch = P.chans[P.instrs[d.instr].channel];
+        mirror_rho(rho, ch.dim);
+        double scale;
+        const int k = decide_branch(rho, ch, P.pool, d.u, &scale);
+        decisions[d.slot].k = k;
+        decisions[d.slot].scale = scale;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tail kernels
+// ---------------------------------------------------------------------------------------------------------------
+// inv_norm2[slot] = 1 / sum_tiles norm_part[slot][tile]
+__global__ void norm_finalize_kernel(const double* __restrict__ norm_part, int ntiles, int nslots, double* __restrict__ inv_norm2) {
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (slot >= nslots) return;
+    double s = 0.0;
+    for (int o = lane; o < ntiles; o += 32) s += norm_part[(long long)slot * ntiles + o];
+    s = warp_sum(s);
+    if (lane == 0) inv_norm2[slot] = 1.0 / s;
+}
+
+// probs[j] += sum_slots |psi_slot[j]|^2 * inv_norm2[slot]   (slots in order: deterministic)
+__global__ void accumulate_kernel(double* __restrict__ probs, const cplx* __restrict__ states, int nbits, int nslots,
+                                  const double* __restrict__ inv_norm2) {
+    const long long dim = 1ll << nbits;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < dim; j += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b < nslots; ++b) {
+            const cplx a = states[((long long)b << nbits) + j];
+            const double p = a.x * a.x + a.y * a.y;
+            s += inv_norm2 ? p * inv_norm2[b] : p;
+        }
+        probs[j] += s;
+    }
+}
+
+// probs[j] += sum_c partial[c][j]
+__global__ void sum_partials_kernel(double* __restrict__ probs, const double* __restrict__ partial, long long dim, int nparts) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < dim; j += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < nparts; ++c) s += partial[c * dim + j];
+        probs[j] += s;
+    }
+}
+
+// probs[r] = Re rho[r][r] with vec index r | (r << nq)
+__global__ void diag_kernel(double* __restrict__ probs, const cplx* __restrict__ rho, int nq) {
+    const long long dim = 1ll << nq;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < dim; r += (long long)gridDim.x * blockDim.x)
+        probs[r] = rho[r | (r << nq)].x;
+}
+
+__global__ void abs2_kernel(double* __restrict__ probs, const cplx* __restrict__ state, long long dim) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < dim; j += (long long)gridDim.x * blockDim.x)
+        probs[j] = cnorm2(state[j]);
+}
+
+__global__ void scale_kernel(double* __restrict__ v, long long dim, double f) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < dim; j += (long long)gridDim.x * blockDim.x) v[j] *= f;
+}
+
+// one read-out error pass: 2x2 real matrix on probability pairs at stride 1 << q (MeasurementErrorApplicator.cpp:65-81)
+__global__ void measurement_error_kernel(double* __restrict__ probs, long long half, int q, double m00, double m01, double m10, double m11) {
+    const long long stride = 1ll << q;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < half; p += (long long)gridDim.x * blockDim.x) {
+        const long long i = (p & (stride - 1)) | ((p & ~(stride - 1)) << 1), j = i | stride;
+        const double p0 = probs[i], p1 = probs[j];
+        probs[i] = m00 * p0 + m01 * p1;
+        probs[j] = m10 * p0 + m11 * p1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// resident kernel: whole trajectory in one CTA's shared memory
+// ---------------------------------------------------------------------------------------------------------------
+struct ResidentArgs {
+    long long traj_begin, traj_count;
+    unsigned long long seed;
+    const double* uniforms;     // NULL: Philox; else [traj_count][G]
+    double* partial_probs;      // [gridDim.x][2^nbits] accumulated |psi|^2 (may be NULL)
+    cplx* states_out;           // optional [traj_count][2^nbits]: final normalised states
+    int normalize;              // divide by the norm (program is not norm preserving)
+    unsigned long long* counters;   // [0] events, [1] state-dependent events
+};
+
+template <int R, bool D4>
+__global__ void __launch_bounds__((D4 || R == 4) ? 256 : 512)
+resident_kernel(DevProgram P, ResidentArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw);                       // 2^K amplitudes
+    double* acc = reinterpret_cast<double*>(sm + (1 << P.K));            // 2^nbits probabilities
+    unsigned* evmask = reinterpret_cast<unsigned*>(acc + (1 << P.nbits));   // ceil(G/32) words
+    __shared__ double s_buf[32 * 20];
+    __shared__ double s_out[RED_VALUES];
+    __shared__ int s_k;
+    __shared__ double s_scale;
+    const int K = P.K, tid = threadIdx.x, nthreads = blockDim.x, dim = 1 << P.nbits;
+    const int nwords = (P.G + 31) >> 5;
+    const Segment* sg = P.segs;     // single segment: tile = whole state (identity map)
+    for (int j = tid; j < dim; j += nthreads) acc[j] = 0.0;
+    unsigned long long n_events = 0, n_hard = 0;
+
+    for (long long tl = blockIdx.x; tl < A.traj_count; tl += gridDim.x) {
+        const unsigned long long traj = (unsigned long long)(A.traj_begin + tl);
+        const double* utab = A.uniforms ? A.uniforms + tl * P.G : nullptr;
+        // ---- plan: which instructions deviate from their base branch? ----
+        for (int i = tid; i < nwords; i += nthreads) evmask[i] = 0u;
+        for (int j = tid; j < (1 << K); j += nthreads) sm[j] = cplx{0.0, 0.0};
+        __syncthreads();
+        if (tid == 0) sm[swz(0)] = cplx{1.0, 0.0};
+        for (int a = tid; a < P.n_noisy; a += nthreads) {
+            const int i = P.noisy[a];
+            const Channel ch = P.chans[P.instrs[i].channel];
+            const double* lo = P.pool + ch.bounds;
+            const double* hi = lo + (ch.count - 1);
+            const double u = utab ? utab[i] : philox_uniform(A.seed, traj, (uint32_t)i);
+            const double left = ch.base == 0 ? -1.0 : hi[ch.base - 1] + EVENT_MARGIN;
+            const double right = ch.base == ch.count - 1 ? 2.0 : lo[ch.base] - EVENT_MARGIN;
+            if (!(u > left && u <= right)) atomicOr(&evmask[i >> 5], 1u << (i & 31));
+        }
+        __syncthreads();
+        // ---- run ----
+        int cur = 0, pcur = sg->pass_begin;
+        while (true) {
+            // next flagged instruction >= cur
+            int e = P.G;
+            for (int wd = cur >> 5; wd < nwords; ++wd) {
+                unsigned m = evmask[wd];
+                if (wd == (cur >> 5)) m &= ~0u << (cur & 31);
+                if (m) { e = (wd << 5) + __ffs(m) - 1; break; }
+            }
+            const bool ev = e < P.G;
+            run_range<R, D4>(sm, P, &pcur, sg->pass_end, cur, ev ? e + 1 : P.G, ev);
+            if (!ev) break;
+            const Instr in = P.instrs[e];
+            const Channel ch = P.chans[in.channel];
+            const double u = utab ? utab[e] : philox_uniform(A.seed, traj, (uint32_t)e);
+            int kmin, kmax;
+            classify_uniform(P.pool + ch.bounds, P.pool + ch.bounds + (ch.count - 1), ch.count, u, &kmin, &kmax);
+            int k = kmin;
+            double scale = 1.0;
+            bool base_after_all = false;
+            if (kmin != kmax) {
+                ++n_hard;
+                if (ch.dim == 2) {
+                    double a8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a8[i] = 0.0;
+                    reduce_rho_thread<2>(sm, K, tid, nthreads, in.q0, -1, a8);
+                    double v[6] = {a8[0], a8[1], a8[4], a8[5], a8[6], a8[7]};
+                    block_reduce<6>(v, s_buf, s_out + 8);
+                    if (tid == 0) {
+                        s_out[0] = s_out[8]; s_out[1] = s_out[9]; s_out[4] = s_out[10]; s_out[5] = s_out[11];
+                        s_out[6] = s_out[12]; s_out[7] = s_out[13];
+                    }
+                } else {
+                    double a32[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) a32[i] = 0.0;
+                    reduce_rho_thread<4>(sm, K, tid, nthreads, in.q0, in.q1, a32);
+                    double v[20];
+                    int n = 0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c <= r; ++c) { v[n++] = a32[2 * (r * 4 + c)]; v[n++] = a32[2 * (r * 4 + c) + 1]; }
+                    block_reduce<20>(v, s_buf, s_buf + 32 * 20 - 20);
+                    if (tid == 0) {
+                        int m = 0;
+                        const double* t = s_buf + 32 * 20 - 20;
+                        for (int r = 0; r < 4; ++r)
+                            for (int c = 0; c <= r; ++c) { s_out[2 * (r * 4 + c)] = t[m++]; s_out[2 * (r * 4 + c) + 1] = t[m++]; }
+                    }
+                }
+                if (tid == 0) {
+                    mirror_rho(s_out, ch.dim);
+                    double sc;
+                    s_k = decide_branch(s_out, ch, P.pool, u, &sc);
+                    s_scale = sc;
+                }
+                __syncthreads();
+                k = s_k; scale = s_scale;
+            } else if (k == ch.base) {
+                base_after_all = true;     // flagged by the cheap test only (u within the margin): base branch
+            }
+            if (!base_after_all) ++n_events;
+            const cplx* M = reinterpret_cast<const cplx*>(P.pool + ch.kraus) + k * ch.dim * ch.dim;
+            tile_apply_dense(sm, K, tid, nthreads, ch.dim, in.q0, in.q1, M, scale);
+            __syncthreads();
+            cur = e + 1;
+        }
+        // ---- accumulate ----
+        double inv = 1.0;
+        if (A.normalize) {
+            double v[1] = {0.0};
+            for (int j = tid; j < (1 << K); j += nthreads) v[0] += cnorm2(sm[j]);
+            block_reduce<1>(v, s_buf, s_out);
+            inv = 1.0 / s_out[0];
+            __syncthreads();
+        }
+        if (A.partial_probs)
+            for (int j = tid; j < dim; j += nthreads) acc[j] += cnorm2(sm[swz(j)]) * inv;
+        if (A.states_out) {
+            const double f = sqrt(inv);
+            for (int j = tid; j < dim; j += nthreads) {
+                cplx a = sm[swz(j)];
+                a.x *= f; a.y *= f;
+                A.states_out[tl * dim + j] = a;
+            }
+        }
+        __syncthreads();
+    }
+    if (A.partial_probs)
+        for (int j = tid; j < dim; j += nthreads) A.partial_probs[(long long)blockIdx.x * dim + j] = acc[j];
+    if (tid == 0 && A.counters) {
+        atomicAdd(&A.counters[0], n_events);
+        atomicAdd(&A.counters[1], n_hard);
+    }
+}
+
+}  // namespace ncb

@@ -1,0 +1,231 @@
+// TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// CPU emulation of the tile kernel (noisycircuits_b200/csrc/ncb_kernels.cuh): the same host compiler
+// (ncb_compile.cpp), the same batch scheduler (ncb_schedule.h) and the same per-thread executors (ncb_common.h) are
+// driven thread by thread, CTA by CTA, launch by launch.  It exists so that the host planner, the scheduler, the tile
+// geometry and the register-blocked index maps can be tested on machines without a GPU (pytest -m "not gpu").
+// CUDA-only pieces (cp.async, warp shuffles, launch configuration) are not covered here; the -m gpu tests are.
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ncb200.h"
+#include "../../noisycircuits_b200/csrc/ncb_compile.h"
+#include "../../noisycircuits_b200/csrc/ncb_schedule.h"
+
+using namespace ncb;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Emu {
+    Program P;
+};
+
+template <int R>
+void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, std::vector<double>& red_part,
+                  std::vector<double>& norm_part, const std::vector<Decision>& decisions) {
+    const int K = P.K, nthreads = 1 << (K - R);
+    const int tile_shift = P.nbits > K ? P.nbits - K : 0, ntiles = 1 << tile_shift;
+    const Segment& sg = P.segs[w.seg];
+    const long long limit = 1ll << P.nbits;
+    std::vector<cplx> sm(1 << K);
+    for (int o = 0; o < ntiles; ++o) {
+        const long long base = tile_base(sg, K, P.nbits, o);
+        cplx* st = states.data() + ((long long)w.slot << P.nbits) + base;
+        // load
+        for (int tid = 0; tid < nthreads; ++tid) {
+            const int offA = deposit(tid, sg.tile_q, K - R);
+            for (int it = 0; it < (1 << R); ++it) {
+                const int off = offA | deposit(it, sg.tile_q + (K - R), R);
+                cplx v{0.0, 0.0};
+                if (!(w.flags & WF_INIT) && off < limit) v = st[off];
+                sm[swz(tid + (it << (K - R)))] = v;
+            }
+        }
+        if ((w.flags & WF_INIT) && o == 0) sm[swz(0)] = cplx{1.0, 0.0};
+        // jump operator
+        if (w.flags & (WF_PRO_STATIC | WF_PRO_DYNAMIC)) {
+            const Instr& in = P.instrs[w.ev_instr];
+            const Channel& ch = P.chans[in.channel];
+            int k = w.ev_k;
+            double scale = 1.0;
+            if (w.flags & WF_PRO_DYNAMIC) { k = decisions[w.slot].k; scale = decisions[w.slot].scale; }
+            const cplx* M = reinterpret_cast<const cplx*>(P.pool.data() + ch.kraus) + k * ch.dim * ch.dim;
+            const int p0 = tile_pos(sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(sg, K, in.q1) : -1;
+            for (int tid = 0; tid < nthreads; ++tid) tile_apply_dense(sm.data(), K, tid, nthreads, ch.dim, p0, p1, M, scale);
+        }
+        // passes (same control flow as run_range in ncb_kernels.cuh)
+        const bool bare_last = (w.flags & WF_BARE_LAST) != 0;
+        for (int p = sg.pass_begin; p < sg.pass_end; ++p) {
+            const Pass& ps = P.passes[p];
+            if (ps.instr_lo >= w.instr_hi) break;
+            if (ps.instr_hi > w.instr_lo && ps.op_end > ps.op_begin)
+                for (int tid = 0; tid < nthreads; ++tid)
+                    run_pass_thread<R, true>(sm.data(), K, tid, ps, P.ops.data(), P.pool.data(), w.instr_lo, w.instr_hi, bare_last);
+            if (ps.instr_hi > w.instr_hi) break;
+        }
+        // reductions
+        if (w.flags & WF_REDUCE) {
+            const Instr& in = P.instrs[w.red_instr];
+            const int p0 = tile_pos(sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(sg, K, in.q1) : -1;
+            double acc[32];
+            for (double& a : acc) a = 0.0;
+            for (int tid = 0; tid < nthreads; ++tid) {
+                if (p1 < 0) reduce_rho_thread<2>(sm.data(), K, tid, nthreads, p0, -1, acc);
+                else reduce_rho_thread<4>(sm.data(), K, tid, nthreads, p0, p1, acc);
+            }
+            double* dst = red_part.data() + ((long long)w.slot * ntiles + o) * 32;
+            for (int i = 0; i < 32; ++i) dst[i] = acc[i];
+        }
+        if (w.flags & WF_NORM) {
+            double s = 0.0;
+            for (int i = 0; i < (1 << K); ++i) s += cnorm2(sm[i]);
+            norm_part[(long long)w.slot * ntiles + o] = s;
+        }
+        // store
+        for (int tid = 0; tid < nthreads; ++tid) {
+            const int offA = deposit(tid, sg.tile_q, K - R);
+            for (int it = 0; it < (1 << R); ++it) {
+                const int off = offA | deposit(it, sg.tile_q + (K - R), R);
+                if (off < limit) st[off] = sm[swz(tid + (it << (K - R)))];
+            }
+        }
+    }
+}
+
+void run_plan(const Program& P, const BatchPlan& plan, int B, std::vector<cplx>& states, std::vector<double>& norm_part) {
+    const int tile_shift = P.nbits > P.K ? P.nbits - P.K : 0, ntiles = 1 << tile_shift;
+    std::vector<double> red_part((size_t)B * ntiles * 32, 0.0);
+    norm_part.assign((size_t)B * ntiles, 0.0);
+    std::vector<Decision> decisions(B);
+    for (const LaunchStep& st : plan.steps) {
+        if (st.kind == 0) {
+            for (int i = 0; i < st.count; ++i) {
+                const Work& w = plan.works[st.begin + i];
+                if (P.R == 4) emulate_work<4>(P, w, states, red_part, norm_part, decisions);
+                else emulate_work<3>(P, w, states, red_part, norm_part, decisions);
+            }
+        } else {
+            for (int i = 0; i < st.count; ++i) {
+                const DecideItem& d = plan.decides[st.begin + i];
+                double rho[32];
+                for (int e = 0; e < 32; ++e) {
+                    double s = 0.0;
+                    for (int o = 0; o < ntiles; ++o) s += red_part[((size_t)d.slot * ntiles + o) * 32 + e];
+                    rho[e] = s;
+                }
+                const Channel& ch = P.chans[P.instrs[d.instr].channel];
+                mirror_rho(rho, ch.dim);
+                double scale;
+                decisions[d.slot].k = decide_branch(rho, ch, P.pool.data(), d.u, &scale);
+                decisions[d.slot].scale = scale;
+            }
+        }
+    }
+}
+
+CircuitView view_of(const ncb_circuit* c) {
+    CircuitView v;
+    v.num_qubits = c->num_qubits; v.num_instructions = c->num_instructions;
+    v.opcode = c->opcode; v.q0 = c->q0; v.q1 = c->q1; v.theta = c->theta; v.channel = c->channel;
+    v.unitary_offset = c->unitary_offset; v.unitary_nq = c->unitary_nq; v.unitary_qubits = c->unitary_qubits;
+    v.unitary_pool = c->unitary_pool; v.num_channels = c->num_channels; v.channel_offset = c->channel_offset;
+    v.channel_count = c->channel_count; v.channel_dim = c->channel_dim; v.kraus_pool = c->kraus_pool;
+    return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* emu_last_error() { return g_err.c_str(); }
+
+void* emu_create(const ncb_circuit* c, int mode, int tile_bits, int reg_bits, int low_bits, int fuse) {
+    try {
+        Emu* e = new Emu();
+        CompileOptions opt;
+        opt.tile_bits = tile_bits; opt.reg_bits = reg_bits; opt.low_bits = low_bits; opt.fuse = fuse;
+        compile_program(view_of(c), mode, opt, e->P);
+        return e;
+    } catch (const std::exception& ex) { g_err = ex.what(); return nullptr; }
+}
+void emu_destroy(void* h) { delete static_cast<Emu*>(h); }
+
+long long emu_query(void* h, int what) {
+    const Program& P = static_cast<Emu*>(h)->P;
+    switch (what) {
+    case 0: return P.K; case 1: return P.R; case 2: return (long long)P.segs.size(); case 3: return (long long)P.passes.size();
+    case 4: return (long long)P.ops.size(); case 5: return P.norm_preserving; case 6: return P.nbits; case 7: return P.has_dense4;
+    }
+    return -1;
+}
+
+long long emu_describe(void* h, char* buf, long long len) {
+    const std::string s = describe_program(static_cast<Emu*>(h)->P);
+    if (buf && len > 0) { const size_t n = std::min<size_t>(s.size(), (size_t)len - 1); std::memcpy(buf, s.data(), n); buf[n] = 0; }
+    return (long long)s.size() + 1;
+}
+
+// Runs `count` trajectories (explicit uniforms [count][G]) as ONE batch and returns their final normalised states
+// [count][2^n] (complex interleaved), the number of events / state-dependent events, and the sweeps issued.
+int emu_mcwf_states(void* h, int count, const double* uniforms, double* states_out, long long* stats) {
+    try {
+        const Program& P = static_cast<Emu*>(h)->P;
+        if (P.mode != MODE_MCWF) throw std::runtime_error("not an MCWF program");
+        const long long dim = 1ll << P.nbits;
+        std::vector<std::vector<Event>> events(count);
+        long long nev = 0, nhard = 0;
+        for (int b = 0; b < count; ++b) {
+            plan_events(P, [&](int i) { return uniforms[(size_t)b * P.G + i]; }, events[b]);
+            nev += (long long)events[b].size();
+            for (const Event& e : events[b]) nhard += e.kmin != e.kmax;
+        }
+        BatchPlan plan;
+        schedule_batch(P, events, true, !P.norm_preserving, plan);
+        std::vector<cplx> states((size_t)count * dim, cplx{0.0, 0.0});
+        std::vector<double> norm_part;
+        run_plan(P, plan, count, states, norm_part);
+        const int ntiles = 1 << (P.nbits > P.K ? P.nbits - P.K : 0);
+        for (int b = 0; b < count; ++b) {
+            double n2 = 0.0;
+            for (long long j = 0; j < dim; ++j) n2 += cnorm2(states[(size_t)b * dim + j]);
+            if (!P.norm_preserving) {     // the WF_NORM partials must agree with the direct norm
+                double s = 0.0;
+                for (int o = 0; o < ntiles; ++o) s += norm_part[(size_t)b * ntiles + o];
+                if (std::fabs(s - n2) > 1e-12 * std::max(1.0, n2)) throw std::runtime_error("WF_NORM partials disagree with the state norm");
+            }
+            const double f = 1.0 / std::sqrt(n2);
+            for (long long j = 0; j < dim; ++j) {
+                states_out[2 * ((size_t)b * dim + j)] = states[(size_t)b * dim + j].x * f;
+                states_out[2 * ((size_t)b * dim + j) + 1] = states[(size_t)b * dim + j].y * f;
+            }
+        }
+        if (stats) { stats[0] = nev; stats[1] = nhard; stats[2] = plan.sweeps; stats[3] = (long long)plan.steps.size(); }
+        return 0;
+    } catch (const std::exception& ex) { g_err = ex.what(); return -1; }
+}
+
+// Deterministic programs (PURE / DENSITY): final state vector of 2^nbits amplitudes.
+int emu_run_deterministic(void* h, double* state_out) {
+    try {
+        const Program& P = static_cast<Emu*>(h)->P;
+        const long long dim = 1ll << P.nbits;
+        std::vector<std::vector<Event>> events(1);
+        BatchPlan plan;
+        schedule_batch(P, events, true, false, plan);
+        std::vector<cplx> states(dim, cplx{0.0, 0.0});
+        std::vector<double> norm_part;
+        run_plan(P, plan, 1, states, norm_part);
+        std::memcpy(state_out, states.data(), dim * sizeof(cplx));
+        return 0;
+    } catch (const std::exception& ex) { g_err = ex.what(); return -1; }
+}
+
+// host-side Philox, for cross-checking the device draws
+double emu_philox_uniform(unsigned long long seed, unsigned long long traj, unsigned instr) { return philox_uniform(seed, traj, instr); }
+
+}  // extern "C"

