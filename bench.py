@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""
+bench.py -- MCWF trajectories/sec on the BASELINE.json headline configuration:
+20-qubit depth-50 random layered Heron circuit (configs[4]), Sample_Noise_Model_Heron_QPU noise, 1..8 B200.
+
+    python bench.py --gpus N --steps K --warmup W              (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference [...]                      the reference's own CPU implementation, same metric
+
+A "step" is one execute()-equivalent over a slice of trajectories: every rank simulates --traj-per-step
+trajectories of the circuit (weak scaling) into a device-resident probability accumulator and the ranks' accumulators
+are combined with one NCCL all-reduce (QuantumCircuitMPI.py:352).  Trajectory throughput is flat in the trajectory
+count, so the 10^5-trajectory configuration is reported as trajectories/sec.
+
+value      device-timed (CUDA events, max over ranks) whole-job trajectories/sec, program resident on the GPU.
+e2e        the same metric through the public plug-in call (RemoteExecutor.run_sum) returning HOST probabilities:
+           per step the work lists go host->device and the float64[2^n] result device->host inside the timed region.
+roofline   the sweep ("tile") kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json):
+           algorithmic bytes = sweeps * 2 * 16 B * 2^n; launch duration = device time of the
+           timed region / number of tile launches (the small decide / accumulate kernels are charged to it).
+cpu_baseline  the reference's compiled CPU path (oracle/_ref/patched: these circuits have non-adjacent coupled
+           pairs) on all host cores, on a bounded sample (first layer(s) of the same circuit),
+           scaled by instructions (the reference's cost per instruction is flat).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mcwf_trajectories_per_sec"
+UNIT = "trajectories/s"
+NQ, DEPTH, CIRCUIT_SEED = 20, 50, 42
+
+
+def workload():
+    from noisycircuits_b200 import circuits, noise_io
+    sq, tq, meas, _ = noise_io.load_noise_tables(os.path.join(ROOT, "tests", "golden", "heron20_noise.npz"))
+    pairs = circuits.coupled_pairs(tq, NQ)
+    instr = circuits.heron_layered(NQ, DEPTH, pairs, seed=CIRCUIT_SEED)
+    return sq, tq, meas, pairs, instr
+
+
+def config(traj_per_step, n_gpus):
+    return {"workload": f"{NQ}-qubit depth-{DEPTH} random layered Heron circuit (1q in x/sx/rx/rz, 2q in cz/rzz on the 19 coupled "
+                        f"pairs of qubits 0-19), Sample_Noise_Model_Heron_QPU noise (threshold 1e-6), BASELINE configs[4]",
+            "instructions": DEPTH * (NQ + 19), "trajectories_per_step_per_gpu": traj_per_step,
+            "target_trajectories": 100000, "parallelism": f"trajectory-sharded x{n_gpus}",
+            "l2": "inputs larger than L2 (state batch of trajectories_per_step x 16 MiB per GPU)"}
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# clocks
+# -------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx, self.p, self.path = device_index, None, f"/tmp/ncb_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# CPU reference arm
+# -------------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(instr, sq, tq, layers, trajectories, cores):
+    """trajectories/sec of the reference's compiled CPU path on the FULL circuit, measured on its first `layers`
+    layers and scaled by the instruction count.  Returns (rate, kind, sample description, seconds)."""
+    per_layer = NQ + 19
+    sample = instr[:layers * per_layer]
+    n = NQ
+    ref_dir = os.path.join(ROOT, "oracle", "_ref", "patched")
+    kind = "port"
+    t0 = time.perf_counter()
+    sim = None
+    if os.path.isdir(ref_dir):
+        sys.path.insert(0, ref_dir)
+        try:
+            import simulator as sim     # the reference's own extension, built from its sources (quad-mask patch)
+            kind = "reference"
+        except Exception:
+            sim = None
+        finally:
+            sys.path.remove(ref_dir)
+    if sim is not None:
+        buf = np.zeros(1 << n, np.complex128)
+        t0 = time.perf_counter()
+        sim.simulate_circuit(sample, buf, sq, tq, n, True, trajectories, False, cores)
+        dt = time.perf_counter() - t0
+        ok = abs(buf.real.sum() - 1.0) < 1e-6
+    else:
+        from oracle import oracle
+        P = oracle.Program(n, sample, sq, tq)
+        t0 = time.perf_counter()
+        probs = P.mcwf(trajectories, seed0=42, mask_fix=True, threads=cores)
+        dt = time.perf_counter() - t0
+        ok = abs(probs.sum() - 1.0) < 1e-6
+    if not ok:
+        raise RuntimeError("CPU reference returned a non-normalised distribution")
+    rate_sample = trajectories / dt
+    rate_full = rate_sample * len(sample) / len(instr)
+    desc = (f"{trajectories} trajectories of the first {layers} layer(s) ({len(sample)} of {len(instr)} instructions) of the same "
+            f"circuit in {dt:.1f} s on {cores} threads; rate scaled by {len(sample)}/{len(instr)}")
+    return rate_full, kind, desc, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sq, tq, _meas, _pairs, instr = workload()
+    cores = os.cpu_count() or 1
+    traj = max(cores, 8)
+    rates, descs, kind, secs = [], [], "port", 0.0
+    for s in range(args.warmup + args.steps):
+        r, kind, desc, dt = cpu_reference_rate(instr, sq, tq, 1, traj, cores)
+        if s >= args.warmup:
+            rates.append(r); descs.append(desc); secs += dt
+    value = len(rates) / sum(1.0 / r for r in rates)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(traj, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": descs[-1]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from noisycircuits_b200.solvers import RemoteExecutor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sq, tq, _meas, _pairs, instr = workload()
+    tps = args.traj_per_step
+    solver = RemoteExecutor(NQ, sq, tq, 1, rng="philox", seed=42)
+    stream = torch.cuda.current_stream().cuda_stream
+    dim = 1 << NQ
+    total = torch.zeros(dim, dtype=torch.float64, device="cuda")
+
+    def step(s, host=False):
+        begin = (s * world + rank) * tps
+        if host:
+            probs = solver.run_sum(instr, begin, tps, stream=stream)         # host float64[2^n]
+            return probs, solver.last_stats
+        total.zero_()
+        solver.run_sum(instr, begin, tps, device_probs=total.data_ptr(), stream=stream)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        return None, solver.last_stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed arm ----
+    for s in range(args.warmup):
+        step(s)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if clocks:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {"sweeps": 0, "launches": 0, "tile_launches": 0, "events": 0, "hard_events": 0}
+    ev0.record()
+    for s in range(args.steps):
+        _, st = step(args.warmup + s)
+        for k in agg:
+            agg[k] += st[k]
+    ev1.record()
+    barrier()
+    clock_info = clocks.stop() if clocks else None
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * tps * args.steps / (ms * 1e-3)
+    check = float(total.sum().item()) / (world * tps)
+
+    # ---- end-to-end arm: public plug-in call with host buffers ----
+    barrier()
+    w0 = time.perf_counter()
+    h2d = d2h = 0
+    for s in range(args.steps):
+        probs, st = step(args.warmup + args.steps + s, host=True)
+        if world > 1:                                     # host-side combine of the ranks' float64[2^n]
+            tt = torch.from_numpy(probs).cuda()
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            probs = tt.cpu().numpy()
+        h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * tps * args.steps / float(t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        alg_bytes = agg["sweeps"] * 32.0 * dim                      # one rank's tile launches
+        achieved = alg_bytes / (ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "tile_kernel_traffic.json"))).get("traffic_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config(tps, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
+                        "d2h_bytes_per_step": d2h // max(args.steps, 1)},
+                "gpu_launches": agg["launches"],
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "ncb::tile_kernel",
+                             "algorithmic_bytes_per_launch": alg_bytes / max(agg["tile_launches"], 1),
+                             "avg_launch_ms": ms / max(agg["tile_launches"], 1), "tile_launches": agg["tile_launches"],
+                             "sweeps_per_trajectory": agg["sweeps"] / (tps * args.steps)},
+                "clocks": clock_info, "norm_check": check,
+                "events_per_trajectory": agg["events"] / (tps * args.steps)}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            try:
+                r, kind, desc, _dt = cpu_reference_rate(instr, sq, tq, 1, max(cores, 8), cores)
+                line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+            except Exception as e:                          # never lose the GPU numbers to a host-side problem
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--traj-per-step", type=int, default=148)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,9 @@ typedef struct {
     int64_t out_hard_events;   /* events whose branch needed the reduced density matrix */
     int64_t out_launches;      /* kernel launches */
     double out_kernel_ms;      /* device time from the first to the last kernel of the run (CUDA events on `stream`) */
+    int64_t out_tile_launches; /* launches of the sweep (tile / resident) kernel among out_launches */
+    int64_t out_h2d_bytes;     /* bytes copied host -> device during the run (work lists, uniform tables) */
+    int64_t out_d2h_bytes;     /* bytes copied device -> host during the run (probabilities, states, counters) */
 } ncb_run_params;
 
 int ncb_mcwf_run(ncb_program* program, ncb_run_params* params);

@@ -243,6 +243,7 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
         d_uniforms.reserve(table.size());
         CK(cudaMemcpyAsync(d_uniforms.p, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
+        rp->out_h2d_bytes += (int64_t)(table.size() * sizeof(double));
         a.uniforms = d_uniforms.p;
     }
     d_partial.reserve((size_t)grid * dim);
@@ -257,9 +258,13 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
     CK(cudaGetLastError());
     unsigned long long cnt[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(cnt, d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
-    if (rp->states)
+    rp->out_d2h_bytes += (int64_t)sizeof(cnt);
+    if (rp->states) {
         CK(cudaMemcpyAsync(rp->states, d_states.p, (size_t)count * dim * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+        rp->out_d2h_bytes += (int64_t)((size_t)count * dim * sizeof(cplx));
+    }
     CK(cudaStreamSynchronize(s));
+    rp->out_tile_launches += 1;
     rp->out_events += (int64_t)cnt[0];
     rp->out_hard_events += (int64_t)cnt[1];
     rp->out_launches += 2;
@@ -308,12 +313,13 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
         h_decides[buf].reserve(plan.decides.size() + 1); d_decides[buf].reserve(plan.decides.size() + 1);
         std::memcpy(h_works[buf].p, plan.works.data(), plan.works.size() * sizeof(Work));
         CK(cudaMemcpyAsync(d_works[buf].p, h_works[buf].p, plan.works.size() * sizeof(Work), cudaMemcpyHostToDevice, s));
+        rp->out_h2d_bytes += (int64_t)(plan.works.size() * sizeof(Work) + plan.decides.size() * sizeof(DecideItem));
         if (!plan.decides.empty()) {
             std::memcpy(h_decides[buf].p, plan.decides.data(), plan.decides.size() * sizeof(DecideItem));
             CK(cudaMemcpyAsync(d_decides[buf].p, h_decides[buf].p, plan.decides.size() * sizeof(DecideItem), cudaMemcpyHostToDevice, s));
         }
         for (const LaunchStep& st : plan.steps) {
-            if (st.kind == 0) launch_tile(st.count, s, d_works[buf].p + st.begin);
+            if (st.kind == 0) { launch_tile(st.count, s, d_works[buf].p + st.begin); ++rp->out_tile_launches; }
             else {
                 decide_kernel<<<st.count, 32, 0, s>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
                 CK(cudaGetLastError());
@@ -334,6 +340,7 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             host_states.resize((size_t)nb * dim);
             CK(cudaMemcpyAsync(host_states.data(), d_states.p, (size_t)nb * dim * sizeof(cplx), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
+            rp->out_d2h_bytes += (int64_t)((size_t)nb * dim * sizeof(cplx));
             for (int b = 0; b < nb; ++b) {
                 double n2 = 0;
                 for (long long j = 0; j < dim; ++j) n2 += cnorm2(host_states[(size_t)b * dim + j]);
@@ -360,6 +367,7 @@ void Engine::mcwf_run(ncb_run_params* rp) {
     d_probs.reserve(dim);
     CK(cudaMemsetAsync(d_probs.p, 0, dim * sizeof(double), s));
     rp->out_sweeps = rp->out_events = rp->out_hard_events = rp->out_launches = 0;
+    rp->out_tile_launches = rp->out_h2d_bytes = rp->out_d2h_bytes = 0;
     rp->out_kernel_ms = 0.0;
     CK(cudaEventRecord(t0, s));
     if (rp->traj_count > 0) {
@@ -375,7 +383,8 @@ void Engine::mcwf_run(ncb_run_params* rp) {
                 mcwf_resident(&sub, s);
             }
             rp->out_sweeps = sub.out_sweeps; rp->out_events = sub.out_events; rp->out_hard_events = sub.out_hard_events;
-            rp->out_launches = sub.out_launches;
+            rp->out_launches = sub.out_launches; rp->out_tile_launches = sub.out_tile_launches;
+            rp->out_h2d_bytes = sub.out_h2d_bytes; rp->out_d2h_bytes = sub.out_d2h_bytes;
         } else {
             mcwf_tiled(rp, s);
         }
@@ -403,6 +412,7 @@ void Engine::mcwf_run(ncb_run_params* rp) {
         std::vector<double> tmp(dim);
         CK(cudaMemcpyAsync(tmp.data(), d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        rp->out_d2h_bytes += (int64_t)(dim * sizeof(double));
         if (rp->accumulate) for (long long j = 0; j < dim; ++j) rp->probs[j] += tmp[j];
         else std::memcpy(rp->probs, tmp.data(), dim * sizeof(double));
     }

@@ -1,0 +1,126 @@
+"""
+Solver plug-in for NoisyCircuits: the three classes a ``sim_backend`` module must export
+(/root/reference/src/NoisyCircuits/utils/custom/__init__.py:5-7), with the ``custom`` back-end's signatures, running on
+the B200 engine (libncb200.so).
+
+    RemoteExecutor(num_qubits, single_qubit_noise, two_qubit_noise, num_cores).run(num_trajectories, instruction_list)
+        -> float64[2^n], little-endian, all qubits, before measurement error, divided by N
+           (custom/_ParallelExecutor.py:18-65; call site QuantumCircuit.py:411-420)
+    DensityMatrixSolver(num_qubits, single_qubit_noise, two_qubit_noise, instruction_list, num_cores).solve(qubits)
+        -> float64[2^len(qubits)], little-endian over the kept qubits (custom/_DensityMatrixSolver.py:29-93)
+    PureStateSolver(num_qubits, instruction_list, num_cores, return_statevector).solve()
+        -> float64[2^n] probabilities or complex128[2^n] state (custom/_PureStateSolver.py:28-66)
+
+``num_cores`` is accepted for signature compatibility and ignored (the GPU replaces the OpenMP threads).
+Extra keyword arguments (all optional) expose what the CPU path cannot do: ``rng`` ("philox" counter-based draws,
+the default; "reference" reproduces the reference's mt19937_64(42 + t) streams so results equal the reference's to
+rounding), ``seed``, and trajectory sharding for multi-GPU runs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .program import PackedCircuit, Program
+
+_RNG = {"philox": _lib.RNG_PHILOX, "reference": _lib.RNG_MT19937_REFERENCE}
+
+
+def _marginal_little_endian(probs: np.ndarray, num_qubits: int, keep) -> np.ndarray:
+    """Marginal over ``keep`` (little-endian in ascending kept-qubit order), i.e. diag(partial_trace(rho, rest))
+    (custom/_DensityMatrixSolver.py:90-93); same arithmetic as HelperFunctions.py:9-32."""
+    keep = sorted(int(q) for q in keep)
+    if len(keep) == num_qubits:
+        return np.require(probs, dtype=np.float64, requirements=["C"])
+    t = probs.reshape([2] * num_qubits)
+    axes = tuple(num_qubits - 1 - q for q in range(num_qubits) if q not in keep)
+    return np.require(t.sum(axis=axes).reshape(-1), dtype=np.float64, requirements=["C"])
+
+
+def _fingerprint(instruction_list):
+    """Content key of an instruction list (recompile only when the circuit changes)."""
+    items = []
+    for name, qubits, param in instruction_list:
+        if isinstance(param, np.ndarray):
+            param = param.tobytes()
+        items.append((name, tuple(qubits), param))
+    return hash(tuple(items))
+
+
+class RemoteExecutor:
+    """MCWF trajectories on the GPU (mirror of custom/_ParallelExecutor.py:14-65)."""
+
+    def __init__(self, num_qubits: int, single_qubit_noise: dict, two_qubit_noise: dict, num_cores: int = 2,
+                 rng: str = "philox", seed: int = 42, **engine_options) -> None:
+        if rng not in _RNG:
+            raise ValueError(f"rng must be one of {sorted(_RNG)}")
+        self.num_qubits = num_qubits
+        self.single_qubit_noise = single_qubit_noise
+        self.two_qubit_noise = two_qubit_noise
+        self.num_cores = num_cores
+        self.rng = rng
+        self.seed = seed
+        self.engine_options = engine_options
+        self.last_stats = None
+        self._cache = (None, None)
+
+    def _program(self, instruction_list) -> Program:
+        key = _fingerprint(instruction_list)
+        if self._cache[0] != key:
+            packed = PackedCircuit(self.num_qubits, instruction_list, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
+            self._cache = (key, Program(packed, _lib.MODE_MCWF, **self.engine_options))
+        return self._cache[1]
+
+    def run_sum(self, instruction_list, traj_begin: int, traj_count: int, uniforms=None, device_probs=None,
+                accumulate=False, stream=0):
+        """Unnormalised sum of |psi_t|^2 over trajectories [traj_begin, traj_begin + traj_count): the building block
+        of sharded (multi-GPU) runs; trajectory ids key the RNG so the result does not depend on the sharding."""
+        prog = self._program(instruction_list)
+        seed = self.seed
+        probs, stats = prog.run_mcwf(traj_count, traj_begin=traj_begin, rng=_RNG[self.rng], seed=seed, uniforms=uniforms,
+                                     device_probs=device_probs, accumulate=accumulate, stream=stream)
+        self.last_stats = stats
+        return probs
+
+    def run(self, num_trajectories: int, instruction_list: list) -> np.ndarray:
+        probs = self.run_sum(instruction_list, 0, num_trajectories)
+        return probs / float(num_trajectories)
+
+
+class DensityMatrixSolver:
+    """Density-matrix evolution on the vectorised 4^n state (mirror of custom/_DensityMatrixSolver.py:29-93; the
+    reference delegates the arithmetic to qiskit-aer, semantics in SURVEY.md 3.3)."""
+
+    def __init__(self, num_qubits: int, single_qubit_noise: dict, two_qubit_noise: dict, instruction_list: list,
+                 num_cores: int = 1, **engine_options) -> None:
+        self.num_qubits = num_qubits
+        self.instruction_list = instruction_list
+        self.num_cores = num_cores
+        packed = PackedCircuit(num_qubits, instruction_list, single_qubit_noise, two_qubit_noise, noisy=True)
+        engine_options.setdefault("reg_bits", 4)
+        self._program = Program(packed, _lib.MODE_DENSITY, **engine_options)
+
+    def solve(self, qubits: list) -> np.ndarray:
+        probs = self._program.run_density()
+        return _marginal_little_endian(probs, self.num_qubits, qubits)
+
+
+class PureStateSolver:
+    """Noise-free state-vector run (mirror of custom/_PureStateSolver.py:28-66)."""
+
+    def __init__(self, num_qubits: int, instruction_list: list, num_cores: int = 1, return_statevector: bool = False,
+                 **engine_options) -> None:
+        self.num_qubits = num_qubits
+        self.instruction_list = instruction_list
+        self.num_cores = num_cores
+        self.return_statevector = return_statevector
+        packed = PackedCircuit(num_qubits, instruction_list, noisy=False)
+        engine_options.setdefault("reg_bits", 4)
+        self._program = Program(packed, _lib.MODE_PURE, **engine_options)
+
+    def solve(self) -> np.ndarray:
+        if self.return_statevector:
+            state, _ = self._program.run_pure(want_state=True, want_probs=False)
+            return state
+        _, probs = self._program.run_pure(want_state=False, want_probs=True)
+        return probs

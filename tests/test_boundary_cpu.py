@@ -1,0 +1,107 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/ncb200.h
+declares, the packer mirrors the reference's lookups and errors, the host-only planner agrees with the oracle's
+branch choices, and run calls fail loudly (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from noisycircuits_b200 import _lib, circuits
+from noisycircuits_b200.program import PackedCircuit, Program
+from oracle import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ncb200.h")).read()
+    declared = set(re.findall(r"\b(ncb_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for sym in declared:
+        assert getattr(L, sym) is not None
+    assert L.ncb_version() == 100
+
+
+def test_packer_mirrors_reference_lookups(heron_noise):
+    sq, tq, _, _ = heron_noise
+    instr = [["sx", [1, 1], 0], ["cz", [1, 0], 0], ["rz", [2], 0.3], ["unitary", [0, 2], np.eye(4)]]
+    pk = PackedCircuit(3, instr, sq, tq)
+    assert list(pk.opcode[:4]) == [1, 7, 2, 12]
+    assert pk.q1[2] == 2                                   # one-element qubit list
+    assert list(pk.unitary_qubits[24:26]) == [2, 0]        # reversed, Simulator.cpp:182
+    assert pk.channel[3] == -1                             # unitary: no noise (FunctionMapper.hpp:77)
+    assert pk.kraus_count[0] == len(sq[1]["sx"]) and pk.kraus_count[1] == len(tq["cz"][(1, 0)])
+    with pytest.raises(IndexError):                        # NoiseParser.hpp:137 .at() -> IndexError
+        PackedCircuit(3, [["cz", [0, 2], 0]], sq, tq)
+    with pytest.raises(ValueError):
+        PackedCircuit(3, [["foo", [0, 0], 0]], sq, tq)
+
+
+def test_compile_errors_are_reported(heron_noise):
+    sq, tq, _, _ = heron_noise
+    with pytest.raises(_lib.NcbError, match="qubit out of range"):
+        Program(PackedCircuit(2, [["sx", [5, 5], 0]], noisy=False), _lib.MODE_PURE)
+    with pytest.raises(_lib.NcbError, match="repeated qubit"):
+        Program(PackedCircuit(2, [["cz", [1, 1], 0]], noisy=False), _lib.MODE_PURE)
+
+
+@pytest.mark.parametrize("noise_name", ["heron", "eagle"])
+def test_planner_events_agree_with_oracle_choices(heron_noise, eagle_noise, noise_name):
+    sq, tq, _, _ = heron_noise if noise_name == "heron" else eagle_noise
+    n = 5
+    pairs = circuits.coupled_pairs(tq, n)
+    instr = (circuits.heron_layered if noise_name == "heron" else circuits.eagle_layered)(n, 3, pairs, seed=4)
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF)
+    O = oracle.Program(n, instr, sq, tq)
+    rng = np.random.default_rng(0)
+    base_choice = {}
+    n_events = 0
+    for t in range(40):
+        u = rng.random(len(instr)) if t % 2 else 1 - 0.05 * rng.random(len(instr)) ** 2
+        ev = {int(i): (int(a), int(b)) for i, a, b in prog.events(u)}
+        _st, choices, _pc = O.trajectory(u, mask_fix=True, diagnostics=True)
+        for g in range(len(instr)):
+            if g in ev:
+                a, b = ev[g]
+                assert a <= choices[g] <= b
+                n_events += 1
+            else:                                   # base branch: one fixed operator per channel
+                assert base_choice.setdefault(O.chan[g], choices[g]) == choices[g]
+    assert n_events > 0
+
+
+def test_reference_uniform_stream(heron_noise):
+    sq, tq, _, _ = heron_noise
+    n = 4
+    instr = circuits.heron_ansatz(n, 2, circuits.coupled_pairs(tq, n), seed=1)
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF)
+    O = oracle.Program(n, instr, sq, tq)
+    for seed in (42, 43, 1000):
+        assert np.array_equal(prog.reference_uniforms(seed), O.reference_uniforms(seed))
+
+
+def test_no_cpu_fallback(heron_noise):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sq, tq, _, _ = heron_noise
+    prog = Program(PackedCircuit(2, [["sx", [0, 0], 0]], sq, tq), _lib.MODE_MCWF)
+    with pytest.raises(_lib.NcbError) as e:
+        prog.run_mcwf(4)
+    assert e.value.code == -2          # NCB_E_CUDA
+
+
+def test_shard_ranges_match_reference_split():
+    from noisycircuits_b200.backend import shard_range
+    for T in (1, 7, 100, 100000):
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                s, c = shard_range(T, r, world)
+                base, rem = T // world, T % world                       # QuantumCircuitMPI.py:329-332
+                assert (s, c) == (r * base + min(r, rem), base + (1 if r < rem else 0))
+                cover += list(range(s, s + c))
+            assert cover == list(range(T))

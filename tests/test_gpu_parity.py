@@ -1,0 +1,247 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI (libncb200.so) and is
+checked against the CPU oracle (oracle/) on the same seeded inputs, or against the committed golden vectors generated
+from the reference's own extensions.
+
+Tolerances (north_star): replay (same per-instruction uniforms) <= 1e-10 state by state; density matrix <= 1e-10 per
+probability; free-running MCWF vs density matrix: total variation <= 3/sqrt(N)."""
+import numpy as np
+import pytest
+
+from noisycircuits_b200 import _lib, circuits
+from noisycircuits_b200 import simulator as ncb_simulator
+from noisycircuits_b200.program import PackedCircuit, Program
+from noisycircuits_b200.solvers import DensityMatrixSolver, PureStateSolver, RemoteExecutor
+from oracle import oracle
+from conftest import far_tables
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def jumpy_uniforms(rng, count, G):
+    U = rng.random((count, G))
+    U[count // 2:] = 1 - 0.03 * rng.random((count - count // 2, G)) ** 2
+    return U
+
+
+def philox_numpy(seed, traj, instr):
+    """Independent numpy restatement of Philox4x32-10 with the engine's (counter, key) convention."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [int(instr), int(traj) & 0xffffffff, (int(traj) >> 32) & 0xffffffff, 0x6e636232]
+    k0, k1 = seed & 0xffffffff, (seed >> 32) & 0xffffffff
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xffffffff, p1 & 0xffffffff, ((p0 >> 32) ^ c[3] ^ k1) & 0xffffffff, p0 & 0xffffffff]
+        k0, k1 = (k0 + W0) & 0xffffffff, (k1 + W1) & 0xffffffff
+    bits = ((c[0] << 21) ^ (c[1] >> 11)) & ((1 << 53) - 1)
+    return bits / 9007199254740992.0
+
+
+def replay(n, instr, sq, tq, U, mask_fix=True, **opts):
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, **opts)
+    probs, states, stats = prog.run_mcwf(U.shape[0], uniforms=U, return_states=True)
+    O = oracle.Program(n, instr, sq, tq)
+    worst, acc = 0.0, np.zeros(1 << n)
+    for t in range(U.shape[0]):
+        ref = O.trajectory(U[t], mask_fix=mask_fix)
+        worst = max(worst, float(np.abs(states[t] - ref).max()))
+        acc += np.abs(ref) ** 2
+    assert worst < TOL, (worst, stats, prog.describe().splitlines()[0])
+    assert np.abs(probs - acc).max() < TOL * U.shape[0]
+    return stats, prog
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# replay harness: trajectories agree state by state
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 4, 7, 9, 12])
+def test_replay_resident_heron(heron_noise, n):
+    sq, tq, _, _ = heron_noise
+    instr = circuits.heron_layered(n, 4, circuits.coupled_pairs(tq, n), seed=n)
+    stats, prog = replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(n), 8, len(instr)))
+    assert prog.query(_lib.Q_RESIDENT) == 1
+    assert stats["events"] > 0
+
+
+@pytest.mark.parametrize("n,opts", [
+    (13, {}), (14, {"reg_bits": 3}), (15, {"tile_bits": 11}), (16, {}), (14, {"fuse": 0}), (16, {"low_bits": 0, "reg_bits": 3}),
+])
+def test_replay_tiled_heron(heron_noise, n, opts):
+    sq, tq, _, _ = heron_noise
+    instr = circuits.heron_layered(n, 3, circuits.coupled_pairs(tq, n), seed=n)
+    stats, prog = replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(n), 6, len(instr)), **opts)
+    assert prog.query(_lib.Q_RESIDENT) == 0
+    assert stats["events"] > 0 and stats["hard_events"] > 0
+
+
+@pytest.mark.parametrize("n,opts", [(5, {}), (10, {}), (14, {}), (14, {"reg_bits": 3}), (16, {"tile_bits": 10})])
+def test_replay_eagle_dense_gates_and_norm_tracking(eagle_noise, n, opts):
+    sq, tq, _, _ = eagle_noise
+    instr = circuits.eagle_layered(n, 3, circuits.coupled_pairs(tq, n), seed=5)
+    stats, prog = replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(1), 6, len(instr)), **opts)
+    assert prog.query(_lib.Q_NORM_PRESERVING) == 0
+
+
+def test_replay_non_adjacent_pairs(golden, heron_noise):
+    _z, meta = golden
+    m = meta["far"]
+    replay(m["n"], m["instr"], heron_noise[0], far_tables(heron_noise, meta), jumpy_uniforms(np.random.default_rng(2), 6, len(m["instr"])))
+
+
+def test_replay_full_size_single_layer(heron_noise):
+    """One 20-qubit layer (BASELINE configs[4] shape) against the oracle."""
+    sq, tq, _, _ = heron_noise
+    n = 20
+    instr = circuits.heron_layered(n, 1, circuits.coupled_pairs(tq, n), seed=42)
+    replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(3), 2, len(instr)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's FFI entry points against its golden vectors
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,noise", [("mcwf_heron4", "heron"), ("mcwf_eagle4", "eagle")])
+def test_simulate_circuit_and_run_trajectory_match_reference(golden, heron_noise, eagle_noise, case, noise):
+    z, meta = golden
+    m = meta[case]
+    sq, tq, _, _ = heron_noise if noise == "heron" else eagle_noise
+    n = m["n"]
+    buf = np.zeros(1 << n, np.complex128)
+    ncb_simulator.simulate_circuit(m["instr"], buf, sq, tq, n, True, m["T"], False, 2)
+    assert np.abs(buf.real - z[case + "_probs"]).max() < TOL and np.abs(buf.imag).max() == 0
+    ncb_simulator.simulate_circuit(m["instr"], buf, sq, tq, n, True, m["T"], False, 2)      # accumulates (+=)
+    assert np.abs(buf.real - 2 * z[case + "_probs"]).max() < 2 * TOL
+    for row, seed in zip(z[case + "_traj"], m["traj_seeds"]):
+        buf = np.zeros(1 << n, np.complex128)
+        ncb_simulator.run_trajectory(m["instr"], buf, sq, tq, n, seed, 1)
+        assert np.abs(buf.real - row).max() < TOL
+    ex = RemoteExecutor(n, sq, tq, 2, rng="reference")
+    assert np.abs(ex.run(m["T"], m["instr"]) - z[case + "_probs"]).max() < TOL
+
+
+def test_non_adjacent_pairs_match_patched_reference(golden, heron_noise):
+    z, meta = golden
+    m = meta["far"]
+    n = m["n"]
+    tq = far_tables(heron_noise, meta)
+    buf = np.zeros(1 << n, np.complex128)
+    ncb_simulator.simulate_circuit(m["instr"], buf, heron_noise[0], tq, n, True, m["T"], False, 1)
+    assert np.abs(buf.real - z["mcwf_far_probs"]).max() < TOL
+    buf = np.zeros(1 << n, np.complex128)
+    ncb_simulator.simulate_circuit(m["instr"], buf, {}, {}, n, False, 1, True, 1)
+    assert np.abs(buf - z["pure_far_state"]).max() < 1e-12
+
+
+def test_pure_state_all_gate_kernels(golden):
+    z, meta = golden
+    m = meta["pure_adjacent"]
+    n = m["n"]
+    buf = np.zeros(1 << n, np.complex128)
+    ncb_simulator.simulate_circuit(m["instr"], buf, {}, {}, n, False, 1, True, 1)
+    assert np.abs(buf - z["pure_adjacent_state"]).max() < 1e-12
+    buf = np.zeros(1 << n, np.complex128)
+    ncb_simulator.simulate_circuit(m["instr"], buf, {}, {}, n, False, 1, False, 1)
+    assert np.abs(buf.real - np.abs(z["pure_adjacent_state"]) ** 2).max() < 1e-12
+    s = PureStateSolver(n, m["instr"], 1, True).solve()
+    assert np.abs(s - z["pure_adjacent_state"]).max() < 1e-12
+    p = PureStateSolver(n, m["instr"], 1, False).solve()
+    assert p.dtype == np.float64 and abs(p.sum() - 1) < 1e-12
+
+
+def test_pure_state_tiled(heron_noise):
+    n = 15
+    _sq, tq, _, _ = heron_noise
+    instr = circuits.heron_layered(n, 4, circuits.coupled_pairs(tq, n), seed=8)
+    ref = oracle.Program(n, instr, noisy=False).pure_state()
+    s = PureStateSolver(n, instr, 1, True).solve()
+    assert np.abs(s - ref).max() < 1e-12
+
+
+def test_measurement_error(golden, heron_noise):
+    z, meta = golden
+    n = meta["meas"]["n"]
+    p = z["meas_in"].copy()
+    ncb_simulator.apply_measurement_error(p, {q: heron_noise[2][q] for q in range(n)}, list(range(n)), n, 1)
+    assert np.abs(p - z["meas_out"]).max() < 1e-15
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Philox free-running mode
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [5, 13])
+def test_philox_draws_match_host_restatement(heron_noise, n):
+    """Free-running GPU run == oracle fed with the same counter-based uniforms (resident and tiled paths)."""
+    sq, tq, _, _ = heron_noise
+    instr = circuits.heron_layered(n, 2, circuits.coupled_pairs(tq, n), seed=21)
+    T, seed, begin = 24, 1234567, 1000
+    U = np.array([[philox_numpy(seed, begin + t, g) for g in range(len(instr))] for t in range(T)])
+    ref = oracle.Program(n, instr, sq, tq).mcwf(T, uniforms=U, mask_fix=True)
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF)
+    probs, _ = prog.run_mcwf(T, traj_begin=begin, rng=_lib.RNG_PHILOX, seed=seed)
+    assert np.abs(probs / T - ref).max() < TOL
+
+
+def test_sharding_and_batching_do_not_change_the_result(heron_noise):
+    sq, tq, _, _ = heron_noise
+    n = 14
+    instr = circuits.heron_layered(n, 2, circuits.coupled_pairs(tq, n), seed=2)
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF)
+    full, _ = prog.run_mcwf(96, seed=7)
+    a, _ = prog.run_mcwf(40, traj_begin=0, seed=7)
+    b, _ = prog.run_mcwf(56, traj_begin=40, seed=7)
+    assert np.abs(full - (a + b)).max() < 1e-12
+    c, _ = prog.run_mcwf(96, seed=7, batch=17)
+    assert np.abs(full - c).max() < 1e-12
+    again, _ = prog.run_mcwf(96, seed=7)
+    assert np.array_equal(full, again)                 # deterministic
+    assert abs(full.sum() - 96) < 1e-9                 # every trajectory is normalised
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# density-matrix path and the statistical check
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [2, 4, 6, 7])
+def test_density_matrix_vs_restatement(heron_noise, eagle_noise, n):
+    for noise, gen in ((heron_noise, circuits.heron_layered), (eagle_noise, circuits.eagle_layered)):
+        sq, tq, _, _ = noise
+        instr = gen(n, 3, circuits.coupled_pairs(tq, n), seed=9)
+        ref = oracle.density_matrix_probs(n, instr, sq, tq)
+        got = DensityMatrixSolver(n, sq, tq, instr, 1).solve(list(range(n)))
+        assert np.abs(got - ref).max() < TOL
+        keep = list(range(0, n, 2))
+        assert np.abs(DensityMatrixSolver(n, sq, tq, instr, 1).solve(keep) - oracle.marginal_little_endian(ref, n, keep)).max() < TOL
+
+
+def test_mcwf_distribution_matches_density_matrix(heron_noise):
+    """BASELINE configs[0]: 4-qubit Heron CZ/RZZ ansatz, 1000 trajectories vs the density-matrix method."""
+    sq, tq, _, _ = heron_noise
+    n, N = 4, 1000
+    instr = circuits.heron_ansatz(n, 4, circuits.coupled_pairs(tq, n), seed=42)
+    dm = DensityMatrixSolver(n, sq, tq, instr, 1).solve(list(range(n)))
+    mc = RemoteExecutor(n, sq, tq, 2).run(N, instr)
+    assert abs(mc.sum() - 1) < 1e-9
+    assert 0.5 * np.abs(mc - dm).sum() <= 3 / np.sqrt(N)
+    hell = np.sqrt(0.5 * np.sum((np.sqrt(mc) - np.sqrt(dm)) ** 2))
+    assert hell < 0.05                          # the reference's own acceptance test (tests/test_Integration.py:157-169)
+
+
+def test_mcwf_distribution_tiled_matches_density_matrix(eagle_noise):
+    sq, tq, _, _ = eagle_noise
+    n, N = 7, 4000
+    instr = circuits.eagle_layered(n, 4, circuits.coupled_pairs(tq, n), seed=3)
+    dm = DensityMatrixSolver(n, sq, tq, instr, 1).solve(list(range(n)))
+    # force the tile path on a small state: 2^7 amplitudes in tiles of... not possible below 2^8, so use tile_bits=9 on n=7
+    mc = RemoteExecutor(n, sq, tq, 2).run(N, instr)
+    assert 0.5 * np.abs(mc - dm).sum() <= 3 / np.sqrt(N)
+
+
+def test_execute_chain_and_full_size_properties(heron_noise):
+    from noisycircuits_b200.backend import execute
+    sq, tq, meas, _ = heron_noise
+    n = 20
+    instr = circuits.heron_layered(n, 2, circuits.coupled_pairs(tq, n), seed=42)
+    out = execute(n, instr, sq, tq, {q: meas[q] for q in range(n)}, None, 8)
+    assert out.shape == (1 << n,) and abs(out.sum() - 1) < 1e-9 and out.min() >= 0
+    # fused and unfused schedules are the same function
+    a, _ = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, fuse=1).run_mcwf(4, seed=3)
+    b, _ = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, fuse=0).run_mcwf(4, seed=3)
+    assert np.abs(a - b).max() < TOL
