@@ -53,16 +53,38 @@ enum OpKind : uint8_t {
 // gate merged with the channel's base Kraus operator, `mat_bare` the gate alone (used for the last instruction of a
 // range that ends in a quantum-jump event, where the operator to apply is only known afterwards).
 struct Op {
-    uint32_t kind_nb;  // kind | nb << 8  (nb = number of bits the op acts on)
+    uint32_t kind_nb;  // kind | nb << 8 | tmask << 16 | span << 24 | group << 31
+                       // (nb = bits the op acts on; tmask: DIAG bits that are thread bits; group headers: see executor)
     uint32_t rbs;      // 4 x 8 bit: DENSE*/PERM1: register-bit indices; DIAG: tile-local bit positions
     int32_t instr;     // index of the instruction this op came from
     int32_t mat;
     int32_t mat_bare;
-    int32_t pad;
+    uint32_t midx_lo;  // DIAG: 4-bit table-index contribution of register slot m (slots 0..7), from the register bits
+    uint32_t midx_hi;  //       slots 8..15
+    int32_t pad;       // group headers: instruction index of the last member
 };
 NCB_HD int op_kind(const Op& o) { return (int)(o.kind_nb & 0xff); }
 NCB_HD int op_nb(const Op& o) { return (int)((o.kind_nb >> 8) & 0xff); }
+NCB_HD int op_tmask(const Op& o) { return (int)((o.kind_nb >> 16) & 0xff); }
 NCB_HD int op_rb(const Op& o, int b) { return (int)((o.rbs >> (8 * b)) & 0xff); }
+
+// Bit-field deposit compiled to runs: out = OR_i shift((v & mask[i]), shift[i])  (shift >= 0: left, < 0: right).
+constexpr int MAX_RUNS = 14;
+struct BitRuns {
+    uint32_t mask[MAX_RUNS];
+    int8_t shift[MAX_RUNS];
+    int8_t n;
+    int8_t pad;
+};
+NCB_HD unsigned apply_runs(const BitRuns& r, unsigned v) {
+    unsigned o = 0;
+    for (int i = 0; i < r.n; ++i) {
+        const unsigned x = v & r.mask[i];
+        const int sh = r.shift[i];
+        o |= sh >= 0 ? (x << sh) : (x >> (-sh));
+    }
+    return o;
+}
 
 // A pass: every thread pulls 2^R amplitudes out of the tile (the register bits select which), applies the ops whose
 // bits are register bits (or diagonal), and writes them back.
@@ -72,6 +94,7 @@ struct Pass {
     uint8_t pad[3];
     uint16_t regoff[1 << MAX_REG_BITS];                // tile-local index offset of register slot m
     uint16_t regoff_swz[1 << MAX_REG_BITS];            // swz(regoff[m]) (swz is XOR-linear)
+    BitRuns truns;                                     // thread index -> tile-local index of its slot 0 (= deposit by tpos)
     int32_t op_begin, op_end;                          // ops of this pass
     int32_t instr_lo, instr_hi;                        // instruction range covered: [lo, hi)
 };
@@ -80,9 +103,24 @@ struct Pass {
 struct Segment {
     uint8_t tile_q[MAX_TILE_BITS];   // state bit of tile-local position p, ascending
     uint8_t pad[3];
+    BitRuns eruns;                   // tile-local index (low K-R bits) -> state offset inside the tile
+    BitRuns bruns;                   // tile number -> state offset of the tile (deposit into the non-tile state bits)
+    uint32_t it_off[1 << MAX_REG_BITS];    // state offset of tile-local index (it << (K-R)), it < 2^R
+    uint16_t it_swz[1 << MAX_REG_BITS];    // swz(it << (K-R))
     int32_t pass_begin, pass_end;
     int32_t instr_lo, instr_hi;
 };
+
+// Self-contained copy of one segment's program, staged into shared memory by the tile kernel:
+//   [SegBlob header][Pass x npass][Op x nops][matrix pool (doubles)], every part 16-byte aligned.
+// Pass::op_begin/op_end index the blob's own op array; Op::mat / mat_bare are offsets (doubles) into the blob's pool,
+// or, when negative, -(offset + 1) into the program's global pool (16x16 operators are too big to stage).
+struct SegBlob {
+    Segment seg;
+    int32_t npass, nops, pool_doubles, bytes;
+    int32_t pass_off, op_off, pool_off, pad;    // byte offsets from the start of the blob
+};
+constexpr int MAX_BLOB_BYTES = 16 * 1024;
 
 // Static description of one noise channel (a Kraus list) for the event planner.
 struct Channel {
@@ -273,34 +311,49 @@ NCB_HD void dense4(cplx* a, const cplx* __restrict__ M) {
 
 // Executes the ops of `ps` whose instruction index is in [lo, hi) on this thread's 2^R amplitudes.
 // bare_last: the op(s) of instruction hi-1 use the bare gate matrix.
-template <int R, bool D4>
+constexpr int FEAT_DENSE2 = 1, FEAT_DENSE4 = 2;   // which operator kinds a kernel instantiation carries
+template <int R, int FEAT>
 NCB_HD void run_pass_thread(cplx* sm, int K, int tid, const Pass& ps, const Op* __restrict__ ops,
-                            const double* __restrict__ pool, int lo, int hi, bool bare_last) {
+                            const double* __restrict__ pool, const double* __restrict__ pool_global, int lo, int hi, bool bare_last) {
     constexpr int NA = 1 << R;
-    const int jb = deposit(tid, ps.tpos, K - R);
+    const int jb = (int)apply_runs(ps.truns, (unsigned)tid);
     const int jbs = swz(jb);
     cplx a[NA];
 #pragma unroll
     for (int m = 0; m < NA; ++m) a[m] = sm[jbs ^ ps.regoff_swz[m]];
     for (int o = ps.op_begin; o < ps.op_end; ++o) {
         const Op op = ops[o];
-        if (op.instr < lo || op.instr >= hi) continue;
-        const cplx* M = reinterpret_cast<const cplx*>(pool + ((bare_last && op.instr == hi - 1) ? op.mat_bare : op.mat));
-        const int nb = op_nb(op);
+        int moff;
+        if (op.kind_nb >> 31) {
+            // group header (see ncb_compile.cpp): the product of the next `span` ops; usable when the whole group is
+            // inside [lo, hi) and its last instruction is not the bare one
+            const int span = (int)((op.kind_nb >> 24) & 0x7f), last = op.pad;
+            if (!(op.instr >= lo && (last + 1 < hi || (last + 1 == hi && !bare_last)))) continue;
+            o += span;
+            moff = op.mat;
+        } else {
+            if (op.instr < lo || op.instr >= hi) continue;
+            moff = (bare_last && op.instr == hi - 1) ? op.mat_bare : op.mat;
+        }
+        const cplx* M = reinterpret_cast<const cplx*>(moff >= 0 ? pool + moff : pool_global + (-moff - 1));
         switch (op_kind(op)) {
-        case OPK_DIAG:
+        case OPK_DIAG: {
+            const int nb = op_nb(op), tm = op_tmask(op);
+            int idx_t = 0;                       // table-index bits that come from this thread's fixed tile bits
+            for (int b = 0; b < nb; ++b)
+                if ((tm >> b) & 1) idx_t |= ((jb >> op_rb(op, b)) & 1) << b;
 #pragma unroll
             for (int m = 0; m < NA; ++m) {
-                const int j = jb | ps.regoff[m];
-                int idx = 0;
-                for (int b = 0; b < nb; ++b) idx |= ((j >> op_rb(op, b)) & 1) << b;
+                const unsigned w = m < 8 ? op.midx_lo : op.midx_hi;
+                const int idx = idx_t | (int)((w >> (4 * (m & 7))) & 15u);
                 a[m] = cmul(a[m], M[idx]);
             }
             break;
+        }
         case OPK_DENSE1: dense1<R>(a, op_rb(op, 0), M); break;
         case OPK_PERM1: perm1<R>(a, op_rb(op, 0), M); break;
-        case OPK_DENSE2: dense2<R>(a, op_rb(op, 0), op_rb(op, 1), M); break;
-        case OPK_DENSE4: if (D4) dense4<R>(a, M); break;
+        case OPK_DENSE2: if (FEAT & FEAT_DENSE2) dense2<R>(a, op_rb(op, 0), op_rb(op, 1), M); break;
+        case OPK_DENSE4: if (FEAT & FEAT_DENSE4) dense4<R>(a, M); break;
         }
     }
 #pragma unroll
@@ -383,18 +436,6 @@ NCB_HD void mirror_rho(double* rho, int d) {
         }
 }
 
-// Tile geometry.  base: the tile index o deposited into the state bits that are NOT tile bits (ascending).
-NCB_HD long long tile_base(const Segment& sg, int K, int nbits, int o) {
-    long long base = 0;
-    int src = o, p = 0;
-    for (int b = 0; b < nbits; ++b) {
-        while (p < K && sg.tile_q[p] < b) ++p;
-        if (p < K && sg.tile_q[p] == b) continue;
-        base |= (long long)(src & 1) << b;
-        src >>= 1;
-    }
-    return base;
-}
 // position of state bit q inside the tile
 NCB_HD int tile_pos(const Segment& sg, int K, int q) {
     for (int p = 0; p < K; ++p)

@@ -256,12 +256,32 @@ cmat conj_of(const cmat& a) {
     return r;
 }
 
+// deposit "source bit i -> output bit pos[i]" (i < nbits) as runs of consecutive source bits with consecutive targets
+BitRuns make_runs(const std::vector<int>& pos) {
+    BitRuns r;
+    std::memset(&r, 0, sizeof(r));
+    const int nbits = (int)pos.size();
+    int i = 0;
+    while (i < nbits) {
+        int j = i + 1;
+        while (j < nbits && pos[j] == pos[j - 1] + 1) ++j;
+        if (r.n >= MAX_RUNS) throw std::runtime_error("internal: too many bit runs");
+        r.mask[r.n] = (uint32_t)(((1ull << j) - 1) ^ ((1ull << i) - 1));
+        r.shift[r.n] = (int8_t)(pos[i] - i);
+        ++r.n;
+        i = j;
+    }
+    return r;
+}
+
 struct PassBuild {
     std::vector<int> regset;            // tile-local positions
     std::vector<const LogicalOp*> lops;
 };
 
 }  // namespace
+
+static void build_blobs(Program& P);
 
 void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, Program& P) {
     P = Program();
@@ -354,12 +374,21 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
     };
     const int kfit = std::min(K, P.nbits);
     {
+        // upper bound of what a logical op adds to its segment's shared-memory blob (op records of the op and of a
+        // possible group header, its matrices, a share of a pass record)
+        auto blob_cost = [&](const LogicalOp& l) {
+            const size_t mats = l.diag ? (size_t)(2 << l.nb) * 8 * 2 + 256 : (l.nb <= 2 ? (size_t)(2 << (2 * l.nb)) * 8 * 2 : 0);
+            return 2 * sizeof(Op) + mats + sizeof(Pass) / 2;
+        };
+        size_t cur_cost = sizeof(SegBlob) + sizeof(Pass);
         SegBuild cur{fresh_tile(), 0, 0};
         for (size_t i = 0; i < lops.size(); ++i) {
             std::vector<int> t = tile_union(cur.tile, lops[i]);
             const bool new_instr = i == 0 || lops[i].instr != lops[i - 1].instr;
-            const bool force_split = !opt.fuse && new_instr && cur.lop_end > cur.lop_begin;
+            bool force_split = !opt.fuse && new_instr && cur.lop_end > cur.lop_begin;
+            if (cur_cost + blob_cost(lops[i]) > (size_t)MAX_BLOB_BYTES - 512 && new_instr && cur.lop_end > cur.lop_begin) force_split = true;
             if ((int)t.size() > kfit || force_split) {
+                cur_cost = sizeof(SegBlob) + sizeof(Pass);
                 if (cur.lop_end == cur.lop_begin) throw std::runtime_error("an operation does not fit a tile; increase tile_bits");
                 sb.push_back(cur);
                 cur = SegBuild{fresh_tile(), i, i};
@@ -367,6 +396,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                 if ((int)t.size() > kfit) throw std::runtime_error("an operation does not fit a tile; increase tile_bits");
             }
             cur.tile = t; cur.lop_end = i + 1;
+            cur_cost += blob_cost(lops[i]);
         }
         if (cur.lop_end > cur.lop_begin || sb.empty()) sb.push_back(cur);
     }
@@ -383,6 +413,21 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
         int local_of[64];
         for (int i = 0; i < 64; ++i) local_of[i] = -1;
         for (int p = 0; p < K; ++p) { seg.tile_q[p] = (uint8_t)s.tile[p]; local_of[s.tile[p]] = p; }
+        {
+            std::vector<int> epos(s.tile.begin(), s.tile.begin() + (K - R));
+            seg.eruns = make_runs(epos);
+            for (int it = 0; it < (1 << R); ++it) {
+                unsigned off = 0;
+                for (int b = 0; b < R; ++b)
+                    if ((it >> b) & 1) off |= 1u << s.tile[K - R + b];
+                seg.it_off[it] = off;
+                seg.it_swz[it] = (uint16_t)swz(it << (K - R));
+            }
+            std::vector<int> bpos;
+            for (int b = 0; b < P.nbits; ++b)
+                if (local_of[b] < 0) bpos.push_back(b);
+            seg.bruns = make_runs(bpos);
+        }
         seg.pass_begin = (int)P.passes.size();
         seg.instr_lo = s.lop_end > s.lop_begin ? lops[s.lop_begin].instr : 0;
         seg.instr_hi = s.lop_end > s.lop_begin ? lops[s.lop_end - 1].instr + 1 : 0;
@@ -434,6 +479,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
             for (size_t i = 0; i < rest.size(); ++i)
                 if (!taken[i]) order.push_back(rest[i]);
             for (int i = 0; i < K - R; ++i) ps.tpos[i] = (uint8_t)order[i];
+            ps.truns = make_runs(std::vector<int>(order.begin(), order.begin() + (K - R)));
             for (int m = 0; m < (1 << R); ++m) {
                 const int off = deposit(m, ps.regpos, R);
                 ps.regoff[m] = (uint16_t)off;
@@ -442,8 +488,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
             ps.op_begin = (int)P.ops.size();
             ps.instr_lo = b.lops.empty() ? 0 : b.lops.front()->instr;
             ps.instr_hi = b.lops.empty() ? 0 : b.lops.back()->instr + 1;
-            for (const LogicalOp* lp : b.lops) {
-                const LogicalOp& l = *lp;
+            auto emit = [&](const LogicalOp& l) -> Op {
                 Op op;
                 std::memset(&op, 0, sizeof(op));
                 op.instr = l.instr;
@@ -452,13 +497,25 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                 const int d = 1 << l.nb;
                 if (l.diag) {
                     kind = OPK_DIAG;
-                    for (int i = 0; i < l.nb; ++i) rb[i] = (uint32_t)local_of[l.bits[i]];
+                    uint32_t tmask = 0;
+                    uint64_t midx = 0;
+                    for (int i = 0; i < l.nb; ++i) {
+                        const int pos = local_of[l.bits[i]];
+                        rb[i] = (uint32_t)pos;
+                        if (reg_of[pos] < 0) tmask |= 1u << i;
+                        else
+                            for (int m = 0; m < (1 << R); ++m)
+                                if ((m >> reg_of[pos]) & 1) midx |= (uint64_t)(1u << i) << (4 * m);
+                    }
+                    kind |= (int)(tmask << 16);
+                    op.midx_lo = (uint32_t)midx; op.midx_hi = (uint32_t)(midx >> 32);
                     op.mat = pb.add_doubles(l.mat);
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
                 } else if (l.nb <= 2) {
                     for (int i = 0; i < l.nb; ++i) rb[i] = (uint32_t)reg_of[local_of[l.bits[i]]];
                     const cmat m = read_complex(l.mat.data(), d * d), mb = read_complex(l.bare.data(), d * d);
                     kind = l.nb == 2 ? OPK_DENSE2 : (is_antidiagonal2(m) && is_antidiagonal2(mb) ? OPK_PERM1 : OPK_DENSE1);
+                    if (l.nb == 2) P.has_dense2 = true;
                     op.mat = pb.add_doubles(l.mat);
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
                 } else {
@@ -486,15 +543,134 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     op.mat = pb.add_doubles(remap(l.mat));
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(remap(l.bare));
                 }
-                op.kind_nb = (uint32_t)kind | ((uint32_t)l.nb << 8);
+                op.kind_nb = (uint32_t)(kind & 0xff) | ((uint32_t)l.nb << 8) | ((uint32_t)kind & 0xff0000u);
                 op.rbs = rb[0] | (rb[1] << 8) | (rb[2] << 16) | (rb[3] << 24);
-                P.ops.push_back(op);
+                op.pad = l.instr;
+                return op;
+            };
+            // Peephole groups: runs of adjacent ops that collapse into one table / matrix.  A group is emitted as a
+            // header op (the product, flagged in kind_nb bit 31 with the member count in bits 24..30 and the last
+            // member's instruction in `pad`) followed by its members; the executor takes the header when the whole
+            // group lies inside the instruction range being run, the members otherwise (jump events are rare).
+            struct Group { std::vector<const LogicalOp*> members; LogicalOp merged; };
+            std::vector<Group> groups;
+            auto try_merge = [&](Group& g, const LogicalOp& l) -> bool {
+                if (!opt.fuse || g.members.size() >= 100) return false;
+                LogicalOp& a = g.merged;
+                if (a.diag && l.diag) {
+                    std::vector<int> bits(a.bits, a.bits + a.nb);
+                    for (int i = 0; i < l.nb; ++i)
+                        if (std::find(bits.begin(), bits.end(), l.bits[i]) == bits.end()) bits.push_back(l.bits[i]);
+                    if (bits.size() > 4) return false;
+                    const int nb = (int)bits.size();
+                    std::vector<double> tab(2 << nb);
+                    for (int idx = 0; idx < (1 << nb); ++idx) {
+                        int ia = 0, il = 0;
+                        for (int i = 0; i < a.nb; ++i) ia |= ((idx >> (std::find(bits.begin(), bits.end(), a.bits[i]) - bits.begin())) & 1) << i;
+                        for (int i = 0; i < l.nb; ++i) il |= ((idx >> (std::find(bits.begin(), bits.end(), l.bits[i]) - bits.begin())) & 1) << i;
+                        const cd v = cd(a.mat[2 * ia], a.mat[2 * ia + 1]) * cd(l.mat[2 * il], l.mat[2 * il + 1]);
+                        tab[2 * idx] = v.real(); tab[2 * idx + 1] = v.imag();
+                    }
+                    a.nb = nb;
+                    for (int i = 0; i < 4; ++i) a.bits[i] = i < nb ? bits[i] : -1;
+                    a.mat = tab; a.bare = tab;
+                    return true;
+                }
+                if (a.nb == 1 && l.nb == 1 && a.bits[0] == l.bits[0]) {      // same single bit: 2x2 product, l after a
+                    auto full = [](const LogicalOp& o) {
+                        cmat m(4, cd(0, 0));
+                        if (o.diag) { m[0] = cd(o.mat[0], o.mat[1]); m[3] = cd(o.mat[2], o.mat[3]); }
+                        else m = read_complex(o.mat.data(), 4);
+                        return m;
+                    };
+                    const cmat prod = matmul(full(l), full(a), 2);
+                    LogicalOp r = make_lop(a.instr, {a.bits[0]}, prod, prod);
+                    if (r.diag) return false;       // (cannot happen: diag x diag is handled above)
+                    a = r;
+                    return true;
+                }
+                return false;
+            };
+            for (const LogicalOp* lp : b.lops) {
+                if (!groups.empty() && mode != MODE_DENSITY && try_merge(groups.back(), *lp)) groups.back().members.push_back(lp);
+                else groups.push_back(Group{{lp}, *lp});
+            }
+            for (const Group& g : groups) {
+                if (g.members.size() > 1) {
+                    Op h = emit(g.merged);
+                    h.instr = g.members.front()->instr;
+                    h.pad = g.members.back()->instr;
+                    h.mat_bare = h.mat;
+                    h.kind_nb |= 0x80000000u | ((uint32_t)g.members.size() << 24);
+                    P.ops.push_back(h);
+                }
+                for (const LogicalOp* lp : g.members) P.ops.push_back(emit(*lp));
             }
             ps.op_end = (int)P.ops.size();
             P.passes.push_back(ps);
         }
         seg.pass_end = (int)P.passes.size();
         P.segs.push_back(seg);
+    }
+    build_blobs(P);
+}
+
+// Builds the shared-memory blob of every segment (see SegBlob).
+static void build_blobs(Program& P) {
+    P.blobs.clear(); P.blob_off.clear();
+    for (const Segment& sg : P.segs) {
+        std::vector<Pass> passes(P.passes.begin() + sg.pass_begin, P.passes.begin() + sg.pass_end);
+        std::vector<Op> ops;
+        std::vector<double> pool;
+        std::vector<std::pair<int, int>> moved;      // (global offset, local offset)
+        auto local = [&](int goff, int ndoubles, bool keep_global) {
+            if (keep_global) return -(goff + 1);
+            for (auto& m : moved)
+                if (m.first == goff) return m.second;
+            if (pool.size() & 1) pool.push_back(0.0);
+            const int off = (int)pool.size();
+            pool.insert(pool.end(), P.pool.begin() + goff, P.pool.begin() + goff + ndoubles);
+            moved.push_back({goff, off});
+            return off;
+        };
+        for (Pass& ps : passes) {
+            const int b = (int)ops.size();
+            for (int o = ps.op_begin; o < ps.op_end; ++o) {
+                Op op = P.ops[o];
+                const int kind = op_kind(op), nb = op_nb(op);
+                int nd = 0;
+                switch (kind) {
+                case OPK_DIAG: nd = 2 << nb; break;
+                case OPK_DENSE1: case OPK_PERM1: nd = 8; break;
+                case OPK_DENSE2: nd = 32; break;
+                case OPK_DENSE4: nd = 512; break;
+                }
+                const bool big = kind == OPK_DENSE4;
+                const int m = op.mat, mb = op.mat_bare;
+                op.mat = local(m, nd, big);
+                op.mat_bare = mb == m ? op.mat : local(mb, nd, big);
+                ops.push_back(op);
+            }
+            ps.op_begin = b; ps.op_end = (int)ops.size();
+        }
+        SegBlob h;
+        std::memset(&h, 0, sizeof(h));
+        h.seg = sg;
+        h.seg.pass_begin = 0; h.seg.pass_end = (int)passes.size();
+        h.npass = (int)passes.size(); h.nops = (int)ops.size(); h.pool_doubles = (int)pool.size();
+        auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        h.pass_off = (int)align16(sizeof(SegBlob));
+        h.op_off = (int)align16(h.pass_off + passes.size() * sizeof(Pass));
+        h.pool_off = (int)align16(h.op_off + ops.size() * sizeof(Op));
+        h.bytes = (int)align16(h.pool_off + pool.size() * sizeof(double));
+        if (h.bytes > MAX_BLOB_BYTES) throw std::runtime_error("internal: segment program of " + std::to_string(h.bytes) + " bytes exceeds the shared-memory staging area");
+        const size_t at = P.blobs.size();
+        P.blob_off.push_back((int64_t)at);
+        P.blobs.resize(at + h.bytes, 0);
+        std::memcpy(P.blobs.data() + at, &h, sizeof(h));
+        if (!passes.empty()) std::memcpy(P.blobs.data() + at + h.pass_off, passes.data(), passes.size() * sizeof(Pass));
+        if (!ops.empty()) std::memcpy(P.blobs.data() + at + h.op_off, ops.data(), ops.size() * sizeof(Op));
+        if (!pool.empty()) std::memcpy(P.blobs.data() + at + h.pool_off, pool.data(), pool.size() * sizeof(double));
     }
 }
 
@@ -503,7 +679,8 @@ std::string describe_program(const Program& P) {
     o << "mode=" << P.mode << " nq=" << P.nq << " nbits=" << P.nbits << " K=" << P.K << " R=" << P.R << " G=" << P.G
       << " segments=" << P.segs.size() << " passes=" << P.passes.size() << " ops=" << P.ops.size()
       << " channels=" << P.chans.size() << " noisy=" << P.noisy_instrs.size() << " draws=" << P.num_draws
-      << " norm_preserving=" << P.norm_preserving << " dense4=" << P.has_dense4 << " pool=" << P.pool.size() << "\n";
+      << " norm_preserving=" << P.norm_preserving << " dense2=" << P.has_dense2 << " dense4=" << P.has_dense4
+      << " pool=" << P.pool.size() << "\n";
     for (size_t s = 0; s < P.segs.size(); ++s) {
         const Segment& g = P.segs[s];
         o << "seg " << s << " instr[" << g.instr_lo << "," << g.instr_hi << ") tile{";

@@ -33,7 +33,7 @@ struct CircuitView {               // mirrors ncb_circuit in include/ncb200.h
 
 struct CompileOptions {
     int tile_bits = 12;     // K: amplitudes per shared-memory tile = 2^K
-    int reg_bits = 4;       // R: amplitudes per thread = 2^R
+    int reg_bits = 3;       // R: amplitudes per thread = 2^R
     int low_bits = 3;       // the L lowest state bits are part of every tile (coalescing: runs of 2^L * 16 B)
     int fuse = 1;           // 0: one instruction per segment (debug / ablation)
 };
@@ -55,6 +55,7 @@ struct Program {
     int K = 0, R = 0;      // tile bits (may exceed nbits for tiny states: the extra bits are virtual), register bits
     int G = 0;
     bool has_dense4 = false;
+    bool has_dense2 = false;
     bool norm_preserving = true;
     std::vector<double> pool;
     std::vector<Op> ops;
@@ -65,6 +66,8 @@ struct Program {
     std::vector<int32_t> draw_pos;      // position of the instruction's draw in the reference's MT stream, -1: none
     int num_draws = 0;
     std::vector<int32_t> noisy_instrs;  // instructions that have a channel with >= 2 operators
+    std::vector<unsigned char> blobs;   // SegBlob of every segment, back to back (16-byte aligned)
+    std::vector<int64_t> blob_off;      // byte offset of segment s's blob
     CompileOptions opt;
 };
 

@@ -64,7 +64,7 @@ struct Engine {
     size_t smem_optin = 0;
     DevProgram d{};
     DevBuf<Op> d_ops; DevBuf<Pass> d_passes; DevBuf<Segment> d_segs; DevBuf<Instr> d_instrs; DevBuf<Channel> d_chans;
-    DevBuf<double> d_pool; DevBuf<int32_t> d_noisy;
+    DevBuf<double> d_pool; DevBuf<int32_t> d_noisy; DevBuf<unsigned char> d_blobs;
     DevBuf<cplx> d_states;
     DevBuf<double> d_red, d_norm, d_invnorm, d_probs, d_partial, d_uniforms;
     DevBuf<Decision> d_dec;
@@ -75,10 +75,12 @@ struct Engine {
     PinnedBuf<DecideItem> h_decides[2];
     cudaEvent_t buf_free[2] = {nullptr, nullptr};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool tile_configured = false, resident_configured = false;
+    int tile_ctas = 148;
 
     ~Engine() {
         d_ops.release(); d_passes.release(); d_segs.release(); d_instrs.release(); d_chans.release(); d_pool.release();
-        d_noisy.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_probs.release();
+        d_noisy.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_probs.release();
         d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release();
         for (int i = 0; i < 2; ++i) {
             d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
@@ -113,11 +115,11 @@ struct Engine {
         sm_count = prop.multiProcessorCount;
         smem_optin = prop.sharedMemPerBlockOptin;
         upload(d_ops, P.ops); upload(d_passes, P.passes); upload(d_segs, P.segs); upload(d_instrs, P.instrs);
-        upload(d_chans, P.chans); upload(d_pool, P.pool); upload(d_noisy, P.noisy_instrs);
+        upload(d_chans, P.chans); upload(d_pool, P.pool); upload(d_noisy, P.noisy_instrs); upload(d_blobs, P.blobs);
         d.ops = d_ops.p; d.passes = d_passes.p; d.segs = d_segs.p; d.instrs = d_instrs.p; d.chans = d_chans.p;
         d.pool = d_pool.p; d.noisy = d_noisy.p; d.n_noisy = (int)P.noisy_instrs.size(); d.G = P.G; d.nbits = P.nbits;
-        d.K = P.K; d.R = P.R; d.nseg = (int)P.segs.size();
-        const size_t need = resident() ? resident_smem() : tile_smem();
+        d.K = P.K; d.R = P.R; d.nseg = (int)P.segs.size(); d.npass = (int)P.passes.size();
+        const size_t need = resident() ? resident_smem() : tile_launch_smem();
         if (need + 6 * 1024 > smem_optin)
             throw std::runtime_error("tile does not fit shared memory: need " + std::to_string(need) + " B, device offers " + std::to_string(smem_optin));
         for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&buf_free[i], cudaEventDisableTiming));
@@ -127,43 +129,70 @@ struct Engine {
         uploaded = true;
     }
 
-    // ---- kernel dispatch on (R, dense4) ----------------------------------------------------------------------
-    template <int R, bool D4>
-    void launch_tile_t(int grid, int threads, cudaStream_t s, const Work* works, int tile_shift) {
-        static thread_local bool configured = false;
-        if (!configured) {
-            CK(cudaFuncSetAttribute(tile_kernel<R, D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 8 * 1024));
-            configured = true;
+    // ---- kernel dispatch: three instantiations --------------------------------------------------------------
+    //   <3, 0, 512, 1>           R = 3, no dense two-qubit operators (Heron: cz/rzz are diagonal)
+    //   <3, DENSE2, 512, 1>      R = 3 with dense 4x4 operators (Eagle ecr, cx, swap, non-diagonal Kraus bases)
+    //   <4, DENSE2|DENSE4, 256, 1>  R = 4: 3-4 bit dense operators (density-matrix superoperators, 3-4 qubit unitaries)
+    int variant() const {
+        if (P.R == 4) return 2;
+        if (const char* e = getenv("NCB_VARIANT")) {      // tuning aid: 1 runs the lean programs in the 128-register kernel
+            const int v = atoi(e);
+            if (v == 1 && P.R == 3 && !P.has_dense4) return 1;
         }
-        tile_kernel<R, D4><<<grid, threads, tile_smem(), s>>>(d, works, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p);
-        CK(cudaGetLastError());
+        if (P.R == 3 && !P.has_dense4) return P.has_dense2 ? 1 : 0;
+        throw std::runtime_error("unsupported reg_bits (3, or 4 for 3-4 bit dense operators)");
     }
-    void launch_tile(int nworks, cudaStream_t s, const Work* works) {
+    template <class Kern>
+    void configure(Kern k) {
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 8 * 1024));
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    size_t tile_launch_smem() const { return (size_t)MAX_BLOB_BYTES + 2 * tile_smem(); }
+    void launch_tile(int nworks, cudaStream_t s, const Work* works, int seg) {
         const int tile_shift = P.nbits > P.K ? P.nbits - P.K : 0;
         const int threads = 1 << (P.K - P.R);
-        const long long grid = (long long)nworks << tile_shift;
-        if (grid > 0x7fffffffLL) throw std::runtime_error("launch too large");
-        if (P.R == 4 && P.has_dense4) launch_tile_t<4, true>((int)grid, threads, s, works, tile_shift);
-        else if (P.R == 4) launch_tile_t<4, false>((int)grid, threads, s, works, tile_shift);
-        else if (P.R == 3) launch_tile_t<3, false>((int)grid, threads, s, works, tile_shift);
-        else throw std::runtime_error("unsupported reg_bits (3 or 4)");
-    }
-    template <int R, bool D4>
-    void launch_resident_t(int grid, int threads, cudaStream_t s, const ResidentArgs& a) {
-        static thread_local bool configured = false;
-        if (!configured) {
-            CK(cudaFuncSetAttribute(resident_kernel<R, D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 8 * 1024));
-            configured = true;
+        const long long total = (long long)nworks << tile_shift;
+        const size_t smem = tile_launch_smem();
+        if (!tile_configured) {
+            configure(tile_kernel<3, 0, 512, 1>);
+            configure(tile_kernel<3, FEAT_DENSE2, 512, 1>);
+            configure(tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>);
+            int occ = 1;
+            switch (variant()) {
+            case 0: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<3, 0, 512, 1>, threads, smem)); break;
+            case 1: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<3, FEAT_DENSE2, 512, 1>, threads, smem)); break;
+            default: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>, threads, smem)); break;
+            }
+            if (occ < 1) throw std::runtime_error("tile kernel does not fit on an SM");
+            if (const char* e = getenv("NCB_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
+            tile_ctas = sm_count * occ;
+            tile_configured = true;
         }
-        resident_kernel<R, D4><<<grid, threads, resident_smem(), s>>>(d, a);
+        const int grid = (int)std::min<long long>(total, tile_ctas);
+        if (grid < 1) return;
+        const unsigned char* blob = d_blobs.p + P.blob_off[seg];
+        const int blob_bytes = reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[seg])->bytes;
+        switch (variant()) {
+        case 0: tile_kernel<3, 0, 512, 1><<<grid, threads, smem, s>>>(d, blob, blob_bytes, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p); break;
+        case 1: tile_kernel<3, FEAT_DENSE2, 512, 1><<<grid, threads, smem, s>>>(d, blob, blob_bytes, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p); break;
+        default: tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1><<<grid, threads, smem, s>>>(d, blob, blob_bytes, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p); break;
+        }
         CK(cudaGetLastError());
     }
     void launch_resident(int grid, cudaStream_t s, const ResidentArgs& a) {
         const int threads = 1 << (P.K - P.R);
-        if (P.R == 4 && P.has_dense4) launch_resident_t<4, true>(grid, threads, s, a);
-        else if (P.R == 4) launch_resident_t<4, false>(grid, threads, s, a);
-        else if (P.R == 3) launch_resident_t<3, false>(grid, threads, s, a);
-        else throw std::runtime_error("unsupported reg_bits (3 or 4)");
+        if (!resident_configured) {
+            configure(resident_kernel<3, 0, 512, 1>);
+            configure(resident_kernel<3, FEAT_DENSE2, 512, 1>);
+            configure(resident_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>);
+            resident_configured = true;
+        }
+        switch (variant()) {
+        case 0: resident_kernel<3, 0, 512, 1><<<grid, threads, resident_smem(), s>>>(d, a); break;
+        case 1: resident_kernel<3, FEAT_DENSE2, 512, 1><<<grid, threads, resident_smem(), s>>>(d, a); break;
+        default: resident_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1><<<grid, threads, resident_smem(), s>>>(d, a); break;
+        }
+        CK(cudaGetLastError());
     }
     int resident_ctas_per_sm() const {
         const size_t per = resident_smem() + 8 * 1024;
@@ -319,7 +348,7 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             CK(cudaMemcpyAsync(d_decides[buf].p, h_decides[buf].p, plan.decides.size() * sizeof(DecideItem), cudaMemcpyHostToDevice, s));
         }
         for (const LaunchStep& st : plan.steps) {
-            if (st.kind == 0) { launch_tile(st.count, s, d_works[buf].p + st.begin); ++rp->out_tile_launches; }
+            if (st.kind == 0) { launch_tile(st.count, s, d_works[buf].p + st.begin, st.seg); ++rp->out_tile_launches; }
             else {
                 decide_kernel<<<st.count, 32, 0, s>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
                 CK(cudaGetLastError());
@@ -435,7 +464,7 @@ void Engine::run_deterministic(cudaStream_t s) {
         d_works[0].reserve(plan.works.size() + 1);
         CK(cudaMemcpyAsync(d_works[0].p, plan.works.data(), plan.works.size() * sizeof(Work), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
-        for (const LaunchStep& st : plan.steps) launch_tile(st.count, s, d_works[0].p + st.begin);
+        for (const LaunchStep& st : plan.steps) launch_tile(st.count, s, d_works[0].p + st.begin, st.seg);
     }
 }
 
@@ -481,6 +510,11 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     NCB_TRY
     CompileOptions opt;
     int device = -1;
+    // default register bits: 3; 4 when the program carries 3-4 bit dense operators (density-matrix superoperators,
+    // 3-4 qubit unitaries)
+    opt.reg_bits = mode == NCB_MODE_DENSITY ? 4 : 3;
+    for (int g = 0; g < circuit->num_instructions; ++g)
+        if (circuit->opcode[g] == NCB_UNITARY && circuit->unitary_nq && circuit->unitary_nq[g] >= 3) opt.reg_bits = 4;
     if (options) {
         if (options->tile_bits > 0) opt.tile_bits = options->tile_bits;
         if (options->reg_bits > 0) opt.reg_bits = options->reg_bits;
@@ -493,7 +527,7 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     if (const char* e = getenv("NCB_LOW_BITS")) opt.low_bits = atoi(e);
     if (const char* e = getenv("NCB_FUSE")) opt.fuse = atoi(e);
     if (opt.reg_bits != 3 && opt.reg_bits != 4) return fail(NCB_E_INVALID, "reg_bits must be 3 or 4");
-    opt.tile_bits = std::min(opt.tile_bits, opt.reg_bits == 4 ? 12 : 12);   // <= 256 threads (R = 4) / 512 threads (R = 3)
+    opt.tile_bits = std::min(opt.tile_bits, 12);   // <= 256 threads (R = 4) / 512 threads (R = 3)
     ncb_program* p = new ncb_program();
     try {
         compile_program(view_of(circuit), mode, opt, p->eng.P);

@@ -25,7 +25,7 @@ struct DevProgram {
     const Channel* chans;
     const double* pool;
     const int32_t* noisy;   // instructions with a channel of >= 2 operators
-    int n_noisy, G, nbits, K, R, nseg;
+    int n_noisy, G, nbits, K, R, nseg, npass;
 };
 
 constexpr int RED_VALUES = 32;   // doubles per reduced-density-matrix partial
@@ -69,16 +69,18 @@ __device__ __forceinline__ void block_reduce(const double* vals, double* s_buf, 
 }
 
 // Runs the ops with instruction index in [lo, hi) of the passes [*pcur, pend) on the tile in shared memory.
-// *pcur is advanced past the passes that are entirely below hi.
-template <int R, bool D4>
-__device__ __forceinline__ void run_range(cplx* sm, const DevProgram& P, int* pcur, int pend, int lo, int hi, bool bare_last) {
+// *pcur is advanced past the passes that are entirely below hi.  passes/ops/pool may live in shared memory (the
+// tile kernel's staged segment blob) or in global memory (the resident kernel).
+template <int R, int FEAT>
+__device__ __forceinline__ void run_range(cplx* sm, int K, const Pass* passes, const Op* ops, const double* pool,
+                                          const double* pool_global, int* pcur, int pend, int lo, int hi, bool bare_last) {
     int p = *pcur;
     for (; p < pend; ++p) {
-        const Pass* ps = P.passes + p;
+        const Pass* ps = passes + p;
         const int plo = ps->instr_lo, phi = ps->instr_hi;
         if (plo >= hi) break;
         if (phi > lo && ps->op_end > ps->op_begin) {
-            run_pass_thread<R, D4>(sm, P.K, threadIdx.x, *ps, P.ops, P.pool, lo, hi, bare_last);
+            run_pass_thread<R, FEAT>(sm, K, threadIdx.x, *ps, ops, pool, pool_global, lo, hi, bare_last);
             __syncthreads();
         }
         if (phi > hi) break;      // this pass also holds later instructions: revisit it
@@ -87,109 +89,158 @@ __device__ __forceinline__ void run_range(cplx* sm, const DevProgram& P, int* pc
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// rare (jump event) paths of the tile kernel: kept out of line so that they do not set its register budget
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void event_prologue(cplx* sm, const DevProgram& P, const Segment* sg, const Work& w,
+                                            const Decision* __restrict__ decisions) {
+    const int K = P.K;
+    const Instr in = P.instrs[w.ev_instr];
+    const Channel ch = P.chans[in.channel];
+    int k = w.ev_k;
+    double scale = 1.0;
+    if (w.flags & WF_PRO_DYNAMIC) { k = decisions[w.slot].k; scale = decisions[w.slot].scale; }
+    const cplx* M = reinterpret_cast<const cplx*>(P.pool + ch.kraus) + k * ch.dim * ch.dim;
+    const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;
+    tile_apply_dense(sm, K, threadIdx.x, blockDim.x, ch.dim, p0, p1, M, scale);
+    __syncthreads();
+}
+
+// reduced density matrix of tile positions (p0, p1) -> dst[32] (lower triangle), block-wide
+__device__ __noinline__ void event_reduce(const cplx* sm, int K, int p0, int p1, double* s_buf, double* s_out, double* dst) {
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    if (p1 < 0) {
+        double acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+        reduce_rho_thread<2>(sm, K, tid, nthreads, p0, -1, acc);
+        double v[6] = {acc[0], acc[1], acc[4], acc[5], acc[6], acc[7]};   // (0,0) (1,0) (1,1)
+        block_reduce<6>(v, s_buf, s_out);
+        if (tid == 0) {
+            dst[0] = s_out[0]; dst[1] = s_out[1]; dst[4] = s_out[2]; dst[5] = s_out[3]; dst[6] = s_out[4]; dst[7] = s_out[5];
+        }
+    } else {
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+        reduce_rho_thread<4>(sm, K, tid, nthreads, p0, p1, acc);
+        double v[20];
+        int n = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) { v[n++] = acc[2 * (r * 4 + c)]; v[n++] = acc[2 * (r * 4 + c) + 1]; }
+        block_reduce<20>(v, s_buf, s_out);
+        if (tid == 0) {
+            int m = 0;
+            for (int r = 0; r < 4; ++r)
+                for (int c = 0; c <= r; ++c) { dst[2 * (r * 4 + c)] = s_out[m++]; dst[2 * (r * 4 + c) + 1] = s_out[m++]; }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // tile kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int R, bool D4>
-__global__ void __launch_bounds__((D4 || R == 4) ? 256 : 512)
-tile_kernel(DevProgram P, const Work* __restrict__ works, cplx* __restrict__ states, int tile_shift,
-            double* __restrict__ red_part, double* __restrict__ norm_part, const Decision* __restrict__ decisions) {
+// Persistent: gridDim.x CTAs walk the launch's (work, tile) pairs with stride gridDim.x.  Shared memory holds the
+// segment's program blob and TWO tile buffers: while tile i is processed, tile i+1 streams in through cp.async.
+template <int R, int FEAT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_bytes, const Work* __restrict__ works, int nworks,
+            cplx* __restrict__ states, int tile_shift, double* __restrict__ red_part, double* __restrict__ norm_part,
+            const Decision* __restrict__ decisions) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* sm = reinterpret_cast<cplx*>(smem_raw);
     __shared__ double s_buf[32 * 20];
     __shared__ double s_out[20];
     const int K = P.K, tid = threadIdx.x, nthreads = blockDim.x;
     const int ntiles = 1 << tile_shift;
-    const int wi = blockIdx.x >> tile_shift, o = blockIdx.x & (ntiles - 1);
-    const Work w = works[wi];
-    const Segment* sg = P.segs + w.seg;
+    const long long total = (long long)nworks << tile_shift;
+    cplx* bufs[2];
+    bufs[0] = reinterpret_cast<cplx*>(smem_raw + MAX_BLOB_BYTES);
+    bufs[1] = bufs[0] + (1 << K);
 
-    // tile geometry: base = tile index o deposited into the state bits that are not tile bits
-    const long long base = tile_base(*sg, K, P.nbits, o);
-    const int offA = deposit(tid, sg->tile_q, K - R);
-    cplx* st = states + ((long long)w.slot << P.nbits) + base;
-    const int limit = 1 << P.nbits;
+    // ---- stage the segment program ----
+    for (int i = tid * 16; i < blob_bytes; i += nthreads * 16) cp_async16(smem_raw + i, blob_g + i);
+    cp_async_wait_all();
+    __syncthreads();
+    const SegBlob* blob = reinterpret_cast<const SegBlob*>(smem_raw);
+    const Segment* sg = &blob->seg;
+    const Pass* passes = reinterpret_cast<const Pass*>(smem_raw + blob->pass_off);
+    const Op* ops = reinterpret_cast<const Op*>(smem_raw + blob->op_off);
+    const double* pool = reinterpret_cast<const double*>(smem_raw + blob->pool_off);
+    const int npass = blob->npass;
 
-    // ---- load ----
-    if (w.flags & WF_INIT) {
-#pragma unroll 4
-        for (int it = 0; it < (1 << R); ++it) sm[swz(tid + (it << (K - R)))] = cplx{0.0, 0.0};
-        if (o == 0 && tid == 0) sm[swz(0)] = cplx{1.0, 0.0};
-    } else {
-#pragma unroll 4
+    const unsigned offA = apply_runs(sg->eruns, (unsigned)tid);
+    const int sA = swz(tid);
+    const unsigned limit = 1u << P.nbits;
+
+    auto issue_load = [&](long long t, cplx* sm, const Work& w) {
+        if (w.flags & WF_INIT) return;                           // |0..0> is written by the processing step
+        const unsigned base = apply_runs(sg->bruns, (unsigned)(t & (ntiles - 1)));
+        const cplx* st = states + ((long long)w.slot << P.nbits) + base;
+#pragma unroll
         for (int it = 0; it < (1 << R); ++it) {
-            const int off = offA | deposit(it, sg->tile_q + (K - R), R);
-            cplx* dst = sm + swz(tid + (it << (K - R)));
+            const unsigned off = offA | sg->it_off[it];
+            cplx* dst = sm + (sA ^ sg->it_swz[it]);
             if (off < limit) cp_async16(dst, st + off);
             else *dst = cplx{0.0, 0.0};
         }
-        cp_async_wait_all();
-    }
-    __syncthreads();
+    };
 
-    // ---- jump operator of the event that ended the previous piece ----
-    if (w.flags & (WF_PRO_STATIC | WF_PRO_DYNAMIC)) {
-        const Instr in = P.instrs[w.ev_instr];
-        const Channel ch = P.chans[in.channel];
-        int k = w.ev_k;
-        double scale = 1.0;
-        if (w.flags & WF_PRO_DYNAMIC) { k = decisions[w.slot].k; scale = decisions[w.slot].scale; }
-        const cplx* M = reinterpret_cast<const cplx*>(P.pool + ch.kraus) + k * ch.dim * ch.dim;
-        const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;
-        tile_apply_dense(sm, K, tid, nthreads, ch.dim, p0, p1, M, scale);
+    long long t = blockIdx.x;
+    if (t >= total) return;
+    Work w = works[t >> tile_shift];
+    issue_load(t, bufs[0], w);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int iter = 0; t < total; ++iter, t += gridDim.x) {
+        cplx* sm = bufs[iter & 1];
+        const long long tn = t + gridDim.x;
+        Work wn = w;
+        if (tn < total) {
+            wn = works[tn >> tile_shift];
+            issue_load(tn, bufs[(iter + 1) & 1], wn);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");      // everything but the newest group has landed
         __syncthreads();
-    }
-
-    // ---- the segment's passes ----
-    int pcur = sg->pass_begin;
-    run_range<R, D4>(sm, P, &pcur, sg->pass_end, w.instr_lo, w.instr_hi, (w.flags & WF_BARE_LAST) != 0);
-
-    // ---- reductions ----
-    if (w.flags & WF_REDUCE) {
-        const Instr in = P.instrs[w.red_instr];
-        const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;
-        double* dst = red_part + ((long long)w.slot * ntiles + o) * RED_VALUES;
-        if (p1 < 0) {
-            double acc[8];
+        const int o = (int)(t & (ntiles - 1));
+        if (w.flags & WF_INIT) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-            reduce_rho_thread<2>(sm, K, tid, nthreads, p0, -1, acc);
-            double v[6] = {acc[0], acc[1], acc[4], acc[5], acc[6], acc[7]};   // (0,0) (1,0) (1,1)
-            block_reduce<6>(v, s_buf, s_out);
-            if (tid == 0) {
-                dst[0] = s_out[0]; dst[1] = s_out[1]; dst[4] = s_out[2]; dst[5] = s_out[3]; dst[6] = s_out[4]; dst[7] = s_out[5];
-            }
-        } else {
-            double acc[32];
+            for (int it = 0; it < (1 << R); ++it) sm[sA ^ sg->it_swz[it]] = cplx{0.0, 0.0};
+            if (o == 0 && tid == 0) sm[swz(0)] = cplx{1.0, 0.0};
+            __syncthreads();
+        }
+        // ---- jump operator of the event that ended the previous piece ----
+        if (w.flags & (WF_PRO_STATIC | WF_PRO_DYNAMIC)) event_prologue(sm, P, sg, w, decisions);
+        // ---- the segment's passes ----
+        int pcur = 0;
+        run_range<R, FEAT>(sm, K, passes, ops, pool, P.pool, &pcur, npass, w.instr_lo, w.instr_hi, (w.flags & WF_BARE_LAST) != 0);
+        // ---- reductions ----
+        if (w.flags & WF_REDUCE) {
+            const Instr in = P.instrs[w.red_instr];
+            const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;
+            event_reduce(sm, K, p0, p1, s_buf, s_out, red_part + ((long long)w.slot * ntiles + o) * RED_VALUES);
+        }
+        if (w.flags & WF_NORM) {
+            double v[1] = {0.0};
+            for (int i = tid; i < (1 << K); i += nthreads) v[0] += cnorm2(sm[i]);
+            block_reduce<1>(v, s_buf, s_out);
+            if (tid == 0) norm_part[(long long)w.slot * ntiles + o] = s_out[0];
+        }
+        // ---- store ----
+        {
+            const unsigned base = apply_runs(sg->bruns, (unsigned)o);
+            cplx* st = states + ((long long)w.slot << P.nbits) + base;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = 0.0;
-            reduce_rho_thread<4>(sm, K, tid, nthreads, p0, p1, acc);
-            double v[20];
-            int n = 0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c) { v[n++] = acc[2 * (r * 4 + c)]; v[n++] = acc[2 * (r * 4 + c) + 1]; }
-            block_reduce<20>(v, s_buf, s_out);
-            if (tid == 0) {
-                int m = 0;
-                for (int r = 0; r < 4; ++r)
-                    for (int c = 0; c <= r; ++c) { dst[2 * (r * 4 + c)] = s_out[m++]; dst[2 * (r * 4 + c) + 1] = s_out[m++]; }
+            for (int it = 0; it < (1 << R); ++it) {
+                const unsigned off = offA | sg->it_off[it];
+                if (off < limit) st_stream(st + off, sm[sA ^ sg->it_swz[it]]);
             }
         }
+        __syncthreads();          // the buffer is refilled by the load issued in the next iteration
+        w = wn;
     }
-    if (w.flags & WF_NORM) {
-        double v[1] = {0.0};
-        for (int i = tid; i < (1 << K); i += nthreads) v[0] += cnorm2(sm[i]);
-        block_reduce<1>(v, s_buf, s_out);
-        if (tid == 0) norm_part[(long long)w.slot * ntiles + o] = s_out[0];
-    }
-
-    // ---- store ----
-#pragma unroll 4
-    for (int it = 0; it < (1 << R); ++it) {
-        const int off = offA | deposit(it, sg->tile_q + (K - R), R);
-        if (off < limit) st_stream(st + off, sm[swz(tid + (it << (K - R)))]);
-    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -293,8 +344,8 @@ struct ResidentArgs {
     unsigned long long* counters;   // [0] events, [1] state-dependent events
 };
 
-template <int R, bool D4>
-__global__ void __launch_bounds__((D4 || R == 4) ? 256 : 512)
+template <int R, int FEAT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 resident_kernel(DevProgram P, ResidentArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(smem_raw);                       // 2^K amplitudes
@@ -302,11 +353,13 @@ resident_kernel(DevProgram P, ResidentArgs A) {
     unsigned* evmask = reinterpret_cast<unsigned*>(acc + (1 << P.nbits));   // ceil(G/32) words
     __shared__ double s_buf[32 * 20];
     __shared__ double s_out[RED_VALUES];
+    __shared__ double s_red[20];
     __shared__ int s_k;
     __shared__ double s_scale;
     const int K = P.K, tid = threadIdx.x, nthreads = blockDim.x, dim = 1 << P.nbits;
     const int nwords = (P.G + 31) >> 5;
-    const Segment* sg = P.segs;     // single segment: tile = whole state (identity map)
+    const Segment* sg = P.segs;     // every segment's tile is the whole state (identity map): the passes of all
+                                    // segments form one list
     for (int j = tid; j < dim; j += nthreads) acc[j] = 0.0;
     unsigned long long n_events = 0, n_hard = 0;
 
@@ -340,7 +393,7 @@ resident_kernel(DevProgram P, ResidentArgs A) {
                 if (m) { e = (wd << 5) + __ffs(m) - 1; break; }
             }
             const bool ev = e < P.G;
-            run_range<R, D4>(sm, P, &pcur, sg->pass_end, cur, ev ? e + 1 : P.G, ev);
+            run_range<R, FEAT>(sm, K, P.passes, P.ops, P.pool, P.pool, &pcur, P.npass, cur, ev ? e + 1 : P.G, ev);
             if (!ev) break;
             const Instr in = P.instrs[e];
             const Channel ch = P.chans[in.channel];
@@ -352,36 +405,7 @@ resident_kernel(DevProgram P, ResidentArgs A) {
             bool base_after_all = false;
             if (kmin != kmax) {
                 ++n_hard;
-                if (ch.dim == 2) {
-                    double a8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) a8[i] = 0.0;
-                    reduce_rho_thread<2>(sm, K, tid, nthreads, in.q0, -1, a8);
-                    double v[6] = {a8[0], a8[1], a8[4], a8[5], a8[6], a8[7]};
-                    block_reduce<6>(v, s_buf, s_out + 8);
-                    if (tid == 0) {
-                        s_out[0] = s_out[8]; s_out[1] = s_out[9]; s_out[4] = s_out[10]; s_out[5] = s_out[11];
-                        s_out[6] = s_out[12]; s_out[7] = s_out[13];
-                    }
-                } else {
-                    double a32[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) a32[i] = 0.0;
-                    reduce_rho_thread<4>(sm, K, tid, nthreads, in.q0, in.q1, a32);
-                    double v[20];
-                    int n = 0;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c <= r; ++c) { v[n++] = a32[2 * (r * 4 + c)]; v[n++] = a32[2 * (r * 4 + c) + 1]; }
-                    block_reduce<20>(v, s_buf, s_buf + 32 * 20 - 20);
-                    if (tid == 0) {
-                        int m = 0;
-                        const double* t = s_buf + 32 * 20 - 20;
-                        for (int r = 0; r < 4; ++r)
-                            for (int c = 0; c <= r; ++c) { s_out[2 * (r * 4 + c)] = t[m++]; s_out[2 * (r * 4 + c) + 1] = t[m++]; }
-                    }
-                }
+                event_reduce(sm, K, in.q0, ch.dim == 4 ? in.q1 : -1, s_buf, s_red, s_out);
                 if (tid == 0) {
                     mirror_rho(s_out, ch.dim);
                     double sc;

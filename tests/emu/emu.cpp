@@ -30,20 +30,28 @@ void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, st
                   std::vector<double>& norm_part, const std::vector<Decision>& decisions) {
     const int K = P.K, nthreads = 1 << (K - R);
     const int tile_shift = P.nbits > K ? P.nbits - K : 0, ntiles = 1 << tile_shift;
-    const Segment& sg = P.segs[w.seg];
+    // the staged copy of the segment program (what the tile kernel reads from shared memory)
+    const unsigned char* braw = P.blobs.data() + P.blob_off[w.seg];
+    const SegBlob& blob = *reinterpret_cast<const SegBlob*>(braw);
+    const Segment& sg = blob.seg;
+    const Pass* passes = reinterpret_cast<const Pass*>(braw + blob.pass_off);
+    const Op* ops = reinterpret_cast<const Op*>(braw + blob.op_off);
+    const double* pool = reinterpret_cast<const double*>(braw + blob.pool_off);
+    if (blob.bytes > MAX_BLOB_BYTES) throw std::runtime_error("blob too large");
     const long long limit = 1ll << P.nbits;
     std::vector<cplx> sm(1 << K);
     for (int o = 0; o < ntiles; ++o) {
-        const long long base = tile_base(sg, K, P.nbits, o);
+        const long long base = apply_runs(sg.bruns, (unsigned)o);
         cplx* st = states.data() + ((long long)w.slot << P.nbits) + base;
         // load
         for (int tid = 0; tid < nthreads; ++tid) {
-            const int offA = deposit(tid, sg.tile_q, K - R);
+            const unsigned offA = apply_runs(sg.eruns, (unsigned)tid);
+            const int sA = swz(tid);
             for (int it = 0; it < (1 << R); ++it) {
-                const int off = offA | deposit(it, sg.tile_q + (K - R), R);
+                const unsigned off = offA | sg.it_off[it];
                 cplx v{0.0, 0.0};
                 if (!(w.flags & WF_INIT) && off < limit) v = st[off];
-                sm[swz(tid + (it << (K - R)))] = v;
+                sm[sA ^ sg.it_swz[it]] = v;
             }
         }
         if ((w.flags & WF_INIT) && o == 0) sm[swz(0)] = cplx{1.0, 0.0};
@@ -60,12 +68,12 @@ void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, st
         }
         // passes (same control flow as run_range in ncb_kernels.cuh)
         const bool bare_last = (w.flags & WF_BARE_LAST) != 0;
-        for (int p = sg.pass_begin; p < sg.pass_end; ++p) {
-            const Pass& ps = P.passes[p];
+        for (int p = 0; p < blob.npass; ++p) {
+            const Pass& ps = passes[p];
             if (ps.instr_lo >= w.instr_hi) break;
             if (ps.instr_hi > w.instr_lo && ps.op_end > ps.op_begin)
                 for (int tid = 0; tid < nthreads; ++tid)
-                    run_pass_thread<R, true>(sm.data(), K, tid, ps, P.ops.data(), P.pool.data(), w.instr_lo, w.instr_hi, bare_last);
+                    run_pass_thread<R, 3>(sm.data(), K, tid, ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last);
             if (ps.instr_hi > w.instr_hi) break;
         }
         // reductions
@@ -88,10 +96,11 @@ void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, st
         }
         // store
         for (int tid = 0; tid < nthreads; ++tid) {
-            const int offA = deposit(tid, sg.tile_q, K - R);
+            const unsigned offA = apply_runs(sg.eruns, (unsigned)tid);
+            const int sA = swz(tid);
             for (int it = 0; it < (1 << R); ++it) {
-                const int off = offA | deposit(it, sg.tile_q + (K - R), R);
-                if (off < limit) st[off] = sm[swz(tid + (it << (K - R)))];
+                const unsigned off = offA | sg.it_off[it];
+                if (off < limit) st[off] = sm[sA ^ sg.it_swz[it]];
             }
         }
     }

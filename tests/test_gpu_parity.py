@@ -54,13 +54,25 @@ def replay(n, instr, sq, tq, U, mask_fix=True, **opts):
 # ---------------------------------------------------------------------------------------------------------------
 # replay harness: trajectories agree state by state
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 4, 7, 9, 12])
-def test_replay_resident_heron(heron_noise, n):
+@pytest.mark.parametrize("n,opts", [(1, {}), (2, {}), (4, {}), (7, {}), (9, {}), (12, {}), (6, {"fuse": 0}), (8, {"reg_bits": 4})])
+def test_replay_resident_heron(heron_noise, n, opts):
     sq, tq, _, _ = heron_noise
     instr = circuits.heron_layered(n, 4, circuits.coupled_pairs(tq, n), seed=n)
-    stats, prog = replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(n), 8, len(instr)))
+    stats, prog = replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(n), 8, len(instr)), **opts)
     assert prog.query(_lib.Q_RESIDENT) == 1
     assert stats["events"] > 0
+    if opts.get("fuse") == 0:
+        assert prog.query(_lib.Q_NUM_SEGMENTS) == len(instr)       # many segments, one resident pass list
+
+
+def test_replay_resident_long_program_spans_several_segments(heron_noise):
+    """A long small-state program is cut into several segments (shared-memory staging limit of the tile path); the
+    resident kernel has to walk all of them."""
+    sq, tq, _, _ = heron_noise
+    n = 4
+    instr = circuits.heron_ansatz(n, 12, circuits.coupled_pairs(tq, n), seed=2)
+    stats, prog = replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(5), 6, len(instr)))
+    assert prog.query(_lib.Q_RESIDENT) == 1 and prog.query(_lib.Q_NUM_SEGMENTS) > 1
 
 
 @pytest.mark.parametrize("n,opts", [
