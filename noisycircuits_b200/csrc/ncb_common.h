@@ -24,6 +24,40 @@
 
 namespace ncb {
 
+// Load of program data (ops, matrices).  SMEM = true: the pointer is known to address shared memory (the tile kernel's
+// staged segment blob), so explicit ld.shared is emitted instead of a generic load.
+template <bool SMEM, class T>
+NCB_HD T load_prog(const T* p) {
+#if defined(__CUDA_ARCH__)
+    if (SMEM) {
+        static_assert(sizeof(T) == 16 || sizeof(T) == 32 || sizeof(T) == 4 || sizeof(T) == 2, "unsupported size");
+        T v;
+        const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+        if (sizeof(T) == 16) {
+            unsigned long long x, y;
+            asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
+            reinterpret_cast<unsigned long long*>(&v)[0] = x; reinterpret_cast<unsigned long long*>(&v)[1] = y;
+        } else if (sizeof(T) == 32) {
+            unsigned long long x, y, z, w;
+            asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a));
+            asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(z), "=l"(w) : "r"(a + 16));
+            unsigned long long* q = reinterpret_cast<unsigned long long*>(&v);
+            q[0] = x; q[1] = y; q[2] = z; q[3] = w;
+        } else if (sizeof(T) == 4) {
+            unsigned x;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(a));
+            *reinterpret_cast<unsigned*>(&v) = x;
+        } else {
+            unsigned short x;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(x) : "r"(a));
+            *reinterpret_cast<unsigned short*>(&v) = x;
+        }
+        return v;
+    }
+#endif
+    return *p;
+}
+
 constexpr int MAX_TILE_BITS = 13;   // 2^13 amplitudes * 16 B = 128 KB of shared memory
 constexpr int MAX_REG_BITS = 4;     // 2^4 amplitudes per thread
 constexpr int MAX_QUBITS = 30;
@@ -47,6 +81,9 @@ enum OpKind : uint8_t {
     OPK_DENSE2 = 2,   // 4x4 on register bits rb[0] (matrix bit 0), rb[1] (matrix bit 1)
     OPK_DENSE4 = 3,   // 16x16 on register bits rb[0..3]  (density-matrix superoperators, 3-4 qubit unitaries)
     OPK_PERM1 = 4,    // X-like: anti-diagonal 2x2 on register bit rb[0]: out0 = m01*in1, out1 = m10*in0
+    OPK_SWAP1 = 5,    // exact X: out0 = in1, out1 = in0 (no arithmetic)
+    OPK_RX1 = 6,      // [[a, i b], [i c, d]] with a, b, c, d real (rx, and sx up to a global phase): 8 flops per pair
+    OPK_REAL1 = 7,    // real 2x2 (h, ry): 8 flops per pair
 };
 
 // One executable step inside a pass.  `mat`/`mat_bare` are offsets (in doubles) into the matrix pool: `mat` is the
@@ -95,7 +132,8 @@ struct Pass {
     uint16_t regoff[1 << MAX_REG_BITS];                // tile-local index offset of register slot m
     uint16_t regoff_swz[1 << MAX_REG_BITS];            // swz(regoff[m]) (swz is XOR-linear)
     BitRuns truns;                                     // thread index -> tile-local index of its slot 0 (= deposit by tpos)
-    int32_t op_begin, op_end;                          // ops of this pass
+    int32_t op_begin, op_end;                          // ops of this pass (group headers followed by their members)
+    int32_t fop_begin, fop_end;                        // the same work without the members: used when the whole pass runs
     int32_t instr_lo, instr_hi;                        // instruction range covered: [lo, hi)
 };
 
@@ -242,6 +280,61 @@ NCB_HD void perm1_bit(cplx* a, const cplx* __restrict__ M) {
         a[i1] = cmul(m10, x);
     }
 }
+template <int R, int B>
+NCB_HD void swap1_bit(cplx* a) {
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        const int i1 = i0 | (1 << B);
+        const cplx x = a[i0];
+        a[i0] = a[i1];
+        a[i1] = x;
+    }
+}
+template <int R, int B>
+NCB_HD void rx1_bit(cplx* a, const cplx* __restrict__ M) {
+    const double ma = M[0].x, mb = M[1].y, mc = M[2].y, md = M[3].x;
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        const int i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cplx{ma * x.x - mb * y.y, ma * x.y + mb * y.x};
+        a[i1] = cplx{md * y.x - mc * x.y, md * y.y + mc * x.x};
+    }
+}
+template <int R, int B>
+NCB_HD void real1_bit(cplx* a, const cplx* __restrict__ M) {
+    const double ma = M[0].x, mb = M[1].x, mc = M[2].x, md = M[3].x;
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        const int i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cplx{ma * x.x + mb * y.x, ma * x.y + mb * y.y};
+        a[i1] = cplx{mc * x.x + md * y.x, mc * x.y + md * y.y};
+    }
+}
+// dispatch of the one-bit kinds on the (runtime) register bit
+template <int R, int B>
+NCB_HD void one_bit_op(cplx* a, int kind, const cplx* __restrict__ M) {
+    switch (kind) {
+    case OPK_DENSE1: dense1_bit<R, B>(a, M); break;
+    case OPK_PERM1: perm1_bit<R, B>(a, M); break;
+    case OPK_SWAP1: swap1_bit<R, B>(a); break;
+    case OPK_RX1: rx1_bit<R, B>(a, M); break;
+    case OPK_REAL1: real1_bit<R, B>(a, M); break;
+    }
+}
+template <int R>
+NCB_HD void one_bit(cplx* a, int kind, int b, const cplx* __restrict__ M) {
+    switch (b) {
+    case 0: one_bit_op<R, 0>(a, kind, M); break;
+    case 1: if (R > 1) one_bit_op<R, (R > 1 ? 1 : 0)>(a, kind, M); break;
+    case 2: if (R > 2) one_bit_op<R, (R > 2 ? 2 : 0)>(a, kind, M); break;
+    case 3: if (R > 3) one_bit_op<R, (R > 3 ? 3 : 0)>(a, kind, M); break;
+    }
+}
 template <int R>
 NCB_HD void dense1(cplx* a, int b, const cplx* __restrict__ M) {
     switch (b) {
@@ -313,35 +406,43 @@ NCB_HD void dense4(cplx* a, const cplx* __restrict__ M) {
 // bare_last: the op(s) of instruction hi-1 use the bare gate matrix.
 constexpr int FEAT_DENSE2 = 1, FEAT_DENSE4 = 2;   // which operator kinds a kernel instantiation carries
 template <int R, int FEAT>
-NCB_HD void run_pass_thread(cplx* sm, int K, int tid, const Pass& ps, const Op* __restrict__ ops,
+NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* __restrict__ ops,
                             const double* __restrict__ pool, const double* __restrict__ pool_global, int lo, int hi, bool bare_last) {
     constexpr int NA = 1 << R;
-    const int jb = (int)apply_runs(ps.truns, (unsigned)tid);
+    (void)K;
     const int jbs = swz(jb);
+    // the whole pass lies inside [lo, hi) and none of its instructions is the bare one: take the short op list
+    const bool fast = lo <= ps.instr_lo && hi >= ps.instr_hi && !(bare_last && hi == ps.instr_hi);
     cplx a[NA];
+    int addr[NA];
 #pragma unroll
-    for (int m = 0; m < NA; ++m) a[m] = sm[jbs ^ ps.regoff_swz[m]];
-    for (int o = ps.op_begin; o < ps.op_end; ++o) {
+    for (int m = 0; m < NA; ++m) {
+        addr[m] = jbs ^ ps.regoff_swz[m];
+        a[m] = sm[addr[m]];
+    }
+    const int o_end = fast ? ps.fop_end : ps.op_end;
+    for (int o = fast ? ps.fop_begin : ps.op_begin; o < o_end; ++o) {
         const Op op = ops[o];
-        int moff;
-        if (op.kind_nb >> 31) {
-            // group header (see ncb_compile.cpp): the product of the next `span` ops; usable when the whole group is
-            // inside [lo, hi) and its last instruction is not the bare one
-            const int span = (int)((op.kind_nb >> 24) & 0x7f), last = op.pad;
-            if (!(op.instr >= lo && (last + 1 < hi || (last + 1 == hi && !bare_last)))) continue;
-            o += span;
-            moff = op.mat;
-        } else {
-            if (op.instr < lo || op.instr >= hi) continue;
-            moff = (bare_last && op.instr == hi - 1) ? op.mat_bare : op.mat;
+        int moff = op.mat;
+        if (!fast) {
+            if (op.kind_nb >> 31) {
+                // group header (see ncb_compile.cpp): the product of the next `span` ops; usable when the whole group
+                // is inside [lo, hi) and its last instruction is not the bare one
+                const int span = (int)((op.kind_nb >> 24) & 0x7f), last = op.pad;
+                if (!(op.instr >= lo && (last + 1 < hi || (last + 1 == hi && !bare_last)))) continue;
+                o += span;
+            } else {
+                if (op.instr < lo || op.instr >= hi) continue;
+                if (bare_last && op.instr == hi - 1) moff = op.mat_bare;
+            }
         }
         const cplx* M = reinterpret_cast<const cplx*>(moff >= 0 ? pool + moff : pool_global + (-moff - 1));
         switch (op_kind(op)) {
         case OPK_DIAG: {
-            const int nb = op_nb(op), tm = op_tmask(op);
+            const int tm = op_tmask(op);
             int idx_t = 0;                       // table-index bits that come from this thread's fixed tile bits
-            for (int b = 0; b < nb; ++b)
-                if ((tm >> b) & 1) idx_t |= ((jb >> op_rb(op, b)) & 1) << b;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) idx_t |= ((jb >> op_rb(op, b)) & (tm >> b) & 1) << b;
 #pragma unroll
             for (int m = 0; m < NA; ++m) {
                 const unsigned w = m < 8 ? op.midx_lo : op.midx_hi;
@@ -350,14 +451,15 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int tid, const Pass& ps, const Op* 
             }
             break;
         }
-        case OPK_DENSE1: dense1<R>(a, op_rb(op, 0), M); break;
-        case OPK_PERM1: perm1<R>(a, op_rb(op, 0), M); break;
+        case OPK_DENSE1: case OPK_PERM1: case OPK_SWAP1: case OPK_RX1: case OPK_REAL1:
+            one_bit<R>(a, op_kind(op), op_rb(op, 0), M);
+            break;
         case OPK_DENSE2: if (FEAT & FEAT_DENSE2) dense2<R>(a, op_rb(op, 0), op_rb(op, 1), M); break;
         case OPK_DENSE4: if (FEAT & FEAT_DENSE4) dense4<R>(a, M); break;
         }
     }
 #pragma unroll
-    for (int m = 0; m < NA; ++m) sm[jbs ^ ps.regoff_swz[m]] = a[m];
+    for (int m = 0; m < NA; ++m) sm[addr[m]] = a[m];
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -250,6 +250,44 @@ LogicalOp make_lop(int instr, const std::vector<int>& bits, const cmat& merged, 
     return l;
 }
 
+// One-qubit operator patterns the executor has cheap kernels for (ncb_common.h: OPK_*).
+int pattern_1q(const cmat& m, double tol) {
+    const double s = std::max(1.0, max_abs(m));
+    auto z = [&](double x) { return std::fabs(x) <= tol * s; };
+    if (z(m[0].real()) && z(m[0].imag()) && z(m[3].real()) && z(m[3].imag())) {
+        if (m[1] == cd(1, 0) && m[2] == cd(1, 0)) return OPK_SWAP1;
+        return OPK_PERM1;
+    }
+    if (z(m[0].imag()) && z(m[3].imag()) && z(m[1].real()) && z(m[2].real())) return OPK_RX1;
+    if (z(m[0].imag()) && z(m[1].imag()) && z(m[2].imag()) && z(m[3].imag())) return OPK_REAL1;
+    return OPK_DENSE1;
+}
+void snap_pattern(cmat& m, int kind) {      // remove the rounding dust the pattern ignores
+    switch (kind) {
+    case OPK_SWAP1: case OPK_PERM1: m[0] = 0; m[3] = 0; break;
+    case OPK_RX1: m[0] = m[0].real(); m[3] = m[3].real(); m[1] = cd(0, m[1].imag()); m[2] = cd(0, m[2].imag()); break;
+    case OPK_REAL1: for (cd& x : m) x = x.real(); break;
+    }
+}
+// Factors a global phase e^{i phi} out of a one-qubit gate (bare and merged with its base Kraus operator alike) when
+// that turns it into one of the cheap patterns (sx = e^{i pi/4} rx(pi/2)).  Returns phi (0: nothing factored).
+double dephase_1q(cmat& merged, cmat& bare) {
+    const double tol = 4e-16;
+    if (pattern_1q(bare, tol) != OPK_DENSE1 && pattern_1q(merged, tol) != OPK_DENSE1) return 0.0;
+    std::vector<double> cands;
+    for (const cd& x : bare)
+        if (std::abs(x) > 1e-3) { cands.push_back(std::arg(x)); cands.push_back(std::arg(x) - M_PI / 2); }
+    for (double phi : cands) {
+        const cd f = std::polar(1.0, -phi);
+        cmat b2(bare), m2(merged);
+        for (cd& x : b2) x *= f;
+        for (cd& x : m2) x *= f;
+        const int kb = pattern_1q(b2, tol), km = pattern_1q(m2, tol);
+        if (kb != OPK_DENSE1 && km == kb) { bare = b2; merged = m2; return phi; }
+    }
+    return 0.0;
+}
+
 cmat conj_of(const cmat& a) {
     cmat r(a);
     for (cd& x : r) x = std::conj(x);
@@ -360,6 +398,13 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
             if (cinfo[ch].certain_nonunitary) P.norm_preserving = false;
             if (P.chans[ch].count >= 2) { P.draw_pos[g] = P.num_draws++; P.noisy_instrs.push_back(g); }
         }
+        if (qb.size() == 1 && !(is_diagonal(merged, 2) && is_diagonal(U, 2))) {
+            const double phi = dephase_1q(merged, U);
+            if (phi != 0.0) {
+                const cd gp = cd(P.global_phase[0], P.global_phase[1]) * std::polar(1.0, phi);
+                P.global_phase[0] = gp.real(); P.global_phase[1] = gp.imag();
+            }
+        }
         lops.push_back(make_lop(g, qb, merged, U));
     }
 
@@ -378,7 +423,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
         // possible group header, its matrices, a share of a pass record)
         auto blob_cost = [&](const LogicalOp& l) {
             const size_t mats = l.diag ? (size_t)(2 << l.nb) * 8 * 2 + 256 : (l.nb <= 2 ? (size_t)(2 << (2 * l.nb)) * 8 * 2 : 0);
-            return 2 * sizeof(Op) + mats + sizeof(Pass) / 2;
+            return 3 * sizeof(Op) + mats + sizeof(Pass) / 2;
         };
         size_t cur_cost = sizeof(SegBlob) + sizeof(Pass);
         SegBuild cur{fresh_tile(), 0, 0};
@@ -513,11 +558,15 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
                 } else if (l.nb <= 2) {
                     for (int i = 0; i < l.nb; ++i) rb[i] = (uint32_t)reg_of[local_of[l.bits[i]]];
-                    const cmat m = read_complex(l.mat.data(), d * d), mb = read_complex(l.bare.data(), d * d);
-                    kind = l.nb == 2 ? OPK_DENSE2 : (is_antidiagonal2(m) && is_antidiagonal2(mb) ? OPK_PERM1 : OPK_DENSE1);
-                    if (l.nb == 2) P.has_dense2 = true;
-                    op.mat = pb.add_doubles(l.mat);
-                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
+                    cmat m = read_complex(l.mat.data(), d * d), mb = read_complex(l.bare.data(), d * d);
+                    if (l.nb == 2) { kind = OPK_DENSE2; P.has_dense2 = true; }
+                    else {
+                        const int km = pattern_1q(m, 4e-16), kb = pattern_1q(mb, 4e-16);
+                        kind = km == kb ? km : ((km == OPK_SWAP1 && kb == OPK_PERM1) || (km == OPK_PERM1 && kb == OPK_SWAP1) ? OPK_PERM1 : OPK_DENSE1);
+                        snap_pattern(m, kind); snap_pattern(mb, kind);
+                    }
+                    op.mat = pb.add_doubles(flatten(m));
+                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(flatten(mb));
                 } else {
                     // 3- or 4-bit dense operator: re-index to the pass's four register bits
                     if (R < 4) throw std::runtime_error("dense operators on 3-4 bits need reg_bits = 4");
@@ -595,18 +644,27 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                 if (!groups.empty() && mode != MODE_DENSITY && try_merge(groups.back(), *lp)) groups.back().members.push_back(lp);
                 else groups.push_back(Group{{lp}, *lp});
             }
+            std::vector<Op> fast_ops;
             for (const Group& g : groups) {
                 if (g.members.size() > 1) {
                     Op h = emit(g.merged);
                     h.instr = g.members.front()->instr;
                     h.pad = g.members.back()->instr;
                     h.mat_bare = h.mat;
+                    fast_ops.push_back(h);                 // plain op in the fast list
                     h.kind_nb |= 0x80000000u | ((uint32_t)g.members.size() << 24);
                     P.ops.push_back(h);
+                    for (const LogicalOp* lp : g.members) P.ops.push_back(emit(*lp));
+                } else {
+                    const Op o1 = emit(*g.members[0]);
+                    P.ops.push_back(o1);
+                    fast_ops.push_back(o1);
                 }
-                for (const LogicalOp* lp : g.members) P.ops.push_back(emit(*lp));
             }
             ps.op_end = (int)P.ops.size();
+            ps.fop_begin = (int)P.ops.size();
+            P.ops.insert(P.ops.end(), fast_ops.begin(), fast_ops.end());
+            ps.fop_end = (int)P.ops.size();
             P.passes.push_back(ps);
         }
         seg.pass_end = (int)P.passes.size();
@@ -635,13 +693,14 @@ static void build_blobs(Program& P) {
         };
         for (Pass& ps : passes) {
             const int b = (int)ops.size();
-            for (int o = ps.op_begin; o < ps.op_end; ++o) {
+            const int gen_count = ps.op_end - ps.op_begin;
+            for (int o = ps.op_begin; o < ps.fop_end; ++o) {      // general list, then the fast list right behind it
                 Op op = P.ops[o];
                 const int kind = op_kind(op), nb = op_nb(op);
                 int nd = 0;
                 switch (kind) {
                 case OPK_DIAG: nd = 2 << nb; break;
-                case OPK_DENSE1: case OPK_PERM1: nd = 8; break;
+                case OPK_DENSE1: case OPK_PERM1: case OPK_SWAP1: case OPK_RX1: case OPK_REAL1: nd = 8; break;
                 case OPK_DENSE2: nd = 32; break;
                 case OPK_DENSE4: nd = 512; break;
                 }
@@ -651,7 +710,8 @@ static void build_blobs(Program& P) {
                 op.mat_bare = mb == m ? op.mat : local(mb, nd, big);
                 ops.push_back(op);
             }
-            ps.op_begin = b; ps.op_end = (int)ops.size();
+            ps.op_begin = b; ps.op_end = b + gen_count;
+            ps.fop_begin = ps.op_end; ps.fop_end = (int)ops.size();
         }
         SegBlob h;
         std::memset(&h, 0, sizeof(h));
@@ -680,7 +740,16 @@ std::string describe_program(const Program& P) {
       << " segments=" << P.segs.size() << " passes=" << P.passes.size() << " ops=" << P.ops.size()
       << " channels=" << P.chans.size() << " noisy=" << P.noisy_instrs.size() << " draws=" << P.num_draws
       << " norm_preserving=" << P.norm_preserving << " dense2=" << P.has_dense2 << " dense4=" << P.has_dense4
-      << " pool=" << P.pool.size() << "\n";
+      << " pool=" << P.pool.size() << " blobs=" << P.blobs.size();
+    {
+        static const char* names[] = {"diag", "dense1", "dense2", "dense4", "perm1", "swap1", "rx1", "real1"};
+        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, groups = 0;
+        for (const Op& op : P.ops) { ++cnt[op_kind(op) & 7]; groups += (int)(op.kind_nb >> 31); }
+        o << " kinds{";
+        for (int k = 0; k < 8; ++k) if (cnt[k]) o << names[k] << ":" << cnt[k] << " ";
+        o << "groups:" << groups << "}";
+    }
+    o << "\n";
     for (size_t s = 0; s < P.segs.size(); ++s) {
         const Segment& g = P.segs[s];
         o << "seg " << s << " instr[" << g.instr_lo << "," << g.instr_hi << ") tile{";

@@ -56,6 +56,8 @@ struct Program {
     int G = 0;
     bool has_dense4 = false;
     bool has_dense2 = false;
+    double global_phase[2] = {1.0, 0.0};   // e^{i Phi}: product of the global phases factored out of one-qubit gates;
+                                           // the engine's raw states are e^{-i Phi} x the true states
     bool norm_preserving = true;
     std::vector<double> pool;
     std::vector<Op> ops;

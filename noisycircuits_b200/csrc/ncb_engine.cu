@@ -147,7 +147,9 @@ struct Engine {
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 8 * 1024));
         CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
-    size_t tile_launch_smem() const { return (size_t)MAX_BLOB_BYTES + 2 * tile_smem(); }
+    size_t tile_launch_smem() const {
+        return (size_t)MAX_BLOB_BYTES + 2 * tile_smem() + (size_t)JB_TABLE_PASSES * sizeof(unsigned short) * ((size_t)1 << (P.K - P.R));
+    }
     void launch_tile(int nworks, cudaStream_t s, const Work* works, int seg) {
         const int tile_shift = P.nbits > P.K ? P.nbits - P.K : 0;
         const int threads = 1 << (P.K - P.R);
@@ -293,6 +295,12 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
         rp->out_d2h_bytes += (int64_t)((size_t)count * dim * sizeof(cplx));
     }
     CK(cudaStreamSynchronize(s));
+    if (rp->states && !(P.global_phase[0] == 1.0 && P.global_phase[1] == 0.0))
+        for (size_t j = 0; j < (size_t)count * dim; ++j) {
+            const double x = rp->states[2 * j], y = rp->states[2 * j + 1];
+            rp->states[2 * j] = x * P.global_phase[0] - y * P.global_phase[1];
+            rp->states[2 * j + 1] = x * P.global_phase[1] + y * P.global_phase[0];
+        }
     rp->out_tile_launches += 1;
     rp->out_events += (int64_t)cnt[0];
     rp->out_hard_events += (int64_t)cnt[1];
@@ -374,9 +382,11 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
                 double n2 = 0;
                 for (long long j = 0; j < dim; ++j) n2 += cnorm2(host_states[(size_t)b * dim + j]);
                 const double f = 1.0 / std::sqrt(n2);
+                const double gx = P.global_phase[0] * f, gy = P.global_phase[1] * f;
                 for (long long j = 0; j < dim; ++j) {
-                    rp->states[2 * ((size_t)(b0 + b) * dim + j)] = host_states[(size_t)b * dim + j].x * f;
-                    rp->states[2 * ((size_t)(b0 + b) * dim + j) + 1] = host_states[(size_t)b * dim + j].y * f;
+                    const cplx a = host_states[(size_t)b * dim + j];
+                    rp->states[2 * ((size_t)(b0 + b) * dim + j)] = a.x * gx - a.y * gy;
+                    rp->states[2 * ((size_t)(b0 + b) * dim + j) + 1] = a.x * gy + a.y * gx;
                 }
             }
         }
@@ -614,6 +624,12 @@ int ncb_pure_run(ncb_program* program, double* state, double* probs, void* strea
         CK(cudaMemcpyAsync(probs, E.d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
+    if (state && !(E.P.global_phase[0] == 1.0 && E.P.global_phase[1] == 0.0))
+        for (long long j = 0; j < dim; ++j) {
+            const double x = state[2 * j], y = state[2 * j + 1];
+            state[2 * j] = x * E.P.global_phase[0] - y * E.P.global_phase[1];
+            state[2 * j + 1] = x * E.P.global_phase[1] + y * E.P.global_phase[0];
+        }
     return NCB_OK;
     NCB_CATCH
 }

@@ -29,6 +29,7 @@ struct DevProgram {
 };
 
 constexpr int RED_VALUES = 32;   // doubles per reduced-density-matrix partial
+constexpr int JB_TABLE_PASSES = 8;   // passes per segment whose per-thread base index is tabulated in shared memory
 
 // ---------------------------------------------------------------------------------------------------------------
 // small device helpers
@@ -71,16 +72,20 @@ __device__ __forceinline__ void block_reduce(const double* vals, double* s_buf, 
 // Runs the ops with instruction index in [lo, hi) of the passes [*pcur, pend) on the tile in shared memory.
 // *pcur is advanced past the passes that are entirely below hi.  passes/ops/pool may live in shared memory (the
 // tile kernel's staged segment blob) or in global memory (the resident kernel).
+// jb_tab (optional, shared memory): jb_tab[p * blockDim.x + tid] = this thread's base tile index in pass p for
+// p < jb_cap (computed once per CTA: it does not depend on the tile).
 template <int R, int FEAT>
 __device__ __forceinline__ void run_range(cplx* sm, int K, const Pass* passes, const Op* ops, const double* pool,
-                                          const double* pool_global, int* pcur, int pend, int lo, int hi, bool bare_last) {
+                                          const double* pool_global, int* pcur, int pend, int lo, int hi, bool bare_last,
+                                          const unsigned short* jb_tab = nullptr, int jb_cap = 0) {
     int p = *pcur;
     for (; p < pend; ++p) {
         const Pass* ps = passes + p;
         const int plo = ps->instr_lo, phi = ps->instr_hi;
         if (plo >= hi) break;
         if (phi > lo && ps->op_end > ps->op_begin) {
-            run_pass_thread<R, FEAT>(sm, K, threadIdx.x, *ps, ops, pool, pool_global, lo, hi, bare_last);
+            const int jb = p < jb_cap ? (int)jb_tab[p * blockDim.x + threadIdx.x] : (int)apply_runs(ps->truns, threadIdx.x);
+            run_pass_thread<R, FEAT>(sm, K, jb, *ps, ops, pool, pool_global, lo, hi, bare_last);
             __syncthreads();
         }
         if (phi > hi) break;      // this pass also holds later instructions: revisit it
@@ -173,6 +178,10 @@ tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_byt
     const unsigned offA = apply_runs(sg->eruns, (unsigned)tid);
     const int sA = swz(tid);
     const unsigned limit = 1u << P.nbits;
+    // per-thread base tile index of every pass: tile independent, computed once per CTA
+    unsigned short* jb_tab = reinterpret_cast<unsigned short*>(bufs[1] + (1 << K));
+    const int jb_cap = npass < JB_TABLE_PASSES ? npass : JB_TABLE_PASSES;
+    for (int p = 0; p < jb_cap; ++p) jb_tab[p * nthreads + tid] = (unsigned short)apply_runs(passes[p].truns, (unsigned)tid);
 
     auto issue_load = [&](long long t, cplx* sm, const Work& w) {
         if (w.flags & WF_INIT) return;                           // |0..0> is written by the processing step
@@ -214,7 +223,7 @@ tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_byt
         if (w.flags & (WF_PRO_STATIC | WF_PRO_DYNAMIC)) event_prologue(sm, P, sg, w, decisions);
         // ---- the segment's passes ----
         int pcur = 0;
-        run_range<R, FEAT>(sm, K, passes, ops, pool, P.pool, &pcur, npass, w.instr_lo, w.instr_hi, (w.flags & WF_BARE_LAST) != 0);
+        run_range<R, FEAT>(sm, K, passes, ops, pool, P.pool, &pcur, npass, w.instr_lo, w.instr_hi, (w.flags & WF_BARE_LAST) != 0, jb_tab, jb_cap);
         // ---- reductions ----
         if (w.flags & WF_REDUCE) {
             const Instr in = P.instrs[w.red_instr];

@@ -73,7 +73,7 @@ void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, st
             if (ps.instr_lo >= w.instr_hi) break;
             if (ps.instr_hi > w.instr_lo && ps.op_end > ps.op_begin)
                 for (int tid = 0; tid < nthreads; ++tid)
-                    run_pass_thread<R, 3>(sm.data(), K, tid, ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last);
+                    run_pass_thread<R, 3>(sm.data(), K, (int)apply_runs(ps.truns, (unsigned)tid), ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last);
             if (ps.instr_hi > w.instr_hi) break;
         }
         // reductions
@@ -208,9 +208,11 @@ int emu_mcwf_states(void* h, int count, const double* uniforms, double* states_o
                 if (std::fabs(s - n2) > 1e-12 * std::max(1.0, n2)) throw std::runtime_error("WF_NORM partials disagree with the state norm");
             }
             const double f = 1.0 / std::sqrt(n2);
+            const double gx = P.global_phase[0] * f, gy = P.global_phase[1] * f;
             for (long long j = 0; j < dim; ++j) {
-                states_out[2 * ((size_t)b * dim + j)] = states[(size_t)b * dim + j].x * f;
-                states_out[2 * ((size_t)b * dim + j) + 1] = states[(size_t)b * dim + j].y * f;
+                const cplx a = states[(size_t)b * dim + j];
+                states_out[2 * ((size_t)b * dim + j)] = a.x * gx - a.y * gy;
+                states_out[2 * ((size_t)b * dim + j) + 1] = a.x * gy + a.y * gx;
             }
         }
         if (stats) { stats[0] = nev; stats[1] = nhard; stats[2] = plan.sweeps; stats[3] = (long long)plan.steps.size(); }
@@ -229,7 +231,10 @@ int emu_run_deterministic(void* h, double* state_out) {
         std::vector<cplx> states(dim, cplx{0.0, 0.0});
         std::vector<double> norm_part;
         run_plan(P, plan, 1, states, norm_part);
-        std::memcpy(state_out, states.data(), dim * sizeof(cplx));
+        for (long long j = 0; j < dim; ++j) {
+            state_out[2 * j] = states[j].x * P.global_phase[0] - states[j].y * P.global_phase[1];
+            state_out[2 * j + 1] = states[j].x * P.global_phase[1] + states[j].y * P.global_phase[0];
+        }
         return 0;
     } catch (const std::exception& ex) { g_err = ex.what(); return -1; }
 }
