@@ -12,6 +12,7 @@
 #if defined(__CUDA_ARCH__)
 // keeps the compiler from hoisting a whole operator matrix into registers across amplitude groups
 #define NCB_NO_HOIST() asm volatile("" ::: "memory")
+#define NCB_UNREACHABLE() __builtin_unreachable()
 #endif
 #else
 #define NCB_HD inline
@@ -20,6 +21,9 @@
 
 #ifndef NCB_NO_HOIST
 #define NCB_NO_HOIST() ((void)0)
+#endif
+#ifndef NCB_UNREACHABLE
+#define NCB_UNREACHABLE() ((void)0)
 #endif
 
 namespace ncb {
@@ -80,10 +84,9 @@ enum OpKind : uint8_t {
     OPK_DENSE1 = 1,   // 2x2 on register bit rb[0]
     OPK_DENSE2 = 2,   // 4x4 on register bits rb[0] (matrix bit 0), rb[1] (matrix bit 1)
     OPK_DENSE4 = 3,   // 16x16 on register bits rb[0..3]  (density-matrix superoperators, 3-4 qubit unitaries)
-    OPK_PERM1 = 4,    // X-like: anti-diagonal 2x2 on register bit rb[0]: out0 = m01*in1, out1 = m10*in0
-    OPK_SWAP1 = 5,    // exact X: out0 = in1, out1 = in0 (no arithmetic)
-    OPK_RX1 = 6,      // [[a, i b], [i c, d]] with a, b, c, d real (rx, and sx up to a global phase): 8 flops per pair
-    OPK_REAL1 = 7,    // real 2x2 (h, ry): 8 flops per pair
+    OPK_RX1 = 4,      // [[a, i b], [i c, d]] with a, b, c, d real: 8 flops per pair.  rx is of this form, sx and x are up
+                      // to a global phase (sx = e^{i pi/4} rx(pi/2), x = i rx(pi)), which the compiler factors out.
+                      // (Deliberately few kinds: every extra case of the executor's switch costs register shuffling.)
 };
 
 // One executable step inside a pass.  `mat`/`mat_bare` are offsets (in doubles) into the matrix pool: `mat` is the
@@ -255,156 +258,120 @@ NCB_HD int deposit(int v, const uint8_t* pos, int nbits) {
 
 // ------------------------------------------------------------------------------------------------------------
 // Register-blocked pass executor (one thread's share)
+//
+// Every operator kernel is OUT OF PLACE: it reads the thread's 2^R amplitudes from `in` and writes all of them to
+// `out`.  The pass loop ping-pongs between two register sets, so no operator needs temporaries and the compiler
+// never has to shuffle the amplitude registers back into place between operators (in-place kernels cost ~32
+// register moves per operator, a quarter of all instructions issued).
 // ------------------------------------------------------------------------------------------------------------
 template <int R, int B>
-NCB_HD void dense1_bit(cplx* a, const cplx* __restrict__ M) {
+NCB_HD void dense1_bit(const cplx* in, cplx* out, const cplx* __restrict__ M) {
     const cplx m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
 #pragma unroll
     for (int g = 0; g < (1 << (R - 1)); ++g) {
         const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
         const int i1 = i0 | (1 << B);
-        const cplx x = a[i0], y = a[i1];
-        a[i0] = cfma(m01, y, cmul(m00, x));
-        a[i1] = cfma(m11, y, cmul(m10, x));
+        out[i0] = cfma(m01, in[i1], cmul(m00, in[i0]));
+        out[i1] = cfma(m11, in[i1], cmul(m10, in[i0]));
     }
 }
 template <int R, int B>
-NCB_HD void perm1_bit(cplx* a, const cplx* __restrict__ M) {
-    const cplx m01 = M[1], m10 = M[2];
-#pragma unroll
-    for (int g = 0; g < (1 << (R - 1)); ++g) {
-        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
-        const int i1 = i0 | (1 << B);
-        const cplx x = a[i0], y = a[i1];
-        a[i0] = cmul(m01, y);
-        a[i1] = cmul(m10, x);
-    }
-}
-template <int R, int B>
-NCB_HD void swap1_bit(cplx* a) {
-#pragma unroll
-    for (int g = 0; g < (1 << (R - 1)); ++g) {
-        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
-        const int i1 = i0 | (1 << B);
-        const cplx x = a[i0];
-        a[i0] = a[i1];
-        a[i1] = x;
-    }
-}
-template <int R, int B>
-NCB_HD void rx1_bit(cplx* a, const cplx* __restrict__ M) {
+NCB_HD void rx1_bit(const cplx* in, cplx* out, const cplx* __restrict__ M) {
     const double ma = M[0].x, mb = M[1].y, mc = M[2].y, md = M[3].x;
 #pragma unroll
     for (int g = 0; g < (1 << (R - 1)); ++g) {
         const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
         const int i1 = i0 | (1 << B);
-        const cplx x = a[i0], y = a[i1];
-        a[i0] = cplx{ma * x.x - mb * y.y, ma * x.y + mb * y.x};
-        a[i1] = cplx{md * y.x - mc * x.y, md * y.y + mc * x.x};
-    }
-}
-template <int R, int B>
-NCB_HD void real1_bit(cplx* a, const cplx* __restrict__ M) {
-    const double ma = M[0].x, mb = M[1].x, mc = M[2].x, md = M[3].x;
-#pragma unroll
-    for (int g = 0; g < (1 << (R - 1)); ++g) {
-        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
-        const int i1 = i0 | (1 << B);
-        const cplx x = a[i0], y = a[i1];
-        a[i0] = cplx{ma * x.x + mb * y.x, ma * x.y + mb * y.y};
-        a[i1] = cplx{mc * x.x + md * y.x, mc * x.y + md * y.y};
-    }
-}
-// dispatch of the one-bit kinds on the (runtime) register bit
-template <int R, int B>
-NCB_HD void one_bit_op(cplx* a, int kind, const cplx* __restrict__ M) {
-    switch (kind) {
-    case OPK_DENSE1: dense1_bit<R, B>(a, M); break;
-    case OPK_PERM1: perm1_bit<R, B>(a, M); break;
-    case OPK_SWAP1: swap1_bit<R, B>(a); break;
-    case OPK_RX1: rx1_bit<R, B>(a, M); break;
-    case OPK_REAL1: real1_bit<R, B>(a, M); break;
-    }
-}
-template <int R>
-NCB_HD void one_bit(cplx* a, int kind, int b, const cplx* __restrict__ M) {
-    switch (b) {
-    case 0: one_bit_op<R, 0>(a, kind, M); break;
-    case 1: if (R > 1) one_bit_op<R, (R > 1 ? 1 : 0)>(a, kind, M); break;
-    case 2: if (R > 2) one_bit_op<R, (R > 2 ? 2 : 0)>(a, kind, M); break;
-    case 3: if (R > 3) one_bit_op<R, (R > 3 ? 3 : 0)>(a, kind, M); break;
-    }
-}
-template <int R>
-NCB_HD void dense1(cplx* a, int b, const cplx* __restrict__ M) {
-    switch (b) {
-    case 0: dense1_bit<R, 0>(a, M); break;
-    case 1: if (R > 1) dense1_bit<R, (R > 1 ? 1 : 0)>(a, M); break;
-    case 2: if (R > 2) dense1_bit<R, (R > 2 ? 2 : 0)>(a, M); break;
-    case 3: if (R > 3) dense1_bit<R, (R > 3 ? 3 : 0)>(a, M); break;
-    }
-}
-template <int R>
-NCB_HD void perm1(cplx* a, int b, const cplx* __restrict__ M) {
-    switch (b) {
-    case 0: perm1_bit<R, 0>(a, M); break;
-    case 1: if (R > 1) perm1_bit<R, (R > 1 ? 1 : 0)>(a, M); break;
-    case 2: if (R > 2) perm1_bit<R, (R > 2 ? 2 : 0)>(a, M); break;
-    case 3: if (R > 3) perm1_bit<R, (R > 3 ? 3 : 0)>(a, M); break;
+        const cplx x = in[i0], y = in[i1];
+        out[i0] = cplx{ma * x.x - mb * y.y, ma * x.y + mb * y.x};
+        out[i1] = cplx{md * y.x - mc * x.y, md * y.y + mc * x.x};
     }
 }
 // 4x4 on register bits (B0 = matrix bit 0, B1 = matrix bit 1), B0 != B1
 template <int R, int B0, int B1>
-NCB_HD void dense2_bits(cplx* a, const cplx* __restrict__ M) {
+NCB_HD void dense2_bits(const cplx* in, cplx* out, const cplx* __restrict__ M) {
     constexpr int LO = B0 < B1 ? B0 : B1, HI = B0 < B1 ? B1 : B0;
 #pragma unroll
     for (int g = 0; g < (1 << (R - 2)); ++g) {
         int base = ((g >> LO) << (LO + 1)) | (g & ((1 << LO) - 1));
         base = ((base >> HI) << (HI + 1)) | (base & ((1 << HI) - 1));
         const int idx[4] = {base, base | (1 << B0), base | (1 << B1), base | (1 << B0) | (1 << B1)};
-        const cplx s0 = a[idx[0]], s1 = a[idx[1]], s2 = a[idx[2]], s3 = a[idx[3]];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            cplx v = cmul(M[4 * r], s0);
-            v = cfma(M[4 * r + 1], s1, v);
-            v = cfma(M[4 * r + 2], s2, v);
-            v = cfma(M[4 * r + 3], s3, v);
-            a[idx[r]] = v;
+            cplx v = cmul(M[4 * r], in[idx[0]]);
+            v = cfma(M[4 * r + 1], in[idx[1]], v);
+            v = cfma(M[4 * r + 2], in[idx[2]], v);
+            v = cfma(M[4 * r + 3], in[idx[3]], v);
+            out[idx[r]] = v;
         }
         NCB_NO_HOIST();
     }
 }
+// 16x16 on all four register bits (the matrix is stored with matrix bit b == register bit b)
 template <int R>
-NCB_HD void dense2(cplx* a, int b0, int b1, const cplx* __restrict__ M) {
-    if (R < 2) return;
-    switch (b0 * 4 + b1) {
-#define NCB_CASE(X, Y) case X * 4 + Y: if (R > X && R > Y) dense2_bits<R, (R > X ? X : 0), (R > Y ? Y : 1)>(a, M); break;
-        NCB_CASE(0, 1) NCB_CASE(0, 2) NCB_CASE(0, 3) NCB_CASE(1, 0) NCB_CASE(1, 2) NCB_CASE(1, 3)
-        NCB_CASE(2, 0) NCB_CASE(2, 1) NCB_CASE(2, 3) NCB_CASE(3, 0) NCB_CASE(3, 1) NCB_CASE(3, 2)
-#undef NCB_CASE
-    }
-}
-// 16x16 on all four register bits; register index bit b <-> matrix bit perm[b] was resolved on the host
-// (the matrix is stored already permuted so that matrix bit b == register bit b).
-template <int R>
-NCB_HD void dense4(cplx* a, const cplx* __restrict__ M) {
+NCB_HD void dense4(const cplx* in, cplx* out, const cplx* __restrict__ M) {
     if (R < 4) return;
     constexpr int MASK = (1 << R) - 1;   // keeps the R < 4 instantiations (never executed) in bounds
-    cplx out[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-        cplx v = cmul(M[16 * r], a[0]);
+        cplx v = cmul(M[16 * r], in[0]);
 #pragma unroll
-        for (int c = 1; c < 16; ++c) v = cfma(M[16 * r + c], a[c & MASK], v);
-        out[r] = v;
+        for (int c = 1; c < 16; ++c) v = cfma(M[16 * r + c], in[c & MASK], v);
+        out[r & MASK] = v;
     }
-#pragma unroll
-    for (int r = 0; r < 16; ++r) a[r & MASK] = out[r];
 }
 
-// Executes the ops of `ps` whose instruction index is in [lo, hi) on this thread's 2^R amplitudes.
-// bare_last: the op(s) of instruction hi-1 use the bare gate matrix.
 constexpr int FEAT_DENSE2 = 1, FEAT_DENSE4 = 2;   // which operator kinds a kernel instantiation carries
+
+// Applies one op: out = op(in).  One flat switch on (kind, register bits) so that the dispatch is a single jump.
+template <int R, int FEAT>
+NCB_HD void apply_op(const Op& op, int jb, const cplx* __restrict__ M, const cplx* in, cplx* out) {
+    constexpr int NA = 1 << R;
+    const int kind = op_kind(op);
+    const int b0 = op_rb(op, 0), b1 = op_rb(op, 1);
+    int sel;
+    if (kind == OPK_DIAG || kind == OPK_DENSE4) sel = kind << 4;
+    else if (kind == OPK_DENSE2) sel = (kind << 4) | (b0 << 2) | b1;
+    else sel = (kind << 4) | b0;
+    switch (sel) {
+    case OPK_DIAG << 4: {
+        const int tm = op_tmask(op);
+        int idx_t = 0;                       // table-index bits that come from this thread's fixed tile bits
+#pragma unroll
+        for (int b = 0; b < 4; ++b) idx_t |= ((jb >> op_rb(op, b)) & (tm >> b) & 1) << b;
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+            const unsigned w = m < 8 ? op.midx_lo : op.midx_hi;
+            const int idx = idx_t | (int)((w >> (4 * (m & 7))) & 15u);
+            out[m] = cmul(in[m], M[idx]);
+        }
+        break;
+    }
+#define NCB_ONE_BIT(B)                                                                   \
+    case (OPK_DENSE1 << 4) | B: if (B < R) dense1_bit<R, (B < R ? B : 0)>(in, out, M); else NCB_UNREACHABLE(); break; \
+    case (OPK_RX1 << 4) | B: if (B < R) rx1_bit<R, (B < R ? B : 0)>(in, out, M); else NCB_UNREACHABLE(); break;
+        NCB_ONE_BIT(0) NCB_ONE_BIT(1) NCB_ONE_BIT(2) NCB_ONE_BIT(3)
+#undef NCB_ONE_BIT
+#define NCB_TWO_BIT(X, Y)                                                                \
+    case (OPK_DENSE2 << 4) | (X << 2) | Y:                                               \
+        if ((FEAT & FEAT_DENSE2) && R > X && R > Y) dense2_bits<R, (R > X ? X : 0), (R > Y ? Y : 1)>(in, out, M); \
+        else NCB_UNREACHABLE();                                                          \
+        break;
+        NCB_TWO_BIT(0, 1) NCB_TWO_BIT(0, 2) NCB_TWO_BIT(0, 3) NCB_TWO_BIT(1, 0) NCB_TWO_BIT(1, 2) NCB_TWO_BIT(1, 3)
+        NCB_TWO_BIT(2, 0) NCB_TWO_BIT(2, 1) NCB_TWO_BIT(2, 3) NCB_TWO_BIT(3, 0) NCB_TWO_BIT(3, 1) NCB_TWO_BIT(3, 2)
+#undef NCB_TWO_BIT
+    case OPK_DENSE4 << 4: if (FEAT & FEAT_DENSE4) dense4<R>(in, out, M); else NCB_UNREACHABLE(); break;
+    default:
+        NCB_UNREACHABLE();        // the host compiler only emits the kinds above
+#if !defined(__CUDA_ARCH__)
+        for (int m = 0; m < NA; ++m) out[m] = in[m];
+#endif
+        break;
+    }
+}
+
+// Executes the ops of `ps` whose instruction index is in [lo, hi) on this thread's 2^R amplitudes (jb: the thread's
+// base tile index in this pass).  bare_last: the op of instruction hi-1 uses the bare gate matrix.
 template <int R, int FEAT>
 NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* __restrict__ ops,
                             const double* __restrict__ pool, const double* __restrict__ pool_global, int lo, int hi, bool bare_last) {
@@ -413,50 +380,49 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
     const int jbs = swz(jb);
     // the whole pass lies inside [lo, hi) and none of its instructions is the bare one: take the short op list
     const bool fast = lo <= ps.instr_lo && hi >= ps.instr_hi && !(bare_last && hi == ps.instr_hi);
-    cplx a[NA];
+    cplx a[NA], b[NA];
     int addr[NA];
 #pragma unroll
     for (int m = 0; m < NA; ++m) {
         addr[m] = jbs ^ ps.regoff_swz[m];
         a[m] = sm[addr[m]];
     }
+    int o = fast ? ps.fop_begin : ps.op_begin;
     const int o_end = fast ? ps.fop_end : ps.op_end;
-    for (int o = fast ? ps.fop_begin : ps.op_begin; o < o_end; ++o) {
-        const Op op = ops[o];
-        int moff = op.mat;
-        if (!fast) {
-            if (op.kind_nb >> 31) {
-                // group header (see ncb_compile.cpp): the product of the next `span` ops; usable when the whole group
-                // is inside [lo, hi) and its last instruction is not the bare one
-                const int span = (int)((op.kind_nb >> 24) & 0x7f), last = op.pad;
-                if (!(op.instr >= lo && (last + 1 < hi || (last + 1 == hi && !bare_last)))) continue;
-                o += span;
-            } else {
-                if (op.instr < lo || op.instr >= hi) continue;
-                if (bare_last && op.instr == hi - 1) moff = op.mat_bare;
+    Op op;
+    const cplx* M = nullptr;
+    // next op to execute at or after position o (range filter, group headers: see ncb_compile.cpp)
+    auto fetch = [&]() -> bool {
+        for (; o < o_end; ++o) {
+            op = ops[o];
+            int moff = op.mat;
+            if (!fast) {
+                if (op.kind_nb >> 31) {
+                    // group header: the product of the next `span` ops; usable when the whole group is inside
+                    // [lo, hi) and its last instruction is not the bare one
+                    const int span = (int)((op.kind_nb >> 24) & 0x7f), last = op.pad;
+                    if (!(op.instr >= lo && (last + 1 < hi || (last + 1 == hi && !bare_last)))) continue;
+                    o += span;
+                } else {
+                    if (op.instr < lo || op.instr >= hi) continue;
+                    if (bare_last && op.instr == hi - 1) moff = op.mat_bare;
+                }
             }
+            M = reinterpret_cast<const cplx*>(moff >= 0 ? pool + moff : pool_global + (-moff - 1));
+            ++o;
+            return true;
         }
-        const cplx* M = reinterpret_cast<const cplx*>(moff >= 0 ? pool + moff : pool_global + (-moff - 1));
-        switch (op_kind(op)) {
-        case OPK_DIAG: {
-            const int tm = op_tmask(op);
-            int idx_t = 0;                       // table-index bits that come from this thread's fixed tile bits
+        return false;
+    };
+    while (true) {
+        if (!fetch()) break;
+        apply_op<R, FEAT>(op, jb, M, a, b);
+        if (!fetch()) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) idx_t |= ((jb >> op_rb(op, b)) & (tm >> b) & 1) << b;
-#pragma unroll
-            for (int m = 0; m < NA; ++m) {
-                const unsigned w = m < 8 ? op.midx_lo : op.midx_hi;
-                const int idx = idx_t | (int)((w >> (4 * (m & 7))) & 15u);
-                a[m] = cmul(a[m], M[idx]);
-            }
+            for (int m = 0; m < NA; ++m) a[m] = b[m];
             break;
         }
-        case OPK_DENSE1: case OPK_PERM1: case OPK_SWAP1: case OPK_RX1: case OPK_REAL1:
-            one_bit<R>(a, op_kind(op), op_rb(op, 0), M);
-            break;
-        case OPK_DENSE2: if (FEAT & FEAT_DENSE2) dense2<R>(a, op_rb(op, 0), op_rb(op, 1), M); break;
-        case OPK_DENSE4: if (FEAT & FEAT_DENSE4) dense4<R>(a, M); break;
-        }
+        apply_op<R, FEAT>(op, jb, M, b, a);
     }
 #pragma unroll
     for (int m = 0; m < NA; ++m) sm[addr[m]] = a[m];

@@ -46,10 +46,6 @@ bool is_diagonal(const cmat& a, int d) {
             if (i != j && std::abs(a[i * d + j]) > tol) return false;
     return true;
 }
-bool is_antidiagonal2(const cmat& a) {
-    const double tol = 1e-17 * std::max(1.0, max_abs(a));
-    return std::abs(a[0]) <= tol && std::abs(a[3]) <= tol;
-}
 
 // Extreme eigenvalues of a Hermitian d x d matrix (d <= 4): cyclic Jacobi on the real symmetric embedding
 // [[A, -B], [B, A]] of H = A + iB (its spectrum is that of H, doubled).
@@ -254,36 +250,26 @@ LogicalOp make_lop(int instr, const std::vector<int>& bits, const cmat& merged, 
 int pattern_1q(const cmat& m, double tol) {
     const double s = std::max(1.0, max_abs(m));
     auto z = [&](double x) { return std::fabs(x) <= tol * s; };
-    if (z(m[0].real()) && z(m[0].imag()) && z(m[3].real()) && z(m[3].imag())) {
-        if (m[1] == cd(1, 0) && m[2] == cd(1, 0)) return OPK_SWAP1;
-        return OPK_PERM1;
-    }
     if (z(m[0].imag()) && z(m[3].imag()) && z(m[1].real()) && z(m[2].real())) return OPK_RX1;
-    if (z(m[0].imag()) && z(m[1].imag()) && z(m[2].imag()) && z(m[3].imag())) return OPK_REAL1;
     return OPK_DENSE1;
 }
 void snap_pattern(cmat& m, int kind) {      // remove the rounding dust the pattern ignores
-    switch (kind) {
-    case OPK_SWAP1: case OPK_PERM1: m[0] = 0; m[3] = 0; break;
-    case OPK_RX1: m[0] = m[0].real(); m[3] = m[3].real(); m[1] = cd(0, m[1].imag()); m[2] = cd(0, m[2].imag()); break;
-    case OPK_REAL1: for (cd& x : m) x = x.real(); break;
-    }
+    if (kind == OPK_RX1) { m[0] = m[0].real(); m[3] = m[3].real(); m[1] = cd(0, m[1].imag()); m[2] = cd(0, m[2].imag()); }
 }
 // Factors a global phase e^{i phi} out of a one-qubit gate (bare and merged with its base Kraus operator alike) when
-// that turns it into one of the cheap patterns (sx = e^{i pi/4} rx(pi/2)).  Returns phi (0: nothing factored).
+// that turns it into the cheap pattern (sx = e^{i pi/4} rx(pi/2), x = i rx(pi)).  Returns phi (0: nothing factored).
 double dephase_1q(cmat& merged, cmat& bare) {
     const double tol = 4e-16;
-    if (pattern_1q(bare, tol) != OPK_DENSE1 && pattern_1q(merged, tol) != OPK_DENSE1) return 0.0;
+    if (pattern_1q(bare, tol) == OPK_RX1 && pattern_1q(merged, tol) == OPK_RX1) return 0.0;
     std::vector<double> cands;
-    for (const cd& x : bare)
-        if (std::abs(x) > 1e-3) { cands.push_back(std::arg(x)); cands.push_back(std::arg(x) - M_PI / 2); }
+    for (int i = 0; i < 4; ++i)
+        if (std::abs(bare[i]) > 1e-3) cands.push_back(std::arg(bare[i]) - ((i == 1 || i == 2) ? M_PI / 2 : 0.0));
     for (double phi : cands) {
         const cd f = std::polar(1.0, -phi);
         cmat b2(bare), m2(merged);
         for (cd& x : b2) x *= f;
         for (cd& x : m2) x *= f;
-        const int kb = pattern_1q(b2, tol), km = pattern_1q(m2, tol);
-        if (kb != OPK_DENSE1 && km == kb) { bare = b2; merged = m2; return phi; }
+        if (pattern_1q(b2, tol) == OPK_RX1 && pattern_1q(m2, tol) == OPK_RX1) { bare = b2; merged = m2; return phi; }
     }
     return 0.0;
 }
@@ -562,7 +548,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     if (l.nb == 2) { kind = OPK_DENSE2; P.has_dense2 = true; }
                     else {
                         const int km = pattern_1q(m, 4e-16), kb = pattern_1q(mb, 4e-16);
-                        kind = km == kb ? km : ((km == OPK_SWAP1 && kb == OPK_PERM1) || (km == OPK_PERM1 && kb == OPK_SWAP1) ? OPK_PERM1 : OPK_DENSE1);
+                        kind = km == kb ? km : OPK_DENSE1;
                         snap_pattern(m, kind); snap_pattern(mb, kind);
                     }
                     op.mat = pb.add_doubles(flatten(m));
@@ -700,7 +686,7 @@ static void build_blobs(Program& P) {
                 int nd = 0;
                 switch (kind) {
                 case OPK_DIAG: nd = 2 << nb; break;
-                case OPK_DENSE1: case OPK_PERM1: case OPK_SWAP1: case OPK_RX1: case OPK_REAL1: nd = 8; break;
+                case OPK_DENSE1: case OPK_RX1: nd = 8; break;
                 case OPK_DENSE2: nd = 32; break;
                 case OPK_DENSE4: nd = 512; break;
                 }
@@ -742,7 +728,7 @@ std::string describe_program(const Program& P) {
       << " norm_preserving=" << P.norm_preserving << " dense2=" << P.has_dense2 << " dense4=" << P.has_dense4
       << " pool=" << P.pool.size() << " blobs=" << P.blobs.size();
     {
-        static const char* names[] = {"diag", "dense1", "dense2", "dense4", "perm1", "swap1", "rx1", "real1"};
+        static const char* names[] = {"diag", "dense1", "dense2", "dense4", "rx1", "?", "?", "?"};
         int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, groups = 0;
         for (const Op& op : P.ops) { ++cnt[op_kind(op) & 7]; groups += (int)(op.kind_nb >> 31); }
         o << " kinds{";

@@ -131,7 +131,7 @@ struct Engine {
 
     // ---- kernel dispatch: three instantiations --------------------------------------------------------------
     //   <3, 0, 512, 1>           R = 3, no dense two-qubit operators (Heron: cz/rzz are diagonal)
-    //   <3, DENSE2, 512, 1>      R = 3 with dense 4x4 operators (Eagle ecr, cx, swap, non-diagonal Kraus bases)
+    //   <3, DENSE2, 256, 1>      R = 3 with dense 4x4 operators (Eagle ecr, cx, swap, non-diagonal Kraus bases); K <= 11
     //   <4, DENSE2|DENSE4, 256, 1>  R = 4: 3-4 bit dense operators (density-matrix superoperators, 3-4 qubit unitaries)
     int variant() const {
         if (P.R == 4) return 2;
@@ -147,51 +147,89 @@ struct Engine {
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 8 * 1024));
         CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
+    // ---- tile launch configuration (decided once per program) -------------------------------------------------
+    int tile_nbuf = 2, tile_blob_cap = MAX_BLOB_BYTES, tile_variant = 0;
     size_t tile_launch_smem() const {
-        return (size_t)MAX_BLOB_BYTES + 2 * tile_smem() + (size_t)JB_TABLE_PASSES * sizeof(unsigned short) * ((size_t)1 << (P.K - P.R));
+        return (size_t)tile_blob_cap + (size_t)tile_nbuf * tile_smem() + (size_t)JB_TABLE_PASSES * sizeof(unsigned short) * ((size_t)1 << (P.K - P.R));
+    }
+    template <class Kern>
+    int occupancy(Kern k, int threads, size_t smem) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem));
+        return occ;
+    }
+    // lean kernel variants (R = 3, no dense two-qubit operators): 0: <512,1> 128 regs; 3: <512,2> 64 regs; 4: <256,3> 85 regs
+    void configure_tile() {
+        if (tile_configured) return;
+        int max_blob = 0;
+        for (size_t sidx = 0; sidx < P.segs.size(); ++sidx)
+            max_blob = std::max(max_blob, reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[sidx])->bytes);
+        tile_blob_cap = (max_blob + 1023) & ~1023;
+        tile_variant = variant();
+        // lean programs: two 64-register CTAs per SM, one tile buffer each (measured best on B200: the second CTA
+        // hides the first one's load latency better than a second buffer does); the register-hungry variants run
+        // one CTA per SM and double-buffer instead
+        if (tile_variant == 0) { tile_variant = 3; tile_nbuf = 1; }
+        if (const char* e = getenv("NCB_TILE_VARIANT")) {
+            const int v = atoi(e);
+            if ((tile_variant == 0 || tile_variant == 3) && (v == 0 || v == 3 || v == 4 || v == 1)) { tile_variant = v; tile_nbuf = v == 3 ? 1 : 2; }
+        }
+        if (const char* e = getenv("NCB_NBUF")) tile_nbuf = atoi(e) == 1 ? 1 : 2;
+        const int threads = 1 << (P.K - P.R);
+        if (tile_variant == 4 && threads > 256) tile_variant = 0;
+        configure(tile_kernel<3, 0, 512, 1>);
+        configure(tile_kernel<3, 0, 512, 2>);
+        configure(tile_kernel<3, 0, 256, 3>);
+        configure(tile_kernel<3, FEAT_DENSE2, 256, 1>);
+        configure(tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>);
+        const size_t smem = tile_launch_smem();
+        int occ = 1;
+        switch (tile_variant) {
+        case 0: occ = occupancy(tile_kernel<3, 0, 512, 1>, threads, smem); break;
+        case 3: occ = occupancy(tile_kernel<3, 0, 512, 2>, threads, smem); break;
+        case 4: occ = occupancy(tile_kernel<3, 0, 256, 3>, threads, smem); break;
+        case 1: occ = occupancy(tile_kernel<3, FEAT_DENSE2, 256, 1>, threads, smem); break;
+        default: occ = occupancy(tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>, threads, smem); break;
+        }
+        if (occ < 1) throw std::runtime_error("tile kernel does not fit on an SM");
+        if (const char* e = getenv("NCB_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
+        tile_ctas = sm_count * occ;
+        if (getenv("NCB_VERBOSE")) fprintf(stderr, "[ncb] tile kernel variant %d, K=%d, %d threads, nbuf=%d, blob cap %d B, smem %zu B, %d CTAs/SM\n",
+                                           tile_variant, P.K, threads, tile_nbuf, tile_blob_cap, smem, occ);
+        tile_configured = true;
     }
     void launch_tile(int nworks, cudaStream_t s, const Work* works, int seg) {
         const int tile_shift = P.nbits > P.K ? P.nbits - P.K : 0;
         const int threads = 1 << (P.K - P.R);
         const long long total = (long long)nworks << tile_shift;
+        configure_tile();
         const size_t smem = tile_launch_smem();
-        if (!tile_configured) {
-            configure(tile_kernel<3, 0, 512, 1>);
-            configure(tile_kernel<3, FEAT_DENSE2, 512, 1>);
-            configure(tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>);
-            int occ = 1;
-            switch (variant()) {
-            case 0: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<3, 0, 512, 1>, threads, smem)); break;
-            case 1: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<3, FEAT_DENSE2, 512, 1>, threads, smem)); break;
-            default: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>, threads, smem)); break;
-            }
-            if (occ < 1) throw std::runtime_error("tile kernel does not fit on an SM");
-            if (const char* e = getenv("NCB_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
-            tile_ctas = sm_count * occ;
-            tile_configured = true;
-        }
         const int grid = (int)std::min<long long>(total, tile_ctas);
         if (grid < 1) return;
         const unsigned char* blob = d_blobs.p + P.blob_off[seg];
         const int blob_bytes = reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[seg])->bytes;
-        switch (variant()) {
-        case 0: tile_kernel<3, 0, 512, 1><<<grid, threads, smem, s>>>(d, blob, blob_bytes, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p); break;
-        case 1: tile_kernel<3, FEAT_DENSE2, 512, 1><<<grid, threads, smem, s>>>(d, blob, blob_bytes, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p); break;
-        default: tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1><<<grid, threads, smem, s>>>(d, blob, blob_bytes, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p); break;
+#define NCB_TILE_ARGS d, blob, blob_bytes, tile_blob_cap, tile_nbuf, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p
+        switch (tile_variant) {
+        case 0: tile_kernel<3, 0, 512, 1><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
+        case 3: tile_kernel<3, 0, 512, 2><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
+        case 4: tile_kernel<3, 0, 256, 3><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
+        case 1: tile_kernel<3, FEAT_DENSE2, 256, 1><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
+        default: tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
         }
+#undef NCB_TILE_ARGS
         CK(cudaGetLastError());
     }
     void launch_resident(int grid, cudaStream_t s, const ResidentArgs& a) {
         const int threads = 1 << (P.K - P.R);
         if (!resident_configured) {
             configure(resident_kernel<3, 0, 512, 1>);
-            configure(resident_kernel<3, FEAT_DENSE2, 512, 1>);
+            configure(resident_kernel<3, FEAT_DENSE2, 256, 1>);
             configure(resident_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>);
             resident_configured = true;
         }
         switch (variant()) {
         case 0: resident_kernel<3, 0, 512, 1><<<grid, threads, resident_smem(), s>>>(d, a); break;
-        case 1: resident_kernel<3, FEAT_DENSE2, 512, 1><<<grid, threads, resident_smem(), s>>>(d, a); break;
+        case 1: resident_kernel<3, FEAT_DENSE2, 256, 1><<<grid, threads, resident_smem(), s>>>(d, a); break;
         default: resident_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1><<<grid, threads, resident_smem(), s>>>(d, a); break;
         }
         CK(cudaGetLastError());
@@ -541,6 +579,10 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     ncb_program* p = new ncb_program();
     try {
         compile_program(view_of(circuit), mode, opt, p->eng.P);
+        if (p->eng.P.R == 3 && p->eng.P.has_dense2 && p->eng.P.K > 11) {     // the dense-4x4 kernel runs 256 threads
+            opt.tile_bits = 11;
+            compile_program(view_of(circuit), mode, opt, p->eng.P);
+        }
     } catch (...) { delete p; throw; }
     p->eng.device = device;
     *out = p;

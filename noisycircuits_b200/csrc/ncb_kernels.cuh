@@ -151,7 +151,8 @@ __device__ __noinline__ void event_reduce(const cplx* sm, int K, int p0, int p1,
 // segment's program blob and TWO tile buffers: while tile i is processed, tile i+1 streams in through cp.async.
 template <int R, int FEAT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_bytes, const Work* __restrict__ works, int nworks,
+tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_bytes, int blob_cap, int nbuf,
+            const Work* __restrict__ works, int nworks,
             cplx* __restrict__ states, int tile_shift, double* __restrict__ red_part, double* __restrict__ norm_part,
             const Decision* __restrict__ decisions) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,9 +161,9 @@ tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_byt
     const int K = P.K, tid = threadIdx.x, nthreads = blockDim.x;
     const int ntiles = 1 << tile_shift;
     const long long total = (long long)nworks << tile_shift;
-    cplx* bufs[2];
-    bufs[0] = reinterpret_cast<cplx*>(smem_raw + MAX_BLOB_BYTES);
-    bufs[1] = bufs[0] + (1 << K);
+    // shared memory: [blob (blob_cap bytes)] [nbuf tile buffers] [jb table]
+    cplx* const buf0 = reinterpret_cast<cplx*>(smem_raw + blob_cap);
+    const int bufmask = nbuf - 1;          // nbuf is 1 or 2
 
     // ---- stage the segment program ----
     for (int i = tid * 16; i < blob_bytes; i += nthreads * 16) cp_async16(smem_raw + i, blob_g + i);
@@ -179,7 +180,7 @@ tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_byt
     const int sA = swz(tid);
     const unsigned limit = 1u << P.nbits;
     // per-thread base tile index of every pass: tile independent, computed once per CTA
-    unsigned short* jb_tab = reinterpret_cast<unsigned short*>(bufs[1] + (1 << K));
+    unsigned short* jb_tab = reinterpret_cast<unsigned short*>(buf0 + ((size_t)nbuf << K));
     const int jb_cap = npass < JB_TABLE_PASSES ? npass : JB_TABLE_PASSES;
     for (int p = 0; p < jb_cap; ++p) jb_tab[p * nthreads + tid] = (unsigned short)apply_runs(passes[p].truns, (unsigned)tid);
 
@@ -199,18 +200,22 @@ tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_byt
     long long t = blockIdx.x;
     if (t >= total) return;
     Work w = works[t >> tile_shift];
-    issue_load(t, bufs[0], w);
+    issue_load(t, buf0, w);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     for (int iter = 0; t < total; ++iter, t += gridDim.x) {
-        cplx* sm = bufs[iter & 1];
+        cplx* sm = buf0 + ((size_t)(iter & bufmask) << K);
         const long long tn = t + gridDim.x;
         Work wn = w;
-        if (tn < total) {
-            wn = works[tn >> tile_shift];
-            issue_load(tn, bufs[(iter + 1) & 1], wn);
+        if (nbuf == 2) {
+            if (tn < total) {
+                wn = works[tn >> tile_shift];
+                issue_load(tn, buf0 + ((size_t)((iter + 1) & 1) << K), wn);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");      // everything but the newest group has landed
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.wait_group 1;\n" ::: "memory");      // everything but the newest group has landed
         __syncthreads();
         const int o = (int)(t & (ntiles - 1));
         if (w.flags & WF_INIT) {
@@ -247,6 +252,11 @@ tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_byt
             }
         }
         __syncthreads();          // the buffer is refilled by the load issued in the next iteration
+        if (nbuf == 1 && tn < total) {
+            wn = works[tn >> tile_shift];
+            issue_load(tn, buf0, wn);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
         w = wn;
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
