@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "mcwf_trajectories_per_sec"
 UNIT = "trajectories/s"
 NQ, DEPTH, CIRCUIT_SEED = 20, 50, 42
+CPU_SAMPLE_LAYERS = 4        # bounded CPU sample: ~10 s of all-core work per measurement
 
 
 def workload():
@@ -156,7 +157,7 @@ def run_reference(args):
     traj = max(cores, 8)
     rates, descs, kind, secs = [], [], "port", 0.0
     for s in range(args.warmup + args.steps):
-        r, kind, desc, dt = cpu_reference_rate(instr, sq, tq, 1, traj, cores)
+        r, kind, desc, dt = cpu_reference_rate(instr, sq, tq, CPU_SAMPLE_LAYERS, traj, cores)
         if s >= args.warmup:
             rates.append(r); descs.append(desc); secs += dt
     value = len(rates) / sum(1.0 / r for r in rates)
@@ -260,9 +261,12 @@ def run_gpu(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         alg_bytes = agg["sweeps"] * 32.0 * dim                      # one rank's tile launches
         achieved = alg_bytes / (ms * 1e-3) / 1e9
+        # DRAM traffic per launch from the committed ncu --set full capture (profiles/): measured there as a ratio to
+        # the algorithmic bytes of the captured launch, applied to this run's bytes per launch
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "tile_kernel_traffic.json"))).get("traffic_bytes_per_launch")
+            ratio = json.load(open(os.path.join(ROOT, "profiles", "tile_kernel_traffic.json")))["traffic_over_algorithmic"]
+            traffic = ratio * alg_bytes / max(agg["tile_launches"], 1)
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -281,7 +285,7 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             try:
-                r, kind, desc, _dt = cpu_reference_rate(instr, sq, tq, 1, max(cores, 8), cores)
+                r, kind, desc, _dt = cpu_reference_rate(instr, sq, tq, CPU_SAMPLE_LAYERS, max(cores, 8), cores)
                 line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
             except Exception as e:                          # never lose the GPU numbers to a host-side problem
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": repr(e)}

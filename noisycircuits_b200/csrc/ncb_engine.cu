@@ -396,7 +396,7 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
         for (const LaunchStep& st : plan.steps) {
             if (st.kind == 0) { launch_tile(st.count, s, d_works[buf].p + st.begin, st.seg); ++rp->out_tile_launches; }
             else {
-                decide_kernel<<<st.count, 32, 0, s>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
+                decide_kernel<<<st.count, 256, 0, s>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
                 CK(cudaGetLastError());
             }
             ++rp->out_launches;

@@ -265,24 +265,35 @@ tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_byt
 // ---------------------------------------------------------------------------------------------------------------
 // decide kernel: one warp per state-dependent event
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void decide_kernel(DevProgram P, const DecideItem* __restrict__ items, int nitems, const double* __restrict__ red_part,
-                              int ntiles, Decision* __restrict__ decisions) {
+__global__ void __launch_bounds__(256)
+decide_kernel(DevProgram P, const DecideItem* __restrict__ items, int nitems, const double* __restrict__ red_part,
+              int ntiles, Decision* __restrict__ decisions) {
+    // one 256-thread block per event: lane e owns value e of the 32-value partial, warp w sums the tiles o = w (mod 8);
+    // the 8 warp partials are then added in warp order, so the result does not depend on scheduling
+    __shared__ double part[8][RED_VALUES];
     __shared__ double rho[RED_VALUES];
     const int it = blockIdx.x;
     if (it >= nitems) return;
     const DecideItem d = items[it];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* src = red_part + (long long)d.slot * ntiles * RED_VALUES;
     double s = 0.0;
-    for (int o = 0; o < ntiles; ++o) s += src[(long long)o * RED_VALUES + threadIdx.x];
-    rho[threadIdx.x] = s;
-    __syncwarp();
-    if (threadIdx.x == 0) {
-        const Channel ch = P.chans[P.instrs[d.instr].channel];
-        mirror_rho(rho, ch.dim);
-        double scale;
-        const int k = decide_branch(rho, ch, P.pool, d.u, &scale);
-        decisions[d.slot].k = k;
-        decisions[d.slot].scale = scale;
+    for (int o = warp; o < ntiles; o += 8) s += src[(long long)o * RED_VALUES + lane];
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        rho[lane] = t;
+        __syncwarp();
+        if (lane == 0) {
+            const Channel ch = P.chans[P.instrs[d.instr].channel];
+            mirror_rho(rho, ch.dim);
+            double scale;
+            const int k = decide_branch(rho, ch, P.pool, d.u, &scale);
+            decisions[d.slot].k = k;
+            decisions[d.slot].scale = scale;
+        }
     }
 }
 
