@@ -106,12 +106,11 @@ def install(name: str = "b200") -> bool:
     package's RemoteExecutor (see INTEGRATION.md for the three-line upstream patch that makes the wrapper unnecessary).
     """
     try:
-        import NoisyCircuits.QuantumCircuit as qc_mod
+        from NoisyCircuits.QuantumCircuit import QuantumCircuit as QC
     except Exception:
         return False
     pkg = sys.modules[__package__]
     sys.modules[f"NoisyCircuits.utils.{name}"] = pkg
-    QC = qc_mod.QuantumCircuit
     if name not in QC.available_sim_backends:
         QC.available_sim_backends.append(name)
     if getattr(QC.execute, "_ncb200", False):
