@@ -78,7 +78,10 @@ typedef struct {
     int32_t low_bits;    /* lowest state bits kept in every tile (-1: default 3) */
     int32_t fuse;        /* 1 (default): fuse runs of instructions into one sweep; 0: one sweep per instruction */
     int32_t device;      /* CUDA device ordinal (-1: current device) */
-    int32_t reserved[3];
+    int32_t strict_order;/* 0 (default): commuting instructions (disjoint qubits) may be executed in a tile-friendly
+                            order -- the same circuit, fewer sweeps; jump events then have the reference's meaning on
+                            that order (ncb_program_order).  1: execute strictly in the caller's order. */
+    int32_t reserved[2];
 } ncb_options;
 
 typedef struct ncb_program ncb_program;
@@ -99,8 +102,11 @@ enum {
 };
 int64_t ncb_program_query(const ncb_program* program, int what);
 
-/* Jump events of one trajectory (host-only; used by tests): for explicit uniforms u[num_instructions] writes up to
- * cap records (instr, kmin, kmax) into out[3*i..] and returns the number of events. */
+/* Execution order: out[pos] = index (in the caller's instruction list) of the instruction executed at position pos. */
+int ncb_program_order(const ncb_program* program, int32_t* out);
+/* Jump events of one trajectory (host-only; used by tests): for explicit uniforms u[num_instructions] (indexed like the
+ * caller's instruction list) writes up to cap records (instr, kmin, kmax) into out[3*i..], in execution order, and
+ * returns the number of events. */
 int64_t ncb_program_events(const ncb_program* program, const double* uniforms, int32_t* out, int64_t cap);
 /* The reference's uniform stream for std::mt19937_64(seed): u[g] for every instruction that consumes a draw
  * (Kraus list with >= 2 operators), 0.5 elsewhere. */

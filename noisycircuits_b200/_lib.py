@@ -26,7 +26,7 @@ class NcbCircuit(C.Structure):
 
 class NcbOptions(C.Structure):
     _fields_ = [("tile_bits", C.c_int32), ("reg_bits", C.c_int32), ("low_bits", C.c_int32), ("fuse", C.c_int32),
-                ("device", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("device", C.c_int32), ("strict_order", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class NcbRunParams(C.Structure):
@@ -40,7 +40,7 @@ class NcbRunParams(C.Structure):
 
 # every symbol include/ncb200.h declares
 EXPORTS = ["ncb_last_error", "ncb_version", "ncb_program_create", "ncb_program_destroy", "ncb_program_describe",
-           "ncb_program_query", "ncb_program_events", "ncb_program_reference_uniforms", "ncb_mcwf_run", "ncb_pure_run",
+           "ncb_program_query", "ncb_program_order", "ncb_program_events", "ncb_program_reference_uniforms", "ncb_mcwf_run", "ncb_pure_run",
            "ncb_density_run", "ncb_apply_measurement_error", "ncb_apply_measurement_error_device",
            "ncb_simulate_circuit", "ncb_run_trajectory"]
 
@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         L.ncb_program_describe.restype = C.c_int64
         L.ncb_program_query.argtypes = [C.c_void_p, C.c_int]
         L.ncb_program_query.restype = C.c_int64
+        L.ncb_program_order.argtypes = [C.c_void_p, C.c_void_p]
         L.ncb_program_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.ncb_program_events.restype = C.c_int64
         L.ncb_program_reference_uniforms.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]

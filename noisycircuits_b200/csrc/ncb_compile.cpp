@@ -394,6 +394,109 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
         lops.push_back(make_lop(g, qb, merged, U));
     }
 
+    const int kfit = std::min(K, P.nbits);
+    // ---- execution order ------------------------------------------------------------------------------------------
+    // Instructions on disjoint bits commute, so any order that keeps the per-bit order is the same circuit.  The
+    // scheduler below picks, segment by segment, a tile (the L low bits + up to kfit - L others) and runs every
+    // instruction that is ready inside it -- several layers deep where the coupling allows (space-time trapezoids) --
+    // which is what decides how many times the state crosses HBM.  Jump events keep the reference's meaning on the
+    // order chosen here: the engine is the reference algorithm applied to this (equivalent) instruction order, and
+    // `orig` lets a caller replay exactly that.
+    {
+        std::vector<std::vector<int>> ilops(P.G);          // lops of each instruction
+        std::vector<uint64_t> ubits(P.G, 0);
+        for (size_t i = 0; i < lops.size(); ++i) {
+            ilops[lops[i].instr].push_back((int)i);
+            for (int b = 0; b < lops[i].nb; ++b) ubits[lops[i].instr] |= 1ull << lops[i].bits[b];
+        }
+        std::vector<int> order;
+        order.reserve(P.G);
+        if (!opt.reorder || !opt.fuse || P.nbits <= kfit) {
+            for (int g = 0; g < P.G; ++g) order.push_back(g);
+        } else {
+            const int nb = P.nbits;
+            std::vector<std::vector<int>> queue(nb);
+            for (int g = 0; g < P.G; ++g)
+                for (int b = 0; b < nb; ++b)
+                    if ((ubits[g] >> b) & 1) queue[b].push_back(g);
+            std::vector<size_t> head(nb, 0);
+            uint64_t low = 0;
+            for (int b = 0; b < L; ++b) low |= 1ull << b;
+            const int max_seg_ops = 40;        // keeps a segment's program inside the shared-memory staging area
+            // runs every ready instruction inside tile S from heads h (modified); returns the executed list
+            auto run = [&](uint64_t S, std::vector<size_t>& h, std::vector<int>* out) {
+                int count = 0;
+                bool progress = true;
+                std::vector<int> ready;
+                while (progress && count < max_seg_ops) {
+                    progress = false;
+                    ready.clear();
+                    for (int b = 0; b < nb; ++b) {
+                        if (!((S >> b) & 1) || h[b] >= queue[b].size()) continue;
+                        const int g = queue[b][h[b]];
+                        if (ubits[g] & ~S) continue;
+                        bool ok = true;
+                        for (int c = 0; c < nb && ok; ++c)
+                            if (((ubits[g] >> c) & 1) && (h[c] >= queue[c].size() || queue[c][h[c]] != g)) ok = false;
+                        if (ok && std::find(ready.begin(), ready.end(), g) == ready.end()) ready.push_back(g);
+                    }
+                    std::sort(ready.begin(), ready.end());
+                    for (int g : ready) {
+                        if (count >= max_seg_ops) break;
+                        for (int c = 0; c < nb; ++c)
+                            if ((ubits[g] >> c) & 1) ++h[c];
+                        if (out) out->push_back(g);
+                        ++count;
+                        progress = true;
+                    }
+                }
+                return count;
+            };
+            std::vector<char> done(P.G, 0);
+            int next_undone = 0;
+            while ((int)order.size() < P.G) {
+                while (next_undone < P.G && done[next_undone]) ++next_undone;
+                // seed: the oldest pending instruction (it is ready: everything before it on its bits is done)
+                uint64_t S = low | ubits[next_undone];
+                if (__builtin_popcountll(S) > kfit) throw std::runtime_error("an operation does not fit a tile; increase tile_bits");
+                while (__builtin_popcountll(S) < kfit) {
+                    int best_bit = -1, best_cnt = -1;
+                    long long best_tie = 0;
+                    for (int c = 0; c < nb; ++c) {
+                        if ((S >> c) & 1) continue;
+                        if (head[c] >= queue[c].size()) continue;              // nothing left on this bit
+                        std::vector<size_t> h(head);
+                        const int cnt = run(S | (1ull << c), h, nullptr);
+                        // tie-break: bits coupled to the tile by a pending instruction first, then the oldest pending work
+                        const int gp = queue[c][head[c]];
+                        const long long tie = ((ubits[gp] & S & ~low) ? (1ll << 40) : 0) - gp;
+                        if (cnt > best_cnt || (cnt == best_cnt && tie > best_tie)) { best_cnt = cnt; best_bit = c; best_tie = tie; }
+                    }
+                    if (best_bit < 0) break;
+                    S |= 1ull << best_bit;
+                }
+                std::vector<int> seg_list;
+                const int cnt = run(S, head, &seg_list);
+                if (cnt == 0) throw std::runtime_error("internal: the scheduler made no progress");
+                for (int g : seg_list) { done[g] = 1; order.push_back(g); }
+            }
+        }
+        // renumber: from here on an instruction's index is its execution position
+        P.orig.assign(order.begin(), order.end());
+        std::vector<LogicalOp> nl;
+        nl.reserve(lops.size());
+        std::vector<Instr> ni(P.G);
+        P.noisy_instrs.clear();
+        for (int pos = 0; pos < P.G; ++pos) {
+            const int g = order[pos];
+            ni[pos] = P.instrs[g];
+            for (int li : ilops[g]) { nl.push_back(lops[li]); nl.back().instr = pos; }
+            if (P.draw_pos[g] >= 0) P.noisy_instrs.push_back(pos);
+        }
+        lops.swap(nl);
+        P.instrs.swap(ni);
+    }
+
     // ---- segmentation: maximal runs of consecutive logical ops whose bits fit one tile --------------------------
     struct SegBuild { std::vector<int> tile; size_t lop_begin, lop_end; };
     std::vector<SegBuild> sb;
@@ -403,7 +506,6 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
             if (std::find(t.begin(), t.end(), l.bits[i]) == t.end()) t.push_back(l.bits[i]);
         return t;
     };
-    const int kfit = std::min(K, P.nbits);
     {
         // upper bound of what a logical op adds to its segment's shared-memory blob (op records of the op and of a
         // possible group header, its matrices, a share of a pass record)
@@ -726,7 +828,7 @@ std::string describe_program(const Program& P) {
       << " segments=" << P.segs.size() << " passes=" << P.passes.size() << " ops=" << P.ops.size()
       << " channels=" << P.chans.size() << " noisy=" << P.noisy_instrs.size() << " draws=" << P.num_draws
       << " norm_preserving=" << P.norm_preserving << " dense2=" << P.has_dense2 << " dense4=" << P.has_dense4
-      << " pool=" << P.pool.size() << " blobs=" << P.blobs.size();
+      << " pool=" << P.pool.size() << " blobs=" << P.blobs.size() << " reorder=" << P.opt.reorder;
     {
         static const char* names[] = {"diag", "dense1", "dense2", "dense4", "rx1", "?", "?", "?"};
         int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, groups = 0;

@@ -36,6 +36,8 @@ struct CompileOptions {
     int reg_bits = 3;       // R: amplitudes per thread = 2^R
     int low_bits = 3;       // the L lowest state bits are part of every tile (coalescing: runs of 2^L * 16 B)
     int fuse = 1;           // 0: one instruction per segment (debug / ablation)
+    int reorder = 1;        // 1: execute commuting instructions in a tile-friendly (dependency-respecting) order;
+                            // 0: strictly in program order
 };
 
 // A logical op in state-bit coordinates, before tiling
@@ -67,7 +69,10 @@ struct Program {
     std::vector<Channel> chans;
     std::vector<int32_t> draw_pos;      // position of the instruction's draw in the reference's MT stream, -1: none
     int num_draws = 0;
-    std::vector<int32_t> noisy_instrs;  // instructions that have a channel with >= 2 operators
+    std::vector<int32_t> noisy_instrs;  // execution positions that have a channel with >= 2 operators
+    std::vector<int32_t> orig;          // orig[pos]: index in the caller's instruction list of the instruction executed
+                                        // at position pos (identity unless reorder).  Inside the engine "instruction
+                                        // index" always means the execution position; uniforms are keyed by orig[pos].
     std::vector<unsigned char> blobs;   // SegBlob of every segment, back to back (16-byte aligned)
     std::vector<int64_t> blob_off;      // byte offset of segment s's blob
     CompileOptions opt;
@@ -86,7 +91,7 @@ struct Event {
     int32_t kmin, kmax;     // kmin == kmax: the branch is known (and differs from the channel's base branch)
     double u;
 };
-// uniform(instr) -> u in [0,1)
+// uniform(instr) -> u in [0,1), instr = index in the caller's instruction list; Event::instr is an execution position
 template <class F>
 inline void plan_events(const Program& P, F&& uniform, std::vector<Event>& out) {
     out.clear();
@@ -94,7 +99,7 @@ inline void plan_events(const Program& P, F&& uniform, std::vector<Event>& out) 
         const Channel& ch = P.chans[P.instrs[i].channel];
         const double* lo = P.pool.data() + ch.bounds;
         const double* hi = lo + (ch.count - 1);
-        const double u = uniform(i);
+        const double u = uniform(P.orig[i]);
         // fast path: inside the base branch's certain interval
         const double left = ch.base == 0 ? -1.0 : hi[ch.base - 1] + EVENT_MARGIN;
         const double right = ch.base == ch.count - 1 ? 2.0 : lo[ch.base] - EVENT_MARGIN;

@@ -64,7 +64,7 @@ struct Engine {
     size_t smem_optin = 0;
     DevProgram d{};
     DevBuf<Op> d_ops; DevBuf<Pass> d_passes; DevBuf<Segment> d_segs; DevBuf<Instr> d_instrs; DevBuf<Channel> d_chans;
-    DevBuf<double> d_pool; DevBuf<int32_t> d_noisy; DevBuf<unsigned char> d_blobs;
+    DevBuf<double> d_pool; DevBuf<int32_t> d_noisy; DevBuf<int32_t> d_orig; DevBuf<unsigned char> d_blobs;
     DevBuf<cplx> d_states;
     DevBuf<double> d_red, d_norm, d_invnorm, d_probs, d_partial, d_uniforms;
     DevBuf<Decision> d_dec;
@@ -80,7 +80,7 @@ struct Engine {
 
     ~Engine() {
         d_ops.release(); d_passes.release(); d_segs.release(); d_instrs.release(); d_chans.release(); d_pool.release();
-        d_noisy.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_probs.release();
+        d_noisy.release(); d_orig.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_probs.release();
         d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release();
         for (int i = 0; i < 2; ++i) {
             d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
@@ -115,9 +115,9 @@ struct Engine {
         sm_count = prop.multiProcessorCount;
         smem_optin = prop.sharedMemPerBlockOptin;
         upload(d_ops, P.ops); upload(d_passes, P.passes); upload(d_segs, P.segs); upload(d_instrs, P.instrs);
-        upload(d_chans, P.chans); upload(d_pool, P.pool); upload(d_noisy, P.noisy_instrs); upload(d_blobs, P.blobs);
+        upload(d_chans, P.chans); upload(d_pool, P.pool); upload(d_noisy, P.noisy_instrs); upload(d_orig, P.orig); upload(d_blobs, P.blobs);
         d.ops = d_ops.p; d.passes = d_passes.p; d.segs = d_segs.p; d.instrs = d_instrs.p; d.chans = d_chans.p;
-        d.pool = d_pool.p; d.noisy = d_noisy.p; d.n_noisy = (int)P.noisy_instrs.size(); d.G = P.G; d.nbits = P.nbits;
+        d.pool = d_pool.p; d.noisy = d_noisy.p; d.orig = d_orig.p; d.n_noisy = (int)P.noisy_instrs.size(); d.G = P.G; d.nbits = P.nbits;
         d.K = P.K; d.R = P.R; d.nseg = (int)P.segs.size(); d.npass = (int)P.passes.size();
         const size_t need = resident() ? resident_smem() : tile_launch_smem();
         if (need + 6 * 1024 > smem_optin)
@@ -274,7 +274,7 @@ struct Engine {
         out.assign((size_t)count * P.G, 0.5);
 #pragma omp parallel for schedule(static)
         for (long long t = 0; t < count; ++t)
-            for (int32_t i : P.noisy_instrs) out[(size_t)t * P.G + i] = us.get(begin + t, i);
+            for (int32_t pos : P.noisy_instrs) out[(size_t)t * P.G + pos] = us.get(begin + t, P.orig[pos]);   // by position
     }
 
     int auto_batch(long long count) const {
@@ -568,12 +568,14 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
         if (options->reg_bits > 0) opt.reg_bits = options->reg_bits;
         if (options->low_bits >= 0) opt.low_bits = options->low_bits;
         opt.fuse = options->fuse;
+        opt.reorder = options->strict_order ? 0 : 1;
         device = options->device;
     }
     if (const char* e = getenv("NCB_TILE_BITS")) opt.tile_bits = atoi(e);
     if (const char* e = getenv("NCB_REG_BITS")) opt.reg_bits = atoi(e);
     if (const char* e = getenv("NCB_LOW_BITS")) opt.low_bits = atoi(e);
     if (const char* e = getenv("NCB_FUSE")) opt.fuse = atoi(e);
+    if (const char* e = getenv("NCB_REORDER")) opt.reorder = atoi(e);
     if (opt.reg_bits != 3 && opt.reg_bits != 4) return fail(NCB_E_INVALID, "reg_bits must be 3 or 4");
     opt.tile_bits = std::min(opt.tile_bits, 12);   // <= 256 threads (R = 4) / 512 threads (R = 3)
     ncb_program* p = new ncb_program();
@@ -622,12 +624,20 @@ int64_t ncb_program_query(const ncb_program* program, int what) {
     return -1;
 }
 
+int ncb_program_order(const ncb_program* program, int32_t* out) {
+    if (!program || !out) return fail(NCB_E_INVALID, "null argument");
+    const Program& P = program->eng.P;
+    for (int i = 0; i < P.G; ++i) out[i] = P.orig[i];
+    return NCB_OK;
+}
+
 int64_t ncb_program_events(const ncb_program* program, const double* uniforms, int32_t* out, int64_t cap) {
     if (!program || !uniforms) return -1;
+    const Program& P = program->eng.P;
     std::vector<Event> ev;
-    plan_events(program->eng.P, [&](int i) { return uniforms[i]; }, ev);
+    plan_events(P, [&](int i) { return uniforms[i]; }, ev);
     for (size_t i = 0; i < ev.size() && (int64_t)i < cap; ++i) {
-        out[3 * i] = ev[i].instr; out[3 * i + 1] = ev[i].kmin; out[3 * i + 2] = ev[i].kmax;
+        out[3 * i] = P.orig[ev[i].instr]; out[3 * i + 1] = ev[i].kmin; out[3 * i + 2] = ev[i].kmax;
     }
     return (int64_t)ev.size();
 }

@@ -24,7 +24,8 @@ struct DevProgram {
     const Instr* instrs;
     const Channel* chans;
     const double* pool;
-    const int32_t* noisy;   // instructions with a channel of >= 2 operators
+    const int32_t* noisy;   // execution positions with a channel of >= 2 operators
+    const int32_t* orig;    // orig[pos]: the caller's instruction index (keys the Philox draw)
     int n_noisy, G, nbits, K, R, nseg, npass;
 };
 
@@ -406,7 +407,7 @@ resident_kernel(DevProgram P, ResidentArgs A) {
             const Channel ch = P.chans[P.instrs[i].channel];
             const double* lo = P.pool + ch.bounds;
             const double* hi = lo + (ch.count - 1);
-            const double u = utab ? utab[i] : philox_uniform(A.seed, traj, (uint32_t)i);
+            const double u = utab ? utab[i] : philox_uniform(A.seed, traj, (uint32_t)P.orig[i]);
             const double left = ch.base == 0 ? -1.0 : hi[ch.base - 1] + EVENT_MARGIN;
             const double right = ch.base == ch.count - 1 ? 2.0 : lo[ch.base] - EVENT_MARGIN;
             if (!(u > left && u <= right)) atomicOr(&evmask[i >> 5], 1u << (i & 31));
@@ -427,7 +428,7 @@ resident_kernel(DevProgram P, ResidentArgs A) {
             if (!ev) break;
             const Instr in = P.instrs[e];
             const Channel ch = P.chans[in.channel];
-            const double u = utab ? utab[e] : philox_uniform(A.seed, traj, (uint32_t)e);
+            const double u = utab ? utab[e] : philox_uniform(A.seed, traj, (uint32_t)P.orig[e]);
             int kmin, kmax;
             classify_uniform(P.pool + ch.bounds, P.pool + ch.bounds + (ch.count - 1), ch.count, u, &kmin, &kmax);
             int k = kmin;

@@ -126,11 +126,11 @@ class Program:
     """A compiled program (``ncb_program``).  Compilation is host-only; the first run uploads it to the GPU."""
 
     def __init__(self, packed: PackedCircuit, mode: int = _lib.MODE_MCWF, tile_bits: int = 0, reg_bits: int = 0,
-                 low_bits: int = -1, fuse: int = 1, device: int = -1):
+                 low_bits: int = -1, fuse: int = 1, device: int = -1, strict_order: bool = False):
         self._h = C.c_void_p(None)
         self.packed = packed
         self.mode = mode
-        opts = _lib.NcbOptions(tile_bits, reg_bits, low_bits, fuse, device, (C.c_int32 * 3)(0, 0, 0))
+        opts = _lib.NcbOptions(tile_bits, reg_bits, low_bits, fuse, device, int(bool(strict_order)), (C.c_int32 * 2)(0, 0))
         _lib.check(_lib.lib().ncb_program_create(C.byref(packed.struct), mode, C.byref(opts), C.byref(self._h)))
         self.num_qubits = packed.num_qubits
         self.num_instructions = packed.num_instructions
@@ -154,6 +154,12 @@ class Program:
         buf = C.create_string_buffer(int(n))
         _lib.lib().ncb_program_describe(self._h, buf, n)
         return buf.value.decode()
+
+    def order(self) -> np.ndarray:
+        """order[pos] = index in the instruction list of the instruction executed at position pos."""
+        out = np.zeros(max(self.num_instructions, 1), np.int32)
+        _lib.check(_lib.lib().ncb_program_order(self._h, _ptr(out)))
+        return out[:self.num_instructions]
 
     def events(self, uniforms) -> np.ndarray:
         """Jump events (instr, kmin, kmax) of the trajectory driven by ``uniforms`` (host-only)."""

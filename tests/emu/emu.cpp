@@ -153,16 +153,20 @@ extern "C" {
 
 const char* emu_last_error() { return g_err.c_str(); }
 
-void* emu_create(const ncb_circuit* c, int mode, int tile_bits, int reg_bits, int low_bits, int fuse) {
+void* emu_create(const ncb_circuit* c, int mode, int tile_bits, int reg_bits, int low_bits, int fuse, int reorder) {
     try {
         Emu* e = new Emu();
         CompileOptions opt;
-        opt.tile_bits = tile_bits; opt.reg_bits = reg_bits; opt.low_bits = low_bits; opt.fuse = fuse;
+        opt.tile_bits = tile_bits; opt.reg_bits = reg_bits; opt.low_bits = low_bits; opt.fuse = fuse; opt.reorder = reorder;
         compile_program(view_of(c), mode, opt, e->P);
         return e;
     } catch (const std::exception& ex) { g_err = ex.what(); return nullptr; }
 }
 void emu_destroy(void* h) { delete static_cast<Emu*>(h); }
+void emu_order(void* h, int* out) {
+    const Program& P = static_cast<Emu*>(h)->P;
+    for (int i = 0; i < P.G; ++i) out[i] = P.orig[i];
+}
 
 long long emu_query(void* h, int what) {
     const Program& P = static_cast<Emu*>(h)->P;

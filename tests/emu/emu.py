@@ -21,7 +21,8 @@ def lib():
             subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", SO] + SRCS, check=True)
         L = C.CDLL(SO)
         L.emu_create.restype = C.c_void_p
-        L.emu_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.emu_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.emu_order.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_destroy.argtypes = [C.c_void_p]
         L.emu_query.argtypes = [C.c_void_p, C.c_int]
         L.emu_query.restype = C.c_longlong
@@ -37,9 +38,9 @@ def lib():
 
 
 class EmuProgram:
-    def __init__(self, packed, mode=0, tile_bits=12, reg_bits=4, low_bits=3, fuse=1):
+    def __init__(self, packed, mode=0, tile_bits=12, reg_bits=4, low_bits=3, fuse=1, reorder=1):
         self.packed = packed
-        self.h = lib().emu_create(C.byref(packed.struct), mode, tile_bits, reg_bits, low_bits, fuse)
+        self.h = lib().emu_create(C.byref(packed.struct), mode, tile_bits, reg_bits, low_bits, fuse, reorder)
         if not self.h:
             raise RuntimeError(lib().emu_last_error().decode())
 
@@ -47,6 +48,11 @@ class EmuProgram:
         if getattr(self, "h", None):
             lib().emu_destroy(self.h)
             self.h = None
+
+    def order(self):
+        out = np.zeros(max(self.packed.num_instructions, 1), np.int32)
+        lib().emu_order(self.h, out.ctypes.data)
+        return out[:self.packed.num_instructions]
 
     def query(self, what):
         return int(lib().emu_query(self.h, what))

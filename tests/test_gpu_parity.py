@@ -38,12 +38,19 @@ def philox_numpy(seed, traj, instr):
 
 
 def replay(n, instr, sq, tq, U, mask_fix=True, **opts):
+    """Seeded replay harness: the same per-instruction uniforms drive the GPU engine and the oracle.  The engine may
+    execute commuting instructions in a tile-friendly order (Program.order(), the same circuit); the oracle runs the
+    reference algorithm on that order, each uniform staying attached to its instruction."""
     prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, **opts)
     probs, states, stats = prog.run_mcwf(U.shape[0], uniforms=U, return_states=True)
-    O = oracle.Program(n, instr, sq, tq)
+    order = prog.order()
+    assert sorted(order) == list(range(len(instr)))
+    if opts.get("strict_order"):
+        assert list(order) == list(range(len(instr)))
+    O = oracle.Program(n, [instr[g] for g in order], sq, tq)
     worst, acc = 0.0, np.zeros(1 << n)
     for t in range(U.shape[0]):
-        ref = O.trajectory(U[t], mask_fix=mask_fix)
+        ref = O.trajectory(U[t][order], mask_fix=mask_fix)
         worst = max(worst, float(np.abs(states[t] - ref).max()))
         acc += np.abs(ref) ** 2
     assert worst < TOL, (worst, stats, prog.describe().splitlines()[0])
@@ -77,6 +84,7 @@ def test_replay_resident_long_program_spans_several_segments(heron_noise):
 
 @pytest.mark.parametrize("n,opts", [
     (13, {}), (14, {"reg_bits": 3}), (15, {"tile_bits": 11}), (16, {}), (14, {"fuse": 0}), (16, {"low_bits": 0, "reg_bits": 3}),
+    (14, {"strict_order": True}), (16, {"strict_order": True, "tile_bits": 10}), (15, {"reg_bits": 4}),
 ])
 def test_replay_tiled_heron(heron_noise, n, opts):
     sq, tq, _, _ = heron_noise
@@ -160,11 +168,14 @@ def test_pure_state_all_gate_kernels(golden):
 
 
 def test_pure_state_tiled(heron_noise):
+    """Noise-free: the reordered program is the same unitary (global phases restored), deep circuit, 8 tiles."""
     n = 15
     _sq, tq, _, _ = heron_noise
-    instr = circuits.heron_layered(n, 4, circuits.coupled_pairs(tq, n), seed=8)
+    instr = circuits.heron_layered(n, 8, circuits.coupled_pairs(tq, n), seed=8)
     ref = oracle.Program(n, instr, noisy=False).pure_state()
     s = PureStateSolver(n, instr, 1, True).solve()
+    assert np.abs(s - ref).max() < 1e-12
+    s = PureStateSolver(n, instr, 1, True, strict_order=True).solve()
     assert np.abs(s - ref).max() < 1e-12
 
 
@@ -236,13 +247,35 @@ def test_mcwf_distribution_matches_density_matrix(heron_noise):
     assert hell < 0.05                          # the reference's own acceptance test (tests/test_Integration.py:157-169)
 
 
-def test_mcwf_distribution_tiled_matches_density_matrix(eagle_noise):
+def test_mcwf_distribution_eagle_matches_density_matrix(eagle_noise):
     sq, tq, _, _ = eagle_noise
     n, N = 7, 4000
     instr = circuits.eagle_layered(n, 4, circuits.coupled_pairs(tq, n), seed=3)
     dm = DensityMatrixSolver(n, sq, tq, instr, 1).solve(list(range(n)))
-    # force the tile path on a small state: 2^7 amplitudes in tiles of... not possible below 2^8, so use tile_bits=9 on n=7
     mc = RemoteExecutor(n, sq, tq, 2).run(N, instr)
+    assert 0.5 * np.abs(mc - dm).sum() <= 3 / np.sqrt(N)
+
+
+def test_mcwf_distribution_tiled_reordered_matches_density_matrix(heron_noise):
+    """Free-running, tile path (n = 9 in 2^8-amplitude tiles), reordered execution, noise amplified 40x so that jump
+    events (incl. state-dependent ones) are frequent: the distribution still is the density-matrix one."""
+    sq, tq, _, _ = heron_noise
+    n, N = 9, 6000
+
+    def amplify(ops, f=40.0):
+        # p_k -> f p_k for the error branches, identity branch rescaled: stays CPTP for these mixed-unitary + reset lists
+        w = [np.trace(k.conj().T @ k).real / k.shape[0] for k in ops]
+        err = sum(w[1:])
+        out = [np.sqrt(max(1 - f * err, 0.0) / w[0]) * ops[0]] + [np.sqrt(f) * k for k in ops[1:]]
+        return out
+    good = [q for q in range(n) if q not in (4, 9)]          # T2 <= T1 qubits: every list starts with the scaled identity
+    sq2 = {q: {g: (amplify(ops) if q in good else ops) for g, ops in gates.items()} for q, gates in sq.items()}
+    instr = circuits.heron_layered(n, 5, circuits.coupled_pairs(tq, n), seed=12)
+    dm = DensityMatrixSolver(n, sq2, tq, instr, 1).solve(list(range(n)))
+    ex = RemoteExecutor(n, sq2, tq, 2, tile_bits=8)
+    mc = ex.run(N, instr)
+    assert ex.last_stats["events"] > N // 2 and ex.last_stats["hard_events"] > N // 20 and ex.last_stats["sweeps"] > 0
+    assert abs(mc.sum() - 1) < 1e-9
     assert 0.5 * np.abs(mc - dm).sum() <= 3 / np.sqrt(N)
 
 
@@ -253,7 +286,7 @@ def test_execute_chain_and_full_size_properties(heron_noise):
     instr = circuits.heron_layered(n, 2, circuits.coupled_pairs(tq, n), seed=42)
     out = execute(n, instr, sq, tq, {q: meas[q] for q in range(n)}, None, 8)
     assert out.shape == (1 << n,) and abs(out.sum() - 1) < 1e-9 and out.min() >= 0
-    # fused and unfused schedules are the same function
-    a, _ = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, fuse=1).run_mcwf(4, seed=3)
+    # fused and unfused schedules are the same function (both strictly in program order)
+    a, _ = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, fuse=1, strict_order=True).run_mcwf(4, seed=3)
     b, _ = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, fuse=0).run_mcwf(4, seed=3)
     assert np.abs(a - b).max() < TOL

@@ -21,13 +21,19 @@ def jumpy_uniforms(rng, count, G):
 
 
 def check_replay(n, instr, sq, tq, U, **opts):
+    """Engine (emulated) vs the reference algorithm on the engine's execution order: the engine may run commuting
+    instructions in another order (the same circuit); uniforms stay attached to their instructions."""
     pk = PackedCircuit(n, instr, sq, tq)
     E = EmuProgram(pk, 0, **opts)
-    O = oracle.Program(n, instr, sq, tq)
+    order = E.order()
+    assert sorted(order) == list(range(len(instr)))
+    if not opts.get("reorder", 1):
+        assert list(order) == list(range(len(instr)))
+    O = oracle.Program(n, [instr[g] for g in order], sq, tq)
     st, stats = E.mcwf_states(U)
     worst = 0.0
     for t in range(U.shape[0]):
-        ref = O.trajectory(U[t], mask_fix=True)
+        ref = O.trajectory(U[t][order], mask_fix=True)
         worst = max(worst, np.abs(st[t] - ref).max())
     assert worst < TOL, (worst, stats, E.describe())
     return stats, E
@@ -38,12 +44,13 @@ def check_replay(n, instr, sq, tq, U, **opts):
     (10, 9, 4, 3, 1), (10, 8, 3, 2, 1), (11, 9, 4, 0, 1),        # tiled: 2..8 tiles per trajectory
     (10, 9, 4, 3, 0), (11, 8, 3, 3, 0),                         # one sweep per instruction
 ])
-def test_heron_replay(heron_noise, n, tile_bits, reg_bits, low_bits, fuse):
+@pytest.mark.parametrize("reorder", [0, 1])
+def test_heron_replay(heron_noise, n, tile_bits, reg_bits, low_bits, fuse, reorder):
     sq, tq, _, _ = heron_noise
     pairs = circuits.coupled_pairs(tq, n)
     instr = circuits.heron_layered(n, 3, pairs, seed=n)
     U = jumpy_uniforms(np.random.default_rng(n), 6, len(instr))
-    stats, E = check_replay(n, instr, sq, tq, U, tile_bits=tile_bits, reg_bits=reg_bits, low_bits=low_bits, fuse=fuse)
+    stats, E = check_replay(n, instr, sq, tq, U, tile_bits=tile_bits, reg_bits=reg_bits, low_bits=low_bits, fuse=fuse, reorder=reorder)
     assert stats["events"] > 0 and stats["hard_events"] > 0
     if not fuse:
         assert E.query(2) == len(instr)
@@ -116,6 +123,20 @@ def test_density_matrix_superoperators(heron_noise, eagle_noise, n, tile_bits):
         ref = oracle.density_matrix(n, instr, sq, tq)
         assert np.abs(rho - ref).max() < TOL
         assert abs(np.trace(rho).real - 1) < 1e-12
+
+
+def test_reordering_is_the_same_circuit_and_saves_sweeps(heron_noise):
+    """Without noise the reordered program is the same unitary; with noise it needs fewer segments."""
+    sq, tq, _, _ = heron_noise
+    n = 12
+    instr = circuits.heron_layered(n, 6, circuits.coupled_pairs(tq, n), seed=1)
+    ref = oracle.Program(n, instr, noisy=False).pure_state()
+    segs = {}
+    for reorder in (0, 1):
+        E = EmuProgram(PackedCircuit(n, instr, noisy=False), 2, tile_bits=9, reg_bits=4, reorder=reorder)
+        assert np.abs(E.run_deterministic() - ref).max() < 1e-12
+        segs[reorder] = E.query(2)
+    assert segs[1] < segs[0]
 
 
 def test_event_classification_is_exact_for_pauli_channels(heron_noise):
