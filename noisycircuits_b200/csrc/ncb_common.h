@@ -93,8 +93,9 @@ enum OpKind : uint8_t {
 // gate merged with the channel's base Kraus operator, `mat_bare` the gate alone (used for the last instruction of a
 // range that ends in a quantum-jump event, where the operator to apply is only known afterwards).
 struct Op {
-    uint32_t kind_nb;  // kind | nb << 8 | tmask << 16 | span << 24 | group << 31
-                       // (nb = bits the op acts on; tmask: DIAG bits that are thread bits; group headers: see executor)
+    uint32_t kind_nb;  // kind | nb << 8 | tmask << 16 | regmask << 20 | span << 24 | group << 31
+                       // (nb = bits the op acts on; DIAG: tmask = op bits that are thread bits, regmask = register bits
+                       //  the op involves; group headers: see executor)
     uint32_t rbs;      // 4 x 8 bit: DENSE*/PERM1: register-bit indices; DIAG: tile-local bit positions
     int32_t instr;     // index of the instruction this op came from
     int32_t mat;
@@ -105,7 +106,8 @@ struct Op {
 };
 NCB_HD int op_kind(const Op& o) { return (int)(o.kind_nb & 0xff); }
 NCB_HD int op_nb(const Op& o) { return (int)((o.kind_nb >> 8) & 0xff); }
-NCB_HD int op_tmask(const Op& o) { return (int)((o.kind_nb >> 16) & 0xff); }
+NCB_HD int op_tmask(const Op& o) { return (int)((o.kind_nb >> 16) & 0xf); }
+NCB_HD int op_regmask(const Op& o) { return (int)((o.kind_nb >> 20) & 0xf); }
 NCB_HD int op_rb(const Op& o, int b) { return (int)((o.rbs >> (8 * b)) & 0xff); }
 
 // Bit-field deposit compiled to runs: out = OR_i shift((v & mask[i]), shift[i])  (shift >= 0: left, < 0: right).
@@ -162,6 +164,24 @@ struct SegBlob {
     int32_t pass_off, op_off, pool_off, pad;    // byte offsets from the start of the blob
 };
 constexpr int MAX_BLOB_BYTES = 16 * 1024;
+
+// The hot, warp-uniform part of a segment's program, passed to the tile kernel BY VALUE as a __grid_constant__
+// parameter: it then lives in the constant bank and is read with LDC (constant cache) instead of broadcast
+// shared-memory loads, which were > 40 % of the LSU wavefronts of the kernel.  Holds the FAST op lists (whole passes,
+// no jump event inside) only; partial ranges use the shared-memory blob.
+constexpr int SC_MAX_OPS = 64, SC_MAX_PASSES = 12, SC_MAX_COEF = 256;
+struct PassHot {
+    uint16_t regoff_swz[1 << MAX_REG_BITS];
+    int32_t fop_begin, fop_end;        // into SegConst::ops
+    int32_t instr_lo, instr_hi;
+};
+struct SegConst {
+    int32_t valid;                     // 0: the segment did not fit; use the blob for everything
+    int32_t npass, nops, ncoef;
+    PassHot pass[SC_MAX_PASSES];
+    Op ops[SC_MAX_OPS];                // mat: rx1 / dense1 -> index into coef (4 / 8 doubles); other kinds -> as in the blob
+    double coef[SC_MAX_COEF];
+};
 
 // Static description of one noise channel (a Kraus list) for the event planner.
 struct Channel {
@@ -265,7 +285,7 @@ NCB_HD int deposit(int v, const uint8_t* pos, int nbits) {
 // register moves per operator, a quarter of all instructions issued).
 // ------------------------------------------------------------------------------------------------------------
 template <int R, int B>
-NCB_HD void dense1_bit(const cplx* in, cplx* out, const cplx* __restrict__ M) {
+NCB_HD void dense1_bit(const cplx* in, cplx* out, const cplx* M) {      // M: four values in registers
     const cplx m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
 #pragma unroll
     for (int g = 0; g < (1 << (R - 1)); ++g) {
@@ -276,7 +296,7 @@ NCB_HD void dense1_bit(const cplx* in, cplx* out, const cplx* __restrict__ M) {
     }
 }
 template <int R, int B>
-NCB_HD void rx1_bit(const cplx* in, cplx* out, const cplx* __restrict__ M) {
+NCB_HD void rx1_bit(const cplx* in, cplx* out, const cplx* M) {         // M: four values in registers
     const double ma = M[0].x, mb = M[1].y, mc = M[2].y, md = M[3].x;
 #pragma unroll
     for (int g = 0; g < (1 << (R - 1)); ++g) {
@@ -321,35 +341,51 @@ NCB_HD void dense4(const cplx* in, cplx* out, const cplx* __restrict__ M) {
     }
 }
 
+// Diagonal operator whose table index takes its register-dependent bits from the register bits in MASK only: the
+// 2^popc(MASK) distinct phases are looked up once and reused by the 2^R amplitudes (a table lookup per amplitude costs
+// four LSU wavefronts per warp; most diagonal operators involve 0-2 register bits).
+template <int R, int MASK>
+NCB_HD void diag_mask(const Op& op, int jb, const cplx* __restrict__ T, const cplx* in, cplx* out) {
+    constexpr int NA = 1 << R;
+    const int tm = op_tmask(op);
+    int idx_t = 0;                       // table-index bits that come from this thread's fixed tile bits
+#pragma unroll
+    for (int b = 0; b < 4; ++b) idx_t |= ((jb >> op_rb(op, b)) & (tm >> b) & 1) << b;
+    cplx ph[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) {
+        if ((m & ~MASK) == 0) {          // representative of its class: the register bits outside MASK are 0
+            const unsigned w = m < 8 ? op.midx_lo : op.midx_hi;
+            ph[m] = T[idx_t | (int)((w >> (4 * (m & 7))) & 15u)];
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NA; ++m) out[m] = cmul(in[m], ph[m & MASK]);
+}
+
 constexpr int FEAT_DENSE2 = 1, FEAT_DENSE4 = 2;   // which operator kinds a kernel instantiation carries
 
 // Applies one op: out = op(in).  One flat switch on (kind, register bits) so that the dispatch is a single jump.
+// M: table / matrix in memory (diag, dense2, dense4); m4: the 2x2 of the one-bit kinds, already in registers.
 template <int R, int FEAT>
-NCB_HD void apply_op(const Op& op, int jb, const cplx* __restrict__ M, const cplx* in, cplx* out) {
+NCB_HD void apply_op(const Op& op, int jb, const cplx* __restrict__ M, const cplx* m4, const cplx* in, cplx* out) {
     constexpr int NA = 1 << R;
     const int kind = op_kind(op);
     const int b0 = op_rb(op, 0), b1 = op_rb(op, 1);
     int sel;
-    if (kind == OPK_DIAG || kind == OPK_DENSE4) sel = kind << 4;
+    if (kind == OPK_DIAG) sel = (kind << 4) | op_regmask(op);
+    else if (kind == OPK_DENSE4) sel = kind << 4;
     else if (kind == OPK_DENSE2) sel = (kind << 4) | (b0 << 2) | b1;
     else sel = (kind << 4) | b0;
+    (void)NA;
     switch (sel) {
-    case OPK_DIAG << 4: {
-        const int tm = op_tmask(op);
-        int idx_t = 0;                       // table-index bits that come from this thread's fixed tile bits
-#pragma unroll
-        for (int b = 0; b < 4; ++b) idx_t |= ((jb >> op_rb(op, b)) & (tm >> b) & 1) << b;
-#pragma unroll
-        for (int m = 0; m < NA; ++m) {
-            const unsigned w = m < 8 ? op.midx_lo : op.midx_hi;
-            const int idx = idx_t | (int)((w >> (4 * (m & 7))) & 15u);
-            out[m] = cmul(in[m], M[idx]);
-        }
-        break;
-    }
+#define NCB_DIAG(MK) case (OPK_DIAG << 4) | MK: if (MK < (1 << R)) diag_mask<R, (MK < (1 << R) ? MK : 0)>(op, jb, M, in, out); else NCB_UNREACHABLE(); break;
+        NCB_DIAG(0) NCB_DIAG(1) NCB_DIAG(2) NCB_DIAG(3) NCB_DIAG(4) NCB_DIAG(5) NCB_DIAG(6) NCB_DIAG(7)
+        NCB_DIAG(8) NCB_DIAG(9) NCB_DIAG(10) NCB_DIAG(11) NCB_DIAG(12) NCB_DIAG(13) NCB_DIAG(14) NCB_DIAG(15)
+#undef NCB_DIAG
 #define NCB_ONE_BIT(B)                                                                   \
-    case (OPK_DENSE1 << 4) | B: if (B < R) dense1_bit<R, (B < R ? B : 0)>(in, out, M); else NCB_UNREACHABLE(); break; \
-    case (OPK_RX1 << 4) | B: if (B < R) rx1_bit<R, (B < R ? B : 0)>(in, out, M); else NCB_UNREACHABLE(); break;
+    case (OPK_DENSE1 << 4) | B: if (B < R) dense1_bit<R, (B < R ? B : 0)>(in, out, m4); else NCB_UNREACHABLE(); break; \
+    case (OPK_RX1 << 4) | B: if (B < R) rx1_bit<R, (B < R ? B : 0)>(in, out, m4); else NCB_UNREACHABLE(); break;
         NCB_ONE_BIT(0) NCB_ONE_BIT(1) NCB_ONE_BIT(2) NCB_ONE_BIT(3)
 #undef NCB_ONE_BIT
 #define NCB_TWO_BIT(X, Y)                                                                \
@@ -370,30 +406,51 @@ NCB_HD void apply_op(const Op& op, int jb, const cplx* __restrict__ M, const cpl
     }
 }
 
-// Executes the ops of `ps` whose instruction index is in [lo, hi) on this thread's 2^R amplitudes (jb: the thread's
+// Executes the ops of pass `ps` whose instruction index is in [lo, hi) on this thread's 2^R amplitudes (jb: the thread's
 // base tile index in this pass).  bare_last: the op of instruction hi-1 uses the bare gate matrix.
-template <int R, int FEAT>
+// USE_SC: when the whole pass runs (the common case), read the pass record, the ops and the 2x2 coefficients from the
+// constant bank (sc.pass[sc_pass], see SegConst) instead of memory.
+template <int R, int FEAT, bool USE_SC>
 NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* __restrict__ ops,
-                            const double* __restrict__ pool, const double* __restrict__ pool_global, int lo, int hi, bool bare_last) {
+                            const double* __restrict__ pool, const double* __restrict__ pool_global, int lo, int hi, bool bare_last,
+                            const SegConst& sc, int sc_pass) {
     constexpr int NA = 1 << R;
     (void)K;
     const int jbs = swz(jb);
+    const bool use_sc = USE_SC && sc.valid != 0;
+    const int p_lo = use_sc ? sc.pass[sc_pass].instr_lo : ps.instr_lo, p_hi = use_sc ? sc.pass[sc_pass].instr_hi : ps.instr_hi;
     // the whole pass lies inside [lo, hi) and none of its instructions is the bare one: take the short op list
-    const bool fast = lo <= ps.instr_lo && hi >= ps.instr_hi && !(bare_last && hi == ps.instr_hi);
+    const bool fast = lo <= p_lo && hi >= p_hi && !(bare_last && hi == p_hi);
+    const bool cst = fast && use_sc;
     cplx a[NA], b[NA];
     int addr[NA];
 #pragma unroll
     for (int m = 0; m < NA; ++m) {
-        addr[m] = jbs ^ ps.regoff_swz[m];
+        addr[m] = jbs ^ (cst ? sc.pass[sc_pass].regoff_swz[m] : ps.regoff_swz[m]);
         a[m] = sm[addr[m]];
     }
-    int o = fast ? ps.fop_begin : ps.op_begin;
-    const int o_end = fast ? ps.fop_end : ps.op_end;
+    int o = cst ? sc.pass[sc_pass].fop_begin : (fast ? ps.fop_begin : ps.op_begin);
+    const int o_end = cst ? sc.pass[sc_pass].fop_end : (fast ? ps.fop_end : ps.op_end);
     Op op;
     const cplx* M = nullptr;
+    cplx m4[4];
     // next op to execute at or after position o (range filter, group headers: see ncb_compile.cpp)
     auto fetch = [&]() -> bool {
         for (; o < o_end; ++o) {
+            if (cst) {
+                op = sc.ops[o];
+                const int kind = op_kind(op);
+                if (kind == OPK_RX1) {
+                    m4[0].x = sc.coef[op.mat]; m4[1].y = sc.coef[op.mat + 1]; m4[2].y = sc.coef[op.mat + 2]; m4[3].x = sc.coef[op.mat + 3];
+                } else if (kind == OPK_DENSE1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { m4[i].x = sc.coef[op.mat + 2 * i]; m4[i].y = sc.coef[op.mat + 2 * i + 1]; }
+                } else {
+                    M = reinterpret_cast<const cplx*>(op.mat >= 0 ? pool + op.mat : pool_global + (-op.mat - 1));
+                }
+                ++o;
+                return true;
+            }
             op = ops[o];
             int moff = op.mat;
             if (!fast) {
@@ -409,6 +466,11 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
                 }
             }
             M = reinterpret_cast<const cplx*>(moff >= 0 ? pool + moff : pool_global + (-moff - 1));
+            const int kind = op_kind(op);
+            if (kind == OPK_RX1 || kind == OPK_DENSE1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m4[i] = M[i];
+            }
             ++o;
             return true;
         }
@@ -416,13 +478,13 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
     };
     while (true) {
         if (!fetch()) break;
-        apply_op<R, FEAT>(op, jb, M, a, b);
+        apply_op<R, FEAT>(op, jb, M, m4, a, b);
         if (!fetch()) {
 #pragma unroll
             for (int m = 0; m < NA; ++m) a[m] = b[m];
             break;
         }
-        apply_op<R, FEAT>(op, jb, M, b, a);
+        apply_op<R, FEAT>(op, jb, M, m4, b, a);
     }
 #pragma unroll
     for (int m = 0; m < NA; ++m) sm[addr[m]] = a[m];

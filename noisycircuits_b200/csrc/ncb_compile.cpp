@@ -630,17 +630,19 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                 const int d = 1 << l.nb;
                 if (l.diag) {
                     kind = OPK_DIAG;
-                    uint32_t tmask = 0;
+                    uint32_t tmask = 0, regmask = 0;
                     uint64_t midx = 0;
                     for (int i = 0; i < l.nb; ++i) {
                         const int pos = local_of[l.bits[i]];
                         rb[i] = (uint32_t)pos;
                         if (reg_of[pos] < 0) tmask |= 1u << i;
-                        else
+                        else {
+                            regmask |= 1u << reg_of[pos];
                             for (int m = 0; m < (1 << R); ++m)
                                 if ((m >> reg_of[pos]) & 1) midx |= (uint64_t)(1u << i) << (4 * m);
+                        }
                     }
-                    kind |= (int)(tmask << 16);
+                    kind |= (int)(tmask << 16) | (int)(regmask << 20);
                     op.midx_lo = (uint32_t)midx; op.midx_hi = (uint32_t)(midx >> 32);
                     op.mat = pb.add_doubles(l.mat);
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
@@ -680,7 +682,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     op.mat = pb.add_doubles(remap(l.mat));
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(remap(l.bare));
                 }
-                op.kind_nb = (uint32_t)(kind & 0xff) | ((uint32_t)l.nb << 8) | ((uint32_t)kind & 0xff0000u);
+                op.kind_nb = (uint32_t)(kind & 0xff) | ((uint32_t)l.nb << 8) | ((uint32_t)kind & 0xffff00u & 0xff0000u);
                 op.rbs = rb[0] | (rb[1] << 8) | (rb[2] << 16) | (rb[3] << 24);
                 op.pad = l.instr;
                 return op;
@@ -763,7 +765,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
 
 // Builds the shared-memory blob of every segment (see SegBlob).
 static void build_blobs(Program& P) {
-    P.blobs.clear(); P.blob_off.clear();
+    P.blobs.clear(); P.blob_off.clear(); P.segconst.clear();
     for (const Segment& sg : P.segs) {
         std::vector<Pass> passes(P.passes.begin() + sg.pass_begin, P.passes.begin() + sg.pass_end);
         std::vector<Op> ops;
@@ -800,6 +802,39 @@ static void build_blobs(Program& P) {
             }
             ps.op_begin = b; ps.op_end = b + gen_count;
             ps.fop_begin = ps.op_end; ps.fop_end = (int)ops.size();
+        }
+        // constant-bank copy of the fast lists (see SegConst)
+        {
+            SegConst sc;
+            std::memset(&sc, 0, sizeof(sc));
+            bool fits = (int)passes.size() <= SC_MAX_PASSES;
+            int nops = 0, ncoef = 0;
+            for (size_t pi = 0; pi < passes.size() && fits; ++pi) {
+                const Pass& ps = passes[pi];
+                PassHot& ph = sc.pass[pi];
+                for (int m = 0; m < (1 << MAX_REG_BITS); ++m) ph.regoff_swz[m] = ps.regoff_swz[m];
+                ph.instr_lo = ps.instr_lo; ph.instr_hi = ps.instr_hi;
+                ph.fop_begin = nops;
+                for (int o = ps.fop_begin; o < ps.fop_end && fits; ++o) {
+                    if (nops >= SC_MAX_OPS) { fits = false; break; }
+                    Op op = ops[o];
+                    const int kind = op_kind(op);
+                    if (kind == OPK_RX1 || kind == OPK_DENSE1) {
+                        const int need = kind == OPK_RX1 ? 4 : 8;
+                        if (ncoef + need > SC_MAX_COEF) { fits = false; break; }
+                        const double* m = pool.data() + op.mat;       // 4 complex, row-major
+                        if (kind == OPK_RX1) { sc.coef[ncoef] = m[0]; sc.coef[ncoef + 1] = m[3]; sc.coef[ncoef + 2] = m[5]; sc.coef[ncoef + 3] = m[6]; }
+                        else for (int i = 0; i < 8; ++i) sc.coef[ncoef + i] = m[i];
+                        op.mat = ncoef; op.mat_bare = ncoef;
+                        ncoef += need;
+                    }
+                    sc.ops[nops++] = op;
+                }
+                ph.fop_end = nops;
+            }
+            sc.valid = fits ? 1 : 0;
+            sc.npass = (int)passes.size(); sc.nops = nops; sc.ncoef = ncoef;
+            P.segconst.push_back(sc);
         }
         SegBlob h;
         std::memset(&h, 0, sizeof(h));

@@ -75,6 +75,7 @@ struct Program {
                                         // index" always means the execution position; uniforms are keyed by orig[pos].
     std::vector<unsigned char> blobs;   // SegBlob of every segment, back to back (16-byte aligned)
     std::vector<int64_t> blob_off;      // byte offset of segment s's blob
+    std::vector<SegConst> segconst;     // constant-bank part of every segment (kernel parameter of its launches)
     CompileOptions opt;
 };
 

@@ -208,7 +208,7 @@ struct Engine {
         if (grid < 1) return;
         const unsigned char* blob = d_blobs.p + P.blob_off[seg];
         const int blob_bytes = reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[seg])->bytes;
-#define NCB_TILE_ARGS d, blob, blob_bytes, tile_blob_cap, tile_nbuf, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p
+#define NCB_TILE_ARGS d, P.segconst[seg], blob, blob_bytes, tile_blob_cap, tile_nbuf, works, nworks, d_states.p, tile_shift, d_red.p, d_norm.p, d_dec.p
         switch (tile_variant) {
         case 0: tile_kernel<3, 0, 512, 1><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
         case 3: tile_kernel<3, 0, 512, 2><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;

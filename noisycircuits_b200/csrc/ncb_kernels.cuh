@@ -75,18 +75,19 @@ __device__ __forceinline__ void block_reduce(const double* vals, double* s_buf, 
 // tile kernel's staged segment blob) or in global memory (the resident kernel).
 // jb_tab (optional, shared memory): jb_tab[p * blockDim.x + tid] = this thread's base tile index in pass p for
 // p < jb_cap (computed once per CTA: it does not depend on the tile).
-template <int R, int FEAT>
+template <int R, int FEAT, bool USE_SC>
 __device__ __forceinline__ void run_range(cplx* sm, int K, const Pass* passes, const Op* ops, const double* pool,
                                           const double* pool_global, int* pcur, int pend, int lo, int hi, bool bare_last,
-                                          const unsigned short* jb_tab = nullptr, int jb_cap = 0) {
+                                          const SegConst& sc, const unsigned short* jb_tab = nullptr, int jb_cap = 0) {
     int p = *pcur;
     for (; p < pend; ++p) {
         const Pass* ps = passes + p;
-        const int plo = ps->instr_lo, phi = ps->instr_hi;
+        const bool cst = USE_SC && sc.valid != 0;
+        const int plo = cst ? sc.pass[p].instr_lo : ps->instr_lo, phi = cst ? sc.pass[p].instr_hi : ps->instr_hi;
         if (plo >= hi) break;
-        if (phi > lo && ps->op_end > ps->op_begin) {
+        if (phi > lo && phi > plo) {
             const int jb = p < jb_cap ? (int)jb_tab[p * blockDim.x + threadIdx.x] : (int)apply_runs(ps->truns, threadIdx.x);
-            run_pass_thread<R, FEAT>(sm, K, jb, *ps, ops, pool, pool_global, lo, hi, bare_last);
+            run_pass_thread<R, FEAT, USE_SC>(sm, K, jb, *ps, ops, pool, pool_global, lo, hi, bare_last, sc, p);
             __syncthreads();
         }
         if (phi > hi) break;      // this pass also holds later instructions: revisit it
@@ -152,7 +153,7 @@ __device__ __noinline__ void event_reduce(const cplx* sm, int K, int p0, int p1,
 // segment's program blob and TWO tile buffers: while tile i is processed, tile i+1 streams in through cp.async.
 template <int R, int FEAT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_bytes, int blob_cap, int nbuf,
+tile_kernel(DevProgram P, const __grid_constant__ SegConst sc, const unsigned char* __restrict__ blob_g, int blob_bytes, int blob_cap, int nbuf,
             const Work* __restrict__ works, int nworks,
             cplx* __restrict__ states, int tile_shift, double* __restrict__ red_part, double* __restrict__ norm_part,
             const Decision* __restrict__ decisions) {
@@ -229,7 +230,7 @@ tile_kernel(DevProgram P, const unsigned char* __restrict__ blob_g, int blob_byt
         if (w.flags & (WF_PRO_STATIC | WF_PRO_DYNAMIC)) event_prologue(sm, P, sg, w, decisions);
         // ---- the segment's passes ----
         int pcur = 0;
-        run_range<R, FEAT>(sm, K, passes, ops, pool, P.pool, &pcur, npass, w.instr_lo, w.instr_hi, (w.flags & WF_BARE_LAST) != 0, jb_tab, jb_cap);
+        run_range<R, FEAT, true>(sm, K, passes, ops, pool, P.pool, &pcur, npass, w.instr_lo, w.instr_hi, (w.flags & WF_BARE_LAST) != 0, sc, jb_tab, jb_cap);
         // ---- reductions ----
         if (w.flags & WF_REDUCE) {
             const Instr in = P.instrs[w.red_instr];
@@ -424,7 +425,7 @@ resident_kernel(DevProgram P, ResidentArgs A) {
                 if (m) { e = (wd << 5) + __ffs(m) - 1; break; }
             }
             const bool ev = e < P.G;
-            run_range<R, FEAT>(sm, K, P.passes, P.ops, P.pool, P.pool, &pcur, P.npass, cur, ev ? e + 1 : P.G, ev);
+            run_range<R, FEAT, false>(sm, K, P.passes, P.ops, P.pool, P.pool, &pcur, P.npass, cur, ev ? e + 1 : P.G, ev, *reinterpret_cast<const SegConst*>(P.pool));
             if (!ev) break;
             const Instr in = P.instrs[e];
             const Channel ch = P.chans[in.channel];

@@ -71,9 +71,9 @@ void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, st
         for (int p = 0; p < blob.npass; ++p) {
             const Pass& ps = passes[p];
             if (ps.instr_lo >= w.instr_hi) break;
-            if (ps.instr_hi > w.instr_lo && ps.op_end > ps.op_begin)
+            if (ps.instr_hi > w.instr_lo && ps.instr_hi > ps.instr_lo)
                 for (int tid = 0; tid < nthreads; ++tid)
-                    run_pass_thread<R, 3>(sm.data(), K, (int)apply_runs(ps.truns, (unsigned)tid), ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last);
+                    run_pass_thread<R, 3, true>(sm.data(), K, (int)apply_runs(ps.truns, (unsigned)tid), ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last, P.segconst[w.seg], p);
             if (ps.instr_hi > w.instr_hi) break;
         }
         // reductions
