@@ -730,9 +730,29 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                 }
                 return false;
             };
+            auto disjoint = [](const LogicalOp& x, const LogicalOp& y) {
+                for (int i = 0; i < x.nb; ++i)
+                    for (int j = 0; j < y.nb; ++j)
+                        if (x.bits[i] == y.bits[j]) return false;
+                return true;
+            };
             for (const LogicalOp* lp : b.lops) {
-                if (!groups.empty() && mode != MODE_DENSITY && try_merge(groups.back(), *lp)) groups.back().members.push_back(lp);
-                else groups.push_back(Group{{lp}, *lp});
+                bool placed = false;
+                if (mode != MODE_DENSITY && opt.fuse) {
+                    if (lp->diag) {
+                        // a diagonal operator commutes with diagonal operators and with anything on other bits: walk
+                        // back to the nearest diagonal group it can join
+                        for (int gi = (int)groups.size() - 1; gi >= 0 && !placed; --gi) {
+                            Group& g = groups[gi];
+                            if (g.merged.diag && try_merge(g, *lp)) { g.members.push_back(lp); placed = true; break; }
+                            if (!(g.merged.diag || disjoint(g.merged, *lp))) break;
+                        }
+                    } else if (!groups.empty() && try_merge(groups.back(), *lp)) {
+                        groups.back().members.push_back(lp);
+                        placed = true;
+                    }
+                }
+                if (!placed) groups.push_back(Group{{lp}, *lp});
             }
             std::vector<Op> fast_ops;
             for (const Group& g : groups) {
@@ -871,6 +891,12 @@ std::string describe_program(const Program& P) {
         o << " kinds{";
         for (int k = 0; k < 8; ++k) if (cnt[k]) o << names[k] << ":" << cnt[k] << " ";
         o << "groups:" << groups << "}";
+        int fast = 0, fdiag = 0;
+        for (const Pass& ps : P.passes)
+            for (int i = ps.fop_begin; i < ps.fop_end; ++i) { ++fast; fdiag += op_kind(P.ops[i]) == OPK_DIAG; }
+        int valid = 0;
+        for (const SegConst& sc : P.segconst) valid += sc.valid;
+        o << " fast_ops=" << fast << " (diag " << fdiag << ") const_segments=" << valid << "/" << P.segconst.size();
     }
     o << "\n";
     for (size_t s = 0; s < P.segs.size(); ++s) {
