@@ -93,22 +93,27 @@ enum OpKind : uint8_t {
 // gate merged with the channel's base Kraus operator, `mat_bare` the gate alone (used for the last instruction of a
 // range that ends in a quantum-jump event, where the operator to apply is only known afterwards).
 struct Op {
-    uint32_t kind_nb;  // kind | nb << 8 | tmask << 16 | regmask << 20 | span << 24 | group << 31
+    uint32_t kind_nb;  // packed kind / nb / tmask / regmask / span / group flag (see the accessors below)
                        // (nb = bits the op acts on; DIAG: tmask = op bits that are thread bits, regmask = register bits
                        //  the op involves; group headers: see executor)
-    uint32_t rbs;      // 4 x 8 bit: DENSE*/PERM1: register-bit indices; DIAG: tile-local bit positions
+    uint32_t rbs;      // 8 x 4 bit: dense kinds: register-bit indices; DIAG: tile-local bit positions
     int32_t instr;     // index of the instruction this op came from
     int32_t mat;
     int32_t mat_bare;
-    uint32_t midx_lo;  // DIAG: 4-bit table-index contribution of register slot m (slots 0..7), from the register bits
-    uint32_t midx_hi;  //       slots 8..15
+    uint32_t midx_lo;  // DIAG: table-index contribution of register slot m from the register bits, (64 >> R)-bit fields:
+    uint32_t midx_hi;  //       low / high word of the 64-bit field array
     int32_t pad;       // group headers: instruction index of the last member
 };
-NCB_HD int op_kind(const Op& o) { return (int)(o.kind_nb & 0xff); }
-NCB_HD int op_nb(const Op& o) { return (int)((o.kind_nb >> 8) & 0xff); }
-NCB_HD int op_tmask(const Op& o) { return (int)((o.kind_nb >> 16) & 0xf); }
-NCB_HD int op_regmask(const Op& o) { return (int)((o.kind_nb >> 20) & 0xf); }
-NCB_HD int op_rb(const Op& o, int b) { return (int)((o.rbs >> (8 * b)) & 0xff); }
+// kind_nb layout: kind [0,4) | nb [4,8) | tmask [8,16) | regmask [16,20) | span [24,31) | group header [31]
+// rbs: eight 4-bit fields (register-bit indices / tile-local positions are < 16)
+NCB_HD int op_kind(const Op& o) { return (int)(o.kind_nb & 0xf); }
+NCB_HD int op_nb(const Op& o) { return (int)((o.kind_nb >> 4) & 0xf); }
+NCB_HD int op_tmask(const Op& o) { return (int)((o.kind_nb >> 8) & 0xff); }
+NCB_HD int op_regmask(const Op& o) { return (int)((o.kind_nb >> 16) & 0xf); }
+NCB_HD int op_rb(const Op& o, int b) { return (int)((o.rbs >> (4 * b)) & 0xf); }
+// diagonal operators act on up to this many bits (table of 2^bits phases; the per-slot index fields of midx are
+// 64 >> R bits wide)
+NCB_HD constexpr int max_diag_bits(int R) { return R <= 3 ? 6 : 4; }
 
 // Bit-field deposit compiled to runs: out = OR_i shift((v & mask[i]), shift[i])  (shift >= 0: left, < 0: right).
 constexpr int MAX_RUNS = 14;
@@ -347,16 +352,17 @@ NCB_HD void dense4(const cplx* in, cplx* out, const cplx* __restrict__ M) {
 template <int R, int MASK>
 NCB_HD void diag_mask(const Op& op, int jb, const cplx* __restrict__ T, const cplx* in, cplx* out) {
     constexpr int NA = 1 << R;
+    constexpr int FW = 64 >> R, PER_WORD = 32 / FW;      // index field width, fields per 32-bit word
     const int tm = op_tmask(op);
     int idx_t = 0;                       // table-index bits that come from this thread's fixed tile bits
 #pragma unroll
-    for (int b = 0; b < 4; ++b) idx_t |= ((jb >> op_rb(op, b)) & (tm >> b) & 1) << b;
+    for (int b = 0; b < max_diag_bits(R); ++b) idx_t |= ((jb >> op_rb(op, b)) & (tm >> b) & 1) << b;
     cplx ph[NA];
 #pragma unroll
     for (int m = 0; m < NA; ++m) {
         if ((m & ~MASK) == 0) {          // representative of its class: the register bits outside MASK are 0
-            const unsigned w = m < 8 ? op.midx_lo : op.midx_hi;
-            ph[m] = T[idx_t | (int)((w >> (4 * (m & 7))) & 15u)];
+            const unsigned w = m < PER_WORD ? op.midx_lo : op.midx_hi;
+            ph[m] = T[idx_t | (int)((w >> (FW * (m % PER_WORD))) & ((1u << FW) - 1))];
         }
     }
 #pragma unroll

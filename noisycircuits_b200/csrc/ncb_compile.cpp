@@ -238,7 +238,7 @@ LogicalOp make_lop(int instr, const std::vector<int>& bits, const cmat& merged, 
     LogicalOp l;
     l.instr = instr;
     l.nb = (int)bits.size();
-    for (int i = 0; i < 4; ++i) l.bits[i] = i < l.nb ? bits[i] : -1;
+    for (int i = 0; i < 8; ++i) l.bits[i] = i < l.nb ? bits[i] : -1;
     const int d = 1 << l.nb;
     l.diag = is_diagonal(merged, d) && is_diagonal(bare, d);
     if (l.diag) { l.mat = flatten(diag_of(merged, d)); l.bare = flatten(diag_of(bare, d)); }
@@ -626,12 +626,13 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                 std::memset(&op, 0, sizeof(op));
                 op.instr = l.instr;
                 int kind = OPK_DIAG;
-                uint32_t rb[4] = {0, 0, 0, 0};
+                uint32_t rb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 const int d = 1 << l.nb;
                 if (l.diag) {
                     kind = OPK_DIAG;
                     uint32_t tmask = 0, regmask = 0;
                     uint64_t midx = 0;
+                    const int fw = 64 >> R;
                     for (int i = 0; i < l.nb; ++i) {
                         const int pos = local_of[l.bits[i]];
                         rb[i] = (uint32_t)pos;
@@ -639,10 +640,10 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                         else {
                             regmask |= 1u << reg_of[pos];
                             for (int m = 0; m < (1 << R); ++m)
-                                if ((m >> reg_of[pos]) & 1) midx |= (uint64_t)(1u << i) << (4 * m);
+                                if ((m >> reg_of[pos]) & 1) midx |= (uint64_t)(1u << i) << (fw * m);
                         }
                     }
-                    kind |= (int)(tmask << 16) | (int)(regmask << 20);
+                    kind |= (int)(tmask << 8) | (int)(regmask << 16);
                     op.midx_lo = (uint32_t)midx; op.midx_hi = (uint32_t)(midx >> 32);
                     op.mat = pb.add_doubles(l.mat);
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
@@ -682,8 +683,9 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     op.mat = pb.add_doubles(remap(l.mat));
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(remap(l.bare));
                 }
-                op.kind_nb = (uint32_t)(kind & 0xff) | ((uint32_t)l.nb << 8) | ((uint32_t)kind & 0xffff00u & 0xff0000u);
-                op.rbs = rb[0] | (rb[1] << 8) | (rb[2] << 16) | (rb[3] << 24);
+                op.kind_nb = (uint32_t)(kind & 0xf) | ((uint32_t)l.nb << 4) | ((uint32_t)kind & 0x0fff00u);
+                op.rbs = 0;
+                for (int i = 0; i < 8; ++i) op.rbs |= (rb[i] & 0xfu) << (4 * i);
                 op.pad = l.instr;
                 return op;
             };
@@ -700,7 +702,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     std::vector<int> bits(a.bits, a.bits + a.nb);
                     for (int i = 0; i < l.nb; ++i)
                         if (std::find(bits.begin(), bits.end(), l.bits[i]) == bits.end()) bits.push_back(l.bits[i]);
-                    if (bits.size() > 4) return false;
+                    if ((int)bits.size() > max_diag_bits(R)) return false;
                     const int nb = (int)bits.size();
                     std::vector<double> tab(2 << nb);
                     for (int idx = 0; idx < (1 << nb); ++idx) {
@@ -711,7 +713,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                         tab[2 * idx] = v.real(); tab[2 * idx + 1] = v.imag();
                     }
                     a.nb = nb;
-                    for (int i = 0; i < 4; ++i) a.bits[i] = i < nb ? bits[i] : -1;
+                    for (int i = 0; i < 8; ++i) a.bits[i] = i < nb ? bits[i] : -1;
                     a.mat = tab; a.bare = tab;
                     return true;
                 }

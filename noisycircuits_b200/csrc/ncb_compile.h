@@ -44,7 +44,7 @@ struct CompileOptions {
 struct LogicalOp {
     int instr;
     int nb;                       // number of state bits
-    int bits[4];                  // matrix bit i <-> state bit bits[i]
+    int bits[8];                  // matrix bit i <-> state bit bits[i] (dense: <= 4 bits; merged diagonals: <= 6)
     bool diag;
     std::vector<double> mat;      // merged (2^nb x 2^nb complex, interleaved) or, if diag, 2^nb phases
     std::vector<double> bare;
