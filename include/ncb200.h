@@ -73,9 +73,9 @@ typedef struct {
 enum { NCB_MODE_MCWF = 0, NCB_MODE_DENSITY = 1, NCB_MODE_PURE = 2 };
 
 typedef struct {
-    int32_t tile_bits;   /* amplitudes per shared-memory tile = 2^tile_bits (0: default 12) */
+    int32_t tile_bits;   /* amplitudes per shared-memory tile = 2^tile_bits (0: default 11) */
     int32_t reg_bits;    /* amplitudes per thread = 2^reg_bits (0: default 3; 4 is needed for 3-4 qubit unitaries and density-matrix runs) */
-    int32_t low_bits;    /* lowest state bits kept in every tile (-1: default 3) */
+    int32_t low_bits;    /* lowest state bits kept in every tile (-1: default 2) */
     int32_t fuse;        /* 1 (default): fuse runs of instructions into one sweep; 0: one sweep per instruction */
     int32_t device;      /* CUDA device ordinal (-1: current device) */
     int32_t strict_order;/* 0 (default): commuting instructions (disjoint qubits) may be executed in a tile-friendly

@@ -317,7 +317,8 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
     P.R = std::min(std::max(opt.reg_bits, 1), MAX_REG_BITS);
     const int kmin = P.R + 5;
     P.K = std::min(std::max({opt.tile_bits, kmin}), MAX_TILE_BITS);
-    if (P.nbits <= P.K) P.K = std::max(P.nbits, kmin);          // whole state in one tile (extra bits are virtual)
+    if (P.nbits <= std::max(P.K, std::min(opt.resident_bits, MAX_TILE_BITS - 1)))
+        P.K = std::max(P.nbits, kmin);                           // whole state in one tile (extra bits are virtual)
     const int K = P.K, R = P.R;
     const int L = std::min(std::max(opt.low_bits, 0), std::min(K - 4, P.nbits));
     PoolBuilder pb{P.pool};

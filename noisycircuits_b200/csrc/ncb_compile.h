@@ -32,9 +32,10 @@ struct CircuitView {               // mirrors ncb_circuit in include/ncb200.h
 };
 
 struct CompileOptions {
-    int tile_bits = 12;     // K: amplitudes per shared-memory tile = 2^K
+    int tile_bits = 11;     // K: amplitudes per shared-memory tile = 2^K (11: 32 KB tiles, 4 CTAs per SM)
+    int resident_bits = 12; // states of up to 2^resident_bits amplitudes stay in one CTA's shared memory (resident kernel)
     int reg_bits = 3;       // R: amplitudes per thread = 2^R
-    int low_bits = 3;       // the L lowest state bits are part of every tile (coalescing: runs of 2^L * 16 B)
+    int low_bits = 2;       // the L lowest state bits are part of every tile (coalescing: runs of 2^L * 16 B = 64 B)
     int fuse = 1;           // 0: one instruction per segment (debug / ablation)
     int reorder = 1;        // 1: execute commuting instructions in a tile-friendly (dependency-respecting) order;
                             // 0: strictly in program order

@@ -564,14 +564,14 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     for (int g = 0; g < circuit->num_instructions; ++g)
         if (circuit->opcode[g] == NCB_UNITARY && circuit->unitary_nq && circuit->unitary_nq[g] >= 3) opt.reg_bits = 4;
     if (options) {
-        if (options->tile_bits > 0) opt.tile_bits = options->tile_bits;
+        if (options->tile_bits > 0) { opt.tile_bits = options->tile_bits; opt.resident_bits = options->tile_bits; }
         if (options->reg_bits > 0) opt.reg_bits = options->reg_bits;
         if (options->low_bits >= 0) opt.low_bits = options->low_bits;
         opt.fuse = options->fuse;
         opt.reorder = options->strict_order ? 0 : 1;
         device = options->device;
     }
-    if (const char* e = getenv("NCB_TILE_BITS")) opt.tile_bits = atoi(e);
+    if (const char* e = getenv("NCB_TILE_BITS")) { opt.tile_bits = atoi(e); opt.resident_bits = opt.tile_bits; }
     if (const char* e = getenv("NCB_REG_BITS")) opt.reg_bits = atoi(e);
     if (const char* e = getenv("NCB_LOW_BITS")) opt.low_bits = atoi(e);
     if (const char* e = getenv("NCB_FUSE")) opt.fuse = atoi(e);

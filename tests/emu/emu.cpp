@@ -157,7 +157,7 @@ void* emu_create(const ncb_circuit* c, int mode, int tile_bits, int reg_bits, in
     try {
         Emu* e = new Emu();
         CompileOptions opt;
-        opt.tile_bits = tile_bits; opt.reg_bits = reg_bits; opt.low_bits = low_bits; opt.fuse = fuse; opt.reorder = reorder;
+        opt.tile_bits = tile_bits; opt.resident_bits = tile_bits; opt.reg_bits = reg_bits; opt.low_bits = low_bits; opt.fuse = fuse; opt.reorder = reorder;
         compile_program(view_of(c), mode, opt, e->P);
         return e;
     } catch (const std::exception& ex) { g_err = ex.what(); return nullptr; }
