@@ -278,10 +278,13 @@ struct Engine {
     }
 
     int auto_batch(long long count) const {
+        // enough trajectories per launch that (a) the persistent grid runs many tiles per CTA and (b) the small extra
+        // launches of the jump-event rounds (a few slots each) are amortised; capped by memory (8 GB of state)
         const long long tiles = 1ll << std::max(P.nbits - P.K, 0);
-        long long b = (148ll * 256 + tiles - 1) / tiles;
+        long long b = (148ll * 1024 + tiles - 1) / tiles;
         b = ((b + 36) / 37) * 37;
-        const long long mem_cap = std::max<long long>(1, (6ll << 30) / ((long long)sizeof(cplx) << P.nbits));
+        if (const char* e = getenv("NCB_BATCH")) b = std::max(1, atoi(e));
+        const long long mem_cap = std::max<long long>(1, (8ll << 30) / ((long long)sizeof(cplx) << P.nbits));
         b = std::min(b, mem_cap);
         return (int)std::max<long long>(1, std::min(b, count));
     }
