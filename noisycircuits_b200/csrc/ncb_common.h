@@ -284,10 +284,9 @@ NCB_HD int deposit(int v, const uint8_t* pos, int nbits) {
 // ------------------------------------------------------------------------------------------------------------
 // Register-blocked pass executor (one thread's share)
 //
-// Every operator kernel is OUT OF PLACE: it reads the thread's 2^R amplitudes from `in` and writes all of them to
-// `out`.  The pass loop ping-pongs between two register sets, so no operator needs temporaries and the compiler
-// never has to shuffle the amplitude registers back into place between operators (in-place kernels cost ~32
-// register moves per operator, a quarter of all instructions issued).
+// Every operator kernel reads the thread's 2^R amplitudes from `in` and writes all of them to `out`.  The kernels
+// that carry the 4x4 / 16x16 kinds ping-pong between two register sets (those operators need all inputs for every
+// output); the one-bit and diagonal kernels are alias-safe (in == out) and the lean kernels run them in place.
 // ------------------------------------------------------------------------------------------------------------
 template <int R, int B>
 NCB_HD void dense1_bit(const cplx* in, cplx* out, const cplx* M) {      // M: four values in registers
@@ -296,8 +295,9 @@ NCB_HD void dense1_bit(const cplx* in, cplx* out, const cplx* M) {      // M: fo
     for (int g = 0; g < (1 << (R - 1)); ++g) {
         const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
         const int i1 = i0 | (1 << B);
-        out[i0] = cfma(m01, in[i1], cmul(m00, in[i0]));
-        out[i1] = cfma(m11, in[i1], cmul(m10, in[i0]));
+        const cplx x = in[i0], y = in[i1];
+        out[i0] = cfma(m01, y, cmul(m00, x));
+        out[i1] = cfma(m11, y, cmul(m10, x));
     }
 }
 template <int R, int B>
@@ -428,7 +428,7 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
     // the whole pass lies inside [lo, hi) and none of its instructions is the bare one: take the short op list
     const bool fast = lo <= p_lo && hi >= p_hi && !(bare_last && hi == p_hi);
     const bool cst = fast && use_sc;
-    cplx a[NA], b[NA];
+    cplx a[NA];
     int addr[NA];
 #pragma unroll
     for (int m = 0; m < NA; ++m) {
@@ -482,15 +482,21 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
         }
         return false;
     };
-    while (true) {
-        if (!fetch()) break;
-        apply_op<R, FEAT>(op, jb, M, m4, a, b);
-        if (!fetch()) {
+    if constexpr (FEAT == 0) {
+        // one-bit and diagonal kernels only: they are alias-safe, so the ops run in place (half the amplitude registers)
+        while (fetch()) apply_op<R, FEAT>(op, jb, M, m4, a, a);
+    } else {
+        cplx b[NA];
+        while (true) {
+            if (!fetch()) break;
+            apply_op<R, FEAT>(op, jb, M, m4, a, b);
+            if (!fetch()) {
 #pragma unroll
-            for (int m = 0; m < NA; ++m) a[m] = b[m];
-            break;
+                for (int m = 0; m < NA; ++m) a[m] = b[m];
+                break;
+            }
+            apply_op<R, FEAT>(op, jb, M, m4, b, a);
         }
-        apply_op<R, FEAT>(op, jb, M, m4, b, a);
     }
 #pragma unroll
     for (int m = 0; m < NA; ++m) sm[addr[m]] = a[m];

@@ -17,6 +17,21 @@
 
 namespace ncb {
 
+// The kernel variants are instantiated one per translation unit (ncb_tile_inst.cu, see the Makefile).
+#define NCB_EXTERN_TILE(R, F, T, B)                                                                                     \
+    extern template __global__ void tile_kernel<R, F, T, B>(DevProgram, const __grid_constant__ SegConst, const unsigned char*, int, \
+                                                            int, int, const Work*, int, cplx*, int, double*, double*,     \
+                                                            const Decision*);
+NCB_EXTERN_TILE(3, 0, 512, 1)
+NCB_EXTERN_TILE(3, 0, 512, 2)
+NCB_EXTERN_TILE(3, 0, 256, 3)
+NCB_EXTERN_TILE(3, FEAT_DENSE2, 256, 1)
+NCB_EXTERN_TILE(4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1)
+#undef NCB_EXTERN_TILE
+extern template __global__ void resident_kernel<3, 0, 512, 1>(DevProgram, ResidentArgs);
+extern template __global__ void resident_kernel<3, FEAT_DENSE2, 256, 1>(DevProgram, ResidentArgs);
+extern template __global__ void resident_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>(DevProgram, ResidentArgs);
+
 static thread_local std::string g_error;
 
 struct CudaError : std::runtime_error {

@@ -98,7 +98,7 @@ __device__ __forceinline__ void run_range(cplx* sm, int K, const Pass* passes, c
 // ---------------------------------------------------------------------------------------------------------------
 // rare (jump event) paths of the tile kernel: kept out of line so that they do not set its register budget
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void event_prologue(cplx* sm, const DevProgram& P, const Segment* sg, const Work& w,
+static __device__ __noinline__ void event_prologue(cplx* sm, const DevProgram& P, const Segment* sg, const Work& w,
                                             const Decision* __restrict__ decisions) {
     const int K = P.K;
     const Instr in = P.instrs[w.ev_instr];
@@ -113,7 +113,7 @@ __device__ __noinline__ void event_prologue(cplx* sm, const DevProgram& P, const
 }
 
 // reduced density matrix of tile positions (p0, p1) -> dst[32] (lower triangle), block-wide
-__device__ __noinline__ void event_reduce(const cplx* sm, int K, int p0, int p1, double* s_buf, double* s_out, double* dst) {
+static __device__ __noinline__ void event_reduce(const cplx* sm, int K, int p0, int p1, double* s_buf, double* s_out, double* dst) {
     const int tid = threadIdx.x, nthreads = blockDim.x;
     if (p1 < 0) {
         double acc[8];
@@ -264,6 +264,7 @@ tile_kernel(DevProgram P, const __grid_constant__ SegConst sc, const unsigned ch
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
+#ifndef NCB_TEMPLATES_ONLY   // the small non-template kernels live in ncb_engine.cu's module only
 // ---------------------------------------------------------------------------------------------------------------
 // decide kernel: one warp per state-dependent event
 // ---------------------------------------------------------------------------------------------------------------
@@ -362,6 +363,7 @@ __global__ void measurement_error_kernel(double* __restrict__ probs, long long h
         probs[j] = m10 * p0 + m11 * p1;
     }
 }
+#endif  // NCB_TEMPLATES_ONLY
 
 // ---------------------------------------------------------------------------------------------------------------
 // resident kernel: whole trajectory in one CTA's shared memory
