@@ -104,12 +104,15 @@ struct Op {
     uint32_t midx_hi;  //       low / high word of the 64-bit field array
     int32_t pad;       // group headers: instruction index of the last member
 };
-// kind_nb layout: kind [0,4) | nb [4,8) | tmask [8,16) | regmask [16,20) | span [24,31) | group header [31]
+// kind_nb layout: kind [0,4) | nb [4,8) | tmask [8,16) | regmask [16,20) | lean selector [20,24) | span [24,31) |
+// group header [31].  Lean selector (R = 3 programs without dense two-qubit operators): the case of the lean executor's
+// jump table: 0-7 diagonal with that register mask, 8+b RX1 on register bit b, 11+b DENSE1 on register bit b.
 // rbs: eight 4-bit fields (register-bit indices / tile-local positions are < 16)
 NCB_HD int op_kind(const Op& o) { return (int)(o.kind_nb & 0xf); }
 NCB_HD int op_nb(const Op& o) { return (int)((o.kind_nb >> 4) & 0xf); }
 NCB_HD int op_tmask(const Op& o) { return (int)((o.kind_nb >> 8) & 0xff); }
 NCB_HD int op_regmask(const Op& o) { return (int)((o.kind_nb >> 16) & 0xf); }
+NCB_HD int op_lean_sel(const Op& o) { return (int)((o.kind_nb >> 20) & 0xf); }
 NCB_HD int op_rb(const Op& o, int b) { return (int)((o.rbs >> (4 * b)) & 0xf); }
 // diagonal operators act on up to this many bits (table of 2^bits phases; the per-slot index fields of midx are
 // 64 >> R bits wide)
@@ -482,6 +485,36 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
         }
         return false;
     };
+    if constexpr (R == 3 && FEAT == 0) {
+        if (cst) {
+            // hot loop of the lean kernels: the ops come from the constant bank and carry their jump-table case
+            for (; o < o_end; ++o) {
+                const Op& cop = sc.ops[o];
+                const int mat = cop.mat;
+                switch (op_lean_sel(cop)) {
+#define NCB_LEAN_DIAG(MK) case MK: diag_mask<R, MK>(cop, jb, reinterpret_cast<const cplx*>(mat >= 0 ? pool + mat : pool_global + (-mat - 1)), a, a); break;
+                    NCB_LEAN_DIAG(0) NCB_LEAN_DIAG(1) NCB_LEAN_DIAG(2) NCB_LEAN_DIAG(3)
+                    NCB_LEAN_DIAG(4) NCB_LEAN_DIAG(5) NCB_LEAN_DIAG(6) NCB_LEAN_DIAG(7)
+#undef NCB_LEAN_DIAG
+#define NCB_LEAN_ONE(B)                                                                                              \
+    case 8 + B:                                                                                                      \
+        m4[0].x = sc.coef[mat]; m4[1].y = sc.coef[mat + 1]; m4[2].y = sc.coef[mat + 2]; m4[3].x = sc.coef[mat + 3];  \
+        rx1_bit<R, B>(a, a, m4);                                                                                     \
+        break;                                                                                                       \
+    case 11 + B:                                                                                                     \
+        for (int i = 0; i < 4; ++i) { m4[i].x = sc.coef[mat + 2 * i]; m4[i].y = sc.coef[mat + 2 * i + 1]; }          \
+        dense1_bit<R, B>(a, a, m4);                                                                                  \
+        break;
+                    NCB_LEAN_ONE(0) NCB_LEAN_ONE(1) NCB_LEAN_ONE(2)
+#undef NCB_LEAN_ONE
+                default: NCB_UNREACHABLE(); break;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < NA; ++m) sm[addr[m]] = a[m];
+            return;
+        }
+    }
     if constexpr (FEAT == 0) {
         // one-bit and diagonal kernels only: they are alias-safe, so the ops run in place (half the amplitude registers)
         while (fetch()) apply_op<R, FEAT>(op, jb, M, m4, a, a);

@@ -685,6 +685,11 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(remap(l.bare));
                 }
                 op.kind_nb = (uint32_t)(kind & 0xf) | ((uint32_t)l.nb << 4) | ((uint32_t)kind & 0x0fff00u);
+                if (R == 3) {   // jump-table case of the lean executor (see ncb_common.h)
+                    const int k = kind & 0xf;
+                    const uint32_t lsel = k == OPK_DIAG ? ((uint32_t)kind >> 16) & 0x7u : k == OPK_RX1 ? 8u + rb[0] : k == OPK_DENSE1 ? 11u + rb[0] : 15u;
+                    op.kind_nb |= lsel << 20;
+                }
                 op.rbs = 0;
                 for (int i = 0; i < 8; ++i) op.rbs |= (rb[i] & 0xfu) << (4 * i);
                 op.pad = l.instr;

@@ -27,6 +27,7 @@ NCB_EXTERN_TILE(3, 0, 512, 2)
 NCB_EXTERN_TILE(3, 0, 256, 3)
 NCB_EXTERN_TILE(3, FEAT_DENSE2, 256, 1)
 NCB_EXTERN_TILE(4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1)
+NCB_EXTERN_TILE(4, 0, 256, 2)
 #undef NCB_EXTERN_TILE
 extern template __global__ void resident_kernel<3, 0, 512, 1>(DevProgram, ResidentArgs);
 extern template __global__ void resident_kernel<3, FEAT_DENSE2, 256, 1>(DevProgram, ResidentArgs);
@@ -149,7 +150,7 @@ struct Engine {
     //   <3, DENSE2, 256, 1>      R = 3 with dense 4x4 operators (Eagle ecr, cx, swap, non-diagonal Kraus bases); K <= 11
     //   <4, DENSE2|DENSE4, 256, 1>  R = 4: 3-4 bit dense operators (density-matrix superoperators, 3-4 qubit unitaries)
     int variant() const {
-        if (P.R == 4) return 2;
+        if (P.R == 4) return (!P.has_dense2 && !P.has_dense4) ? 5 : 2;
         if (const char* e = getenv("NCB_VARIANT")) {      // tuning aid: 1 runs the lean programs in the 128-register kernel
             const int v = atoi(e);
             if (v == 1 && P.R == 3 && !P.has_dense4) return 1;
@@ -185,6 +186,7 @@ struct Engine {
         // hides the first one's load latency better than a second buffer does); the register-hungry variants run
         // one CTA per SM and double-buffer instead
         if (tile_variant == 0) { tile_variant = 3; tile_nbuf = 1; }
+        if (tile_variant == 5) tile_nbuf = 1;
         if (const char* e = getenv("NCB_TILE_VARIANT")) {
             const int v = atoi(e);
             if ((tile_variant == 0 || tile_variant == 3) && (v == 0 || v == 3 || v == 4 || v == 1)) { tile_variant = v; tile_nbuf = v == 3 ? 1 : 2; }
@@ -197,6 +199,7 @@ struct Engine {
         configure(tile_kernel<3, 0, 256, 3>);
         configure(tile_kernel<3, FEAT_DENSE2, 256, 1>);
         configure(tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>);
+        configure(tile_kernel<4, 0, 256, 2>);
         const size_t smem = tile_launch_smem();
         int occ = 1;
         switch (tile_variant) {
@@ -204,6 +207,7 @@ struct Engine {
         case 3: occ = occupancy(tile_kernel<3, 0, 512, 2>, threads, smem); break;
         case 4: occ = occupancy(tile_kernel<3, 0, 256, 3>, threads, smem); break;
         case 1: occ = occupancy(tile_kernel<3, FEAT_DENSE2, 256, 1>, threads, smem); break;
+        case 5: occ = occupancy(tile_kernel<4, 0, 256, 2>, threads, smem); break;
         default: occ = occupancy(tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>, threads, smem); break;
         }
         if (occ < 1) throw std::runtime_error("tile kernel does not fit on an SM");
@@ -229,6 +233,7 @@ struct Engine {
         case 3: tile_kernel<3, 0, 512, 2><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
         case 4: tile_kernel<3, 0, 256, 3><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
         case 1: tile_kernel<3, FEAT_DENSE2, 256, 1><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
+        case 5: tile_kernel<4, 0, 256, 2><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
         default: tile_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1><<<grid, threads, smem, s>>>(NCB_TILE_ARGS); break;
         }
 #undef NCB_TILE_ARGS

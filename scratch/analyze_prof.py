@@ -27,8 +27,9 @@ for l in txt[start+1:]:
     if m: ins.append((cur, m.group(2).strip()))
 rows = list(csv.reader(open(f'{td}/src.csv')))
 hidx = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
-h = rows[hidx[0]]; end = hidx[1]-1 if len(hidx) > 1 else len(rows)
-body = [r for r in rows[hidx[0]+1:end] if len(r) > 6]
+LI = int(os.environ.get('LAUNCH', '0'))
+h = rows[hidx[LI]]; end = hidx[LI+1]-1 if len(hidx) > LI+1 else len(rows)
+body = [r for r in rows[hidx[LI]+1:end] if len(r) > 6]
 iS = h.index('# Samples'); iE = h.index('Instructions Executed'); iSrc = h.index('Source')
 print('sass', len(ins), 'ncu', len(body))
 n = min(len(ins), len(body))
