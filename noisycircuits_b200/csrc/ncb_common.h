@@ -94,14 +94,16 @@ enum OpKind : uint8_t {
 // range that ends in a quantum-jump event, where the operator to apply is only known afterwards).
 struct Op {
     uint32_t kind_nb;  // packed kind / nb / tmask / regmask / span / group flag (see the accessors below)
-                       // (nb = bits the op acts on; DIAG: tmask = op bits that are thread bits, regmask = register bits
+                       // (nb = bits the op acts on; DIAG: tmask = 2^(bits of gather A), regmask = register bits
                        //  the op involves; group headers: see executor)
-    uint32_t rbs;      // 8 x 4 bit: dense kinds: register-bit indices; DIAG: tile-local bit positions
+    uint32_t rbs;      // dense kinds: 8 x 4 bit register-bit indices; DIAG: masks of the tile-index bits of gathers A
+                       // (low half) and B (high half)
     int32_t instr;     // index of the instruction this op came from
     int32_t mat;
     int32_t mat_bare;
-    uint32_t midx_lo;  // DIAG: table-index contribution of register slot m from the register bits, (64 >> R)-bit fields:
-    uint32_t midx_hi;  //       low / high word of the 64-bit field array
+    uint32_t midx_lo;  // DIAG: multipliers of gathers A and B.  The op's thread bits (<= 6 tile-index bits) are split in two
+    uint32_t midx_hi;  //       groups of <= 3; ((jb & mask) * multiplier) >> 29 maps each group's 2^n settings one-to-one onto
+                       //       [0, 2^n) (found by search on the host), and the table row is hB * 2^nA + hA (2^nA = tmask field)
     int32_t pad;       // group headers: instruction index of the last member
 };
 // kind_nb layout: kind [0,4) | nb [4,8) | tmask [8,16) | regmask [16,20) | lean selector [20,24) | span [24,31) |
@@ -114,9 +116,8 @@ NCB_HD int op_tmask(const Op& o) { return (int)((o.kind_nb >> 8) & 0xff); }
 NCB_HD int op_regmask(const Op& o) { return (int)((o.kind_nb >> 16) & 0xf); }
 NCB_HD int op_lean_sel(const Op& o) { return (int)((o.kind_nb >> 20) & 0xf); }
 NCB_HD int op_rb(const Op& o, int b) { return (int)((o.rbs >> (4 * b)) & 0xf); }
-// diagonal operators act on up to this many bits (table of 2^bits phases; the per-slot index fields of midx are
-// 64 >> R bits wide)
-NCB_HD constexpr int max_diag_bits(int R) { return R <= 3 ? 6 : 4; }
+// diagonal operators act on up to this many bits (table of 2^bits phases)
+NCB_HD constexpr int max_diag_bits(int) { return 6; }
 
 // Bit-field deposit compiled to runs: out = OR_i shift((v & mask[i]), shift[i])  (shift >= 0: left, < 0: right).
 constexpr int MAX_RUNS = 14;
@@ -349,27 +350,30 @@ NCB_HD void dense4(const cplx* in, cplx* out, const cplx* __restrict__ M) {
     }
 }
 
-// Diagonal operator whose table index takes its register-dependent bits from the register bits in MASK only: the
-// 2^popc(MASK) distinct phases are looked up once and reused by the 2^R amplitudes (a table lookup per amplitude costs
-// four LSU wavefronts per warp; most diagonal operators involve 0-2 register bits).
+// Diagonal operator.  MASK = the register bits it involves: the 2^popc(MASK) phases a thread needs are adjacent in
+// the table (the host lays the table out as [thread-bit hash][register bits in MASK]), so one index computation and
+// popc(MASK) vector loads serve the 2^R amplitudes.
+NCB_HD constexpr int popc_c(int v) { return v ? (v & 1) + popc_c(v >> 1) : 0; }
+// bits of m selected by MASK, packed towards bit 0 (pext)
+NCB_HD constexpr int pext_c(int m, int MASK) {
+    int r = 0, k = 0;
+    for (int b = 0; b < 8; ++b)
+        if ((MASK >> b) & 1) { r |= ((m >> b) & 1) << k; ++k; }
+    return r;
+}
 template <int R, int MASK>
 NCB_HD void diag_mask(const Op& op, int jb, const cplx* __restrict__ T, const cplx* in, cplx* out) {
-    constexpr int NA = 1 << R;
-    constexpr int FW = 64 >> R, PER_WORD = 32 / FW;      // index field width, fields per 32-bit word
-    const int tm = op_tmask(op);
-    int idx_t = 0;                       // table-index bits that come from this thread's fixed tile bits
+    constexpr int NA = 1 << R, NR = popc_c(MASK);
+    // the thread's part of the table index: two multiply-gathers of <= 3 tile bits each (see the Op comment)
+    const unsigned x = (unsigned)jb;
+    const unsigned hA = ((x & (op.rbs & 0xffffu)) * op.midx_lo) >> 29;
+    const unsigned hB = ((x & (op.rbs >> 16)) * op.midx_hi) >> 29;
+    const cplx* Tb = T + ((hB * (unsigned)op_tmask(op) + hA) << NR);
+    cplx ph[1 << NR];
 #pragma unroll
-    for (int b = 0; b < max_diag_bits(R); ++b) idx_t |= ((jb >> op_rb(op, b)) & (tm >> b) & 1) << b;
-    cplx ph[NA];
+    for (int r = 0; r < (1 << NR); ++r) ph[r] = Tb[r];
 #pragma unroll
-    for (int m = 0; m < NA; ++m) {
-        if ((m & ~MASK) == 0) {          // representative of its class: the register bits outside MASK are 0
-            const unsigned w = m < PER_WORD ? op.midx_lo : op.midx_hi;
-            ph[m] = T[idx_t | (int)((w >> (FW * (m % PER_WORD))) & ((1u << FW) - 1))];
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < NA; ++m) out[m] = cmul(in[m], ph[m & MASK]);
+    for (int m = 0; m < NA; ++m) out[m] = cmul(in[m], ph[pext_c(m, MASK)]);
 }
 
 constexpr int FEAT_DENSE2 = 1, FEAT_DENSE4 = 2;   // which operator kinds a kernel instantiation carries

@@ -9,6 +9,43 @@
 #include <stdexcept>
 
 namespace ncb {
+
+// Multiply-gather of <= 3 tile-index bits (positions `pos`, each < 16): finds `magic` such that
+// h(x) = ((x & mask) * magic) >> 29 (32-bit arithmetic) maps the 2^n settings of those bits one-to-one onto [0, 2^n).
+// The search space is small (every position set below 16 bits resolves within a few hundred candidates).
+struct Gather { uint32_t mask, magic; };
+static Gather find_gather(const std::vector<int>& pos) {
+    const int n = (int)pos.size();
+    Gather g{0u, 0u};
+    if (n == 0) return g;
+    if (n > 3) throw std::runtime_error("find_gather: more than 3 bits");
+    uint32_t keys[8];
+    for (int s = 0; s < (1 << n); ++s) {
+        keys[s] = 0;
+        for (int i = 0; i < n; ++i) {
+            if (pos[i] < 0 || pos[i] > 15) throw std::runtime_error("find_gather: bit position out of range");
+            keys[s] |= (uint32_t)((s >> i) & 1) << pos[i];
+        }
+    }
+    g.mask = keys[(1 << n) - 1];
+    uint64_t st = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (uint32_t)(st >> 16); };
+    for (long long t = 0; t < 50000000ll; ++t) {
+        uint32_t m = 0;
+        if (t == 0) { for (int i = 0; i < n; ++i) m += 1u << (29 + i - pos[i]); }
+        else if (t == 1) { for (int i = 0; i < n; ++i) m += 1u << (29 + (n - 1 - i) - pos[i]); }
+        else { m = rnd(); if (t % 3) m &= rnd(); if (t % 3 == 2) m &= rnd(); }
+        uint32_t seen = 0;
+        bool ok = true;
+        for (int s = 0; s < (1 << n) && ok; ++s) {
+            const uint32_t h = (keys[s] * m) >> 29;
+            if (h >= (1u << n) || ((seen >> h) & 1u)) ok = false;
+            seen |= 1u << h;
+        }
+        if (ok) { g.magic = m; return g; }
+    }
+    throw std::runtime_error("find_gather: no multiplier found");
+}
 namespace {
 
 using cd = std::complex<double>;
@@ -627,27 +664,42 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                 std::memset(&op, 0, sizeof(op));
                 op.instr = l.instr;
                 int kind = OPK_DIAG;
-                uint32_t rb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                uint32_t rb[8] = {0, 0, 0, 0, 0, 0, 0, 0}, diag_rbs = 0;
                 const int d = 1 << l.nb;
                 if (l.diag) {
                     kind = OPK_DIAG;
-                    uint32_t tmask = 0, regmask = 0;
-                    uint64_t midx = 0;
-                    const int fw = 64 >> R;
+                    // table row = hash of the op's thread bits (two multiply-gathers of <= 3 bits), column = its register
+                    // bits packed in ascending register order: see diag_mask
+                    std::vector<std::pair<int, int>> tb, rg;      // (tile position | register index, op bit)
                     for (int i = 0; i < l.nb; ++i) {
                         const int pos = local_of[l.bits[i]];
-                        rb[i] = (uint32_t)pos;
-                        if (reg_of[pos] < 0) tmask |= 1u << i;
-                        else {
-                            regmask |= 1u << reg_of[pos];
-                            for (int m = 0; m < (1 << R); ++m)
-                                if ((m >> reg_of[pos]) & 1) midx |= (uint64_t)(1u << i) << (fw * m);
-                        }
+                        if (reg_of[pos] < 0) tb.push_back({pos, i}); else rg.push_back({reg_of[pos], i});
                     }
-                    kind |= (int)(tmask << 8) | (int)(regmask << 16);
-                    op.midx_lo = (uint32_t)midx; op.midx_hi = (uint32_t)(midx >> 32);
-                    op.mat = pb.add_doubles(l.mat);
-                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(l.bare);
+                    std::sort(rg.begin(), rg.end());
+                    const int nt = (int)tb.size(), nr = (int)rg.size(), nA = (nt + 1) / 2;
+                    if (nt > 6) throw std::runtime_error("diagonal operator with more than 6 thread bits");
+                    std::vector<int> posA, posB;
+                    for (int i = 0; i < nt; ++i) (i < nA ? posA : posB).push_back(tb[i].first);
+                    const Gather gA = find_gather(posA), gB = find_gather(posB);
+                    uint32_t regmask = 0;
+                    for (auto& r : rg) regmask |= 1u << r.first;
+                    kind |= (int)((1u << nA) << 8) | (int)(regmask << 16);
+                    diag_rbs = gA.mask | (gB.mask << 16);
+                    op.midx_lo = gA.magic; op.midx_hi = gB.magic;
+                    auto layout = [&](const std::vector<double>& src) {
+                        std::vector<double> dst(src.size());
+                        for (int s = 0; s < d; ++s) {
+                            uint32_t x = 0, col = 0;
+                            for (auto& t : tb) x |= (uint32_t)((s >> t.second) & 1) << t.first;
+                            for (int j = 0; j < nr; ++j) col |= (uint32_t)((s >> rg[j].second) & 1) << j;
+                            const uint32_t row = (((x & gB.mask) * gB.magic) >> 29) * (1u << nA) + (((x & gA.mask) * gA.magic) >> 29);
+                            const size_t e = ((size_t)row << nr) | col;
+                            dst[2 * e] = src[2 * (size_t)s]; dst[2 * e + 1] = src[2 * (size_t)s + 1];
+                        }
+                        return dst;
+                    };
+                    op.mat = pb.add_doubles(layout(l.mat));
+                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(layout(l.bare));
                 } else if (l.nb <= 2) {
                     for (int i = 0; i < l.nb; ++i) rb[i] = (uint32_t)reg_of[local_of[l.bits[i]]];
                     cmat m = read_complex(l.mat.data(), d * d), mb = read_complex(l.bare.data(), d * d);
@@ -690,8 +742,9 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     const uint32_t lsel = k == OPK_DIAG ? ((uint32_t)kind >> 16) & 0x7u : k == OPK_RX1 ? 8u + rb[0] : k == OPK_DENSE1 ? 11u + rb[0] : 15u;
                     op.kind_nb |= lsel << 20;
                 }
-                op.rbs = 0;
-                for (int i = 0; i < 8; ++i) op.rbs |= (rb[i] & 0xfu) << (4 * i);
+                op.rbs = diag_rbs;
+                if (!l.diag)
+                    for (int i = 0; i < 8; ++i) op.rbs |= (rb[i] & 0xfu) << (4 * i);
                 op.pad = l.instr;
                 return op;
             };
