@@ -22,6 +22,7 @@ cpu_baseline  the reference's compiled CPU path (oracle/_ref/patched: these circ
            scaled by instructions (the reference's cost per instruction is flat).
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -60,7 +61,7 @@ def config(traj_per_step, n_gpus):
 # clocks
 # -------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
@@ -73,6 +74,10 @@ class ClockSampler:
                                        "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark(self):
+        """Start of the timed region: earlier samples (nvidia-smi start-up happens during the warm-up) are dropped."""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.p:
@@ -88,6 +93,12 @@ class ClockSampler:
         for line in open(self.path):
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = float("inf")
+            if ts < getattr(self, "t_mark", 0.0) - 0.05:
                 continue
             try:
                 sm.append(float(parts[1])); mx.append(float(parts[2]))
@@ -209,12 +220,14 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-timed arm ----
+    clocks = ClockSampler(local_rank) if rank == 0 and not os.environ.get("NCB_BENCH_NO_CLOCKS") else None
+    if clocks:
+        clocks.start()            # nvidia-smi starts (and initialises NVML) during the warm-up, samples through the timed region
     for s in range(args.warmup):
         step(s)
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if clocks:
-        clocks.start()
+        clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = {"sweeps": 0, "launches": 0, "tile_launches": 0, "events": 0, "hard_events": 0}
     ev0.record()
@@ -300,8 +313,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--traj-per-step", type=int, default=296)
     ap.add_argument("--no-cpu-baseline", action="store_true")

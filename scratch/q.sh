@@ -1,0 +1,6 @@
+#!/bin/bash
+# usage: scratch/q.sh "ENV.. -- bench args" ...
+for cfg in "$@"; do
+  envs="${cfg%%--*}"; args="${cfg#*--}"
+  env $envs python bench.py --no-cpu-baseline $args 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$cfg |', round(d['value'],1), round(d['e2e']['value'],1), round(d['ms_per_step'],1), d['clocks'])"
+done
