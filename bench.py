@@ -60,6 +60,77 @@ def config(traj_per_step, n_gpus):
 # -------------------------------------------------------------------------------------------------------------------
 # clocks
 # -------------------------------------------------------------------------------------------------------------------
+class NvmlClockSampler:
+    """In-process NVML polling thread (nvidia_ml_py): the same fields as the nvidia-smi clocks line of the profiling
+    recipe, without a second process re-initialising NVML next to the timed region."""
+
+    def __init__(self, device_index, period=0.1):
+        import pynvml
+        import threading
+        self.nv, self.period, self.samples, self.t_mark = pynvml, period, [], 0.0
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of torch's device
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+            dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+            dev = torch.cuda.get_device_properties(device_index).pci_device_id
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08X}:{bus:02X}:{dev:02X}.0".encode())
+        except Exception:
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        self.stop_flag = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.time(), sm, mx, rs))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def start(self):
+        self.thread.start()
+
+    def mark(self):
+        self.t_mark = time.time()
+
+    def stop(self):
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        keep = [x for x in self.samples if x[0] >= self.t_mark]
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(n for n, b in bits.items() if any(x[3] & b for x in keep))
+        try:
+            nv.nvmlShutdown()
+        except Exception:
+            pass
+        return {"sm_mhz": statistics.median([x[1] for x in keep]) if keep else None,
+                "sm_max_mhz": max([x[2] for x in keep]) if keep else None, "reasons": reasons, "samples": len(keep),
+                "source": "nvml"}
+
+
+def make_clock_sampler(device_index):
+    mode = os.environ.get("NCB_BENCH_CLOCKS", "nvml")
+    if mode == "none":
+        return None
+    if mode == "nvml":
+        try:
+            return NvmlClockSampler(device_index)
+        except Exception:
+            pass
+    return ClockSampler(device_index)
+
+
 class ClockSampler:
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -220,7 +291,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-timed arm ----
-    clocks = ClockSampler(local_rank) if rank == 0 and not os.environ.get("NCB_BENCH_NO_CLOCKS") else None
+    clocks = make_clock_sampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()            # nvidia-smi starts (and initialises NVML) during the warm-up, samples through the timed region
     for s in range(args.warmup):
