@@ -311,6 +311,74 @@ double dephase_1q(cmat& merged, cmat& bare) {
     return 0.0;
 }
 
+// Two-qubit gate U (index = b0 + 2 b1) as (A1 x A0) . D . (B1 x B0) with D diagonal, for gates that map each basis
+// state of one "control" bit to a basis state of it (controlled-V, ecr, cx, cy, ...):
+//   U = P_c . sum_b |b><b|_c (x) V_b,   V_0^+ V_1 = Q L Q^+   =>   A_c = P_c (1 or X), A_t = V_0 Q, B_t = Q^+, B_c = 1,
+//   D = diag over (c, t): 1 for c = 0, L_t for c = 1.
+// The dense 4x4 then runs as one-qubit operators (which merge with their neighbours) and a diagonal table in the lean
+// kernels.  Returns false when U has no such form (swap, generic unitaries): those stay dense.
+struct ControlledForm { cmat A[2], B[2], D; };
+bool controlled_form(const cmat& U, ControlledForm& f) {
+    const double tol = 1e-13;
+    for (int c = 0; c < 2; ++c) {
+        const int t = 1 - c;
+        auto at = [&](int cr, int tr, int cc, int tc) { return U[(size_t)((cr << c) | (tr << t)) * 4 + ((cc << c) | (tc << t))]; };
+        int pi[2];
+        bool ok = true;
+        for (int cc = 0; cc < 2 && ok; ++cc) {
+            double w[2] = {0, 0};
+            for (int cr = 0; cr < 2; ++cr)
+                for (int tr = 0; tr < 2; ++tr)
+                    for (int tc = 0; tc < 2; ++tc) w[cr] = std::max(w[cr], std::abs(at(cr, tr, cc, tc)));
+            if (w[0] > tol && w[1] > tol) ok = false;
+            pi[cc] = w[1] > w[0] ? 1 : 0;
+        }
+        if (!ok || pi[0] == pi[1]) continue;
+        cmat V[2];
+        for (int cc = 0; cc < 2; ++cc) V[cc] = {at(pi[cc], 0, cc, 0), at(pi[cc], 0, cc, 1), at(pi[cc], 1, cc, 0), at(pi[cc], 1, cc, 1)};
+        auto dagger = [](const cmat& m) { return cmat{std::conj(m[0]), std::conj(m[2]), std::conj(m[1]), std::conj(m[3])}; };
+        const cmat W = matmul(dagger(V[0]), V[1], 2);
+        // eigen-decomposition of the 2x2 unitary W
+        cmat Q{1, 0, 0, 1};
+        cd l0 = W[0], l1 = W[3];
+        if (std::abs(W[1]) > 1e-15 || std::abs(W[2]) > 1e-15) {
+            const cd tr = W[0] + W[3], det = W[0] * W[3] - W[1] * W[2];
+            const cd disc = std::sqrt(tr * tr - 4.0 * det);
+            l0 = 0.5 * (tr + disc);
+            cd v0, v1;
+            if (std::abs(W[1]) >= std::abs(W[2])) { v0 = W[1]; v1 = l0 - W[0]; } else { v0 = l0 - W[3]; v1 = W[2]; }
+            const double nv = std::sqrt(std::norm(v0) + std::norm(v1));
+            if (nv < 1e-14) continue;
+            v0 /= nv; v1 /= nv;
+            Q = {v0, -std::conj(v1), v1, std::conj(v0)};       // columns: eigenvector, its orthogonal complement
+            const cmat L = matmul(dagger(Q), matmul(W, Q, 2), 2);
+            if (std::abs(L[1]) > tol || std::abs(L[2]) > tol) continue;
+            l0 = L[0]; l1 = L[3];
+        }
+        const cmat one{1, 0, 0, 1}, X{0, 1, 1, 0};
+        f.A[c] = pi[0] == 0 ? one : X;
+        f.A[t] = matmul(V[0], Q, 2);
+        f.B[c] = one;
+        f.B[t] = dagger(Q);
+        f.D.assign(4, cd(1, 0));
+        for (int tb = 0; tb < 2; ++tb) f.D[(size_t)((1 << c) | (tb << t))] = tb ? l1 : l0;
+        // verify
+        auto kron = [](const cmat& m1, const cmat& m0) {     // m1 on bit 1, m0 on bit 0
+            cmat k(16);
+            for (int r = 0; r < 4; ++r)
+                for (int cc = 0; cc < 4; ++cc) k[(size_t)r * 4 + cc] = m1[(size_t)(r >> 1) * 2 + (cc >> 1)] * m0[(size_t)(r & 1) * 2 + (cc & 1)];
+            return k;
+        };
+        cmat Dm(16, cd(0, 0));
+        for (int i = 0; i < 4; ++i) Dm[(size_t)i * 5] = f.D[i];
+        const cmat R = matmul(kron(f.A[1], f.A[0]), matmul(Dm, kron(f.B[1], f.B[0]), 4), 4);
+        double err = 0;
+        for (int i = 0; i < 16; ++i) err = std::max(err, std::abs(R[i] - U[i]));
+        if (err < 1e-13) return true;
+    }
+    return false;
+}
+
 cmat conj_of(const cmat& a) {
     cmat r(a);
     for (cd& x : r) x = std::conj(x);
@@ -422,12 +490,32 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
             if (cinfo[ch].certain_nonunitary) P.norm_preserving = false;
             if (P.chans[ch].count >= 2) { P.draw_pos[g] = P.num_draws++; P.noisy_instrs.push_back(g); }
         }
-        if (qb.size() == 1 && !(is_diagonal(merged, 2) && is_diagonal(U, 2))) {
-            const double phi = dephase_1q(merged, U);
-            if (phi != 0.0) {
-                const cd gp = cd(P.global_phase[0], P.global_phase[1]) * std::polar(1.0, phi);
-                P.global_phase[0] = gp.real(); P.global_phase[1] = gp.imag();
+        auto push_1q = [&](int q, cmat m, cmat b) {     // one-qubit lop with its global phase factored out
+            if (!(is_diagonal(m, 2) && is_diagonal(b, 2))) {
+                const double phi = dephase_1q(m, b);
+                if (phi != 0.0) {
+                    const cd gp = cd(P.global_phase[0], P.global_phase[1]) * std::polar(1.0, phi);
+                    P.global_phase[0] = gp.real(); P.global_phase[1] = gp.imag();
+                }
             }
+            lops.push_back(make_lop(g, std::vector<int>{q}, m, b));
+        };
+        if (qb.size() == 1) { push_1q(qb[0], merged, U); continue; }
+        // controlled-type two-qubit gates (ecr, cx): one-qubit factors + a diagonal table instead of a dense 4x4, when
+        // the channel's base operator is diagonal too (it then is one more diagonal lop whose bare form is the identity)
+        ControlledForm cf;
+        const bool base_diag = ch < 0 || is_diagonal(cinfo[ch].scaled[P.chans[ch].base], 4);
+        if (qb.size() == 2 && opt.fuse && opt.decompose && !is_diagonal(U, 4) && base_diag && controlled_form(U, cf)) {
+            auto is_one = [](const cmat& m) { return m[0] == cd(1, 0) && m[3] == cd(1, 0) && m[1] == cd(0, 0) && m[2] == cd(0, 0); };
+            for (int b = 0; b < 2; ++b)
+                if (!is_one(cf.B[b])) push_1q(qb[b], cf.B[b], cf.B[b]);
+            cmat Dm(16, cd(0, 0)), one4(16, cd(0, 0));
+            for (int i = 0; i < 4; ++i) { Dm[(size_t)i * 5] = cf.D[i]; one4[(size_t)i * 5] = 1; }
+            lops.push_back(make_lop(g, qb, Dm, Dm));
+            for (int b = 0; b < 2; ++b)
+                if (!is_one(cf.A[b])) push_1q(qb[b], cf.A[b], cf.A[b]);
+            if (ch >= 0) lops.push_back(make_lop(g, qb, cinfo[ch].scaled[P.chans[ch].base], one4));
+            continue;
         }
         lops.push_back(make_lop(g, qb, merged, U));
     }
@@ -460,7 +548,8 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
             std::vector<size_t> head(nb, 0);
             uint64_t low = 0;
             for (int b = 0; b < L; ++b) low |= 1ull << b;
-            const int max_seg_ops = 40;        // keeps a segment's program inside the shared-memory staging area
+            int max_seg_ops = 40;        // keeps a segment's program inside the shared-memory staging area
+            if (const char* e = getenv("NCB_MAX_SEG_OPS")) max_seg_ops = std::max(1, atoi(e));
             // runs every ready instruction inside tile S from heads h (modified); returns the executed list
             auto run = [&](uint64_t S, std::vector<size_t>& h, std::vector<int>* out) {
                 int count = 0;
@@ -548,14 +637,19 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
         // upper bound of what a logical op adds to its segment's shared-memory blob (op records of the op and of a
         // possible group header, its matrices, a share of a pass record)
         auto blob_cost = [&](const LogicalOp& l) {
-            const size_t mats = l.diag ? (size_t)(2 << l.nb) * 8 * 2 + 256 : (l.nb <= 2 ? (size_t)(2 << (2 * l.nb)) * 8 * 2 : 0);
-            return 3 * sizeof(Op) + mats + sizeof(Pass) / 2;
+            const size_t copies = l.bare == l.mat ? 1 : 2;
+            const size_t mats = l.diag ? ((size_t)16 << l.nb) * copies + 128 : (l.nb <= 2 ? ((size_t)16 << (2 * l.nb)) * copies : 0);
+            return 2 * sizeof(Op) + sizeof(Op) / 2 + mats + sizeof(Pass) / 3;
         };
         size_t cur_cost = sizeof(SegBlob) + sizeof(Pass);
         SegBuild cur{fresh_tile(), 0, 0};
         for (size_t i = 0; i < lops.size(); ++i) {
-            std::vector<int> t = tile_union(cur.tile, lops[i]);
             const bool new_instr = i == 0 || lops[i].instr != lops[i - 1].instr;
+            // an instruction's lops stay in one segment (a jump event reduces over the instruction's qubits right after
+            // its last lop): the tile has to take all of them
+            std::vector<int> t = tile_union(cur.tile, lops[i]);
+            if (new_instr)
+                for (size_t j = i + 1; j < lops.size() && lops[j].instr == lops[i].instr; ++j) t = tile_union(t, lops[j]);
             bool force_split = !opt.fuse && new_instr && cur.lop_end > cur.lop_begin;
             if (cur_cost + blob_cost(lops[i]) > (size_t)MAX_BLOB_BYTES - 512 && new_instr && cur.lop_end > cur.lop_begin) force_split = true;
             if ((int)t.size() > kfit || force_split) {
@@ -564,6 +658,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                 sb.push_back(cur);
                 cur = SegBuild{fresh_tile(), i, i};
                 t = tile_union(cur.tile, lops[i]);
+                for (size_t j = i + 1; j < lops.size() && lops[j].instr == lops[i].instr; ++j) t = tile_union(t, lops[j]);
                 if ((int)t.size() > kfit) throw std::runtime_error("an operation does not fit a tile; increase tile_bits");
             }
             cur.tile = t; cur.lop_end = i + 1;

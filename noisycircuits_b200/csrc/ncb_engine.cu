@@ -599,6 +599,7 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     if (const char* e = getenv("NCB_LOW_BITS")) opt.low_bits = atoi(e);
     if (const char* e = getenv("NCB_FUSE")) opt.fuse = atoi(e);
     if (const char* e = getenv("NCB_REORDER")) opt.reorder = atoi(e);
+    if (const char* e = getenv("NCB_DECOMPOSE")) opt.decompose = atoi(e);
     if (opt.reg_bits != 3 && opt.reg_bits != 4) return fail(NCB_E_INVALID, "reg_bits must be 3 or 4");
     opt.tile_bits = std::min(opt.tile_bits, 12);   // <= 256 threads (R = 4) / 512 threads (R = 3)
     ncb_program* p = new ncb_program();
