@@ -81,7 +81,11 @@ typedef struct {
     int32_t strict_order;/* 0 (default): commuting instructions (disjoint qubits) may be executed in a tile-friendly
                             order -- the same circuit, fewer sweeps; jump events then have the reference's meaning on
                             that order (ncb_program_order).  1: execute strictly in the caller's order. */
-    int32_t reserved[2];
+    int32_t independent_trajectories;
+                         /* 0 (default): the batched MCWF run computes the evolution every trajectory shares before its
+                            first jump event once per batch (results per trajectory are bit-identical; fewer sweeps).
+                            1: every trajectory is swept on its own from |0..0>. */
+    int32_t reserved;
 } ncb_options;
 
 typedef struct ncb_program ncb_program;

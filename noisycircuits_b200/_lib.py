@@ -26,7 +26,8 @@ class NcbCircuit(C.Structure):
 
 class NcbOptions(C.Structure):
     _fields_ = [("tile_bits", C.c_int32), ("reg_bits", C.c_int32), ("low_bits", C.c_int32), ("fuse", C.c_int32),
-                ("device", C.c_int32), ("strict_order", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("device", C.c_int32), ("strict_order", C.c_int32), ("independent_trajectories", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class NcbRunParams(C.Structure):

@@ -222,7 +222,8 @@ enum WorkFlags : int32_t {
     WF_NORM = 32,          // finally accumulate the squared norm
 };
 struct Work {
-    int32_t slot, seg, instr_lo, instr_hi;
+    int32_t slot, src, instr_lo, instr_hi;     // src: slot the tiles are READ from (== slot except when a trajectory
+                                               // forks from the shared no-jump prefix, see ncb_schedule.h)
     int32_t flags, ev_instr, ev_k, red_instr;
 };
 struct DecideItem {

@@ -82,7 +82,8 @@ struct Engine {
     DevBuf<Op> d_ops; DevBuf<Pass> d_passes; DevBuf<Segment> d_segs; DevBuf<Instr> d_instrs; DevBuf<Channel> d_chans;
     DevBuf<double> d_pool; DevBuf<int32_t> d_noisy; DevBuf<int32_t> d_orig; DevBuf<unsigned char> d_blobs;
     DevBuf<cplx> d_states;
-    DevBuf<double> d_red, d_norm, d_invnorm, d_probs, d_partial, d_uniforms;
+    DevBuf<double> d_red, d_norm, d_invnorm, d_weight, d_probs, d_partial, d_uniforms;
+    bool independent = false;          // ncb_options.independent_trajectories: no shared no-jump prefix
     DevBuf<Decision> d_dec;
     DevBuf<unsigned long long> d_counters;
     DevBuf<Work> d_works[2];
@@ -96,7 +97,7 @@ struct Engine {
 
     ~Engine() {
         d_ops.release(); d_passes.release(); d_segs.release(); d_instrs.release(); d_chans.release(); d_pool.release();
-        d_noisy.release(); d_orig.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_probs.release();
+        d_noisy.release(); d_orig.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_weight.release(); d_probs.release();
         d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release();
         for (int i = 0; i < 2; ++i) {
             d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
@@ -373,18 +374,23 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
     const long long dim = 1ll << P.nbits, count = rp->traj_count;
     const int ntiles = 1 << (P.nbits - P.K);
     const int B = rp->batch > 0 ? (int)std::min<long long>(rp->batch, count) : auto_batch(count);
-    d_states.reserve((size_t)B * dim);
-    d_red.reserve((size_t)B * ntiles * RED_VALUES);
-    d_norm.reserve((size_t)B * ntiles);
-    d_invnorm.reserve(B);
-    d_dec.reserve(B);
+    // trajectories are one and the same evolution until their first jump: computed once per batch (ncb_schedule.h)
+    bool share = !rp->states && !independent;
+    if (const char* e = getenv("NCB_SHARE_PREFIX")) share = share && atoi(e) != 0;
+    const int SL = B + 2;                       // state slots: B trajectories + the two trunk slots
+    d_states.reserve((size_t)SL * dim);
+    d_red.reserve((size_t)SL * ntiles * RED_VALUES);
+    d_norm.reserve((size_t)SL * ntiles);
+    d_invnorm.reserve(SL);
+    d_weight.reserve(SL);
+    d_dec.reserve(SL);
     UniformSource us{rp->rng, rp->seed, rp->traj_begin, rp->uniforms, P.G};
     std::vector<std::vector<Event>> events;
     BatchPlan plan;
     std::vector<cplx> host_states;
     int buf = 0;
     const bool want_norm = !P.norm_preserving;
-    CK(cudaMemsetAsync(d_red.p, 0, (size_t)B * ntiles * RED_VALUES * sizeof(double), s));
+    CK(cudaMemsetAsync(d_red.p, 0, (size_t)SL * ntiles * RED_VALUES * sizeof(double), s));
     for (long long b0 = 0; b0 < count; b0 += B) {
         const int nb = (int)std::min<long long>(B, count - b0);
         if (rp->rng == NCB_RNG_MT19937_REFERENCE) {
@@ -399,7 +405,7 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             const long long tl = mt ? b : b0 + b;
             plan_events(P, [&](int i) { return us.get(tl, i); }, events[b]);
         }
-        schedule_batch(P, events, true, want_norm, plan);
+        schedule_batch(P, events, true, want_norm, plan, share);
         for (int b = 0; b < nb; ++b) {
             rp->out_events += (int64_t)events[b].size();
             for (const Event& e : events[b]) rp->out_hard_events += e.kmin != e.kmax;
@@ -425,13 +431,15 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             ++rp->out_launches;
         }
         CK(cudaEventRecord(buf_free[buf], s));
+        CK(cudaMemcpyAsync(d_weight.p, plan.weight.data(), plan.weight.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        rp->out_h2d_bytes += (int64_t)(plan.weight.size() * sizeof(double));
         if (want_norm) {
-            norm_finalize_kernel<<<(nb + 7) / 8, 256, 0, s>>>(d_norm.p, ntiles, nb, d_invnorm.p);
+            norm_finalize_kernel<<<(plan.nslots + 7) / 8, 256, 0, s>>>(d_norm.p, ntiles, plan.nslots, d_weight.p, d_invnorm.p);
             CK(cudaGetLastError());
         }
         int g, bl;
         grid_1d(dim, &g, &bl);
-        accumulate_kernel<<<g, bl, 0, s>>>(d_probs.p, d_states.p, P.nbits, nb, want_norm ? d_invnorm.p : nullptr);
+        accumulate_kernel<<<g, bl, 0, s>>>(d_probs.p, d_states.p, P.nbits, plan.nslots, want_norm ? d_invnorm.p : d_weight.p);
         CK(cudaGetLastError());
         rp->out_launches += want_norm ? 2 : 1;
         if (rp->states) {
@@ -611,6 +619,7 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
         }
     } catch (...) { delete p; throw; }
     p->eng.device = device;
+    p->eng.independent = options && options->independent_trajectories != 0;
     *out = p;
     return NCB_OK;
     NCB_CATCH

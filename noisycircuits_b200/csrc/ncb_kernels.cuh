@@ -189,7 +189,7 @@ tile_kernel(DevProgram P, const __grid_constant__ SegConst sc, const unsigned ch
     auto issue_load = [&](long long t, cplx* sm, const Work& w) {
         if (w.flags & WF_INIT) return;                           // |0..0> is written by the processing step
         const unsigned base = apply_runs(sg->bruns, (unsigned)(t & (ntiles - 1)));
-        const cplx* st = states + ((long long)w.slot << P.nbits) + base;
+        const cplx* st = states + ((long long)w.src << P.nbits) + base;
 #pragma unroll
         for (int it = 0; it < (1 << R); ++it) {
             const unsigned off = offA | sg->it_off[it];
@@ -303,26 +303,30 @@ decide_kernel(DevProgram P, const DecideItem* __restrict__ items, int nitems, co
 // ---------------------------------------------------------------------------------------------------------------
 // tail kernels
 // ---------------------------------------------------------------------------------------------------------------
-// inv_norm2[slot] = 1 / sum_tiles norm_part[slot][tile]
-__global__ void norm_finalize_kernel(const double* __restrict__ norm_part, int ntiles, int nslots, double* __restrict__ inv_norm2) {
+// scale[slot] = weight[slot] / sum_tiles norm_part[slot][tile]   (weight: how many trajectories end in this slot's state)
+__global__ void norm_finalize_kernel(const double* __restrict__ norm_part, int ntiles, int nslots, const double* __restrict__ weight,
+                                     double* __restrict__ scale) {
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (slot >= nslots) return;
+    const double w = weight[slot];
+    if (w == 0.0) { if (lane == 0) scale[slot] = 0.0; return; }      // unused slot: its partials are stale
     double s = 0.0;
     for (int o = lane; o < ntiles; o += 32) s += norm_part[(long long)slot * ntiles + o];
     s = warp_sum(s);
-    if (lane == 0) inv_norm2[slot] = 1.0 / s;
+    if (lane == 0) scale[slot] = w / s;
 }
 
-// probs[j] += sum_slots |psi_slot[j]|^2 * inv_norm2[slot]   (slots in order: deterministic)
+// probs[j] += sum_slots |psi_slot[j]|^2 * scale[slot]   (slots in order: deterministic; slots with scale 0 are not read)
 __global__ void accumulate_kernel(double* __restrict__ probs, const cplx* __restrict__ states, int nbits, int nslots,
-                                  const double* __restrict__ inv_norm2) {
+                                  const double* __restrict__ scale) {
     const long long dim = 1ll << nbits;
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < dim; j += (long long)gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int b = 0; b < nslots; ++b) {
+            const double f = scale[b];
+            if (f == 0.0) continue;
             const cplx a = states[((long long)b << nbits) + j];
-            const double p = a.x * a.x + a.y * a.y;
-            s += inv_norm2 ? p * inv_norm2[b] : p;
+            s += (a.x * a.x + a.y * a.y) * f;
         }
         probs[j] += s;
     }

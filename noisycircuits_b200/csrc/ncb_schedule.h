@@ -7,6 +7,7 @@
 // reduced-density-matrix reduction), then -- after the decide step -- the chosen Kraus operator followed by
 // [e+1, ..).  The pieces after the first are issued as extra, small launches ("rounds") over the affected slots only.
 #pragma once
+#include <algorithm>
 #include <vector>
 
 #include "ncb_compile.h"
@@ -23,19 +24,54 @@ struct BatchPlan {
     std::vector<DecideItem> decides;
     std::vector<LaunchStep> steps;
     long long sweeps = 0;          // slot-sweeps issued (works)
+    // state slots the plan uses: [0, B) one per trajectory, then (shared prefix only) two trunk slots
+    int nslots = 0;
+    int trunk_slot = -1;           // slot holding the no-jump trajectory's final state (-1: none)
+    std::vector<double> weight;    // [nslots] trajectories whose final state is this slot's (0: slot unused)
 };
 
 // events[slot]: that trajectory's events in instruction order.  init: the batch starts from |0..0> (first segment
 // does not read the state).  want_norm: emit WF_NORM on every slot's final work.
+//
+// share_prefix: every trajectory is the SAME deterministic evolution until its first jump event, so that prefix is
+// computed once per batch.  A "trunk" walks all segments (ping-ponging between the two extra slots B and B+1, so a
+// launch never reads a slot it writes); a trajectory joins at the segment of its first event with its tiles READ from
+// the trunk's state at the start of that segment (Work::src) and written to its own slot; trajectories without any
+// event are the trunk (weight = their number).  The numbers produced per trajectory are bit-identical to the unshared
+// schedule: the same kernels run on the same data, fewer times.
 inline void schedule_batch(const Program& P, const std::vector<std::vector<Event>>& events, bool init, bool want_norm,
-                           BatchPlan& out) {
+                           BatchPlan& out, bool share_prefix = false) {
     out.works.clear(); out.decides.clear(); out.steps.clear(); out.sweeps = 0;
     const int B = (int)events.size(), S = (int)P.segs.size();
+    share_prefix = share_prefix && init && B > 1 && S > 0;
+    out.nslots = share_prefix ? B + 2 : B;
+    out.trunk_slot = -1;
+    out.weight.assign(out.nslots, share_prefix ? 0.0 : 1.0);
+    // segment of each trajectory's first event (S: none)
+    std::vector<int> first_seg(B, share_prefix ? S : 0);
+    int trunk_until = -1;                     // the trunk has to produce the state at the start of segment trunk_until
+    if (share_prefix) {
+        int never = 0;
+        for (int b = 0; b < B; ++b) {
+            if (events[b].empty()) { ++never; continue; }
+            int s = 0;
+            while (s < S && P.segs[s].instr_hi <= events[b][0].instr) ++s;
+            first_seg[b] = s;
+            trunk_until = std::max(trunk_until, s);
+            out.weight[b] = 1.0;
+        }
+        if (never) {
+            trunk_until = S;
+            out.trunk_slot = B + (S & 1);
+            out.weight[out.trunk_slot] = (double)never;
+        }
+    }
     std::vector<size_t> cur(B, 0);
     std::vector<int> live, next;
     for (int s = 0; s < S; ++s) {
         const Segment& sg = P.segs[s];
         const bool first = init && s == 0, last = s == S - 1;
+        const int tin = B + (s & 1), tout = B + ((s + 1) & 1);
         // events of this segment per slot: [cur[b], end[b])
         std::vector<size_t> end(B);
         for (int b = 0; b < B; ++b) {
@@ -44,10 +80,16 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
             end[b] = e;
         }
         // main launch
-        LaunchStep st{0, (int)out.works.size(), B, s};
+        LaunchStep st{0, (int)out.works.size(), 0, s};
         live.clear();
+        if (share_prefix && s < trunk_until) {
+            Work w{tout, tin, sg.instr_lo, sg.instr_hi, first ? WF_INIT : 0, -1, -1, -1};
+            if (last && want_norm) w.flags |= WF_NORM;
+            out.works.push_back(w);
+        }
         for (int b = 0; b < B; ++b) {
-            Work w{b, s, sg.instr_lo, sg.instr_hi, first ? WF_INIT : 0, -1, -1, -1};
+            if (first_seg[b] > s) continue;                       // still on the trunk
+            Work w{b, first_seg[b] == s && share_prefix ? tin : b, sg.instr_lo, sg.instr_hi, first ? WF_INIT : 0, -1, -1, -1};
             if (cur[b] < end[b]) {
                 const Event& e = events[b][cur[b]];
                 w.instr_hi = e.instr + 1;
@@ -59,8 +101,9 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
             }
             out.works.push_back(w);
         }
-        out.steps.push_back(st);
-        out.sweeps += B;
+        st.count = (int)out.works.size() - st.begin;
+        if (st.count) out.steps.push_back(st);
+        out.sweeps += st.count;
         // rounds
         while (!live.empty()) {
             LaunchStep ds{1, (int)out.decides.size(), 0, s};
@@ -74,7 +117,7 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
             for (int b : live) {
                 const Event& e = events[b][cur[b]];
                 ++cur[b];
-                Work w{b, s, e.instr + 1, sg.instr_hi, 0, e.instr, e.kmin, -1};
+                Work w{b, b, e.instr + 1, sg.instr_hi, 0, e.instr, e.kmin, -1};
                 w.flags |= (e.kmin == e.kmax) ? WF_PRO_STATIC : WF_PRO_DYNAMIC;
                 if (cur[b] < end[b]) {
                     const Event& f = events[b][cur[b]];

@@ -126,11 +126,13 @@ class Program:
     """A compiled program (``ncb_program``).  Compilation is host-only; the first run uploads it to the GPU."""
 
     def __init__(self, packed: PackedCircuit, mode: int = _lib.MODE_MCWF, tile_bits: int = 0, reg_bits: int = 0,
-                 low_bits: int = -1, fuse: int = 1, device: int = -1, strict_order: bool = False):
+                 low_bits: int = -1, fuse: int = 1, device: int = -1, strict_order: bool = False,
+                 independent_trajectories: bool = False):
         self._h = C.c_void_p(None)
         self.packed = packed
         self.mode = mode
-        opts = _lib.NcbOptions(tile_bits, reg_bits, low_bits, fuse, device, int(bool(strict_order)), (C.c_int32 * 2)(0, 0))
+        opts = _lib.NcbOptions(tile_bits, reg_bits, low_bits, fuse, device, int(bool(strict_order)),
+                               int(bool(independent_trajectories)), 0)
         _lib.check(_lib.lib().ncb_program_create(C.byref(packed.struct), mode, C.byref(opts), C.byref(self._h)))
         self.num_qubits = packed.num_qubits
         self.num_instructions = packed.num_instructions

@@ -26,12 +26,12 @@ struct Emu {
 };
 
 template <int R>
-void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, std::vector<double>& red_part,
+void emulate_work(const Program& P, const Work& w, int seg, std::vector<cplx>& states, std::vector<double>& red_part,
                   std::vector<double>& norm_part, const std::vector<Decision>& decisions) {
     const int K = P.K, nthreads = 1 << (K - R);
     const int tile_shift = P.nbits > K ? P.nbits - K : 0, ntiles = 1 << tile_shift;
     // the staged copy of the segment program (what the tile kernel reads from shared memory)
-    const unsigned char* braw = P.blobs.data() + P.blob_off[w.seg];
+    const unsigned char* braw = P.blobs.data() + P.blob_off[seg];
     const SegBlob& blob = *reinterpret_cast<const SegBlob*>(braw);
     const Segment& sg = blob.seg;
     const Pass* passes = reinterpret_cast<const Pass*>(braw + blob.pass_off);
@@ -43,6 +43,7 @@ void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, st
     for (int o = 0; o < ntiles; ++o) {
         const long long base = apply_runs(sg.bruns, (unsigned)o);
         cplx* st = states.data() + ((long long)w.slot << P.nbits) + base;
+        const cplx* st_src = states.data() + ((long long)w.src << P.nbits) + base;
         // load
         for (int tid = 0; tid < nthreads; ++tid) {
             const unsigned offA = apply_runs(sg.eruns, (unsigned)tid);
@@ -50,7 +51,7 @@ void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, st
             for (int it = 0; it < (1 << R); ++it) {
                 const unsigned off = offA | sg.it_off[it];
                 cplx v{0.0, 0.0};
-                if (!(w.flags & WF_INIT) && off < limit) v = st[off];
+                if (!(w.flags & WF_INIT) && off < limit) v = st_src[off];
                 sm[sA ^ sg.it_swz[it]] = v;
             }
         }
@@ -73,7 +74,7 @@ void emulate_work(const Program& P, const Work& w, std::vector<cplx>& states, st
             if (ps.instr_lo >= w.instr_hi) break;
             if (ps.instr_hi > w.instr_lo && ps.instr_hi > ps.instr_lo)
                 for (int tid = 0; tid < nthreads; ++tid)
-                    run_pass_thread<R, 3, true>(sm.data(), K, (int)apply_runs(ps.truns, (unsigned)tid), ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last, P.segconst[w.seg], p);
+                    run_pass_thread<R, 3, true>(sm.data(), K, (int)apply_runs(ps.truns, (unsigned)tid), ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last, P.segconst[seg], p);
             if (ps.instr_hi > w.instr_hi) break;
         }
         // reductions
@@ -115,8 +116,8 @@ void run_plan(const Program& P, const BatchPlan& plan, int B, std::vector<cplx>&
         if (st.kind == 0) {
             for (int i = 0; i < st.count; ++i) {
                 const Work& w = plan.works[st.begin + i];
-                if (P.R == 4) emulate_work<4>(P, w, states, red_part, norm_part, decisions);
-                else emulate_work<3>(P, w, states, red_part, norm_part, decisions);
+                if (P.R == 4) emulate_work<4>(P, w, st.seg, states, red_part, norm_part, decisions);
+                else emulate_work<3>(P, w, st.seg, states, red_part, norm_part, decisions);
             }
         } else {
             for (int i = 0; i < st.count; ++i) {
@@ -185,7 +186,7 @@ long long emu_describe(void* h, char* buf, long long len) {
 
 // Runs `count` trajectories (explicit uniforms [count][G]) as ONE batch and returns their final normalised states
 // [count][2^n] (complex interleaved), the number of events / state-dependent events, and the sweeps issued.
-int emu_mcwf_states(void* h, int count, const double* uniforms, double* states_out, long long* stats) {
+int emu_mcwf_states(void* h, int count, const double* uniforms, double* states_out, long long* stats, int share) {
     try {
         const Program& P = static_cast<Emu*>(h)->P;
         if (P.mode != MODE_MCWF) throw std::runtime_error("not an MCWF program");
@@ -198,23 +199,28 @@ int emu_mcwf_states(void* h, int count, const double* uniforms, double* states_o
             for (const Event& e : events[b]) nhard += e.kmin != e.kmax;
         }
         BatchPlan plan;
-        schedule_batch(P, events, true, !P.norm_preserving, plan);
-        std::vector<cplx> states((size_t)count * dim, cplx{0.0, 0.0});
+        schedule_batch(P, events, true, !P.norm_preserving, plan, share != 0);
+        // unused slots start as NaN: a schedule that reads a slot nobody wrote cannot pass
+        std::vector<cplx> states((size_t)plan.nslots * dim, cplx{std::nan(""), std::nan("")});
         std::vector<double> norm_part;
-        run_plan(P, plan, count, states, norm_part);
+        run_plan(P, plan, plan.nslots, states, norm_part);
         const int ntiles = 1 << (P.nbits > P.K ? P.nbits - P.K : 0);
         for (int b = 0; b < count; ++b) {
+            // a trajectory without any jump ends in the shared trunk's state
+            const int sl = plan.weight[b] != 0.0 ? b : plan.trunk_slot;
+            if (sl < 0) throw std::runtime_error("schedule lost a trajectory");
+            const cplx* fin = states.data() + (size_t)sl * dim;
             double n2 = 0.0;
-            for (long long j = 0; j < dim; ++j) n2 += cnorm2(states[(size_t)b * dim + j]);
+            for (long long j = 0; j < dim; ++j) n2 += cnorm2(fin[j]);
             if (!P.norm_preserving) {     // the WF_NORM partials must agree with the direct norm
                 double s = 0.0;
-                for (int o = 0; o < ntiles; ++o) s += norm_part[(size_t)b * ntiles + o];
+                for (int o = 0; o < ntiles; ++o) s += norm_part[(size_t)sl * ntiles + o];
                 if (std::fabs(s - n2) > 1e-12 * std::max(1.0, n2)) throw std::runtime_error("WF_NORM partials disagree with the state norm");
             }
             const double f = 1.0 / std::sqrt(n2);
             const double gx = P.global_phase[0] * f, gy = P.global_phase[1] * f;
             for (long long j = 0; j < dim; ++j) {
-                const cplx a = states[(size_t)b * dim + j];
+                const cplx a = fin[j];
                 states_out[2 * ((size_t)b * dim + j)] = a.x * gx - a.y * gy;
                 states_out[2 * ((size_t)b * dim + j) + 1] = a.x * gy + a.y * gx;
             }

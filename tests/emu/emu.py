@@ -28,7 +28,7 @@ def lib():
         L.emu_query.restype = C.c_longlong
         L.emu_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
         L.emu_describe.restype = C.c_longlong
-        L.emu_mcwf_states.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_mcwf_states.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_run_deterministic.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_last_error.restype = C.c_char_p
         L.emu_philox_uniform.restype = C.c_double
@@ -63,13 +63,13 @@ class EmuProgram:
         lib().emu_describe(self.h, buf, n)
         return buf.value.decode()
 
-    def mcwf_states(self, uniforms):
+    def mcwf_states(self, uniforms, share=False):
         u = np.ascontiguousarray(uniforms, np.float64)
         count = u.shape[0]
         nbits = self.query(6)
         out = np.empty((count, 1 << nbits), np.complex128)
         stats = np.zeros(4, np.int64)
-        if lib().emu_mcwf_states(self.h, count, u.ctypes.data, out.ctypes.data, stats.ctypes.data) != 0:
+        if lib().emu_mcwf_states(self.h, count, u.ctypes.data, out.ctypes.data, stats.ctypes.data, int(share)) != 0:
             raise RuntimeError(lib().emu_last_error().decode())
         return out, {"events": int(stats[0]), "hard_events": int(stats[1]), "sweeps": int(stats[2]), "steps": int(stats[3])}
 

@@ -219,6 +219,32 @@ def test_sharding_and_batching_do_not_change_the_result(heron_noise):
     assert abs(full.sum() - 96) < 1e-9                 # every trajectory is normalised
 
 
+def test_shared_no_jump_prefix_is_the_same_computation(heron_noise):
+    """The batched run computes the evolution all trajectories share before their first jump once per batch
+    (ncb_schedule.h).  Against a program compiled with independent_trajectories: same probabilities (only the order of
+    the final sum changes), same events, fewer sweeps; and both equal the oracle fed with the same uniforms."""
+    sq, tq, _, _ = heron_noise
+    n = 14
+    instr = circuits.heron_layered(n, 8, circuits.coupled_pairs(tq, n), seed=4)
+    pk = PackedCircuit(n, instr, sq, tq)
+    shared = Program(pk, _lib.MODE_MCWF)
+    indep = Program(pk, _lib.MODE_MCWF, independent_trajectories=True)
+    T, seed = 200, 99
+    a, sa = shared.run_mcwf(T, seed=seed)
+    b, sb = indep.run_mcwf(T, seed=seed)
+    assert np.abs(a - b).max() < 1e-12
+    assert sa["events"] == sb["events"] and sa["hard_events"] == sb["hard_events"] and sa["events"] > 0
+    assert sa["sweeps"] < sb["sweeps"]
+    assert abs(a.sum() - T) < 1e-9
+    c, _ = shared.run_mcwf(T, seed=seed, batch=33)          # several batches, each with its own trunk
+    assert np.abs(a - c).max() < 1e-12
+    Tq = 12
+    U = np.array([[philox_numpy(seed, t, g) for g in range(len(instr))] for t in range(Tq)])
+    ref = oracle.Program(n, instr, sq, tq).mcwf(Tq, uniforms=U, mask_fix=True)
+    q, _ = shared.run_mcwf(Tq, seed=seed)
+    assert np.abs(q / Tq - ref).max() < TOL
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # density-matrix path and the statistical check
 # ---------------------------------------------------------------------------------------------------------------

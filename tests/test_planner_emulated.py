@@ -36,6 +36,10 @@ def check_replay(n, instr, sq, tq, U, **opts):
         ref = O.trajectory(U[t][order], mask_fix=True)
         worst = max(worst, np.abs(st[t] - ref).max())
     assert worst < TOL, (worst, stats, E.describe())
+    # the shared no-jump prefix is the same computation done once: states bit-identical, never more sweeps
+    st2, stats2 = E.mcwf_states(U, share=True)
+    assert np.array_equal(st, st2), np.abs(st - st2).max()
+    assert stats2["sweeps"] <= stats["sweeps"] + 2 * E.query(2)
     return stats, E
 
 
@@ -164,3 +168,29 @@ def test_philox_is_the_reference_philox4x32_10():
     assert len({L.emu_philox_uniform(s, t, i) for s in range(3) for t in range(3) for i in range(3)}) == 27
     xs = np.array([L.emu_philox_uniform(7, t, 11) for t in range(20000)])
     assert abs(xs.mean() - 0.5) < 0.01 and abs(xs.var() - 1 / 12) < 0.005
+
+
+def test_shared_prefix_schedule(heron_noise):
+    """Trajectories share one evolution until their first jump: late first events, no events at all, events in the
+    first and in the last segment -- the shared schedule must reproduce the independent one bit for bit and save the
+    sweeps of the common prefix."""
+    sq, tq, _, _ = heron_noise
+    n = 10
+    pairs = circuits.coupled_pairs(tq, n)
+    instr = circuits.heron_layered(n, 6, pairs, seed=3)
+    G = len(instr)
+    rng = np.random.default_rng(7)
+    U = np.full((8, G), 0.5)                      # no events anywhere
+    U[1, G - 1] = 1 - 1e-9                        # first event in the last segment
+    U[2, 0] = 1 - 1e-9                            # first event at the first instruction
+    U[3, G // 2] = 1 - 1e-9                       # one event in the middle
+    U[4, G // 2:] = 1 - 0.03 * rng.random(G - G // 2) ** 2      # many events from the middle on
+    U[5] = 1 - 0.03 * rng.random(G) ** 2          # events everywhere
+    E = EmuProgram(PackedCircuit(n, instr, sq, tq), 0, tile_bits=8, reg_bits=3, low_bits=2, fuse=1, reorder=1)
+    assert E.query(2) > 3                         # several segments
+    a, sa = E.mcwf_states(U, share=False)
+    b, sb = E.mcwf_states(U, share=True)
+    assert np.array_equal(a, b)
+    assert np.array_equal(b[0], b[6]) and np.array_equal(b[0], b[7])      # the event-free trajectories are the trunk
+    assert sb["sweeps"] < sa["sweeps"]
+    assert sa["events"] == sb["events"] and sa["events"] > 10
