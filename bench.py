@@ -54,7 +54,8 @@ def config(traj_per_step, n_gpus):
                         f"pairs of qubits 0-19), Sample_Noise_Model_Heron_QPU noise (threshold 1e-6), BASELINE configs[4]",
             "instructions": DEPTH * (NQ + 19), "trajectories_per_step_per_gpu": traj_per_step,
             "target_trajectories": 100000, "parallelism": f"trajectory-sharded x{n_gpus}",
-            "l2": "inputs larger than L2 (state batch of trajectories_per_step x 16 MiB per GPU)"}
+            "l2": "inputs larger than L2 (state batch of trajectories_per_step x 16 MiB per GPU)",
+            "shared_no_jump_prefix": os.environ.get("NCB_SHARE_PREFIX", "1") != "0"}
 
 
 # -------------------------------------------------------------------------------------------------------------------
