@@ -187,6 +187,14 @@ struct PassHot {
 struct SegConst {
     int32_t valid;                     // 0: the segment did not fit; use the blob for everything
     int32_t npass, nops, ncoef;
+    // Direct store of the last pass (whole-segment works without events, direct_kernel): the last pass writes its
+    // amplitudes from registers to HBM, skipping a shared-memory round trip.  Possible when the L low state bits are the
+    // low thread-index bits of that pass (64-byte runs per 4 lanes).  State offset of thread `tid`, register slot m:
+    // apply_runs(gruns_last, tid) | goff_last[m].
+    int32_t direct;
+    int32_t pad_[3];
+    uint32_t goff_last[1 << MAX_REG_BITS];
+    BitRuns gruns_last;
     PassHot pass[SC_MAX_PASSES];
     Op ops[SC_MAX_OPS];                // mat: rx1 / dense1 -> index into coef (4 / 8 doubles); other kinds -> as in the blob
     double coef[SC_MAX_COEF];
@@ -293,6 +301,23 @@ NCB_HD int deposit(int v, const uint8_t* pos, int nbits) {
 // that carry the 4x4 / 16x16 kinds ping-pong between two register sets (those operators need all inputs for every
 // output); the one-bit and diagonal kernels are alias-safe (in == out) and the lean kernels run them in place.
 // ------------------------------------------------------------------------------------------------------------
+// streaming (evict-first) 128-bit global accesses: every amplitude crosses HBM once per sweep
+NCB_HD cplx ld_stream(const cplx* p) {
+#if defined(__CUDA_ARCH__)
+    cplx v;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+NCB_HD void st_stream(cplx* p, cplx v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+#else
+    *p = v;
+#endif
+}
 template <int R, int B>
 NCB_HD void dense1_bit(const cplx* in, cplx* out, const cplx* M) {      // M: four values in registers
     const cplx m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
@@ -424,10 +449,15 @@ NCB_HD void apply_op(const Op& op, int jb, const cplx* __restrict__ M, const cpl
 // base tile index in this pass).  bare_last: the op of instruction hi-1 uses the bare gate matrix.
 // USE_SC: when the whole pass runs (the common case), read the pass record, the ops and the 2x2 coefficients from the
 // constant bank (sc.pass[sc_pass], see SegConst) instead of memory.
-template <int R, int FEAT, bool USE_SC>
+// gdst (optional, SegConst::direct): the pass writes its amplitudes to global memory at gdst[gj | sc.goff_last[m]]
+// instead of the shared-memory tile; after_load() runs once the pass holds its amplitudes in registers (the direct
+// kernel refills the tile buffer with the next tile from there).
+struct NoHook { NCB_HD void operator()() const {} };
+template <int R, int FEAT, bool USE_SC, class AfterLoad = NoHook>
 NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* __restrict__ ops,
                             const double* __restrict__ pool, const double* __restrict__ pool_global, int lo, int hi, bool bare_last,
-                            const SegConst& sc, int sc_pass) {
+                            const SegConst& sc, int sc_pass, cplx* __restrict__ gdst = nullptr, unsigned gj = 0,
+                            AfterLoad after_load = AfterLoad()) {
     constexpr int NA = 1 << R;
     (void)K;
     const int jbs = swz(jb);
@@ -437,12 +467,16 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
     const bool fast = lo <= p_lo && hi >= p_hi && !(bare_last && hi == p_hi);
     const bool cst = fast && use_sc;
     cplx a[NA];
-    int addr[NA];
+    // shared-memory address of register slot m; recomputed at the store (one LOP each) rather than kept in 2^R
+    // registers across the op loop -- the laundered copy of jbs stops the compiler from keeping the first set alive
+    auto slot_addr = [&](int base, int m) { return base ^ (cst ? sc.pass[sc_pass].regoff_swz[m] : ps.regoff_swz[m]); };
+    int jbs_st = jbs;
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(jbs_st));
+#endif
 #pragma unroll
-    for (int m = 0; m < NA; ++m) {
-        addr[m] = jbs ^ (cst ? sc.pass[sc_pass].regoff_swz[m] : ps.regoff_swz[m]);
-        a[m] = sm[addr[m]];
-    }
+    for (int m = 0; m < NA; ++m) a[m] = sm[slot_addr(jbs, m)];
+    after_load();
     int o = cst ? sc.pass[sc_pass].fop_begin : (fast ? ps.fop_begin : ps.op_begin);
     const int o_end = cst ? sc.pass[sc_pass].fop_end : (fast ? ps.fop_end : ps.op_end);
     Op op;
@@ -515,8 +549,13 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
                 default: NCB_UNREACHABLE(); break;
                 }
             }
+            if (gdst) {
 #pragma unroll
-            for (int m = 0; m < NA; ++m) sm[addr[m]] = a[m];
+                for (int m = 0; m < NA; ++m) st_stream(gdst + (gj | sc.goff_last[m]), a[m]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < NA; ++m) sm[slot_addr(jbs_st, m)] = a[m];
+            }
             return;
         }
     }
@@ -536,8 +575,13 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
             apply_op<R, FEAT>(op, jb, M, m4, b, a);
         }
     }
+    if (gdst) {
 #pragma unroll
-    for (int m = 0; m < NA; ++m) sm[addr[m]] = a[m];
+        for (int m = 0; m < NA; ++m) st_stream(gdst + (gj | sc.goff_last[m]), a[m]);
+    } else {
+#pragma unroll
+        for (int m = 0; m < NA; ++m) sm[slot_addr(jbs_st, m)] = a[m];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

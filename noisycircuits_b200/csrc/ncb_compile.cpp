@@ -1010,6 +1010,26 @@ static void build_blobs(Program& P) {
             }
             sc.valid = fits ? 1 : 0;
             sc.npass = (int)passes.size(); sc.nops = nops; sc.ncoef = ncoef;
+            // direct store of the last pass
+            if (fits && !passes.empty() && P.nbits > P.K && P.opt.direct && P.R == 3 && !P.has_dense2 && !P.has_dense4) {
+                const int Lb = std::min(std::max(P.opt.low_bits, 0), std::min(P.K - 4, P.nbits));
+                bool ok = Lb >= 2;
+                auto describe_pass = [&](const Pass& ps, uint32_t* goff, BitRuns& gruns) {
+                    for (int i = 0; i < Lb; ++i)
+                        if (ps.tpos[i] != i || sg.tile_q[i] != i) ok = false;
+                    for (int m = 0; m < (1 << P.R); ++m) {
+                        uint32_t off = 0;
+                        for (int r = 0; r < P.R; ++r)
+                            if ((m >> r) & 1) off |= 1u << sg.tile_q[ps.regpos[r]];
+                        goff[m] = off;
+                    }
+                    std::vector<int> gpos;
+                    for (int i = 0; i < P.K - P.R; ++i) gpos.push_back(sg.tile_q[ps.tpos[i]]);
+                    gruns = make_runs(gpos);
+                };
+                describe_pass(passes.back(), sc.goff_last, sc.gruns_last);
+                sc.direct = ok ? 1 : 0;
+            }
             P.segconst.push_back(sc);
         }
         SegBlob h;
@@ -1050,9 +1070,9 @@ std::string describe_program(const Program& P) {
         int fast = 0, fdiag = 0;
         for (const Pass& ps : P.passes)
             for (int i = ps.fop_begin; i < ps.fop_end; ++i) { ++fast; fdiag += op_kind(P.ops[i]) == OPK_DIAG; }
-        int valid = 0;
-        for (const SegConst& sc : P.segconst) valid += sc.valid;
-        o << " fast_ops=" << fast << " (diag " << fdiag << ") const_segments=" << valid << "/" << P.segconst.size();
+        int valid = 0, direct = 0;
+        for (const SegConst& sc : P.segconst) { valid += sc.valid; direct += sc.direct; }
+        o << " fast_ops=" << fast << " (diag " << fdiag << ") const_segments=" << valid << "/" << P.segconst.size() << " direct_segments=" << direct;
     }
     o << "\n";
     for (size_t s = 0; s < P.segs.size(); ++s) {

@@ -29,6 +29,8 @@ NCB_EXTERN_TILE(3, FEAT_DENSE2, 256, 1)
 NCB_EXTERN_TILE(4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1)
 NCB_EXTERN_TILE(4, 0, 256, 2)
 #undef NCB_EXTERN_TILE
+extern template __global__ void direct_kernel<512, 2>(DevProgram, const __grid_constant__ SegConst, const unsigned char*, int, int, const Work*, int,
+                                                     cplx*, int);
 extern template __global__ void resident_kernel<3, 0, 512, 1>(DevProgram, ResidentArgs);
 extern template __global__ void resident_kernel<3, FEAT_DENSE2, 256, 1>(DevProgram, ResidentArgs);
 extern template __global__ void resident_kernel<4, FEAT_DENSE2 | FEAT_DENSE4, 256, 1>(DevProgram, ResidentArgs);
@@ -240,6 +242,34 @@ struct Engine {
 #undef NCB_TILE_ARGS
         CK(cudaGetLastError());
     }
+    // direct kernel (works that run a whole segment without an event; lean programs only)
+    int direct_ctas = 0;
+    size_t direct_smem() const {
+        return (size_t)tile_blob_cap + tile_smem() + (size_t)SC_MAX_PASSES * sizeof(unsigned short) * ((size_t)1 << (P.K - P.R));
+    }
+    void launch_direct(int nworks, cudaStream_t s, const Work* works, int seg) {
+        configure_tile();
+        const int tile_shift = P.nbits - P.K, threads = 1 << (P.K - P.R);
+        if (!direct_ctas) {
+            configure(direct_kernel<512, 2>);
+            int occ = occupancy(direct_kernel<512, 2>, threads, direct_smem());
+            if (occ < 1) throw std::runtime_error("direct kernel does not fit on an SM");
+            if (const char* e = getenv("NCB_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
+            direct_ctas = sm_count * occ;
+            if (getenv("NCB_VERBOSE")) fprintf(stderr, "[ncb] direct kernel: %d threads, smem %zu B, %d CTAs/SM\n", threads, direct_smem(), occ);
+        }
+        const long long total = (long long)nworks << tile_shift;
+        const int grid = (int)std::min<long long>(total, direct_ctas);
+        if (grid < 1) return;
+        const unsigned char* blob = d_blobs.p + P.blob_off[seg];
+        const int blob_bytes = reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[seg])->bytes;
+        direct_kernel<512, 2><<<grid, threads, direct_smem(), s>>>(d, P.segconst[seg], blob, blob_bytes, tile_blob_cap, works, nworks, d_states.p, tile_shift);
+        CK(cudaGetLastError());
+    }
+    void launch_step(const LaunchStep& st, cudaStream_t s, const Work* works) {
+        if (st.direct) launch_direct(st.count, s, works + st.begin, st.seg);
+        else launch_tile(st.count, s, works + st.begin, st.seg);
+    }
     void launch_resident(int grid, cudaStream_t s, const ResidentArgs& a) {
         const int threads = 1 << (P.K - P.R);
         if (!resident_configured) {
@@ -423,7 +453,7 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             CK(cudaMemcpyAsync(d_decides[buf].p, h_decides[buf].p, plan.decides.size() * sizeof(DecideItem), cudaMemcpyHostToDevice, s));
         }
         for (const LaunchStep& st : plan.steps) {
-            if (st.kind == 0) { launch_tile(st.count, s, d_works[buf].p + st.begin, st.seg); ++rp->out_tile_launches; }
+            if (st.kind == 0) { launch_step(st, s, d_works[buf].p); ++rp->out_tile_launches; }
             else {
                 decide_kernel<<<st.count, 256, 0, s>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
                 CK(cudaGetLastError());
@@ -543,7 +573,7 @@ void Engine::run_deterministic(cudaStream_t s) {
         d_works[0].reserve(plan.works.size() + 1);
         CK(cudaMemcpyAsync(d_works[0].p, plan.works.data(), plan.works.size() * sizeof(Work), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
-        for (const LaunchStep& st : plan.steps) launch_tile(st.count, s, d_works[0].p + st.begin, st.seg);
+        for (const LaunchStep& st : plan.steps) launch_step(st, s, d_works[0].p);
     }
 }
 
@@ -608,6 +638,7 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     if (const char* e = getenv("NCB_FUSE")) opt.fuse = atoi(e);
     if (const char* e = getenv("NCB_REORDER")) opt.reorder = atoi(e);
     if (const char* e = getenv("NCB_DECOMPOSE")) opt.decompose = atoi(e);
+    if (const char* e = getenv("NCB_DIRECT")) opt.direct = atoi(e);
     if (opt.reg_bits != 3 && opt.reg_bits != 4) return fail(NCB_E_INVALID, "reg_bits must be 3 or 4");
     opt.tile_bits = std::min(opt.tile_bits, 12);   // <= 256 threads (R = 4) / 512 threads (R = 3)
     ncb_program* p = new ncb_program();

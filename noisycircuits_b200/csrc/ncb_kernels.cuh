@@ -41,10 +41,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-__device__ __forceinline__ void st_stream(cplx* p, cplx v) {
-    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -262,6 +258,67 @@ tile_kernel(DevProgram P, const __grid_constant__ SegConst sc, const unsigned ch
         w = wn;
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// direct kernel: the sweep of the works that run a WHOLE segment without any jump event (most of them)
+// ---------------------------------------------------------------------------------------------------------------
+// Same persistent walk and tile geometry as tile_kernel, lean operator set, no event / reduction code.  Two things
+// differ: the LAST pass stores its amplitudes from registers straight to HBM (64-byte runs per 4 lanes: the low state
+// bits are the low thread-index bits of that pass, SegConst::direct) instead of going back through shared memory, and
+// as soon as the last pass holds its amplitudes in registers the tile buffer is refilled with the CTA's next tile
+// (cp.async), so that load overlaps the last pass' arithmetic and stores.  Works: slot (written), src (read).
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+direct_kernel(DevProgram P, const __grid_constant__ SegConst sc, const unsigned char* __restrict__ blob_g, int blob_bytes, int blob_cap,
+              const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int tile_shift) {
+    constexpr int R = 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = P.K, tid = threadIdx.x, nthreads = blockDim.x;
+    const int ntiles = 1 << tile_shift;
+    const long long total = (long long)nworks << tile_shift;
+    cplx* const sm = reinterpret_cast<cplx*>(smem_raw + blob_cap);
+    for (int i = tid * 16; i < blob_bytes; i += nthreads * 16) cp_async16(smem_raw + i, blob_g + i);
+    cp_async_wait_all();
+    __syncthreads();
+    const SegBlob* blob = reinterpret_cast<const SegBlob*>(smem_raw);
+    const Segment* sg = &blob->seg;
+    const Pass* passes = reinterpret_cast<const Pass*>(smem_raw + blob->pass_off);
+    const Op* ops = reinterpret_cast<const Op*>(smem_raw + blob->op_off);
+    const double* pool = reinterpret_cast<const double*>(smem_raw + blob->pool_off);
+    const int npass = sc.npass;
+    // per-thread constants of the CTA's lifetime: base tile index of every pass, state offset of the last pass
+    unsigned short* jb_tab = reinterpret_cast<unsigned short*>(sm + ((size_t)1 << K));
+    for (int p = 0; p < npass; ++p) jb_tab[p * nthreads + tid] = (unsigned short)apply_runs(passes[p].truns, (unsigned)tid);
+    const unsigned gj_last = apply_runs(sc.gruns_last, (unsigned)tid);
+    const unsigned offA = apply_runs(sg->eruns, (unsigned)tid);
+    const int sA = swz(tid);
+    const int lo = sg->instr_lo, hi = sg->instr_hi;
+    auto issue_load = [&](long long tt) {
+        const cplx* st = states + ((long long)works[tt >> tile_shift].src << P.nbits) + apply_runs(sg->bruns, (unsigned)(tt & (ntiles - 1)));
+#pragma unroll
+        for (int it = 0; it < (1 << R); ++it) cp_async16(sm + (sA ^ sg->it_swz[it]), st + (offA | sg->it_off[it]));
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    long long t = blockIdx.x;
+    if (t >= total) return;
+    issue_load(t);
+    for (; t < total; t += gridDim.x) {
+        const long long tn = t + gridDim.x;
+        cplx* const dst = states + ((long long)works[t >> tile_shift].slot << P.nbits) + apply_runs(sg->bruns, (unsigned)(t & (ntiles - 1)));
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        for (int p = 0; p < npass; ++p) {
+            const bool last = p == npass - 1;
+            run_pass_thread<R, 0, true>(sm, K, (int)jb_tab[p * nthreads + tid], passes[p], ops, pool, P.pool, lo, hi, false, sc, p,
+                                        last ? dst : nullptr, gj_last, [&]() {
+                                            if (!last) return;
+                                            __syncthreads();             // every thread holds its amplitudes: the buffer is free
+                                            if (tn < total) issue_load(tn);
+                                        });
+            if (!last) __syncthreads();
+        }
+    }
 }
 
 #ifndef NCB_TEMPLATES_ONLY   // the small non-template kernels live in ncb_engine.cu's module only

@@ -18,6 +18,7 @@ struct LaunchStep {
     int kind;          // 0: tile launch over works[begin, begin+count); 1: decide launch over decides[begin, begin+count)
     int begin, count;
     int seg;           // tile launches: segment (all works of a launch share it)
+    int direct;        // tile launches: 1 = every work runs the whole segment without an event (direct kernel)
 };
 struct BatchPlan {
     std::vector<Work> works;
@@ -80,7 +81,7 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
             end[b] = e;
         }
         // main launch
-        LaunchStep st{0, (int)out.works.size(), 0, s};
+        LaunchStep st{0, (int)out.works.size(), 0, s, 0};
         live.clear();
         if (share_prefix && s < trunk_until) {
             Work w{tout, tin, sg.instr_lo, sg.instr_hi, first ? WF_INIT : 0, -1, -1, -1};
@@ -102,17 +103,28 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
             out.works.push_back(w);
         }
         st.count = (int)out.works.size() - st.begin;
-        if (st.count) out.steps.push_back(st);
         out.sweeps += st.count;
+        // works that run the whole segment without an event go to the direct kernel where the segment allows it
+        const bool seg_direct = (size_t)s < P.segconst.size() && P.segconst[s].valid && P.segconst[s].direct;
+        if (seg_direct && st.count) {
+            auto first = out.works.begin() + st.begin;
+            auto mid = std::stable_partition(first, out.works.end(), [&](const Work& w) {
+                return w.flags == 0 && w.instr_lo <= sg.instr_lo && w.instr_hi >= sg.instr_hi; });
+            const int nd = (int)(mid - first);
+            if (nd) out.steps.push_back(LaunchStep{0, st.begin, nd, s, 1});
+            if (st.count - nd) out.steps.push_back(LaunchStep{0, st.begin + nd, st.count - nd, s, 0});
+        } else if (st.count) {
+            out.steps.push_back(st);
+        }
         // rounds
         while (!live.empty()) {
-            LaunchStep ds{1, (int)out.decides.size(), 0, s};
+            LaunchStep ds{1, (int)out.decides.size(), 0, s, 0};
             for (int b : live) {
                 const Event& e = events[b][cur[b]];
                 if (e.kmin != e.kmax) { out.decides.push_back(DecideItem{b, e.instr, e.u}); ++ds.count; }
             }
             if (ds.count) out.steps.push_back(ds);
-            LaunchStep ts{0, (int)out.works.size(), (int)live.size(), s};
+            LaunchStep ts{0, (int)out.works.size(), (int)live.size(), s, 0};
             next.clear();
             for (int b : live) {
                 const Event& e = events[b][cur[b]];

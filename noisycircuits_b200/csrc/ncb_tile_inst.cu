@@ -9,6 +9,9 @@ namespace ncb {
 template __global__ void tile_kernel<NCB_INST_R, NCB_INST_FEAT, NCB_INST_MAXT, NCB_INST_MINB>(
     DevProgram, const __grid_constant__ SegConst, const unsigned char*, int, int, int, const Work*, int, cplx*, int, double*, double*,
     const Decision*);
+#elif defined(NCB_INST_DIRECT)
+template __global__ void direct_kernel<NCB_INST_MAXT, NCB_INST_MINB>(DevProgram, const __grid_constant__ SegConst, const unsigned char*, int, int,
+                                                                     const Work*, int, cplx*, int);
 #else
 template __global__ void resident_kernel<NCB_INST_R, NCB_INST_FEAT, NCB_INST_MAXT, NCB_INST_MINB>(DevProgram, ResidentArgs);
 #endif

@@ -4,7 +4,7 @@ rep, so = sys.argv[1], sys.argv[2]
 kern = sys.argv[3] if len(sys.argv) > 3 else 'tile_kernelILi3ELi0ELi512ELi2'
 td = tempfile.mkdtemp()
 subprocess.run(f"cd {td} && cuobjdump -xelf all {so} >/dev/null 2>&1 && (for f in *.cubin; do nvdisasm -g -c $f; done) > all.sass 2>/dev/null", shell=True)
-subprocess.run(f"ncu -i {rep} --page source --csv --kernel-name regex:tile_kernel > {td}/src.csv 2>/dev/null; ncu -i {rep} --page raw --csv > {td}/raw.csv 2>/dev/null", shell=True)
+subprocess.run(f"ncu -i {rep} --page source --csv --kernel-name regex:$KREGEX > {td}/src.csv 2>/dev/null; ncu -i {rep} --page raw --csv > {td}/raw.csv 2>/dev/null", shell=True)
 rows = list(csv.reader(open(f'{td}/raw.csv'))); hdr = rows[0]
 for w in ('gpu__time_duration.sum','smsp__inst_executed.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed','sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','sm__warps_active.avg.pct_of_peak_sustained_active','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','launch__grid_size','launch__block_size'):
     if w in hdr:

@@ -107,6 +107,43 @@ void emulate_work(const Program& P, const Work& w, int seg, std::vector<cplx>& s
     }
 }
 
+// the direct kernel (ncb_kernels.cuh: direct_kernel): tile loaded like the tile kernel, last pass stored from registers
+void emulate_direct_work(const Program& P, const Work& w, int seg, std::vector<cplx>& states) {
+    constexpr int R = 3;
+    if (P.R != 3) throw std::runtime_error("direct launch on a program with reg_bits != 3");
+    const int K = P.K, nthreads = 1 << (K - R);
+    const int tile_shift = P.nbits - K, ntiles = 1 << tile_shift;
+    const unsigned char* braw = P.blobs.data() + P.blob_off[seg];
+    const SegBlob& blob = *reinterpret_cast<const SegBlob*>(braw);
+    const Segment& sg = blob.seg;
+    const Pass* passes = reinterpret_cast<const Pass*>(braw + blob.pass_off);
+    const Op* ops = reinterpret_cast<const Op*>(braw + blob.op_off);
+    const double* pool = reinterpret_cast<const double*>(braw + blob.pool_off);
+    const SegConst& sc = P.segconst[seg];
+    if (!sc.valid || !sc.direct) throw std::runtime_error("direct launch on a segment that does not allow it");
+    if (w.flags != 0 || w.instr_lo > sg.instr_lo || w.instr_hi < sg.instr_hi) throw std::runtime_error("direct launch with a partial work");
+    std::vector<cplx> sm((size_t)1 << K);
+    for (int o = 0; o < ntiles; ++o) {
+        const long long base = apply_runs(sg.bruns, (unsigned)o);
+        const cplx* src = states.data() + ((long long)w.src << P.nbits) + base;
+        cplx* dst = states.data() + ((long long)w.slot << P.nbits) + base;
+        for (int tid = 0; tid < nthreads; ++tid) {
+            const unsigned offA = apply_runs(sg.eruns, (unsigned)tid);
+            const int sA = swz(tid);
+            for (int it = 0; it < (1 << R); ++it) sm[sA ^ sg.it_swz[it]] = src[offA | sg.it_off[it]];
+        }
+        for (int p = 0; p < sc.npass; ++p) {
+            const bool last = p == sc.npass - 1;
+            // the last pass reads the tile into "registers" for every thread before any of them stores: the kernel's
+            // barrier in after_load; here the stores go to global memory, which the loads never read (src was consumed)
+            for (int tid = 0; tid < nthreads; ++tid)
+                run_pass_thread<R, 0, true>(sm.data(), K, (int)apply_runs(passes[p].truns, (unsigned)tid), passes[p], ops, pool, P.pool.data(),
+                                            sg.instr_lo, sg.instr_hi, false, sc, p, last ? dst : nullptr,
+                                            last ? apply_runs(sc.gruns_last, (unsigned)tid) : 0u);
+        }
+    }
+}
+
 void run_plan(const Program& P, const BatchPlan& plan, int B, std::vector<cplx>& states, std::vector<double>& norm_part) {
     const int tile_shift = P.nbits > P.K ? P.nbits - P.K : 0, ntiles = 1 << tile_shift;
     std::vector<double> red_part((size_t)B * ntiles * 32, 0.0);
@@ -116,6 +153,7 @@ void run_plan(const Program& P, const BatchPlan& plan, int B, std::vector<cplx>&
         if (st.kind == 0) {
             for (int i = 0; i < st.count; ++i) {
                 const Work& w = plan.works[st.begin + i];
+                if (st.direct) { emulate_direct_work(P, w, st.seg, states); continue; }
                 if (P.R == 4) emulate_work<4>(P, w, st.seg, states, red_part, norm_part, decisions);
                 else emulate_work<3>(P, w, st.seg, states, red_part, norm_part, decisions);
             }
