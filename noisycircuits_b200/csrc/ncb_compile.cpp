@@ -1015,8 +1015,16 @@ static void build_blobs(Program& P) {
                 const int Lb = std::min(std::max(P.opt.low_bits, 0), std::min(P.K - 4, P.nbits));
                 bool ok = Lb >= 2;
                 auto describe_pass = [&](const Pass& ps, uint32_t* goff, BitRuns& gruns) {
-                    for (int i = 0; i < Lb; ++i)
-                        if (ps.tpos[i] != i || sg.tile_q[i] != i) ok = false;
+                    // every 32-byte sector a warp's store touches must be completed by the same warp: state bits 0 and 1
+                    // have to be lane bits (in order) or register bits (the thread writes the neighbours itself)
+                    for (int i = 0, lane = 0; i < Lb; ++i) {
+                        if (sg.tile_q[i] != i) ok = false;
+                        bool is_reg = false;
+                        for (int r = 0; r < P.R; ++r) is_reg = is_reg || ps.regpos[r] == i;
+                        if (is_reg) continue;
+                        if (ps.tpos[lane] != i) ok = false;
+                        ++lane;
+                    }
                     for (int m = 0; m < (1 << P.R); ++m) {
                         uint32_t off = 0;
                         for (int r = 0; r < P.R; ++r)
