@@ -85,6 +85,7 @@ struct Engine {
     DevBuf<double> d_pool; DevBuf<int32_t> d_noisy; DevBuf<int32_t> d_orig; DevBuf<unsigned char> d_blobs;
     DevBuf<cplx> d_states;
     DevBuf<double> d_red, d_norm, d_invnorm, d_weight, d_probs, d_partial, d_uniforms;
+    bool overlap_streams = true;
     bool independent = false;          // ncb_options.independent_trajectories: no shared no-jump prefix
     DevBuf<Decision> d_dec;
     DevBuf<unsigned long long> d_counters;
@@ -94,6 +95,10 @@ struct Engine {
     PinnedBuf<DecideItem> h_decides[2];
     cudaEvent_t buf_free[2] = {nullptr, nullptr};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // second stream: a segment's jump-event chain (first pieces, decide, rounds) runs beside the direct launch of the
+    // trajectories without an event in that segment (disjoint slots), joined at every segment boundary
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     bool tile_configured = false, resident_configured = false;
     int tile_ctas = 148;
 
@@ -105,6 +110,9 @@ struct Engine {
             d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
             if (buf_free[i]) cudaEventDestroy(buf_free[i]);
         }
+        if (s2) cudaStreamDestroy(s2);
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
     }
@@ -144,6 +152,15 @@ struct Engine {
         for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&buf_free[i], cudaEventDisableTiming));
         CK(cudaEventCreate(&t0));
         CK(cudaEventCreate(&t1));
+        {
+            int lo_pri = 0, hi_pri = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+            CK(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_pri));
+            CK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
+            if (const char* e = getenv("NCB_DIRECT_CHUNK")) direct_chunk = atoi(e);
+            if (const char* e = getenv("NCB_OVERLAP")) overlap_streams = atoi(e) != 0;
+        }
         d_counters.reserve(4);
         uploaded = true;
     }
@@ -243,7 +260,7 @@ struct Engine {
         CK(cudaGetLastError());
     }
     // direct kernel (works that run a whole segment without an event; lean programs only)
-    int direct_ctas = 0;
+    int direct_ctas = 0, direct_chunk = 16;      // tiles per direct-kernel CTA: CTA turnover lets the (higher-priority) event chain in
     size_t direct_smem() const {
         return (size_t)tile_blob_cap + tile_smem() + (size_t)SC_MAX_PASSES * sizeof(unsigned short) * ((size_t)1 << (P.K - P.R));
     }
@@ -259,7 +276,9 @@ struct Engine {
             if (getenv("NCB_VERBOSE")) fprintf(stderr, "[ncb] direct kernel: %d threads, smem %zu B, %d CTAs/SM\n", threads, direct_smem(), occ);
         }
         const long long total = (long long)nworks << tile_shift;
-        const int grid = (int)std::min<long long>(total, direct_ctas);
+        long long want = direct_ctas;
+        if (direct_chunk > 0) want = std::max<long long>(want, (total + direct_chunk - 1) / direct_chunk);   // CTA turnover lets the event chain in
+        const int grid = (int)std::min<long long>(total, want);
         if (grid < 1) return;
         const unsigned char* blob = d_blobs.p + P.blob_off[seg];
         const int blob_bytes = reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[seg])->bytes;
@@ -452,14 +471,27 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             std::memcpy(h_decides[buf].p, plan.decides.data(), plan.decides.size() * sizeof(DecideItem));
             CK(cudaMemcpyAsync(d_decides[buf].p, h_decides[buf].p, plan.decides.size() * sizeof(DecideItem), cudaMemcpyHostToDevice, s));
         }
+        const bool overlap = overlap_streams && share;
+        auto join = [&]() {          // both streams wait for each other
+            CK(cudaEventRecord(ev_a, s));
+            CK(cudaEventRecord(ev_b, s2));
+            CK(cudaStreamWaitEvent(s, ev_b, 0));
+            CK(cudaStreamWaitEvent(s2, ev_a, 0));
+        };
+        int cur_seg = -1;
+        if (overlap) join();         // the uploads above and the previous batch's tail
         for (const LaunchStep& st : plan.steps) {
-            if (st.kind == 0) { launch_step(st, s, d_works[buf].p); ++rp->out_tile_launches; }
+            if (overlap && st.seg != cur_seg && cur_seg >= 0) join();
+            cur_seg = st.seg;
+            cudaStream_t q = overlap && !(st.kind == 0 && st.direct) ? s2 : s;
+            if (st.kind == 0) { launch_step(st, q, d_works[buf].p); ++rp->out_tile_launches; }
             else {
-                decide_kernel<<<st.count, 256, 0, s>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
+                decide_kernel<<<st.count, 256, 0, q>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
                 CK(cudaGetLastError());
             }
             ++rp->out_launches;
         }
+        if (overlap) join();
         CK(cudaEventRecord(buf_free[buf], s));
         CK(cudaMemcpyAsync(d_weight.p, plan.weight.data(), plan.weight.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         rp->out_h2d_bytes += (int64_t)(plan.weight.size() * sizeof(double));
