@@ -54,7 +54,7 @@ def config(traj_per_step, n_gpus):
                         f"pairs of qubits 0-19), Sample_Noise_Model_Heron_QPU noise (threshold 1e-6), BASELINE configs[4]",
             "instructions": DEPTH * (NQ + 19), "trajectories_per_step_per_gpu": traj_per_step,
             "target_trajectories": 100000, "parallelism": f"trajectory-sharded x{n_gpus}",
-            "l2": "inputs larger than L2 (state batch of trajectories_per_step x 16 MiB per GPU)",
+            "l2": "inputs larger than L2 (every sweep launch walks a state batch of up to 296 trajectories x 16 MiB = 4.7 GB per GPU)",
             "shared_no_jump_prefix": os.environ.get("NCB_SHARE_PREFIX", "1") != "0"}
 
 
@@ -385,10 +385,10 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--traj-per-step", type=int, default=296)
+    ap.add_argument("--traj-per-step", type=int, default=592)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -8,6 +8,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ncb200.h"
@@ -347,6 +348,16 @@ struct Engine {
             for (int32_t pos : P.noisy_instrs) out[(size_t)t * P.G + pos] = us.get(begin + t, P.orig[pos]);   // by position
     }
 
+    // host threads of the event planner: launchers like torchrun export OMP_NUM_THREADS=1, which would serialise the
+    // planning of a batch (tens of ms at the start of every call); take this rank's share of the cores instead
+    static int plan_threads() {
+        if (const char* e = getenv("NCB_PLAN_THREADS")) return std::max(1, atoi(e));
+        int hw = (int)std::thread::hardware_concurrency();
+        if (hw < 1) hw = 1;
+        int ranks = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        return std::max(1, std::min(16, hw / ranks));
+    }
     int auto_batch(long long count) const {
         // enough trajectories per launch that (a) the persistent grid runs many tiles per CTA and (b) the small extra
         // launches of the jump-event rounds (a few slots each) are amortised; capped by memory (8 GB of state)
@@ -354,7 +365,7 @@ struct Engine {
         long long b = (148ll * 1024 + tiles - 1) / tiles;
         b = ((b + 36) / 37) * 37;
         if (const char* e = getenv("NCB_BATCH")) b = std::max(1, atoi(e));
-        const long long mem_cap = std::max<long long>(1, (8ll << 30) / ((long long)sizeof(cplx) << P.nbits));
+        const long long mem_cap = std::max<long long>(1, (16ll << 30) / ((long long)sizeof(cplx) << P.nbits));
         b = std::min(b, mem_cap);
         return (int)std::max<long long>(1, std::min(b, count));
     }
@@ -449,7 +460,7 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
         }
         events.assign(nb, {});
         const bool mt = rp->rng == NCB_RNG_MT19937_REFERENCE;
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(plan_threads())
         for (int b = 0; b < nb; ++b) {
             const long long tl = mt ? b : b0 + b;
             plan_events(P, [&](int i) { return us.get(tl, i); }, events[b]);
