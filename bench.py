@@ -39,6 +39,7 @@ METRIC = "mcwf_trajectories_per_sec"
 UNIT = "trajectories/s"
 NQ, DEPTH, CIRCUIT_SEED = 20, 50, 42
 CPU_SAMPLE_LAYERS = 4        # bounded CPU sample: ~10 s of all-core work per measurement
+PREWARM_S = 3.0              # untimed pre-warm before the warm-up steps (seconds)
 
 
 def workload():
@@ -295,6 +296,14 @@ def run_gpu(args):
     clocks = make_clock_sampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()            # nvidia-smi starts (and initialises NVML) during the warm-up, samples through the timed region
+    # pre-warm: a process on a freshly provisioned box runs its first seconds visibly slower (library pages, NCCL
+    # channels, power state) -- untimed steps until PREWARM_S have passed, then the W warm-up steps of the contract
+    t_pre = time.perf_counter()
+    s_pre = 0
+    while time.perf_counter() - t_pre < PREWARM_S:
+        step(1000 + s_pre)
+        s_pre += 1
+        barrier()
     for s in range(args.warmup):
         step(s)
     barrier()

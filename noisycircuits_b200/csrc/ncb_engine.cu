@@ -59,6 +59,7 @@ struct DevBuf {
         CK(cudaMalloc(&p, n * sizeof(T)));
         cap = n;
     }
+    void reserve_growing(size_t n) { if (n > cap) reserve(n + n / 4 + 64); }   // per-batch lists: sizes vary a few percent
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 template <class T>
@@ -72,6 +73,7 @@ struct PinnedBuf {
         CK(cudaMallocHost(&p, n * sizeof(T)));
         cap = n;
     }
+    void reserve_growing(size_t n) { if (n > cap) reserve(n + n / 4 + 64); }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
@@ -473,8 +475,8 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
         rp->out_sweeps += plan.sweeps;
         // upload the batch's work lists (double-buffered so planning overlaps the previous batch's kernels)
         CK(cudaEventSynchronize(buf_free[buf]));
-        h_works[buf].reserve(plan.works.size() + 1); d_works[buf].reserve(plan.works.size() + 1);
-        h_decides[buf].reserve(plan.decides.size() + 1); d_decides[buf].reserve(plan.decides.size() + 1);
+        h_works[buf].reserve_growing(plan.works.size() + 1); d_works[buf].reserve_growing(plan.works.size() + 1);
+        h_decides[buf].reserve_growing(plan.decides.size() + 1); d_decides[buf].reserve_growing(plan.decides.size() + 1);
         std::memcpy(h_works[buf].p, plan.works.data(), plan.works.size() * sizeof(Work));
         CK(cudaMemcpyAsync(d_works[buf].p, h_works[buf].p, plan.works.size() * sizeof(Work), cudaMemcpyHostToDevice, s));
         rp->out_h2d_bytes += (int64_t)(plan.works.size() * sizeof(Work) + plan.decides.size() * sizeof(DecideItem));
