@@ -87,6 +87,7 @@ struct Engine {
     DevBuf<Op> d_ops; DevBuf<Pass> d_passes; DevBuf<Segment> d_segs; DevBuf<Instr> d_instrs; DevBuf<Channel> d_chans;
     DevBuf<double> d_pool; DevBuf<int32_t> d_noisy; DevBuf<int32_t> d_orig; DevBuf<unsigned char> d_blobs;
     DevBuf<cplx> d_states;
+    DevBuf<double> d_trunk;
     DevBuf<double> d_red, d_norm, d_invnorm, d_weight, d_probs, d_partial, d_uniforms;
     bool overlap_streams = true;
     bool independent = false;          // ncb_options.independent_trajectories: no shared no-jump prefix
@@ -107,7 +108,7 @@ struct Engine {
 
     ~Engine() {
         d_ops.release(); d_passes.release(); d_segs.release(); d_instrs.release(); d_chans.release(); d_pool.release();
-        d_noisy.release(); d_orig.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_weight.release(); d_probs.release();
+        d_noisy.release(); d_orig.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_weight.release(); d_trunk.release(); d_probs.release();
         d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release();
         for (int i = 0; i < 2; ++i) {
             d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
@@ -406,10 +407,14 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
     if (rp->states) { d_states.reserve((size_t)count * dim); a.states_out = d_states.p; }
     CK(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(unsigned long long), s));
     a.counters = d_counters.p;
+    a.share = (!rp->states && !independent) ? 1 : 0;
+    if (const char* e = getenv("NCB_SHARE_PREFIX")) a.share = a.share && atoi(e) != 0;
+    d_trunk.reserve(dim);
+    a.trunk_probs = d_trunk.p;
     launch_resident(grid, s, a);
     int g, b;
     grid_1d(dim, &g, &b);
-    sum_partials_kernel<<<g, b, 0, s>>>(d_probs.p, d_partial.p, dim, grid);
+    sum_partials_kernel<<<g, b, 0, s>>>(d_probs.p, d_partial.p, dim, grid, a.share ? d_trunk.p : nullptr, d_counters.p + 2);
     CK(cudaGetLastError());
     unsigned long long cnt[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(cnt, d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));

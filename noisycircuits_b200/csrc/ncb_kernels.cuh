@@ -390,10 +390,14 @@ __global__ void accumulate_kernel(double* __restrict__ probs, const cplx* __rest
 }
 
 // probs[j] += sum_c partial[c][j]
-__global__ void sum_partials_kernel(double* __restrict__ probs, const double* __restrict__ partial, long long dim, int nparts) {
+// trunk (optional): + n_trunk[0] * trunk[j], the trajectories without any jump (resident_kernel, ResidentArgs::share)
+__global__ void sum_partials_kernel(double* __restrict__ probs, const double* __restrict__ partial, long long dim, int nparts,
+                                    const double* __restrict__ trunk = nullptr, const unsigned long long* __restrict__ n_trunk = nullptr) {
+    const double wt = trunk ? (double)n_trunk[0] : 0.0;
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < dim; j += (long long)gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int c = 0; c < nparts; ++c) s += partial[c * dim + j];
+        if (wt != 0.0) s += wt * trunk[j];
         probs[j] += s;
     }
 }
@@ -436,7 +440,11 @@ struct ResidentArgs {
     double* partial_probs;      // [gridDim.x][2^nbits] accumulated |psi|^2 (may be NULL)
     cplx* states_out;           // optional [traj_count][2^nbits]: final normalised states
     int normalize;              // divide by the norm (program is not norm preserving)
-    unsigned long long* counters;   // [0] events, [1] state-dependent events
+    unsigned long long* counters;   // [0] events, [1] state-dependent events, [2] trajectories without any event (share)
+    // share: a trajectory whose draws all pick the base branch is the same evolution for everybody: block 0 computes it
+    // once into trunk_probs (normalised |psi|^2), the others are only counted
+    int share;
+    double* trunk_probs;
 };
 
 template <int R, int FEAT, int MAXT, int MINB>
@@ -458,15 +466,19 @@ resident_kernel(DevProgram P, ResidentArgs A) {
     for (int j = tid; j < dim; j += nthreads) acc[j] = 0.0;
     unsigned long long n_events = 0, n_hard = 0;
 
-    for (long long tl = blockIdx.x; tl < A.traj_count; tl += gridDim.x) {
+    unsigned long long n_trunk = 0;
+    // block 0 runs one extra iteration first (tl < 0): the jump-free trajectory
+    for (long long tl = (long long)blockIdx.x - ((A.share && blockIdx.x == 0) ? (long long)gridDim.x : 0); tl < A.traj_count; tl += gridDim.x) {
+        const bool is_trunk = tl < 0;
         const unsigned long long traj = (unsigned long long)(A.traj_begin + tl);
-        const double* utab = A.uniforms ? A.uniforms + tl * P.G : nullptr;
+        const double* utab = A.uniforms && !is_trunk ? A.uniforms + tl * P.G : nullptr;
         // ---- plan: which instructions deviate from their base branch? ----
         for (int i = tid; i < nwords; i += nthreads) evmask[i] = 0u;
         for (int j = tid; j < (1 << K); j += nthreads) sm[j] = cplx{0.0, 0.0};
         __syncthreads();
         if (tid == 0) sm[swz(0)] = cplx{1.0, 0.0};
-        for (int a = tid; a < P.n_noisy; a += nthreads) {
+        int flagged = 0;
+        for (int a = tid; a < P.n_noisy && !is_trunk; a += nthreads) {
             const int i = P.noisy[a];
             const Channel ch = P.chans[P.instrs[i].channel];
             const double* lo = P.pool + ch.bounds;
@@ -474,9 +486,13 @@ resident_kernel(DevProgram P, ResidentArgs A) {
             const double u = utab ? utab[i] : philox_uniform(A.seed, traj, (uint32_t)P.orig[i]);
             const double left = ch.base == 0 ? -1.0 : hi[ch.base - 1] + EVENT_MARGIN;
             const double right = ch.base == ch.count - 1 ? 2.0 : lo[ch.base] - EVENT_MARGIN;
-            if (!(u > left && u <= right)) atomicOr(&evmask[i >> 5], 1u << (i & 31));
+            if (!(u > left && u <= right)) { atomicOr(&evmask[i >> 5], 1u << (i & 31)); flagged = 1; }
         }
-        __syncthreads();
+        if (A.share && !is_trunk) {
+            if (!__syncthreads_or(flagged)) { ++n_trunk; continue; }      // block 0's trunk stands for this trajectory
+        } else {
+            __syncthreads();
+        }
         // ---- run ----
         int cur = 0, pcur = sg->pass_begin;
         while (true) {
@@ -527,8 +543,11 @@ resident_kernel(DevProgram P, ResidentArgs A) {
             inv = 1.0 / s_out[0];
             __syncthreads();
         }
-        if (A.partial_probs)
+        if (is_trunk) {
+            for (int j = tid; j < dim; j += nthreads) A.trunk_probs[j] = cnorm2(sm[swz(j)]) * inv;
+        } else if (A.partial_probs) {
             for (int j = tid; j < dim; j += nthreads) acc[j] += cnorm2(sm[swz(j)]) * inv;
+        }
         if (A.states_out) {
             const double f = sqrt(inv);
             for (int j = tid; j < dim; j += nthreads) {
@@ -544,6 +563,7 @@ resident_kernel(DevProgram P, ResidentArgs A) {
     if (tid == 0 && A.counters) {
         atomicAdd(&A.counters[0], n_events);
         atomicAdd(&A.counters[1], n_hard);
+        atomicAdd(&A.counters[2], n_trunk);
     }
 }
 

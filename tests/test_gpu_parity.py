@@ -219,6 +219,32 @@ def test_sharding_and_batching_do_not_change_the_result(heron_noise):
     assert abs(full.sum() - 96) < 1e-9                 # every trajectory is normalised
 
 
+def test_shared_jump_free_trajectory_resident(heron_noise):
+    """Resident path (n <= 12): trajectories whose draws all pick the base branch are one and the same evolution; block 0
+    computes it once and the others are counted.  Same result as independent trajectories and as the oracle."""
+    sq, tq, _, _ = heron_noise
+    n = 8
+    instr = circuits.heron_layered(n, 4, circuits.coupled_pairs(tq, n), seed=11)
+    pk = PackedCircuit(n, instr, sq, tq)
+    shared = Program(pk, _lib.MODE_MCWF)
+    indep = Program(pk, _lib.MODE_MCWF, independent_trajectories=True)
+    T, seed = 3000, 5
+    a, sa = shared.run_mcwf(T, seed=seed)
+    b, sb = indep.run_mcwf(T, seed=seed)
+    assert np.abs(a - b).max() < 1e-10 * T / 100
+    assert sa["events"] == sb["events"] and 0 < sa["events"] < T          # most trajectories are jump free here
+    assert abs(a.sum() - T) < 1e-8
+    Tq = 40
+    U = np.array([[philox_numpy(seed, t, g) for g in range(len(instr))] for t in range(Tq)])
+    ref = oracle.Program(n, instr, sq, tq).mcwf(Tq, uniforms=U, mask_fix=True)
+    q, _ = shared.run_mcwf(Tq, seed=seed)
+    assert np.abs(q / Tq - ref).max() < TOL
+    # explicit uniforms: all 0.5 -> every trajectory is the trunk
+    flat, st = shared.run_mcwf(16, rng=_lib.RNG_EXPLICIT, uniforms=np.full((16, len(instr)), 0.5))
+    one, _ = indep.run_mcwf(1, rng=_lib.RNG_EXPLICIT, uniforms=np.full((1, len(instr)), 0.5))
+    assert st["events"] == 0 and np.abs(flat - 16 * one).max() < 1e-12
+
+
 def test_shared_no_jump_prefix_is_the_same_computation(heron_noise):
     """The batched run computes the evolution all trajectories share before their first jump once per batch
     (ncb_schedule.h).  Against a program compiled with independent_trajectories: same probabilities (only the order of
