@@ -373,7 +373,8 @@ def run_gpu(args):
                         "d2h_bytes_per_step": d2h // max(args.steps, 1)},
                 "gpu_launches": agg["launches"],
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "ncb::tile_kernel",
+                             "traffic": traffic, "peak_source": peak_src,
+                             "kernel": "ncb::direct_kernel (whole-segment sweeps) + ncb::tile_kernel (jump-event pieces)",
                              "algorithmic_bytes_per_launch": alg_bytes / max(agg["tile_launches"], 1),
                              "avg_launch_ms": ms / max(agg["tile_launches"], 1), "tile_launches": agg["tile_launches"],
                              "sweeps_per_trajectory": agg["sweeps"] / (tps * args.steps)},

@@ -1,9 +1,9 @@
 """Summarise an `ncu --set full` capture of the sweep kernel into profiles/ (markdown table + traffic json).
 
-usage: python scripts/summarize_ncu.py <capture.ncu-rep> <round tag, e.g. r01> <trajectories per launch> "<command line captured>"
+usage: python scripts/summarize_ncu.py <capture.ncu-rep> <round tag, e.g. r01> <kernel: direct|tile> "<command line captured>"
 
-Reads the report with `ncu -i ... --page raw --csv` (no GPU needed).  Launches whose grid covers the whole batch
-(duration > 1 ms) are the per-segment sweeps; the short ones are jump-event rounds over a handful of trajectories.
+Reads the report with `ncu -i ... --page raw --csv` (no GPU needed).  Every launch sweeps the state of the trajectories
+in its work list once; the number of tiles comes from the grid (direct kernel: 16 tiles of 2^11 amplitudes per CTA).
 """
 import csv
 import json
@@ -38,35 +38,40 @@ def to_bytes(value, unit):
 
 
 def main():
-    rep, tag, traj, cmd = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
+    rep, tag, kern, cmd = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, body = rows[0], rows[1], rows[2:]
     col = {n: i for i, n in enumerate(hdr)}
+    body = [r for r in body if (kern + "_kernel") in r[col["Kernel Name"]]]
     name = body[0][col["Kernel Name"]]
-    out = [f"# ncu --set full capture of the sweep kernel ({tag})", "", f"Command (B200, gpurun): `{cmd}`", "",
-           f"Kernel: `{name}`; 20-qubit depth-50 Heron circuit (BASELINE configs[4]), {traj} trajectories per launch "
-           f"({traj} x 16 MiB state).  Launches longer than 1 ms sweep the whole batch once (one segment); the short "
-           "ones are jump-event rounds over the few trajectories that had an event in the segment.", "",
-           f"Algorithmic bytes of one full sweep (SURVEY 8(d)): {traj} trajectories x 2 x 16 B x 2^20 = "
-           f"{traj * 32 * 2 ** 20 / 1e6:.1f} MB.", ""]
+    tiles_per_cta = 16 if kern == "direct" else None
+    tile_bytes = 2 * 16 * 2 ** 11          # one read + one write of a 2^11-amplitude tile
+    out = [f"# ncu --set full capture of the {kern} sweep kernel ({tag})", "", f"Command (B200, gpurun): `{cmd}`", "",
+           f"Kernel: `{name}`; 20-qubit depth-50 Heron circuit (BASELINE configs[4]), engine batches of 296 trajectories "
+           "(296 x 16 MiB state).  With the shared no-jump prefix a segment's launch covers the trajectories that have "
+           "already had their first jump (plus the trunk), so launches grow along the circuit.", ""]
     out.append("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(body))) + " |")
     out.append("|---|---|" + "---|" * len(body))
     for m in METRICS:
         if m in col:
             out.append(f"| {m} | {units[col[m]]} | " + " | ".join(r[col[m]] for r in body) + " |")
-    full = [r for r in body if to_bytes(r[col["gpu__time_duration.sum"]], "byte") * {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}[units[col["gpu__time_duration.sum"]]] > 1.0]
-    alg = traj * 32.0 * 2 ** 20
-    rd = sum(to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) for r in full) / max(len(full), 1)
-    wr = sum(to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]]) for r in full) / max(len(full), 1)
-    out += ["", f"Full sweeps in this capture: {len(full)}.  Mean DRAM traffic per full sweep: read {rd / 1e6:.1f} MB + write "
-            f"{wr / 1e6:.1f} MB = {(rd + wr) / alg:.3f} x the algorithmic bytes (the 126 MB L2 keeps part of the previous "
-            "sweep's tail; nothing is re-read)."]
-    md = os.path.join(ROOT, "profiles", f"{tag}_tile_kernel_ncu_full.md")
+    rd = wr = alg = 0.0
+    if tiles_per_cta:
+        for r in body:
+            grid = float(r[col["launch__grid_size"]].replace(",", ""))
+            alg += grid * tiles_per_cta * tile_bytes
+            rd += to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
+            wr += to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+        out += ["", f"Algorithmic bytes of these launches (SURVEY 8(d): 2 x 16 B per amplitude per sweep; tiles = grid x "
+                f"{tiles_per_cta}, exact to one CTA): {alg / 1e6:.1f} MB.  DRAM traffic (ncu): read {rd / 1e6:.1f} MB + write "
+                f"{wr / 1e6:.1f} MB = {(rd + wr) / alg:.3f} x the algorithmic bytes."]
+    md = os.path.join(ROOT, "profiles", f"{tag}_{kern}_kernel_ncu_full.md")
     open(md, "w").write("\n".join(out) + "\n")
-    json.dump({"kernel": name, "capture": os.path.relpath(md, ROOT), "trajectories_per_launch": traj, "dram_bytes_read": rd,
-               "dram_bytes_write": wr, "algorithmic_bytes": alg, "traffic_over_algorithmic": (rd + wr) / alg},
-              open(os.path.join(ROOT, "profiles", "tile_kernel_traffic.json"), "w"), indent=1)
+    if tiles_per_cta:
+        json.dump({"kernel": name, "capture": os.path.relpath(md, ROOT), "launches": len(body), "dram_bytes_read": rd,
+                   "dram_bytes_write": wr, "algorithmic_bytes": alg, "traffic_over_algorithmic": (rd + wr) / alg},
+                  open(os.path.join(ROOT, "profiles", "tile_kernel_traffic.json"), "w"), indent=1)
     print(open(md).read())
 
 
