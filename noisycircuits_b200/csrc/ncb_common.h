@@ -106,15 +106,18 @@ struct Op {
                        //       [0, 2^n) (found by search on the host), and the table row is hB * 2^nA + hA (2^nA = tmask field)
     int32_t pad;       // group headers: instruction index of the last member
 };
-// kind_nb layout: kind [0,4) | nb [4,8) | tmask [8,16) | regmask [16,20) | lean selector [20,24) | span [24,31) |
+// kind_nb layout: kind [0,4) | nb [4,8) | tmask [8,16) | regmask [16,20) | lean selector [20,25) | span [25,31) |
 // group header [31].  Lean selector (R = 3 programs without dense two-qubit operators): the case of the lean executor's
-// jump table: 0-7 diagonal with that register mask, 8+b RX1 on register bit b, 11+b DENSE1 on register bit b.
+// jump table: 0-7 diagonal with that register mask, 8+b RX1 on register bit b, 11+b DENSE1 on register bit b, and the
+// fused rotations the constant-bank fast list is rewritten with (they commute: different bits): 14/15/16 RX1 on bits
+// (0,1)/(0,2)/(1,2), 17 RX1 on all three bits; coefficients consecutive in SegConst::coef in ascending bit order.
+constexpr int LSEL_X2 = 14, LSEL_X3 = 17;
 // rbs: eight 4-bit fields (register-bit indices / tile-local positions are < 16)
 NCB_HD int op_kind(const Op& o) { return (int)(o.kind_nb & 0xf); }
 NCB_HD int op_nb(const Op& o) { return (int)((o.kind_nb >> 4) & 0xf); }
 NCB_HD int op_tmask(const Op& o) { return (int)((o.kind_nb >> 8) & 0xff); }
 NCB_HD int op_regmask(const Op& o) { return (int)((o.kind_nb >> 16) & 0xf); }
-NCB_HD int op_lean_sel(const Op& o) { return (int)((o.kind_nb >> 20) & 0xf); }
+NCB_HD int op_lean_sel(const Op& o) { return (int)((o.kind_nb >> 20) & 0x1f); }
 NCB_HD int op_rb(const Op& o, int b) { return (int)((o.rbs >> (4 * b)) & 0xf); }
 // diagonal operators act on up to this many bits (table of 2^bits phases)
 NCB_HD constexpr int max_diag_bits(int) { return 6; }
@@ -505,7 +508,7 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
                 if (op.kind_nb >> 31) {
                     // group header: the product of the next `span` ops; usable when the whole group is inside
                     // [lo, hi) and its last instruction is not the bare one
-                    const int span = (int)((op.kind_nb >> 24) & 0x7f), last = op.pad;
+                    const int span = (int)((op.kind_nb >> 25) & 0x3f), last = op.pad;
                     if (!(op.instr >= lo && (last + 1 < hi || (last + 1 == hi && !bare_last)))) continue;
                     o += span;
                 } else {
@@ -546,6 +549,12 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
         break;
                     NCB_LEAN_ONE(0) NCB_LEAN_ONE(1) NCB_LEAN_ONE(2)
 #undef NCB_LEAN_ONE
+#define NCB_LEAN_RX(B, AT) m4[0].x = sc.coef[mat + AT]; m4[1].y = sc.coef[mat + AT + 1]; m4[2].y = sc.coef[mat + AT + 2]; m4[3].x = sc.coef[mat + AT + 3]; rx1_bit<R, B>(a, a, m4);
+                case LSEL_X2 + 0: NCB_LEAN_RX(0, 0) NCB_LEAN_RX(1, 4) break;
+                case LSEL_X2 + 1: NCB_LEAN_RX(0, 0) NCB_LEAN_RX(2, 4) break;
+                case LSEL_X2 + 2: NCB_LEAN_RX(1, 0) NCB_LEAN_RX(2, 4) break;
+                case LSEL_X3: NCB_LEAN_RX(0, 0) NCB_LEAN_RX(1, 4) NCB_LEAN_RX(2, 8) break;
+#undef NCB_LEAN_RX
                 default: NCB_UNREACHABLE(); break;
                 }
             }

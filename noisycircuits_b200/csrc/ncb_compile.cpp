@@ -850,7 +850,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
             struct Group { std::vector<const LogicalOp*> members; LogicalOp merged; };
             std::vector<Group> groups;
             auto try_merge = [&](Group& g, const LogicalOp& l) -> bool {
-                if (!opt.fuse || g.members.size() >= 100) return false;
+                if (!opt.fuse || g.members.size() >= 60) return false;
                 LogicalOp& a = g.merged;
                 if (a.diag && l.diag) {
                     std::vector<int> bits(a.bits, a.bits + a.nb);
@@ -918,7 +918,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                     h.pad = g.members.back()->instr;
                     h.mat_bare = h.mat;
                     fast_ops.push_back(h);                 // plain op in the fast list
-                    h.kind_nb |= 0x80000000u | ((uint32_t)g.members.size() << 24);
+                    h.kind_nb |= 0x80000000u | ((uint32_t)g.members.size() << 25);
                     P.ops.push_back(h);
                     for (const LogicalOp* lp : g.members) P.ops.push_back(emit(*lp));
                 } else {
@@ -991,9 +991,73 @@ static void build_blobs(Program& P) {
                 for (int m = 0; m < (1 << MAX_REG_BITS); ++m) ph.regoff_swz[m] = ps.regoff_swz[m];
                 ph.instr_lo = ps.instr_lo; ph.instr_hi = ps.instr_hi;
                 ph.fop_begin = nops;
-                for (int o = ps.fop_begin; o < ps.fop_end && fits; ++o) {
+                // Lean programs: the pass's ops are re-ordered among commuting neighbours (diagonals commute with each
+                // other and with one-bit ops on register bits outside their mask; one-bit ops on different bits
+                // commute) so that the rx-like rotations come in groups, and each group becomes ONE fused op (a single
+                // dispatch for up to three rotations).  Only this constant-bank list is rewritten; event pieces keep the
+                // program order.
+                std::vector<Op> flist(ops.begin() + ps.fop_begin, ops.begin() + ps.fop_end);
+                const bool lean = P.R == 3 && !P.has_dense2 && !P.has_dense4 && P.opt.fuse && P.opt.fuse_rotations;
+                struct FastItem { Op op; std::vector<Op> rot; };    // rot non-empty: fused rotations (ascending bit order)
+                std::vector<FastItem> items;
+                if (lean) {
+                    const int n = (int)flist.size();
+                    auto bitmask = [&](const Op& o) { return op_kind(o) == OPK_DIAG ? op_regmask(o) : 1 << op_rb(o, 0); };
+                    auto commute = [&](const Op& x, const Op& y) {
+                        const bool dx = op_kind(x) == OPK_DIAG, dy = op_kind(y) == OPK_DIAG;
+                        if (dx && dy) return true;
+                        return (bitmask(x) & bitmask(y)) == 0;
+                    };
+                    std::vector<char> done(n, 0);
+                    auto ready = [&](int j) {
+                        for (int i = 0; i < j; ++i)
+                            if (!done[i] && !commute(flist[i], flist[j])) return false;
+                        return true;
+                    };
+                    int left = n;
+                    while (left > 0) {
+                        bool any = false;
+                        for (int j = 0; j < n; ++j)                  // every ready diagonal first
+                            if (!done[j] && op_kind(flist[j]) == OPK_DIAG && ready(j)) { items.push_back({flist[j], {}}); done[j] = 1; --left; any = true; }
+                        std::vector<int> grp;                        // then the ready rx-like rotations, as one op
+                        int used = 0;
+                        for (int j = 0; j < n; ++j)
+                            if (!done[j] && op_kind(flist[j]) == OPK_RX1 && ready(j) && !(used & bitmask(flist[j]))) { grp.push_back(j); used |= bitmask(flist[j]); }
+                        if (grp.size() >= 2) {
+                            FastItem it{flist[grp[0]], {}};
+                            std::sort(grp.begin(), grp.end(), [&](int x, int y) { return op_rb(flist[x], 0) < op_rb(flist[y], 0); });
+                            for (int j : grp) { it.rot.push_back(flist[j]); done[j] = 1; --left; }
+                            items.push_back(it);
+                            any = true;
+                        } else {
+                            for (int j = 0; j < n; ++j)              // a single rotation / generic one-bit op: as it is
+                                if (!done[j] && op_kind(flist[j]) != OPK_DIAG && ready(j)) { items.push_back({flist[j], {}}); done[j] = 1; --left; any = true; break; }
+                        }
+                        if (!any) throw std::runtime_error("internal: fast-list reordering made no progress");
+                    }
+                } else {
+                    for (const Op& o : flist) items.push_back({o, {}});
+                }
+                for (size_t fi = 0; fi < items.size() && fits; ++fi) {
                     if (nops >= SC_MAX_OPS) { fits = false; break; }
-                    Op op = ops[o];
+                    Op op = items[fi].op;
+                    if (!items[fi].rot.empty()) {
+                        const std::vector<Op>& rot = items[fi].rot;
+                        const int need = 4 * (int)rot.size();
+                        if (ncoef + need > SC_MAX_COEF) { fits = false; break; }
+                        int bits = 0;
+                        for (size_t r = 0; r < rot.size(); ++r) {
+                            const double* m = pool.data() + rot[r].mat;
+                            sc.coef[ncoef + 4 * r] = m[0]; sc.coef[ncoef + 4 * r + 1] = m[3]; sc.coef[ncoef + 4 * r + 2] = m[5]; sc.coef[ncoef + 4 * r + 3] = m[6];
+                            bits |= 1 << op_rb(rot[r], 0);
+                        }
+                        const uint32_t lsel = rot.size() == 3 ? (uint32_t)LSEL_X3 : (uint32_t)(LSEL_X2 + (bits == 3 ? 0 : bits == 5 ? 1 : 2));
+                        op.kind_nb = (op.kind_nb & ~(0x1fu << 20)) | (lsel << 20);
+                        op.mat = ncoef; op.mat_bare = ncoef;
+                        ncoef += need;
+                        sc.ops[nops++] = op;
+                        continue;
+                    }
                     const int kind = op_kind(op);
                     if (kind == OPK_RX1 || kind == OPK_DENSE1) {
                         const int need = kind == OPK_RX1 ? 4 : 8;
@@ -1087,7 +1151,26 @@ std::string describe_program(const Program& P) {
         const Segment& g = P.segs[s];
         o << "seg " << s << " instr[" << g.instr_lo << "," << g.instr_hi << ") tile{";
         for (int p = 0; p < P.K; ++p) o << (p ? "," : "") << (int)g.tile_q[p];
-        o << "} passes " << g.pass_end - g.pass_begin << "\n";
+        o << "} passes " << g.pass_end - g.pass_begin;
+        // fast op list of every pass: d<regmask> diagonal, x<bit> rx-like, u<bit> generic one-bit, D dense 4x4 / 16x16
+        if (s < P.segconst.size() && P.segconst[s].valid) {
+            const SegConst& sc = P.segconst[s];
+            o << " ops";
+            for (int p = 0; p < sc.npass; ++p) {
+                o << " [";
+                for (int i = sc.pass[p].fop_begin; i < sc.pass[p].fop_end; ++i) {
+                    const Op& op = sc.ops[i];
+                    const int k = op_kind(op);
+                    if (k == OPK_DIAG) o << "d" << op_regmask(op);
+                    else if (k == OPK_RX1) o << "x" << op_rb(op, 0);
+                    else if (k == OPK_DENSE1) o << "u" << op_rb(op, 0);
+                    else o << "D";
+                    if (i + 1 < sc.pass[p].fop_end) o << " ";
+                }
+                o << "]";
+            }
+        }
+        o << "\n";
     }
     return o.str();
 }

@@ -175,10 +175,6 @@ struct Engine {
     //   <4, DENSE2|DENSE4, 256, 1>  R = 4: 3-4 bit dense operators (density-matrix superoperators, 3-4 qubit unitaries)
     int variant() const {
         if (P.R == 4) return (!P.has_dense2 && !P.has_dense4) ? 5 : 2;
-        if (const char* e = getenv("NCB_VARIANT")) {      // tuning aid: 1 runs the lean programs in the 128-register kernel
-            const int v = atoi(e);
-            if (v == 1 && P.R == 3 && !P.has_dense4) return 1;
-        }
         if (P.R == 3 && !P.has_dense4) return P.has_dense2 ? 1 : 0;
         throw std::runtime_error("unsupported reg_bits (3, or 4 for 3-4 bit dense operators)");
     }
@@ -213,7 +209,7 @@ struct Engine {
         if (tile_variant == 5) tile_nbuf = 1;
         if (const char* e = getenv("NCB_TILE_VARIANT")) {
             const int v = atoi(e);
-            if ((tile_variant == 0 || tile_variant == 3) && (v == 0 || v == 3 || v == 4 || v == 1)) { tile_variant = v; tile_nbuf = v == 3 ? 1 : 2; }
+            if ((tile_variant == 0 || tile_variant == 3) && (v == 0 || v == 3 || v == 4)) { tile_variant = v; tile_nbuf = v == 3 ? 1 : 2; }
         }
         if (const char* e = getenv("NCB_NBUF")) tile_nbuf = atoi(e) == 1 ? 1 : 2;
         const int threads = 1 << (P.K - P.R);
@@ -689,6 +685,7 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     if (const char* e = getenv("NCB_REORDER")) opt.reorder = atoi(e);
     if (const char* e = getenv("NCB_DECOMPOSE")) opt.decompose = atoi(e);
     if (const char* e = getenv("NCB_DIRECT")) opt.direct = atoi(e);
+    if (const char* e = getenv("NCB_FUSE_ROT")) opt.fuse_rotations = atoi(e);
     if (opt.reg_bits != 3 && opt.reg_bits != 4) return fail(NCB_E_INVALID, "reg_bits must be 3 or 4");
     opt.tile_bits = std::min(opt.tile_bits, 12);   // <= 256 threads (R = 4) / 512 threads (R = 3)
     ncb_program* p = new ncb_program();

@@ -73,8 +73,14 @@ void emulate_work(const Program& P, const Work& w, int seg, std::vector<cplx>& s
             const Pass& ps = passes[p];
             if (ps.instr_lo >= w.instr_hi) break;
             if (ps.instr_hi > w.instr_lo && ps.instr_hi > ps.instr_lo)
-                for (int tid = 0; tid < nthreads; ++tid)
-                    run_pass_thread<R, 3, true>(sm.data(), K, (int)apply_runs(ps.truns, (unsigned)tid), ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last, P.segconst[seg], p);
+                for (int tid = 0; tid < nthreads; ++tid) {
+                    // the lean kernels (FEAT = 0) run the programs without dense two-qubit operators, like the engine
+                    const int jb = (int)apply_runs(ps.truns, (unsigned)tid);
+                    if (R == 3 && !P.has_dense2 && !P.has_dense4)
+                        run_pass_thread<R, 0, true>(sm.data(), K, jb, ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last, P.segconst[seg], p);
+                    else
+                        run_pass_thread<R, 3, true>(sm.data(), K, jb, ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last, P.segconst[seg], p);
+                }
             if (ps.instr_hi > w.instr_hi) break;
         }
         // reductions
