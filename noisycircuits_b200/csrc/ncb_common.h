@@ -390,17 +390,33 @@ NCB_HD constexpr int pext_c(int m, int MASK) {
         if ((MASK >> b) & 1) { r |= ((m >> b) & 1) << k; ++k; }
     return r;
 }
-template <int R, int MASK>
+// column swizzle key of diagonal-table row h when a row has 2^nr columns (see diag_mask)
+NCB_HD constexpr unsigned diag_col_key(unsigned h, int nr) { return nr == 0 ? 0u : (h >> (nr < 3 ? 3 - nr : 0)) & ((1u << nr) - 1u); }
+// 128-bit load from a table known to be in shared memory (the generic-address form costs an address-space check per load)
+NCB_HD cplx ld_shared_cplx(const cplx* p) {
+#if defined(__CUDA_ARCH__)
+    cplx v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+}
+template <int R, int MASK, bool SHARED_T = false>
 NCB_HD void diag_mask(const Op& op, int jb, const cplx* __restrict__ T, const cplx* in, cplx* out) {
     constexpr int NA = 1 << R, NR = popc_c(MASK);
     // the thread's part of the table index: two multiply-gathers of <= 3 tile bits each (see the Op comment)
     const unsigned x = (unsigned)jb;
     const unsigned hA = ((x & (op.rbs & 0xffffu)) * op.midx_lo) >> 29;
     const unsigned hB = ((x & (op.rbs >> 16)) * op.midx_hi) >> 29;
-    const cplx* Tb = T + ((hB * (unsigned)op_tmask(op) + hA) << NR);
+    const unsigned h = hB * (unsigned)op_tmask(op) + hA;
+    const cplx* Tb = T + (h << NR);
+    // the 2^NR columns of a row are stored XOR-ed with the row bits that alias rows onto the same shared-memory banks
+    // (rows are 2^NR x 16 B, a quarter warp reads 8 x 16 B): lanes on different rows then read different banks
+    const unsigned key = diag_col_key(h, NR);
     cplx ph[1 << NR];
 #pragma unroll
-    for (int r = 0; r < (1 << NR); ++r) ph[r] = Tb[r];
+    for (int r = 0; r < (1 << NR); ++r) ph[r] = SHARED_T ? ld_shared_cplx(Tb + (r ^ key)) : Tb[r ^ key];
 #pragma unroll
     for (int m = 0; m < NA; ++m) out[m] = cmul(in[m], ph[pext_c(m, MASK)]);
 }
@@ -534,7 +550,7 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
                 const Op& cop = sc.ops[o];
                 const int mat = cop.mat;
                 switch (op_lean_sel(cop)) {
-#define NCB_LEAN_DIAG(MK) case MK: diag_mask<R, MK>(cop, jb, reinterpret_cast<const cplx*>(mat >= 0 ? pool + mat : pool_global + (-mat - 1)), a, a); break;
+#define NCB_LEAN_DIAG(MK) case MK: diag_mask<R, MK, true>(cop, jb, reinterpret_cast<const cplx*>(pool + mat), a, a); break;   /* phase tables are always in the staged pool */
                     NCB_LEAN_DIAG(0) NCB_LEAN_DIAG(1) NCB_LEAN_DIAG(2) NCB_LEAN_DIAG(3)
                     NCB_LEAN_DIAG(4) NCB_LEAN_DIAG(5) NCB_LEAN_DIAG(6) NCB_LEAN_DIAG(7)
 #undef NCB_LEAN_DIAG

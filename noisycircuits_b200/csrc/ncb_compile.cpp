@@ -788,7 +788,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
                             for (auto& t : tb) x |= (uint32_t)((s >> t.second) & 1) << t.first;
                             for (int j = 0; j < nr; ++j) col |= (uint32_t)((s >> rg[j].second) & 1) << j;
                             const uint32_t row = (((x & gB.mask) * gB.magic) >> 29) * (1u << nA) + (((x & gA.mask) * gA.magic) >> 29);
-                            const size_t e = ((size_t)row << nr) | col;
+                            const size_t e = ((size_t)row << nr) | (col ^ diag_col_key(row, nr));
                             dst[2 * e] = src[2 * (size_t)s]; dst[2 * e + 1] = src[2 * (size_t)s + 1];
                         }
                         return dst;
