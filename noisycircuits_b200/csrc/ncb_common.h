@@ -472,7 +472,9 @@ NCB_HD void apply_op(const Op& op, int jb, const cplx* __restrict__ M, const cpl
 // instead of the shared-memory tile; after_load() runs once the pass holds its amplitudes in registers (the direct
 // kernel refills the tile buffer with the next tile from there).
 struct NoHook { NCB_HD void operator()() const {} };
-template <int R, int FEAT, bool USE_SC, class AfterLoad = NoHook>
+// ONLY_CST: the caller guarantees the constant-bank fast list applies (whole pass, valid SegConst): the general op
+// lists are not compiled in.
+template <int R, int FEAT, bool USE_SC, class AfterLoad = NoHook, bool ONLY_CST = false>
 NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* __restrict__ ops,
                             const double* __restrict__ pool, const double* __restrict__ pool_global, int lo, int hi, bool bare_last,
                             const SegConst& sc, int sc_pass, cplx* __restrict__ gdst = nullptr, unsigned gj = 0,
@@ -484,7 +486,7 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
     const int p_lo = use_sc ? sc.pass[sc_pass].instr_lo : ps.instr_lo, p_hi = use_sc ? sc.pass[sc_pass].instr_hi : ps.instr_hi;
     // the whole pass lies inside [lo, hi) and none of its instructions is the bare one: take the short op list
     const bool fast = lo <= p_lo && hi >= p_hi && !(bare_last && hi == p_hi);
-    const bool cst = fast && use_sc;
+    const bool cst = ONLY_CST ? true : (fast && use_sc);
     cplx a[NA];
     // shared-memory address of register slot m; recomputed at the store (one LOP each) rather than kept in 2^R
     // registers across the op loop -- the laundered copy of jbs stops the compiler from keeping the first set alive
@@ -584,7 +586,9 @@ NCB_HD void run_pass_thread(cplx* sm, int K, int jb, const Pass& ps, const Op* _
             return;
         }
     }
-    if constexpr (FEAT == 0) {
+    if constexpr (ONLY_CST && R == 3 && FEAT == 0) {
+        return;                                   // unreachable: the lean loop above returned
+    } else if constexpr (FEAT == 0) {
         // one-bit and diagonal kernels only: they are alias-safe, so the ops run in place (half the amplitude registers)
         while (fetch()) apply_op<R, FEAT>(op, jb, M, m4, a, a);
     } else {

@@ -310,12 +310,13 @@ direct_kernel(DevProgram P, const __grid_constant__ SegConst sc, const unsigned 
         __syncthreads();
         for (int p = 0; p < npass; ++p) {
             const bool last = p == npass - 1;
-            run_pass_thread<R, 0, true>(sm, K, (int)jb_tab[p * nthreads + tid], passes[p], ops, pool, P.pool, lo, hi, false, sc, p,
-                                        last ? dst : nullptr, gj_last, [&]() {
-                                            if (!last) return;
-                                            __syncthreads();             // every thread holds its amplitudes: the buffer is free
-                                            if (tn < total) issue_load(tn);
-                                        });
+            auto refill = [&]() {
+                if (!last) return;
+                __syncthreads();             // every thread holds its amplitudes: the buffer is free
+                if (tn < total) issue_load(tn);
+            };
+            run_pass_thread<R, 0, true, decltype(refill), true>(sm, K, (int)jb_tab[p * nthreads + tid], passes[p], ops, pool, P.pool, lo, hi, false,
+                                                                sc, p, last ? dst : nullptr, gj_last, refill);
             if (!last) __syncthreads();
         }
     }
