@@ -228,14 +228,16 @@ enum WorkFlags : int32_t {
     WF_BARE_LAST = 1,      // instruction instr_hi-1 ends in a jump event: apply the bare gate (no base Kraus operator)
     WF_PRO_STATIC = 2,     // first apply Kraus operator ev_k of instruction ev_instr (branch known from u alone)
     WF_PRO_DYNAMIC = 4,    // first apply the operator the decide kernel chose for this slot
-    WF_REDUCE = 8,         // finally accumulate the reduced density matrix of instruction red_instr's qubits
+    WF_REDUCE = 8,         // finally accumulate the reduced density matrix of the qubits of instruction instr_hi-1
     WF_INIT = 16,          // the state is |0...0>: do not read it
     WF_NORM = 32,          // finally accumulate the squared norm
+    WF_MID = 64,           // a jump whose branch is known from u alone happens INSIDE the range: run [instr_lo, mid_instr]
+                           // with the bare gate, apply Kraus operator (flags >> 16) of mid_instr, go on with the rest
 };
 struct Work {
     int32_t slot, src, instr_lo, instr_hi;     // src: slot the tiles are READ from (== slot except when a trajectory
                                                // forks from the shared no-jump prefix, see ncb_schedule.h)
-    int32_t flags, ev_instr, ev_k, red_instr;
+    int32_t flags, ev_instr, ev_k, mid_instr;
 };
 struct DecideItem {
     int32_t slot, instr;

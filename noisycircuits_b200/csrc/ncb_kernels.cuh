@@ -94,14 +94,10 @@ __device__ __forceinline__ void run_range(cplx* sm, int K, const Pass* passes, c
 // ---------------------------------------------------------------------------------------------------------------
 // rare (jump event) paths of the tile kernel: kept out of line so that they do not set its register budget
 // ---------------------------------------------------------------------------------------------------------------
-static __device__ __noinline__ void event_prologue(cplx* sm, const DevProgram& P, const Segment* sg, const Work& w,
-                                            const Decision* __restrict__ decisions) {
+static __device__ __noinline__ void event_apply(cplx* sm, const DevProgram& P, const Segment* sg, int instr, int k, double scale) {
     const int K = P.K;
-    const Instr in = P.instrs[w.ev_instr];
+    const Instr in = P.instrs[instr];
     const Channel ch = P.chans[in.channel];
-    int k = w.ev_k;
-    double scale = 1.0;
-    if (w.flags & WF_PRO_DYNAMIC) { k = decisions[w.slot].k; scale = decisions[w.slot].scale; }
     const cplx* M = reinterpret_cast<const cplx*>(P.pool + ch.kraus) + k * ch.dim * ch.dim;
     const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;
     tile_apply_dense(sm, K, threadIdx.x, blockDim.x, ch.dim, p0, p1, M, scale);
@@ -223,13 +219,24 @@ tile_kernel(DevProgram P, const __grid_constant__ SegConst sc, const unsigned ch
             __syncthreads();
         }
         // ---- jump operator of the event that ended the previous piece ----
-        if (w.flags & (WF_PRO_STATIC | WF_PRO_DYNAMIC)) event_prologue(sm, P, sg, w, decisions);
-        // ---- the segment's passes ----
-        int pcur = 0;
-        run_range<R, FEAT, true>(sm, K, passes, ops, pool, P.pool, &pcur, npass, w.instr_lo, w.instr_hi, (w.flags & WF_BARE_LAST) != 0, sc, jb_tab, jb_cap);
+        if (w.flags & WF_PRO_STATIC) event_apply(sm, P, sg, w.ev_instr, w.ev_k, 1.0);
+        else if (w.flags & WF_PRO_DYNAMIC) event_apply(sm, P, sg, w.ev_instr, decisions[w.slot].k, decisions[w.slot].scale);
+        // ---- the segment's passes; a jump known from its uniform alone is applied on the way (WF_MID) ----
+        {
+            int pcur = 0, lo = w.instr_lo;
+            for (int part = (w.flags & WF_MID) ? 0 : 1; part < 2; ++part) {
+                const int hi = part == 0 ? w.mid_instr + 1 : w.instr_hi;
+                const bool bare = part == 0 ? true : (w.flags & WF_BARE_LAST) != 0;
+                run_range<R, FEAT, true>(sm, K, passes, ops, pool, P.pool, &pcur, npass, lo, hi, bare, sc, jb_tab, jb_cap);
+                if (part == 0) {
+                    event_apply(sm, P, sg, w.mid_instr, (int)((unsigned)w.flags >> 16), 1.0);
+                    lo = w.mid_instr + 1;
+                }
+            }
+        }
         // ---- reductions ----
         if (w.flags & WF_REDUCE) {
-            const Instr in = P.instrs[w.red_instr];
+            const Instr in = P.instrs[w.instr_hi - 1];
             const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;
             event_reduce(sm, K, p0, p1, s_buf, s_out, red_part + ((long long)w.slot * ntiles + o) * RED_VALUES);
         }

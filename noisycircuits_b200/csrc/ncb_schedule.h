@@ -41,7 +41,7 @@ struct BatchPlan {
 // event are the trunk (weight = their number).  The numbers produced per trajectory are bit-identical to the unshared
 // schedule: the same kernels run on the same data, fewer times.
 inline void schedule_batch(const Program& P, const std::vector<std::vector<Event>>& events, bool init, bool want_norm,
-                           BatchPlan& out, bool share_prefix = false) {
+                           BatchPlan& out, bool share_prefix = false, bool inline_certain = true) {
     out.works.clear(); out.decides.clear(); out.steps.clear(); out.sweeps = 0;
     const int B = (int)events.size(), S = (int)P.segs.size();
     share_prefix = share_prefix && init && B > 1 && S > 0;
@@ -80,6 +80,27 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
             while (e < events[b].size() && events[b][e].instr < sg.instr_hi) ++e;
             end[b] = e;
         }
+        // End of a piece that starts at w.instr_lo: it runs to the trajectory's next event in this segment (returns true:
+        // a round follows) or to the end of the segment.  A jump whose branch is known from the uniform alone
+        // (kmin == kmax) needs no reduction, so ONE such jump per piece is applied in-line (WF_MID) instead of costing the
+        // trajectory another sweep.
+        auto finish_piece = [&](Work& w, int b) -> bool {
+            if (inline_certain && cur[b] < end[b] && events[b][cur[b]].kmin == events[b][cur[b]].kmax && events[b][cur[b]].kmin < 0x8000) {
+                const Event& m = events[b][cur[b]];
+                w.flags |= WF_MID | (m.kmin << 16);
+                w.mid_instr = m.instr;
+                ++cur[b];
+            }
+            if (cur[b] < end[b]) {
+                const Event& e = events[b][cur[b]];
+                w.instr_hi = e.instr + 1;
+                w.flags |= WF_BARE_LAST;
+                if (e.kmin != e.kmax) w.flags |= WF_REDUCE;
+                return true;
+            }
+            if (last && want_norm) w.flags |= WF_NORM;
+            return false;
+        };
         // main launch
         LaunchStep st{0, (int)out.works.size(), 0, s, 0};
         live.clear();
@@ -91,15 +112,7 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
         for (int b = 0; b < B; ++b) {
             if (first_seg[b] > s) continue;                       // still on the trunk
             Work w{b, first_seg[b] == s && share_prefix ? tin : b, sg.instr_lo, sg.instr_hi, first ? WF_INIT : 0, -1, -1, -1};
-            if (cur[b] < end[b]) {
-                const Event& e = events[b][cur[b]];
-                w.instr_hi = e.instr + 1;
-                w.flags |= WF_BARE_LAST;
-                if (e.kmin != e.kmax) { w.flags |= WF_REDUCE; w.red_instr = e.instr; }
-                live.push_back(b);
-            } else if (last && want_norm) {
-                w.flags |= WF_NORM;
-            }
+            if (finish_piece(w, b)) live.push_back(b);
             out.works.push_back(w);
         }
         st.count = (int)out.works.size() - st.begin;
@@ -131,15 +144,7 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
                 ++cur[b];
                 Work w{b, b, e.instr + 1, sg.instr_hi, 0, e.instr, e.kmin, -1};
                 w.flags |= (e.kmin == e.kmax) ? WF_PRO_STATIC : WF_PRO_DYNAMIC;
-                if (cur[b] < end[b]) {
-                    const Event& f = events[b][cur[b]];
-                    w.instr_hi = f.instr + 1;
-                    w.flags |= WF_BARE_LAST;
-                    if (f.kmin != f.kmax) { w.flags |= WF_REDUCE; w.red_instr = f.instr; }
-                    next.push_back(b);
-                } else if (last && want_norm) {
-                    w.flags |= WF_NORM;
-                }
+                if (finish_piece(w, b)) next.push_back(b);
                 out.works.push_back(w);
             }
             out.steps.push_back(ts);

@@ -57,35 +57,42 @@ void emulate_work(const Program& P, const Work& w, int seg, std::vector<cplx>& s
         }
         if ((w.flags & WF_INIT) && o == 0) sm[swz(0)] = cplx{1.0, 0.0};
         // jump operator
-        if (w.flags & (WF_PRO_STATIC | WF_PRO_DYNAMIC)) {
-            const Instr& in = P.instrs[w.ev_instr];
+        auto apply_event = [&](int instr, int k, double scale) {
+            const Instr& in = P.instrs[instr];
             const Channel& ch = P.chans[in.channel];
-            int k = w.ev_k;
-            double scale = 1.0;
-            if (w.flags & WF_PRO_DYNAMIC) { k = decisions[w.slot].k; scale = decisions[w.slot].scale; }
             const cplx* M = reinterpret_cast<const cplx*>(P.pool.data() + ch.kraus) + k * ch.dim * ch.dim;
             const int p0 = tile_pos(sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(sg, K, in.q1) : -1;
             for (int tid = 0; tid < nthreads; ++tid) tile_apply_dense(sm.data(), K, tid, nthreads, ch.dim, p0, p1, M, scale);
-        }
-        // passes (same control flow as run_range in ncb_kernels.cuh)
-        const bool bare_last = (w.flags & WF_BARE_LAST) != 0;
-        for (int p = 0; p < blob.npass; ++p) {
-            const Pass& ps = passes[p];
-            if (ps.instr_lo >= w.instr_hi) break;
-            if (ps.instr_hi > w.instr_lo && ps.instr_hi > ps.instr_lo)
-                for (int tid = 0; tid < nthreads; ++tid) {
-                    // the lean kernels (FEAT = 0) run the programs without dense two-qubit operators, like the engine
-                    const int jb = (int)apply_runs(ps.truns, (unsigned)tid);
-                    if (R == 3 && !P.has_dense2 && !P.has_dense4)
-                        run_pass_thread<R, 0, true>(sm.data(), K, jb, ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last, P.segconst[seg], p);
-                    else
-                        run_pass_thread<R, 3, true>(sm.data(), K, jb, ps, ops, pool, P.pool.data(), w.instr_lo, w.instr_hi, bare_last, P.segconst[seg], p);
-                }
-            if (ps.instr_hi > w.instr_hi) break;
+        };
+        if (w.flags & WF_PRO_STATIC) apply_event(w.ev_instr, w.ev_k, 1.0);
+        else if (w.flags & WF_PRO_DYNAMIC) apply_event(w.ev_instr, decisions[w.slot].k, decisions[w.slot].scale);
+        // passes (same control flow as run_range in ncb_kernels.cuh); WF_MID: a jump applied on the way
+        int lo_i = w.instr_lo;
+        for (int part = (w.flags & WF_MID) ? 0 : 1; part < 2; ++part) {
+            const int hi_i = part == 0 ? w.mid_instr + 1 : w.instr_hi;
+            const bool bare_last = part == 0 ? true : (w.flags & WF_BARE_LAST) != 0;
+            for (int p = 0; p < blob.npass; ++p) {
+                const Pass& ps = passes[p];
+                if (ps.instr_lo >= hi_i) break;
+                if (ps.instr_hi > lo_i && ps.instr_hi > ps.instr_lo)
+                    for (int tid = 0; tid < nthreads; ++tid) {
+                        // the lean kernels (FEAT = 0) run the programs without dense two-qubit operators, like the engine
+                        const int jb = (int)apply_runs(ps.truns, (unsigned)tid);
+                        if (R == 3 && !P.has_dense2 && !P.has_dense4)
+                            run_pass_thread<R, 0, true>(sm.data(), K, jb, ps, ops, pool, P.pool.data(), lo_i, hi_i, bare_last, P.segconst[seg], p);
+                        else
+                            run_pass_thread<R, 3, true>(sm.data(), K, jb, ps, ops, pool, P.pool.data(), lo_i, hi_i, bare_last, P.segconst[seg], p);
+                    }
+                if (ps.instr_hi > hi_i) break;
+            }
+            if (part == 0) {
+                apply_event(w.mid_instr, (int)((unsigned)w.flags >> 16), 1.0);
+                lo_i = w.mid_instr + 1;
+            }
         }
         // reductions
         if (w.flags & WF_REDUCE) {
-            const Instr& in = P.instrs[w.red_instr];
+            const Instr& in = P.instrs[w.instr_hi - 1];
             const int p0 = tile_pos(sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(sg, K, in.q1) : -1;
             double acc[32];
             for (double& a : acc) a = 0.0;
