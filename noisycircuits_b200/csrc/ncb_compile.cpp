@@ -411,8 +411,27 @@ struct PassBuild {
 }  // namespace
 
 static void build_blobs(Program& P);
+static void compile_program_once(const CircuitView& c, int mode, const CompileOptions& opt, Program& P);
 
+namespace { struct BlobOverflow : std::runtime_error { using std::runtime_error::runtime_error; }; }
+
+// The segmenter cuts segments with an ESTIMATE of their staged program size; should a segment still come out larger
+// than the staging area, the program is compiled again with a more cautious estimate.
 void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, Program& P) {
+    CompileOptions o = opt;
+    for (int attempt = 0;; ++attempt) {
+        try {
+            compile_program_once(c, mode, o, P);
+            P.opt.blob_cost_scale = opt.blob_cost_scale;
+            return;
+        } catch (const BlobOverflow&) {
+            if (attempt >= 4) throw;
+            o.blob_cost_scale *= 1.6;
+        }
+    }
+}
+
+static void compile_program_once(const CircuitView& c, int mode, const CompileOptions& opt, Program& P) {
     P = Program();
     P.mode = mode; P.opt = opt;
     P.nq = c.num_qubits; P.G = c.num_instructions;
@@ -548,7 +567,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
             std::vector<size_t> head(nb, 0);
             uint64_t low = 0;
             for (int b = 0; b < L; ++b) low |= 1ull << b;
-            int max_seg_ops = 40;        // keeps a segment's program inside the shared-memory staging area
+            int max_seg_ops = 50;        // keeps a segment's program inside the shared-memory staging area
             if (const char* e = getenv("NCB_MAX_SEG_OPS")) max_seg_ops = std::max(1, atoi(e));
             // runs every ready instruction inside tile S from heads h (modified); returns the executed list
             auto run = [&](uint64_t S, std::vector<size_t>& h, std::vector<int>* out) {
@@ -639,7 +658,7 @@ void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, 
         auto blob_cost = [&](const LogicalOp& l) {
             const size_t copies = l.bare == l.mat ? 1 : 2;
             const size_t mats = l.diag ? ((size_t)16 << l.nb) * copies + 128 : (l.nb <= 2 ? ((size_t)16 << (2 * l.nb)) * copies : 0);
-            return 2 * sizeof(Op) + sizeof(Op) / 2 + mats + sizeof(Pass) / 3;
+            return (size_t)(opt.blob_cost_scale * (double)(2 * sizeof(Op) + sizeof(Op) / 2 + mats + sizeof(Pass) / 3));
         };
         size_t cur_cost = sizeof(SegBlob) + sizeof(Pass);
         SegBuild cur{fresh_tile(), 0, 0};
@@ -1114,7 +1133,7 @@ static void build_blobs(Program& P) {
         h.op_off = (int)align16(h.pass_off + passes.size() * sizeof(Pass));
         h.pool_off = (int)align16(h.op_off + ops.size() * sizeof(Op));
         h.bytes = (int)align16(h.pool_off + pool.size() * sizeof(double));
-        if (h.bytes > MAX_BLOB_BYTES) throw std::runtime_error("internal: segment program of " + std::to_string(h.bytes) + " bytes exceeds the shared-memory staging area");
+        if (h.bytes > MAX_BLOB_BYTES) throw BlobOverflow("internal: segment program of " + std::to_string(h.bytes) + " bytes exceeds the shared-memory staging area");
         const size_t at = P.blobs.size();
         P.blob_off.push_back((int64_t)at);
         P.blobs.resize(at + h.bytes, 0);
