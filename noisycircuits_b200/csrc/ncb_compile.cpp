@@ -419,13 +419,15 @@ namespace { struct BlobOverflow : std::runtime_error { using std::runtime_error:
 // than the staging area, the program is compiled again with a more cautious estimate.
 void compile_program(const CircuitView& c, int mode, const CompileOptions& opt, Program& P) {
     CompileOptions o = opt;
+    if (const char* e = getenv("NCB_BLOB_COST_SCALE")) o.blob_cost_scale = std::max(1e-3, atof(e));      // test hook
     for (int attempt = 0;; ++attempt) {
         try {
             compile_program_once(c, mode, o, P);
             P.opt.blob_cost_scale = opt.blob_cost_scale;
+            P.compile_attempts = attempt + 1;
             return;
         } catch (const BlobOverflow&) {
-            if (attempt >= 4) throw;
+            if (attempt >= 12) throw;
             o.blob_cost_scale *= 1.6;
         }
     }
@@ -1150,7 +1152,7 @@ std::string describe_program(const Program& P) {
       << " segments=" << P.segs.size() << " passes=" << P.passes.size() << " ops=" << P.ops.size()
       << " channels=" << P.chans.size() << " noisy=" << P.noisy_instrs.size() << " draws=" << P.num_draws
       << " norm_preserving=" << P.norm_preserving << " dense2=" << P.has_dense2 << " dense4=" << P.has_dense4
-      << " pool=" << P.pool.size() << " blobs=" << P.blobs.size() << " reorder=" << P.opt.reorder;
+      << " pool=" << P.pool.size() << " blobs=" << P.blobs.size() << " reorder=" << P.opt.reorder << " attempts=" << P.compile_attempts;
     {
         static const char* names[] = {"diag", "dense1", "dense2", "dense4", "rx1", "?", "?", "?"};
         int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, groups = 0;

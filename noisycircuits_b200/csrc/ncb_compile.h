@@ -82,6 +82,7 @@ struct Program {
     std::vector<int64_t> blob_off;      // byte offset of segment s's blob
     std::vector<SegConst> segconst;     // constant-bank part of every segment (kernel parameter of its launches)
     CompileOptions opt;
+    int compile_attempts = 1;            // > 1: the segmenter's size estimate had to be raised (see compile_program)
 };
 
 // Throws std::runtime_error with a descriptive message on invalid input.

@@ -194,3 +194,17 @@ def test_shared_prefix_schedule(heron_noise):
     assert np.array_equal(b[0], b[6]) and np.array_equal(b[0], b[7])      # the event-free trajectories are the trunk
     assert sb["sweeps"] < sa["sweeps"]
     assert sa["events"] == sb["events"] and sa["events"] > 10
+
+
+def test_compile_retries_when_a_segment_program_overflows(heron_noise, monkeypatch):
+    """The segmenter cuts with an estimate of the staged program size; with the estimate sabotaged (test hook) the
+    first attempts overflow the 16 KB staging area and compile_program must converge by itself."""
+    sq, tq, _, _ = heron_noise
+    n = 10
+    instr = circuits.heron_layered(n, 12, circuits.coupled_pairs(tq, n), seed=9)
+    monkeypatch.setenv("NCB_BLOB_COST_SCALE", "0.01")
+    monkeypatch.setenv("NCB_MAX_SEG_OPS", "400")
+    U = jumpy_uniforms(np.random.default_rng(3), 4, len(instr))
+    stats, E = check_replay(n, instr, sq, tq, U, tile_bits=9, reg_bits=3, low_bits=2, fuse=1, reorder=1)
+    assert E.query(2) >= 2
+    assert "attempts=1 " not in E.describe().split("\n")[0]            # the overflow path was really taken
