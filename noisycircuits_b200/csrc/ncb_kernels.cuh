@@ -4,7 +4,9 @@
 //                    128-bit, runs of >= 2^low_bits amplitudes), optional jump operator, the segment's register-blocked
 //                    passes, optional reduced-density-matrix / norm reduction, store.  One launch sweeps the state of
 //                    every trajectory of the batch once (one HBM read + one HBM write per amplitude), whatever the
-//                    number of fused instructions.
+//                    number of fused instructions.  Handles the works that carry a jump event (pieces of a segment).
+//   direct_kernel    the same sweep for the works that run a whole segment without an event (most of them): lean
+//                    operator set only, last pass stored from registers to HBM, next tile's load overlapped with it.
 //   resident_kernel  states of <= 2^K amplitudes: the whole trajectory lives in one CTA's shared memory; persistent
 //                    CTAs loop over trajectories, plan their jump events with Philox draws, handle them inline and
 //                    accumulate |psi|^2 on chip.  HBM is touched only for the final probabilities.
