@@ -154,6 +154,18 @@ int ncb_apply_measurement_error(double* probabilities, const double* mats, const
 int ncb_apply_measurement_error_device(double* probabilities_device, const double* mats, const int32_t* qubits,
                                        int32_t nq, int32_t num_qubits, void* stream);
 
+/* The tail of QuantumCircuit.execute (QuantumCircuit.py:436-445) without leaving the device:
+ *   probabilities_device float64[2^num_qubits], little-endian over all qubits (e.g. the accumulator ncb_mcwf_run filled
+ *   with probs_on_device, or the all-reduced sum of the ranks), is multiplied by `scale`, marginalised over `qubits`
+ *   (HelperFunctions.py:9-32; kept qubits in ascending order), the read-out error is applied exactly as by
+ *   ncb_apply_measurement_error (positional matrices, num_qubits = nq), the index order is reversed to big-endian, and the
+ *   float64[2^nq] result is copied to the host buffer `out`.  mats may be NULL (no read-out error). */
+int ncb_execute_tail_device(const double* probabilities_device, int32_t num_qubits, const int32_t* qubits, int32_t nq,
+                            const double* mats, double scale, double* out, void* stream);
+/* Device scratch for callers without a CUDA allocator of their own (the Python mirror's execute()). */
+int ncb_device_alloc(int64_t bytes, void** out_device_pointer);
+int ncb_device_free(void* device_pointer);
+
 /* The reference's FFI, packed (see the header comment).  statevector: complex128[2^n], caller-owned.
  *   noisy != 0: statevector[i] += mean_t |psi_t[i]|^2 (real part), trajectories seeded 42 + t (Simulator.cpp:118-133);
  *   noisy == 0: statevector := final state (return_state != 0) or its probabilities in the real part. */

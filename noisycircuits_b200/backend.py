@@ -57,8 +57,14 @@ def execute(num_qubits, instruction_list, single_qubit_noise, two_qubit_noise, m
         qubits = list(range(num_qubits))
     _validate(num_qubits, instruction_list, qubits, num_trajectories)
     solver = RemoteExecutor(num_qubits, single_qubit_noise, two_qubit_noise, num_cores, rng=rng, seed=seed, **engine_options)
-    probs = solver.run(num_trajectories, instruction_list)
-    return postprocess(probs, num_qubits, qubits, measurement_error, num_cores)
+    # the sum over trajectories stays on the device; marginal, read-out error and bit reversal run there too and only the
+    # 2^len(qubits) result comes back
+    acc = simulator.DeviceBuffer(1 << num_qubits)
+    try:
+        solver.run_sum(instruction_list, 0, num_trajectories, device_probs=acc.ptr)
+        return simulator.execute_tail_device(acc.ptr, num_qubits, qubits, measurement_error, 1.0 / float(num_trajectories))
+    finally:
+        acc.free()
 
 
 def execute_sharded(num_qubits, instruction_list, single_qubit_noise, two_qubit_noise, measurement_error, qubits=None,
@@ -93,6 +99,10 @@ def execute_sharded(num_qubits, instruction_list, single_qubit_noise, two_qubit_
         total = torch.from_numpy(np.ascontiguousarray(local, np.float64).copy())
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)       # comm.Reduce(SUM) + bcast, :352, :367
+    if shard_runner is None and apply_measurement_error is None:
+        # GPU run: the tail stays on the device, only the 2^len(qubits) result is copied back
+        return simulator.execute_tail_device(total.data_ptr(), num_qubits, qubits, measurement_error, 1.0 / float(num_trajectories),
+                                             stream=torch.cuda.current_stream().cuda_stream)
     probs = total.cpu().numpy() / float(num_trajectories)
     return postprocess(probs, num_qubits, qubits, measurement_error, 1, apply_measurement_error)
 

@@ -834,6 +834,58 @@ int ncb_apply_measurement_error_device(double* probabilities_device, const doubl
     NCB_CATCH
 }
 
+int ncb_execute_tail_device(const double* probabilities_device, int32_t num_qubits, const int32_t* qubits, int32_t nq,
+                            const double* mats, double scale, double* out, void* stream) {
+    if (!probabilities_device || !qubits || !out) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    if (num_qubits < 1 || num_qubits > MAX_QUBITS) throw std::runtime_error("num_qubits out of range");
+    if (nq < 1 || nq > num_qubits) throw std::runtime_error("number of measured qubits out of range");
+    unsigned keep = 0;
+    for (int k = 0; k < nq; ++k) {
+        if (qubits[k] < 0 || qubits[k] >= num_qubits) throw std::runtime_error("measured qubit out of range");
+        if ((keep >> qubits[k]) & 1u) throw std::runtime_error("measured qubit listed twice");
+        keep |= 1u << qubits[k];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long nout = 1ll << nq;
+    double *a = nullptr, *b = nullptr;
+    CK(cudaMalloc(&a, sizeof(double) * nout));
+    if (cudaMalloc(&b, sizeof(double) * nout) != cudaSuccess) { cudaFree(a); throw std::runtime_error("out of device memory"); }
+    int rc = NCB_OK;
+    try {
+        int g, bl;
+        grid_1d(nout, &g, &bl);
+        marginal_kernel<<<g, bl, 0, s>>>(a, probabilities_device, num_qubits, keep, nq, scale);
+        CK(cudaGetLastError());
+        if (mats) rc = ncb_apply_measurement_error_device(a, mats, qubits, nq, nq, stream);
+        if (rc == NCB_OK) {
+            bit_reverse_kernel<<<g, bl, 0, s>>>(b, a, nq);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(out, b, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+    } catch (...) { cudaFree(a); cudaFree(b); throw; }
+    cudaFree(a); cudaFree(b);
+    return rc;
+    NCB_CATCH
+}
+
+int ncb_device_alloc(int64_t bytes, void** out_device_pointer) {
+    if (!out_device_pointer || bytes < 0) return fail(NCB_E_INVALID, "bad argument");
+    NCB_TRY
+    *out_device_pointer = nullptr;
+    CK(cudaMalloc(out_device_pointer, (size_t)std::max<int64_t>(bytes, 1)));
+    return NCB_OK;
+    NCB_CATCH
+}
+
+int ncb_device_free(void* device_pointer) {
+    NCB_TRY
+    if (device_pointer) CK(cudaFree(device_pointer));
+    return NCB_OK;
+    NCB_CATCH
+}
+
 int ncb_apply_measurement_error(double* probabilities, const double* mats, const int32_t* qubits, int32_t nq,
                                 int32_t num_qubits, uint32_t num_threads) {
     (void)num_threads;

@@ -438,6 +438,35 @@ __global__ void measurement_error_kernel(double* __restrict__ probs, long long h
         probs[j] = m10 * p0 + m11 * p1;
     }
 }
+// marginal over the qubits in keep_mask (m of them): out[i] = scale * sum over the other qubits, i little-endian over the
+// kept qubits in ascending order (HelperFunctions.py:9-32; numpy sums the dropped axes, here one thread per output in
+// ascending order of the dropped bits)
+__global__ void marginal_kernel(double* __restrict__ out, const double* __restrict__ in, int nbits, unsigned keep_mask, int m, double scale) {
+    const long long nout = 1ll << m, nrest = 1ll << (nbits - m);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nout; i += (long long)gridDim.x * blockDim.x) {
+        long long base = 0;
+        for (int b = 0, k = 0; b < nbits; ++b)
+            if ((keep_mask >> b) & 1u) { base |= ((i >> k) & 1ll) << b; ++k; }
+        double s = 0.0;
+        for (long long r = 0; r < nrest; ++r) {
+            long long off = 0;
+            for (int b = 0, k = 0; b < nbits; ++b)
+                if (!((keep_mask >> b) & 1u)) { off |= ((r >> k) & 1ll) << b; ++k; }
+            s += in[base | off];
+        }
+        out[i] = s * scale;
+    }
+}
+
+// little-endian -> big-endian index order over m bits (QuantumCircuit.py:445)
+__global__ void bit_reverse_kernel(double* __restrict__ out, const double* __restrict__ in, int m) {
+    const long long n = 1ll << m;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long r = 0;
+        for (int b = 0; b < m; ++b) r |= ((i >> b) & 1ll) << (m - 1 - b);
+        out[r] = in[i];
+    }
+}
 #endif  // NCB_TEMPLATES_ONLY
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -54,3 +54,42 @@ def apply_measurement_error(probabilities_array, measurement_noise, qubit_list, 
         raise IndexError("measurement_noise has fewer entries than measured qubits")
     _lib.check(_lib.lib().ncb_apply_measurement_error(C.c_void_p(p.ctypes.data), C.c_void_p(mats.ctypes.data),
                                                       C.c_void_p(qubits.ctypes.data), len(qubits), int(num_qubits), int(num_threads)))
+
+
+def execute_tail_device(probabilities_device: int, num_qubits: int, qubit_list, measurement_noise=None, scale: float = 1.0,
+                        stream: int = 0) -> np.ndarray:
+    """The tail of QuantumCircuit.execute (QuantumCircuit.py:436-445) on the device: ``probabilities_device`` is a device
+    pointer to float64[2^num_qubits] (little-endian, all qubits); returns scale * marginal over ``qubit_list`` ->
+    read-out error (positional matrices, as apply_measurement_error) -> big-endian order, as a host array."""
+    qubits = np.asarray([int(q) for q in qubit_list], np.int32)
+    out = np.empty(1 << len(qubits), np.float64)
+    mats = None
+    if measurement_noise:
+        mats = np.ascontiguousarray([np.asarray(m, np.float64) for m in measurement_noise.values()], np.float64)
+        if mats.shape[0] < len(qubits):
+            raise IndexError("measurement_noise has fewer entries than measured qubits")
+    _lib.check(_lib.lib().ncb_execute_tail_device(C.c_void_p(int(probabilities_device)), int(num_qubits),
+                                                  C.c_void_p(qubits.ctypes.data), len(qubits),
+                                                  C.c_void_p(mats.ctypes.data) if mats is not None else None, float(scale),
+                                                  C.c_void_p(out.ctypes.data), C.c_void_p(int(stream) or None)))
+    return out
+
+
+class DeviceBuffer:
+    """float64 device scratch owned through the C ABI (for callers that do not bring a CUDA allocator)."""
+
+    def __init__(self, count: int):
+        p = C.c_void_p()
+        _lib.check(_lib.lib().ncb_device_alloc(int(count) * 8, C.byref(p)))
+        self.ptr, self.count = int(p.value), int(count)
+
+    def free(self):
+        if getattr(self, "ptr", 0):
+            _lib.lib().ncb_device_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

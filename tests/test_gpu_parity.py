@@ -342,3 +342,39 @@ def test_execute_chain_and_full_size_properties(heron_noise):
     a, _ = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, fuse=1, strict_order=True).run_mcwf(4, seed=3)
     b, _ = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, fuse=0).run_mcwf(4, seed=3)
     assert np.abs(a - b).max() < TOL
+
+
+def test_execute_tail_on_device_matches_host_chain(heron_noise):
+    """Marginal -> read-out error -> big-endian on the device (ncb_execute_tail_device) against the host chain of
+    QuantumCircuit.py:436-445 (backend.postprocess), and execute() end to end against solver.run + host chain."""
+    from noisycircuits_b200 import simulator
+    from noisycircuits_b200.backend import execute, postprocess
+    from noisycircuits_b200.solvers import RemoteExecutor
+    sq, tq, meas, _ = heron_noise
+    rng = np.random.default_rng(5)
+    n = 9
+    p = rng.random(1 << n)
+    p /= p.sum()
+    import torch                                         # only to put the test vector on the device
+    t = torch.from_numpy(p).cuda()
+    for qubits in (list(range(n)), [0, 1, 2], [0, 1, 2, 3, 4]):
+        m = {q: meas[q] for q in range(len(qubits))}
+        dev = simulator.execute_tail_device(t.data_ptr(), n, qubits, m, 0.5)
+        ref = postprocess(0.5 * p, n, qubits, m, 1)
+        assert dev.shape == ref.shape and np.abs(dev - ref).max() < 1e-14
+    no_err = simulator.execute_tail_device(t.data_ptr(), n, [1, 3], None, 1.0)
+    full = p.reshape([2] * n)
+    drop_axes = tuple(ax for ax in range(n) if (n - 1 - ax) not in (1, 3))
+    marg = full.sum(axis=drop_axes).reshape(-1)                 # little-endian over (1, 3)
+    assert np.abs(no_err - marg.reshape(2, 2).T.reshape(-1)).max() < 1e-14
+    with pytest.raises(Exception):
+        simulator.execute_tail_device(t.data_ptr(), n, [5, 7], {0: meas[0], 1: meas[1]}, 1.0)   # qubit id >= len(qubits)
+    buf = simulator.DeviceBuffer(16)                     # the C ABI's own scratch allocator
+    assert buf.ptr != 0
+    buf.free()
+    n = 10
+    instr = circuits.heron_layered(n, 2, circuits.coupled_pairs(tq, n), seed=8)
+    mdict = {q: meas[q] for q in range(n)}
+    out = execute(n, instr, sq, tq, mdict, None, 64, seed=11)
+    ref = postprocess(RemoteExecutor(n, sq, tq, 1, seed=11).run(64, instr), n, list(range(n)), mdict, 1)
+    assert np.abs(out - ref).max() < 1e-13
