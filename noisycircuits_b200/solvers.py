@@ -86,6 +86,31 @@ class RemoteExecutor:
         probs = self.run_sum(instruction_list, 0, num_trajectories)
         return probs / float(num_trajectories)
 
+    def run_many(self, num_trajectories: int, instruction_lists) -> list:
+        """``run`` for a sequence of circuits (a QNN parameter sweep over one gate skeleton): circuit
+        i + 1 is packed and compiled on a host thread while the GPU runs circuit i.  Same results as calling ``run`` in a
+        loop (trajectory ids 0..N-1 for every circuit)."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        def build(instr):
+            packed = PackedCircuit(self.num_qubits, instr, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
+            return Program(packed, _lib.MODE_MCWF, **self.engine_options)
+
+        lists = list(instruction_lists)
+        out = []
+        if not lists:
+            return out
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            nxt = pool.submit(build, lists[0])
+            for i in range(len(lists)):
+                prog = nxt.result()
+                if i + 1 < len(lists):
+                    nxt = pool.submit(build, lists[i + 1])
+                probs, stats = prog.run_mcwf(num_trajectories, traj_begin=0, rng=_RNG[self.rng], seed=self.seed)
+                self.last_stats = stats
+                out.append(probs / float(num_trajectories))
+        return out
+
 
 class DensityMatrixSolver:
     """Density-matrix evolution on the vectorised 4^n state (mirror of custom/_DensityMatrixSolver.py:29-93; the

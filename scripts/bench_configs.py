@@ -55,3 +55,24 @@ mcwf("C3 12q QNN x1e4", 12, circuits.qnn_circuit(12, 4, circuits.coupled_pairs(h
 mcwf("C4 16q Eagle depth 40", 16, circuits.eagle_layered(16, 40, circuits.coupled_pairs(e_tq, 16), seed=42), e_sq, e_tq, 1184 if quick else 4736)
 # C5: 20-qubit Heron depth 50
 mcwf("C5 20q Heron depth 50", 20, circuits.heron_layered(20, 50, circuits.coupled_pairs(h_tq, 20), seed=42), h_sq, h_tq, 296 if quick else 1184)
+
+
+# C3 sweep: 20 parameter sets of the QNN skeleton (a training loop's inner evaluation): loop of run() vs run_many()
+def sweep(name, n, lists, sq, tq, T):
+    ex = RemoteExecutor(n, sq, tq, 1)
+    ex.run(64, lists[0])
+    t0 = time.perf_counter()
+    a = [ex.run(T, instr) for instr in lists]
+    t_loop = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = ex.run_many(T, lists)
+    t_many = time.perf_counter() - t0
+    same = all(np.array_equal(x, y) for x, y in zip(a, b))
+    print(json.dumps({"config": name, "qubits": n, "circuits": len(lists), "trajectories_per_circuit": T, "seconds_loop": t_loop,
+                      "seconds_run_many": t_many, "circuits_per_s_loop": len(lists) / t_loop,
+                      "circuits_per_s_run_many": len(lists) / t_many, "identical": same}), flush=True)
+
+
+_pairs12 = circuits.coupled_pairs(h_tq, 12, adjacent_only=True)
+sweep("C3 sweep: 20 QNN parameter sets x1e4", 12, [circuits.qnn_circuit(12, 4, _pairs12, seed=100 + i) for i in range(20)], h_sq, h_tq,
+      2000 if quick else 10000)

@@ -378,3 +378,19 @@ def test_execute_tail_on_device_matches_host_chain(heron_noise):
     out = execute(n, instr, sq, tq, mdict, None, 64, seed=11)
     ref = postprocess(RemoteExecutor(n, sq, tq, 1, seed=11).run(64, instr), n, list(range(n)), mdict, 1)
     assert np.abs(out - ref).max() < 1e-13
+
+
+def test_run_many_equals_a_loop_of_run(heron_noise):
+    """Parameter sweep over one gate skeleton (QNN training loop): the pipelined run_many returns what run returns."""
+    from noisycircuits_b200.solvers import RemoteExecutor
+    sq, tq, _, _ = heron_noise
+    n = 8
+    pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)
+    sweeps = [circuits.qnn_circuit(n, 2, pairs, seed=s) for s in range(5)]
+    ex = RemoteExecutor(n, sq, tq, 1, seed=3)
+    many = ex.run_many(500, sweeps)
+    assert len(many) == 5
+    for instr, got in zip(sweeps, many):
+        ref = RemoteExecutor(n, sq, tq, 1, seed=3).run(500, instr)
+        assert np.array_equal(got, ref)
+    assert ex.run_many(10, []) == []
