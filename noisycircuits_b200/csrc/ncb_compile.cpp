@@ -600,6 +600,72 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
                 }
                 return count;
             };
+            // Order INSIDE a segment: a pass holds R bits in registers and runs every operator whose non-diagonal bits are
+            // among them (diagonal operators ride along).  Any order that keeps the per-bit order is the same circuit, so
+            // the segment's instructions are listed pass by pass: drain everything that is ready on the current register
+            // bits -- several layers deep where the coupling allows -- before the register set grows or a new pass
+            // starts.  The pass former below cuts exactly these groups; fewer passes = fewer shared-memory round trips.
+            std::vector<uint64_t> ndbits(P.G, 0);              // bits on which the instruction is NOT diagonal
+            for (const LogicalOp& l : lops)
+                if (!l.diag)
+                    for (int b = 0; b < l.nb; ++b) ndbits[l.instr] |= 1ull << l.bits[b];
+            auto order_for_passes = [&](std::vector<int>& list) {
+                const int n = (int)list.size();
+                if (n < 3) return;
+                std::vector<int> pos_in(P.G, -1);
+                for (int i = 0; i < n; ++i) pos_in[list[i]] = i;
+                // predecessors: the previous instruction of the list on each of its bits
+                std::vector<std::vector<int>> succ(n);
+                std::vector<int> npred(n, 0);
+                {
+                    std::vector<int> last(nb, -1);
+                    for (int i = 0; i < n; ++i) {
+                        const int g = list[i];
+                        for (int b = 0; b < nb; ++b)
+                            if ((ubits[g] >> b) & 1) {
+                                if (last[b] >= 0 && (succ[last[b]].empty() || succ[last[b]].back() != i)) { succ[last[b]].push_back(i); ++npred[i]; }
+                                last[b] = i;
+                            }
+                    }
+                }
+                std::vector<char> emitted(n, 0);
+                std::vector<int> out;
+                out.reserve(n);
+                uint64_t regs = 0;
+                auto emit = [&](int i) {
+                    emitted[i] = 1; out.push_back(list[i]);
+                    for (int j : succ[i]) --npred[j];
+                };
+                while ((int)out.size() < n) {
+                    bool progress = true;
+                    while (progress) {
+                        progress = false;
+                        for (int i = 0; i < n; ++i)               // everything that needs no new register bit
+                            if (!emitted[i] && npred[i] == 0 && (ndbits[list[i]] & ~regs) == 0) { emit(i); progress = true; }
+                        if (progress) continue;
+                        for (int i = 0; i < n; ++i)               // grow the register set with the oldest ready instruction that fits
+                            if (!emitted[i] && npred[i] == 0 && __builtin_popcountll(regs | ndbits[list[i]]) <= R) {
+                                regs |= ndbits[list[i]]; emit(i); progress = true; break;
+                            }
+                    }
+                    regs = 0;                                     // next pass
+                    if ((int)out.size() < n) {
+                        bool any = false;
+                        for (int i = 0; i < n && !any; ++i)
+                            if (!emitted[i] && npred[i] == 0) any = true;
+                        if (!any) throw std::runtime_error("internal: pass ordering found no ready instruction");
+                        // an instruction with more non-diagonal bits than R (dense operators with reg_bits too small) is
+                        // reported by the pass former; emit it here to keep going
+                        bool fits = false;
+                        for (int i = 0; i < n; ++i)
+                            if (!emitted[i] && npred[i] == 0 && __builtin_popcountll(ndbits[list[i]]) <= R) fits = true;
+                        if (!fits)
+                            for (int i = 0; i < n; ++i)
+                                if (!emitted[i] && npred[i] == 0) { emit(i); break; }
+                    }
+                }
+                list.swap(out);
+            };
             std::vector<char> done(P.G, 0);
             int next_undone = 0;
             while ((int)order.size() < P.G) {
@@ -626,6 +692,7 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
                 std::vector<int> seg_list;
                 const int cnt = run(S, head, &seg_list);
                 if (cnt == 0) throw std::runtime_error("internal: the scheduler made no progress");
+                if (opt.pass_order) order_for_passes(seg_list);
                 for (int g : seg_list) { done[g] = 1; order.push_back(g); }
             }
         }

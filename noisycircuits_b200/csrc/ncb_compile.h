@@ -37,6 +37,7 @@ struct CompileOptions {
     int reg_bits = 3;       // R: amplitudes per thread = 2^R
     int low_bits = 2;       // the L lowest state bits are part of every tile (coalescing: runs of 2^L * 16 B = 64 B)
     int fuse = 1;           // 0: one instruction per segment (debug / ablation)
+    int pass_order = 1;     // 1: inside a segment, instructions are ordered pass by pass (see compile_program)
     double blob_cost_scale = 1.0;   // multiplier of the segmenter's program-size estimate (raised automatically on overflow)
     int fuse_rotations = 1; // 1: commuting rx-like rotations of a pass are grouped and dispatched as one op (constant-bank fast list)
     int direct = 1;         // 1: first / last pass of a segment exchange their amplitudes with HBM directly where possible

@@ -686,6 +686,7 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     if (const char* e = getenv("NCB_DECOMPOSE")) opt.decompose = atoi(e);
     if (const char* e = getenv("NCB_DIRECT")) opt.direct = atoi(e);
     if (const char* e = getenv("NCB_FUSE_ROT")) opt.fuse_rotations = atoi(e);
+    if (const char* e = getenv("NCB_PASS_ORDER")) opt.pass_order = atoi(e);
     if (opt.reg_bits != 3 && opt.reg_bits != 4) return fail(NCB_E_INVALID, "reg_bits must be 3 or 4");
     opt.tile_bits = std::min(opt.tile_bits, 12);   // <= 256 threads (R = 4) / 512 threads (R = 3)
     ncb_program* p = new ncb_program();

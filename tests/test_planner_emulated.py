@@ -200,11 +200,11 @@ def test_compile_retries_when_a_segment_program_overflows(heron_noise, monkeypat
     """The segmenter cuts with an estimate of the staged program size; with the estimate sabotaged (test hook) the
     first attempts overflow the 16 KB staging area and compile_program must converge by itself."""
     sq, tq, _, _ = heron_noise
-    n = 10
-    instr = circuits.heron_layered(n, 12, circuits.coupled_pairs(tq, n), seed=9)
+    n = 8                       # the whole state is one tile: only the program size cuts segments
+    instr = circuits.heron_layered(n, 30, circuits.coupled_pairs(tq, n), seed=9)
     monkeypatch.setenv("NCB_BLOB_COST_SCALE", "0.01")
     monkeypatch.setenv("NCB_MAX_SEG_OPS", "400")
     U = jumpy_uniforms(np.random.default_rng(3), 4, len(instr))
-    stats, E = check_replay(n, instr, sq, tq, U, tile_bits=9, reg_bits=3, low_bits=2, fuse=1, reorder=1)
+    stats, E = check_replay(n, instr, sq, tq, U, tile_bits=8, reg_bits=3, low_bits=2, fuse=1, reorder=1)
     assert E.query(2) >= 2
     assert "attempts=1 " not in E.describe().split("\n")[0]            # the overflow path was really taken
