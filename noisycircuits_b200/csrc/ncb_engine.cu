@@ -692,8 +692,9 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     ncb_program* p = new ncb_program();
     try {
         compile_program(view_of(circuit), mode, opt, p->eng.P);
-        if (p->eng.P.R == 3 && p->eng.P.has_dense2 && p->eng.P.K > 11) {     // the dense-4x4 kernel runs 256 threads
+        if (p->eng.P.R == 3 && p->eng.P.has_dense2 && p->eng.P.K > 11) {     // the dense-4x4 kernels run 256 threads
             opt.tile_bits = 11;
+            opt.resident_bits = std::min(opt.resident_bits, 11);             // (a 12-bit state then runs as two tiles)
             compile_program(view_of(circuit), mode, opt, p->eng.P);
         }
     } catch (...) { delete p; throw; }

@@ -4,6 +4,8 @@ from the reference's own extensions.
 
 Tolerances (north_star): replay (same per-instruction uniforms) <= 1e-10 state by state; density matrix <= 1e-10 per
 probability; free-running MCWF vs density matrix: total variation <= 3/sqrt(N)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -394,3 +396,30 @@ def test_run_many_equals_a_loop_of_run(heron_noise):
         ref = RemoteExecutor(n, sq, tq, 1, seed=3).run(500, instr)
         assert np.array_equal(got, ref)
     assert ex.run_many(10, []) == []
+
+
+@pytest.mark.parametrize("case", range(int(os.environ.get("NCB_FUZZ_CASES", "10"))))
+def test_random_circuits_all_gates_random_channels_gpu(case):
+    """The CPU suite's differential fuzz (tests/test_planner_emulated.py) on the real kernels: every gate name, random
+    channels (Pauli / damping / dense), random pairs, resident and tiled geometries, replayed state by state."""
+    from conftest import random_noisy_circuit
+    rng = np.random.default_rng(5000 + case)
+    n = int(rng.integers(3, 15))
+    instr, sq, tq = random_noisy_circuit(rng, n, length=int(rng.integers(20, 60)))
+    opts = {}
+    if n >= 10 and case % 2 == 0:
+        opts["tile_bits"] = 9                     # tiled path below the default residency threshold
+    if case % 3 == 0:
+        opts["reg_bits"] = 4
+    U = np.random.default_rng(case).random((4, len(instr)))
+    U[2:] = 1 - 0.03 * np.random.default_rng(case + 1).random((2, len(instr))) ** 2      # jump-heavy
+    stats, _ = replay(n, instr, sq, tq, U, **opts)
+    assert stats["events"] > 0
+    # free-running batched run (shared prefix, direct kernel, in-line jumps) against the oracle fed the same uniforms
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, **opts)
+    T, seed = 6, 77 + case
+    order = prog.order()
+    Uq = np.array([[philox_numpy(seed, t, g) for g in range(len(instr))] for t in range(T)])
+    ref = oracle.Program(n, [instr[g] for g in order], sq, tq).mcwf(T, uniforms=Uq[:, order], mask_fix=True)
+    got, _ = prog.run_mcwf(T, seed=seed)
+    assert np.abs(got / T - ref).max() < TOL

@@ -1,6 +1,8 @@
 """Host compiler + batch scheduler + tile geometry + register-blocked executors, run on the CPU through the
 thread-by-thread emulation in tests/emu (the same C++ sources the CUDA library is built from), against the oracle.
 Replay harness: identical per-instruction uniforms go to both; states must agree to 1e-10 (north_star)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -8,7 +10,7 @@ from noisycircuits_b200 import circuits
 from noisycircuits_b200.program import PackedCircuit
 from oracle import oracle
 from emu.emu import EmuProgram, lib as emu_lib
-from conftest import far_tables
+from conftest import far_tables, random_noisy_circuit
 
 TOL = 1e-10
 
@@ -208,3 +210,18 @@ def test_compile_retries_when_a_segment_program_overflows(heron_noise, monkeypat
     stats, E = check_replay(n, instr, sq, tq, U, tile_bits=8, reg_bits=3, low_bits=2, fuse=1, reorder=1)
     assert E.query(2) >= 2
     assert "attempts=1 " not in E.describe().split("\n")[0]            # the overflow path was really taken
+
+
+@pytest.mark.parametrize("case", range(int(os.environ.get("NCB_FUZZ_CASES", "12"))))
+def test_random_circuits_all_gates_random_channels(case):
+    """Differential fuzz of everything between the instruction list and the amplitudes: every gate name of the
+    reference (FunctionMapper.hpp:25-79) plus noise-free unitaries, random channels of three kinds on random (also
+    non-adjacent) pairs, tiled and single-tile geometries -- replayed against the oracle with jump-heavy uniforms."""
+    rng = np.random.default_rng(1000 + case)
+    n = int(rng.integers(4, 11))
+    tile_bits = 8 if n > 8 and case % 2 == 0 else 12
+    reg_bits = 3 if case % 3 else 4
+    instr, sq, tq = random_noisy_circuit(rng, n)
+    U = jumpy_uniforms(rng, 4, len(instr))
+    stats, _E = check_replay(n, instr, sq, tq, U, tile_bits=tile_bits, reg_bits=reg_bits, low_bits=2, fuse=1, reorder=1)
+    assert stats["events"] > 0
