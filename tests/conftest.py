@@ -72,13 +72,16 @@ def random_channel(rng, d, kind):
     return [np.ascontiguousarray(q[i * d:(i + 1) * d]) for i in range(m)]
 
 
-def random_noisy_circuit(rng, n, length=None):
+def random_noisy_circuit(rng, n, length=None, lean=False):
     """(instruction list, single-qubit noise, two-qubit noise): every gate name of the reference
     (FunctionMapper.hpp:25-79) with random angles, two-qubit gates on random (also non-adjacent) ordered pairs, noise-free
     1-2 qubit unitaries, a random channel kind per (gate, qubits)."""
-    kinds = ["pauli", "damping", "generic"]
-    one_q, two_q = ["x", "sx", "rz", "rx", "ry", "h", "p"], ["cz", "ecr", "rzz", "cx", "swap"]
-    sq = {q: {g: random_channel(rng, 2, kinds[int(rng.integers(0, 3))]) for g in one_q} for q in range(n)}
+    # lean: only what the lean kernels run (no swap, no dense Kraus operators): the direct kernel, fused rotations and
+    # in-line jumps are exercised instead of the dense 4x4 kernels
+    kinds = ["pauli", "damping"] if lean else ["pauli", "damping", "generic"]
+    one_q = ["x", "sx", "rz", "rx", "ry", "h", "p"]
+    two_q = ["cz", "ecr", "rzz", "cx"] if lean else ["cz", "ecr", "rzz", "cx", "swap"]
+    sq = {q: {g: random_channel(rng, 2, kinds[int(rng.integers(0, len(kinds)))]) for g in one_q} for q in range(n)}
     tq = {g: {} for g in two_q}
     instr = []
     for _ in range(int(length or rng.integers(15, 40))):
@@ -90,10 +93,10 @@ def random_noisy_circuit(rng, n, length=None):
             a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
             g = two_q[int(rng.integers(0, len(two_q)))]
             if (a, b) not in tq[g]:
-                tq[g][(a, b)] = random_channel(rng, 4, kinds[int(rng.integers(0, 3))])
+                tq[g][(a, b)] = random_channel(rng, 4, kinds[int(rng.integers(0, len(kinds)))])
             instr.append([g, [a, b], float(rng.uniform(-6, 6))])
         else:
-            k = int(rng.integers(1, 3))
+            k = 1 if lean else int(rng.integers(1, 3))
             qs = [int(x) for x in rng.choice(n, size=k, replace=False)]
             u = np.linalg.qr(rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k)))[0]
             instr.append(["unitary", qs, u])

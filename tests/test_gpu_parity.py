@@ -405,11 +405,12 @@ def test_random_circuits_all_gates_random_channels_gpu(case):
     from conftest import random_noisy_circuit
     rng = np.random.default_rng(5000 + case)
     n = int(rng.integers(3, 15))
-    instr, sq, tq = random_noisy_circuit(rng, n, length=int(rng.integers(20, 60)))
+    lean = case % 4 >= 2                          # half of the cases stay on the lean kernels (direct kernel, fused rotations)
+    instr, sq, tq = random_noisy_circuit(rng, n, length=int(rng.integers(20, 60)), lean=lean)
     opts = {}
     if n >= 10 and case % 2 == 0:
         opts["tile_bits"] = 9                     # tiled path below the default residency threshold
-    if case % 3 == 0:
+    if case % 3 == 0 and not lean:
         opts["reg_bits"] = 4
     U = np.random.default_rng(case).random((4, len(instr)))
     U[2:] = 1 - 0.03 * np.random.default_rng(case + 1).random((2, len(instr))) ** 2      # jump-heavy

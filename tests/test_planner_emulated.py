@@ -221,7 +221,9 @@ def test_random_circuits_all_gates_random_channels(case):
     n = int(rng.integers(4, 11))
     tile_bits = 8 if n > 8 and case % 2 == 0 else 12
     reg_bits = 3 if case % 3 else 4
-    instr, sq, tq = random_noisy_circuit(rng, n)
+    instr, sq, tq = random_noisy_circuit(rng, n, lean=case % 4 >= 2)
+    if case % 4 >= 2:
+        reg_bits = 3
     U = jumpy_uniforms(rng, 4, len(instr))
     stats, _E = check_replay(n, instr, sq, tq, U, tile_bits=tile_bits, reg_bits=reg_bits, low_bits=2, fuse=1, reorder=1)
     assert stats["events"] > 0
