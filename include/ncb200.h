@@ -129,14 +129,16 @@ typedef struct {
     int32_t accumulate;        /* 1: add to probs, 0: overwrite */
     int32_t batch;             /* trajectories resident at once (0: automatic) */
     double* states;            /* optional [traj_count][2^n] complex: final normalised state of each trajectory */
-    void* stream;              /* cudaStream_t (NULL: default stream) */
+    void* stream;              /* cudaStream_t (NULL: default stream); the engine forks an internal second stream from it
+                                  and joins it back, so the caller only ever orders against this one */
     /* statistics, filled on return */
-    int64_t out_sweeps;        /* state sweeps issued (one read + one write of one trajectory's state each) */
+    int64_t out_sweeps;        /* state sweeps issued (one read + one write of one trajectory's state each), the shared
+                                  no-jump prefix counted once per batch */
     int64_t out_events;        /* jump events (branch != base branch) */
     int64_t out_hard_events;   /* events whose branch needed the reduced density matrix */
     int64_t out_launches;      /* kernel launches */
     double out_kernel_ms;      /* device time from the first to the last kernel of the run (CUDA events on `stream`) */
-    int64_t out_tile_launches; /* launches of the sweep (tile / resident) kernel among out_launches */
+    int64_t out_tile_launches; /* launches of the sweep (direct / tile / resident) kernels among out_launches */
     int64_t out_h2d_bytes;     /* bytes copied host -> device during the run (work lists, uniform tables) */
     int64_t out_d2h_bytes;     /* bytes copied device -> host during the run (probabilities, states, counters) */
 } ncb_run_params;
