@@ -9,12 +9,18 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <atomic>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <fstream>
+#include <sstream>
 #include <vector>
 
 #include "../../include/ncb200.h"
 #include "ncb_compile.h"
 #include "ncb_kernels.cuh"
 #include "ncb_schedule.h"
+#include "ncb_spec.h"
 
 namespace ncb {
 
@@ -77,6 +83,41 @@ struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// specialised sweep kernels (ncb_spec.*): generated per program, compiled with nvcc into a cubin cache, loaded through
+// the driver API (resolved with dlopen, so the library keeps linking against the runtime only)
+// ---------------------------------------------------------------------------------------------------------------
+struct DriverApi {
+    void* lib = nullptr;
+    int (*ModuleLoadData)(void**, const void*) = nullptr;
+    int (*ModuleGetFunction)(void**, void*, const char*) = nullptr;
+    int (*FuncSetAttribute)(void*, int, int) = nullptr;
+    int (*LaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**) = nullptr;
+    int (*ModuleUnload)(void*) = nullptr;
+    bool load() {
+        if (lib) return true;
+        lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        ModuleLoadData = (decltype(ModuleLoadData))dlsym(lib, "cuModuleLoadData");
+        ModuleGetFunction = (decltype(ModuleGetFunction))dlsym(lib, "cuModuleGetFunction");
+        FuncSetAttribute = (decltype(FuncSetAttribute))dlsym(lib, "cuFuncSetAttribute");
+        LaunchKernel = (decltype(LaunchKernel))dlsym(lib, "cuLaunchKernel");
+        ModuleUnload = (decltype(ModuleUnload))dlsym(lib, "cuModuleUnload");
+        return ModuleLoadData && ModuleGetFunction && FuncSetAttribute && LaunchKernel && ModuleUnload;
+    }
+};
+static DriverApi g_drv;
+
+static std::string this_library_dir() {
+    Dl_info info;
+    if (dladdr((void*)&this_library_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        const size_t k = p.find_last_of('/');
+        return k == std::string::npos ? std::string(".") : p.substr(0, k);
+    }
+    return ".";
+}
+
 struct Engine {
     Program P;
     int device = -1;
@@ -114,6 +155,7 @@ struct Engine {
             d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
             if (buf_free[i]) cudaEventDestroy(buf_free[i]);
         }
+        for (void* m : spec_modules) if (g_drv.ModuleUnload) g_drv.ModuleUnload(m);
         if (s2) cudaStreamDestroy(s2);
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
@@ -285,7 +327,109 @@ struct Engine {
         direct_kernel<512, 2><<<grid, threads, direct_smem(), s>>>(d, P.segconst[seg], blob, blob_bytes, tile_blob_cap, works, nworks, d_states.p, tile_shift);
         CK(cudaGetLastError());
     }
+    // ---- specialised kernels -----------------------------------------------------------------------------------
+    bool specialize = false, spec_tried = false;
+    std::vector<void*> spec_modules, spec_fn;          // CUmodule per part, CUfunction per segment (nullptr: interpreter)
+    // Generates, compiles (nvcc, in parallel, into the cubin cache) and loads the specialised kernels of this program.
+    // Any failure leaves the interpreter in charge (and says so with NCB_VERBOSE).
+    static constexpr int SPEC_PER_PART = 4;                  // segments per translation unit
+    // host-only part: sources + nvcc into the cache; returns the cache directory of this program ("" on failure)
+    std::string spec_build() {
+        const bool verbose = getenv("NCB_VERBOSE") != nullptr;
+        int nsupported = 0;
+        for (int sgi = 0; sgi < (int)P.segs.size(); ++sgi) nsupported += spec_supported(P, sgi);
+        if (!nsupported) return "";
+        const std::string libdir = this_library_dir();
+        std::string cache = getenv("NCB_SPEC_CACHE") ? getenv("NCB_SPEC_CACHE") : libdir + "/_speccache";
+        const std::string dir = cache + "/" + spec_key(P);
+        mkdir(cache.c_str(), 0755);
+        mkdir(dir.c_str(), 0755);
+        const int nseg = (int)P.segs.size();
+        const int per = SPEC_PER_PART;
+        const int nparts = (nseg + per - 1) / per;
+        auto exists = [](const std::string& f) { struct stat st; return stat(f.c_str(), &st) == 0 && st.st_size > 0; };
+        std::vector<int> todo;
+        for (int k = 0; k < nparts; ++k)
+            if (!exists(dir + "/part" + std::to_string(k) + ".cubin")) todo.push_back(k);
+        if (!todo.empty()) {
+            const std::string nvcc = getenv("NCB_NVCC") ? getenv("NCB_NVCC") : "/usr/local/cuda/bin/nvcc";
+            if (!exists(nvcc)) { if (verbose) fprintf(stderr, "[ncb] specialised kernels: %s not found\n", nvcc.c_str()); return ""; }
+            std::atomic<int> next{0}, failed{0};
+            auto worker = [&]() {
+                for (;;) {
+                    const int i = next.fetch_add(1);
+                    if (i >= (int)todo.size()) break;
+                    const int k = todo[i];
+                    const std::string base = dir + "/part" + std::to_string(k);
+                    { std::ofstream f(base + ".cu"); f << spec_source(P, k * per, std::min(nseg, (k + 1) * per)); }
+                    const std::string cmd = nvcc + " -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -I" + libdir + "/csrc -cubin -o " +
+                                            base + ".tmp " + base + ".cu > " + base + ".log 2>&1 && mv " + base + ".tmp " + base + ".cubin";
+                    if (system(cmd.c_str()) != 0) failed.fetch_add(1);
+                }
+            };
+            const int nthreads = std::max(1, std::min<int>({(int)todo.size(), plan_threads(), 16}));
+            std::vector<std::thread> pool;
+            for (int i = 0; i < nthreads; ++i) pool.emplace_back(worker);
+            for (auto& t : pool) t.join();
+            if (verbose) fprintf(stderr, "[ncb] specialised kernels: compiled %zu parts with %d threads (%d failed) into %s\n", todo.size(), nthreads,
+                                 failed.load(), dir.c_str());
+            if (failed.load()) return "";
+        }
+        return dir;
+    }
+    void ensure_spec() {
+        if (spec_tried) return;
+        spec_tried = true;
+        spec_fn.assign(P.segs.size(), nullptr);
+        const bool verbose = getenv("NCB_VERBOSE") != nullptr;
+        if (!g_drv.load()) { if (verbose) fprintf(stderr, "[ncb] specialised kernels: libcuda.so.1 not usable\n"); return; }
+        const std::string dir = spec_build();
+        if (dir.empty()) return;
+        const int nseg = (int)P.segs.size(), per = SPEC_PER_PART, nparts = (nseg + per - 1) / per;
+        int loaded = 0;
+        for (int k = 0; k < nparts; ++k) {
+            std::ifstream f(dir + "/part" + std::to_string(k) + ".cubin", std::ios::binary);
+            std::stringstream ss;
+            ss << f.rdbuf();
+            const std::string image = ss.str();
+            void* mod = nullptr;
+            if (image.empty() || g_drv.ModuleLoadData(&mod, image.data()) != 0) continue;
+            spec_modules.push_back(mod);
+            for (int sgi = k * per; sgi < std::min(nseg, (k + 1) * per); ++sgi) {
+                if (!spec_supported(P, sgi)) continue;
+                void* fn = nullptr;
+                if (g_drv.ModuleGetFunction(&fn, mod, ("ncb_seg_" + std::to_string(sgi)).c_str()) != 0) continue;
+                if (g_drv.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem_optin - 8 * 1024) != 0) continue;
+                spec_fn[sgi] = fn;
+                ++loaded;
+            }
+        }
+        if (verbose) fprintf(stderr, "[ncb] specialised kernels: %d of %d segments loaded\n", loaded, nseg);
+    }
     void launch_step(const LaunchStep& st, cudaStream_t s, const Work* works) {
+        if (st.direct && specialize) {
+            ensure_spec();
+            void* fn = st.seg < (int)spec_fn.size() ? spec_fn[st.seg] : nullptr;
+            if (fn) {
+                configure_tile();
+                if (!direct_ctas) launch_direct(0, s, works, st.seg);            // (configures the launch geometry)
+                const int tile_shift = P.nbits - P.K, threads = 1 << (P.K - P.R);
+                const long long total = (long long)st.count << tile_shift;
+                long long want = direct_ctas;
+                if (direct_chunk > 0) want = std::max<long long>(want, (total + direct_chunk - 1) / direct_chunk);
+                const int grid = (int)std::min<long long>(total, want);
+                if (grid < 1) return;
+                const unsigned char* blob = d_blobs.p + P.blob_off[st.seg];
+                int blob_bytes = reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[st.seg])->bytes;
+                int blob_cap = tile_blob_cap, nworks = st.count, tshift = tile_shift;
+                const Work* w = works + st.begin;
+                cplx* states = d_states.p;
+                void* args[] = {(void*)&blob, &blob_bytes, &blob_cap, (void*)&w, &nworks, (void*)&states, &tshift};
+                const int rc = g_drv.LaunchKernel(fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)direct_smem(), (void*)s, args, nullptr);
+                if (rc != 0) throw std::runtime_error("cuLaunchKernel of a specialised kernel failed (" + std::to_string(rc) + ")");
+                return;
+            }
+        }
         if (st.direct) launch_direct(st.count, s, works + st.begin, st.seg);
         else launch_tile(st.count, s, works + st.begin, st.seg);
     }
@@ -700,6 +844,8 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     } catch (...) { delete p; throw; }
     p->eng.device = device;
     p->eng.independent = options && options->independent_trajectories != 0;
+    p->eng.specialize = options && options->reserved == 1;
+    if (const char* e = getenv("NCB_SPECIALIZE")) p->eng.specialize = atoi(e) != 0;
     *out = p;
     return NCB_OK;
     NCB_CATCH
@@ -735,6 +881,27 @@ int64_t ncb_program_query(const ncb_program* program, int what) {
     case NCB_Q_RESIDENT: return program->eng.resident();
     }
     return -1;
+}
+
+// Generates and compiles the specialised kernels of the program into the cubin cache (host only: nvcc, no device).
+int ncb_program_spec_build(ncb_program* program) {
+    if (!program) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    return program->eng.spec_build().empty() ? fail(NCB_E_INVALID, "specialised kernels could not be built (unsupported program or nvcc failure)") : NCB_OK;
+    NCB_CATCH
+}
+
+// Source of the specialised kernels of segments [seg_begin, seg_end) (ncb_spec.cpp); returns the bytes needed.
+int64_t ncb_program_spec_source(const ncb_program* program, int32_t seg_begin, int32_t seg_end, char* buf, int64_t len) {
+    if (!program) return -1;
+    const Program& P = program->eng.P;
+    const std::string s = spec_source(P, std::max(seg_begin, 0), std::min<int>(seg_end, (int)P.segs.size()));
+    if (buf && len > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)len - 1);
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
 }
 
 int ncb_program_order(const ncb_program* program, int32_t* out) {
