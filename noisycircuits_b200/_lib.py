@@ -27,7 +27,7 @@ class NcbCircuit(C.Structure):
 class NcbOptions(C.Structure):
     _fields_ = [("tile_bits", C.c_int32), ("reg_bits", C.c_int32), ("low_bits", C.c_int32), ("fuse", C.c_int32),
                 ("device", C.c_int32), ("strict_order", C.c_int32), ("independent_trajectories", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("specialize", C.c_int32)]
 
 
 class NcbRunParams(C.Structure):
@@ -43,7 +43,7 @@ class NcbRunParams(C.Structure):
 EXPORTS = ["ncb_last_error", "ncb_version", "ncb_program_create", "ncb_program_destroy", "ncb_program_describe",
            "ncb_program_query", "ncb_program_order", "ncb_program_events", "ncb_program_reference_uniforms", "ncb_mcwf_run", "ncb_pure_run",
            "ncb_density_run", "ncb_apply_measurement_error", "ncb_apply_measurement_error_device",
-           "ncb_execute_tail_device", "ncb_device_alloc", "ncb_device_free",
+           "ncb_execute_tail_device", "ncb_device_alloc", "ncb_device_free", "ncb_program_spec_build", "ncb_program_spec_source",
            "ncb_simulate_circuit", "ncb_run_trajectory"]
 
 _lib = None
@@ -84,6 +84,9 @@ def lib() -> C.CDLL:
         L.ncb_execute_tail_device.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         L.ncb_device_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
         L.ncb_device_free.argtypes = [C.c_void_p]
+        L.ncb_program_spec_build.argtypes = [C.c_void_p]
+        L.ncb_program_spec_source.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]
+        L.ncb_program_spec_source.restype = C.c_int64
         L.ncb_simulate_circuit.argtypes = [C.POINTER(NcbCircuit), C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_uint32]
         L.ncb_run_trajectory.argtypes = [C.POINTER(NcbCircuit), C.c_void_p, C.c_uint32, C.c_uint32]
         _lib = L

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <fstream>
 #include <sstream>
 #include <vector>
@@ -108,6 +109,13 @@ struct DriverApi {
 };
 static DriverApi g_drv;
 
+static std::string build_stamp() {
+    uint64_t h = 1469598103934665603ull;
+    for (const char* c = __DATE__ " " __TIME__; *c; ++c) { h ^= (unsigned char)*c; h *= 1099511628211ull; }
+    char b[20];
+    std::snprintf(b, sizeof b, "%08x", (unsigned)(h ^ (h >> 32)));
+    return b;
+}
 static std::string this_library_dir() {
     Dl_info info;
     if (dladdr((void*)&this_library_dir, &info) && info.dli_fname) {
@@ -329,6 +337,7 @@ struct Engine {
     }
     // ---- specialised kernels -----------------------------------------------------------------------------------
     bool specialize = false, spec_tried = false;
+    int spec_nbuf = 2, spec_pool_cap = 0;
     std::vector<void*> spec_modules, spec_fn;          // CUmodule per part, CUfunction per segment (nullptr: interpreter)
     // Generates, compiles (nvcc, in parallel, into the cubin cache) and loads the specialised kernels of this program.
     // Any failure leaves the interpreter in charge (and says so with NCB_VERBOSE).
@@ -341,7 +350,9 @@ struct Engine {
         if (!nsupported) return "";
         const std::string libdir = this_library_dir();
         std::string cache = getenv("NCB_SPEC_CACHE") ? getenv("NCB_SPEC_CACHE") : libdir + "/_speccache";
-        const std::string dir = cache + "/" + spec_key(P);
+        if (const char* e = getenv("NCB_SPEC_NBUF")) spec_nbuf = atoi(e) == 1 ? 1 : 2;
+        // (the cubins depend on the kernel headers too: a rebuilt library starts a new cache generation)
+        const std::string dir = cache + "/" + spec_key(P, spec_nbuf) + "-" + build_stamp();
         mkdir(cache.c_str(), 0755);
         mkdir(dir.c_str(), 0755);
         const int nseg = (int)P.segs.size();
@@ -360,10 +371,12 @@ struct Engine {
                     const int i = next.fetch_add(1);
                     if (i >= (int)todo.size()) break;
                     const int k = todo[i];
-                    const std::string base = dir + "/part" + std::to_string(k);
-                    { std::ofstream f(base + ".cu"); f << spec_source(P, k * per, std::min(nseg, (k + 1) * per)); }
+                    // several processes (one per GPU) may build the same cache at once: private temporaries, atomic renames
+                    const std::string base = dir + "/part" + std::to_string(k), mine = base + "." + std::to_string((long)getpid());
+                    { std::ofstream f(mine + ".cu"); f << spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_nbuf); }
                     const std::string cmd = nvcc + " -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -I" + libdir + "/csrc -cubin -o " +
-                                            base + ".tmp " + base + ".cu > " + base + ".log 2>&1 && mv " + base + ".tmp " + base + ".cubin";
+                                            mine + ".tmp " + mine + ".cu > " + mine + ".log 2>&1 && mv " + mine + ".tmp " + base + ".cubin && mv " +
+                                            mine + ".cu " + base + ".cu && mv " + mine + ".log " + base + ".log";
                     if (system(cmd.c_str()) != 0) failed.fetch_add(1);
                 }
             };
@@ -386,6 +399,12 @@ struct Engine {
         const std::string dir = spec_build();
         if (dir.empty()) return;
         const int nseg = (int)P.segs.size(), per = SPEC_PER_PART, nparts = (nseg + per - 1) / per;
+        spec_pool_cap = 0;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+            int off, bytes;
+            spec_pool(P, sgi, &off, &bytes);
+            spec_pool_cap = std::max(spec_pool_cap, (bytes + 1023) & ~1023);
+        }
         int loaded = 0;
         for (int k = 0; k < nparts; ++k) {
             std::ifstream f(dir + "/part" + std::to_string(k) + ".cubin", std::ios::binary);
@@ -419,13 +438,15 @@ struct Engine {
                 if (direct_chunk > 0) want = std::max<long long>(want, (total + direct_chunk - 1) / direct_chunk);
                 const int grid = (int)std::min<long long>(total, want);
                 if (grid < 1) return;
-                const unsigned char* blob = d_blobs.p + P.blob_off[st.seg];
-                int blob_bytes = reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[st.seg])->bytes;
-                int blob_cap = tile_blob_cap, nworks = st.count, tshift = tile_shift;
+                int pool_off, pool_bytes;
+                spec_pool(P, st.seg, &pool_off, &pool_bytes);
+                const unsigned char* pool_g = d_blobs.p + P.blob_off[st.seg] + pool_off;
+                int pool_cap = spec_pool_cap, nworks = st.count, tshift = tile_shift;
                 const Work* w = works + st.begin;
                 cplx* states = d_states.p;
-                void* args[] = {(void*)&blob, &blob_bytes, &blob_cap, (void*)&w, &nworks, (void*)&states, &tshift};
-                const int rc = g_drv.LaunchKernel(fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)direct_smem(), (void*)s, args, nullptr);
+                void* args[] = {(void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift};
+                const size_t smem = (size_t)spec_pool_cap + (size_t)spec_nbuf * tile_smem();
+                const int rc = g_drv.LaunchKernel(fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (void*)s, args, nullptr);
                 if (rc != 0) throw std::runtime_error("cuLaunchKernel of a specialised kernel failed (" + std::to_string(rc) + ")");
                 return;
             }
@@ -844,7 +865,7 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     } catch (...) { delete p; throw; }
     p->eng.device = device;
     p->eng.independent = options && options->independent_trajectories != 0;
-    p->eng.specialize = options && options->reserved == 1;
+    p->eng.specialize = options && options->specialize == 1;
     if (const char* e = getenv("NCB_SPECIALIZE")) p->eng.specialize = atoi(e) != 0;
     *out = p;
     return NCB_OK;

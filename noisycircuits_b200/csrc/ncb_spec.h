@@ -10,8 +10,10 @@ namespace ncb {
 // direct store)
 bool spec_supported(const Program& P, int seg);
 // CUDA source of `extern "C" __global__ void ncb_seg_<seg>(...)` for segments [seg_begin, seg_end) of P
-std::string spec_source(const Program& P, int seg_begin, int seg_end);
+std::string spec_source(const Program& P, int seg_begin, int seg_end, int nbuf = 2);
+// bytes of segment seg's phase-table pool (the only part of the staged blob a specialised kernel needs) and its offset
+void spec_pool(const Program& P, int seg, int* offset, int* bytes);
 // content hash of everything the generated code depends on (cache key)
-std::string spec_key(const Program& P);
+std::string spec_key(const Program& P, int nbuf = 2);
 
 }  // namespace ncb

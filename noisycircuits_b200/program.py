@@ -127,12 +127,12 @@ class Program:
 
     def __init__(self, packed: PackedCircuit, mode: int = _lib.MODE_MCWF, tile_bits: int = 0, reg_bits: int = 0,
                  low_bits: int = -1, fuse: int = 1, device: int = -1, strict_order: bool = False,
-                 independent_trajectories: bool = False):
+                 independent_trajectories: bool = False, specialize: bool = False):
         self._h = C.c_void_p(None)
         self.packed = packed
         self.mode = mode
         opts = _lib.NcbOptions(tile_bits, reg_bits, low_bits, fuse, device, int(bool(strict_order)),
-                               int(bool(independent_trajectories)), 0)
+                               int(bool(independent_trajectories)), int(bool(specialize)))
         _lib.check(_lib.lib().ncb_program_create(C.byref(packed.struct), mode, C.byref(opts), C.byref(self._h)))
         self.num_qubits = packed.num_qubits
         self.num_instructions = packed.num_instructions
@@ -171,6 +171,18 @@ class Program:
         out = np.zeros((cap, 3), np.int32)
         n = _lib.lib().ncb_program_events(self._h, _ptr(u), _ptr(out), cap)
         return out[:n]
+
+    def specialize_build(self) -> bool:
+        """Generates and compiles this program's specialised kernels into the cubin cache (host only, a few seconds; the
+        first run of a program created with ``specialize=True`` does it implicitly).  False: nothing to specialise or
+        nvcc not usable -- the interpreting kernels are used."""
+        return _lib.lib().ncb_program_spec_build(self._h) == 0
+
+    def specialized_source(self, seg_begin: int = 0, seg_end: int = 1 << 30) -> str:
+        n = _lib.lib().ncb_program_spec_source(self._h, int(seg_begin), int(min(seg_end, 1 << 30)), None, 0)
+        buf = C.create_string_buffer(int(n))
+        _lib.lib().ncb_program_spec_source(self._h, int(seg_begin), int(min(seg_end, 1 << 30)), buf, n)
+        return buf.value.decode()
 
     def reference_uniforms(self, seed: int) -> np.ndarray:
         u = np.empty(max(self.num_instructions, 1), np.float64)

@@ -64,18 +64,24 @@ class RemoteExecutor:
         self.last_stats = None
         self._cache = (None, None)
 
-    def _program(self, instruction_list) -> Program:
-        key = _fingerprint(instruction_list)
+    # from this many trajectories on, a few seconds spent on kernels generated for the circuit (ncb_options.specialize)
+    # pay for themselves; an explicit specialize=True / False in the engine options overrides it
+    SPECIALIZE_FROM = 4096
+
+    def _program(self, instruction_list, traj_count: int = 0) -> Program:
+        opts = dict(self.engine_options)
+        opts.setdefault("specialize", traj_count >= self.SPECIALIZE_FROM)
+        key = (_fingerprint(instruction_list), bool(opts["specialize"]))
         if self._cache[0] != key:
             packed = PackedCircuit(self.num_qubits, instruction_list, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
-            self._cache = (key, Program(packed, _lib.MODE_MCWF, **self.engine_options))
+            self._cache = (key, Program(packed, _lib.MODE_MCWF, **opts))
         return self._cache[1]
 
     def run_sum(self, instruction_list, traj_begin: int, traj_count: int, uniforms=None, device_probs=None,
                 accumulate=False, stream=0):
         """Unnormalised sum of |psi_t|^2 over trajectories [traj_begin, traj_begin + traj_count): the building block
         of sharded (multi-GPU) runs; trajectory ids key the RNG so the result does not depend on the sharding."""
-        prog = self._program(instruction_list)
+        prog = self._program(instruction_list, traj_count)
         seed = self.seed
         probs, stats = prog.run_mcwf(traj_count, traj_begin=traj_begin, rng=_RNG[self.rng], seed=seed, uniforms=uniforms,
                                      device_probs=device_probs, accumulate=accumulate, stream=stream)

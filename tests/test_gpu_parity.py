@@ -424,3 +424,30 @@ def test_random_circuits_all_gates_random_channels_gpu(case):
     ref = oracle.Program(n, [instr[g] for g in order], sq, tq).mcwf(T, uniforms=Uq[:, order], mask_fix=True)
     got, _ = prog.run_mcwf(T, seed=seed)
     assert np.abs(got / T - ref).max() < TOL
+
+
+def test_specialised_kernels_are_the_interpreter_written_out(heron_noise):
+    """ncb_options.specialize: one generated kernel per segment (pass programs with literal coefficients) instead of the
+    interpreting direct kernel.  Same operators in the same order: the probabilities agree to rounding with the
+    interpreter's, the trajectories with the oracle's; the source really is straight-line code."""
+    sq, tq, _, _ = heron_noise
+    n = 14
+    instr = circuits.heron_layered(n, 6, circuits.coupled_pairs(tq, n), seed=12)
+    pk = PackedCircuit(n, instr, sq, tq)
+    spec = Program(pk, _lib.MODE_MCWF, specialize=True)
+    if not spec.specialize_build():
+        pytest.skip("nvcc not usable on this box: the interpreter is the only path")
+    src = spec.specialized_source(0, 1)
+    assert "ncb_seg_0" in src and "spec_rx<" in src and "switch" not in src
+    plain = Program(pk, _lib.MODE_MCWF)
+    T, seed = 300, 21
+    a, sa = spec.run_mcwf(T, seed=seed)
+    b, sb = plain.run_mcwf(T, seed=seed)
+    assert np.abs(a - b).max() < 1e-12 and sa["events"] == sb["events"] and sa["sweeps"] == sb["sweeps"]
+    assert abs(a.sum() - T) < 1e-9
+    Tq = 10
+    order = spec.order()
+    U = np.array([[philox_numpy(seed, t, g) for g in range(len(instr))] for t in range(Tq)])
+    ref = oracle.Program(n, [instr[g] for g in order], sq, tq).mcwf(Tq, uniforms=U[:, order], mask_fix=True)
+    q, _ = spec.run_mcwf(Tq, seed=seed)
+    assert np.abs(q / Tq - ref).max() < TOL
