@@ -350,6 +350,7 @@ struct Engine {
         if (!nsupported) return "";
         const std::string libdir = this_library_dir();
         std::string cache = getenv("NCB_SPEC_CACHE") ? getenv("NCB_SPEC_CACHE") : libdir + "/_speccache";
+        spec_nbuf = P.K >= 12 ? 1 : 2;               // two 64 KB buffers would leave one CTA per SM
         if (const char* e = getenv("NCB_SPEC_NBUF")) spec_nbuf = atoi(e) == 1 ? 1 : 2;
         // (the cubins depend on the kernel headers too: a rebuilt library starts a new cache generation)
         const std::string dir = cache + "/" + spec_key(P, spec_nbuf) + "-" + build_stamp();

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Throughput of the headline workload with one optimisation switched off at a time.
 # usage (on a B200): scripts/ablation.sh > profiles/rNN_ablation.jsonl
-for cfg in "" "NCB_SHARE_PREFIX=0" "NCB_DIRECT=0" "NCB_OVERLAP=0" "NCB_DIRECT_CHUNK=0" "NCB_FUSE_ROT=0" "NCB_PASS_ORDER=0" "NCB_REORDER=0" "NCB_MAX_SEG_OPS=20" "NCB_TILE_BITS=12" "NCB_LOW_BITS=3" "NCB_FUSE=0"; do
+for cfg in "" "NCB_SPECIALIZE=0" "NCB_SHARE_PREFIX=0" "NCB_DIRECT=0" "NCB_OVERLAP=0" "NCB_DIRECT_CHUNK=0" "NCB_FUSE_ROT=0" "NCB_PASS_ORDER=0" "NCB_REORDER=0" "NCB_MAX_SEG_OPS=20" "NCB_TILE_BITS=12" "NCB_LOW_BITS=3" "NCB_FUSE=0"; do
   steps=3; tps=592
   if [ "$cfg" = "NCB_FUSE=0" ]; then steps=1; tps=148; fi
   env $cfg python bench.py --no-cpu-baseline --steps $steps --warmup 2 --traj-per-step $tps 2>/dev/null | tail -1 | CFG="$cfg" python -c "

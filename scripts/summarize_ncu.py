@@ -1,6 +1,6 @@
 """Summarise an `ncu --set full` capture of the sweep kernel into profiles/ (markdown table + traffic json).
 
-usage: python scripts/summarize_ncu.py <capture.ncu-rep> <round tag, e.g. r01> <kernel: direct|tile> "<command line captured>"
+usage: python scripts/summarize_ncu.py <capture.ncu-rep> <round tag, e.g. r01> <kernel: direct|tile|spec> "<command line captured>"
 
 Reads the report with `ncu -i ... --page raw --csv` (no GPU needed).  Every launch sweeps the state of the trajectories
 in its work list once; the number of tiles comes from the grid (direct kernel: 16 tiles of 2^11 amplitudes per CTA).
@@ -43,9 +43,10 @@ def main():
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, body = rows[0], rows[1], rows[2:]
     col = {n: i for i, n in enumerate(hdr)}
-    body = [r for r in body if (kern + "_kernel") in r[col["Kernel Name"]]]
+    match = {"direct": "direct_kernel", "tile": "tile_kernel", "spec": "ncb_seg_"}[kern]
+    body = [r for r in body if match in r[col["Kernel Name"]]]
     name = body[0][col["Kernel Name"]]
-    tiles_per_cta = 16 if kern == "direct" else None
+    tiles_per_cta = 16 if kern in ("direct", "spec") else None
     tile_bytes = 2 * 16 * 2 ** 11          # one read + one write of a 2^11-amplitude tile
     out = [f"# ncu --set full capture of the {kern} sweep kernel ({tag})", "", f"Command (B200, gpurun): `{cmd}`", "",
            f"Kernel: `{name}`; 20-qubit depth-50 Heron circuit (BASELINE configs[4]), engine batches of 296 trajectories "
