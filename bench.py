@@ -39,7 +39,7 @@ METRIC = "mcwf_trajectories_per_sec"
 UNIT = "trajectories/s"
 NQ, DEPTH, CIRCUIT_SEED = 20, 50, 42
 CPU_SAMPLE_LAYERS = 4        # bounded CPU sample: ~10 s of all-core work per measurement
-PREWARM_S = 3.0              # untimed pre-warm before the warm-up steps (seconds)
+PREWARM_STEPS = 10           # untimed pre-warm steps before the warm-up steps (about 3 s)
 
 
 def workload():
@@ -280,11 +280,8 @@ def run_gpu(args):
     t_spec = time.perf_counter()
     spec_built = False
     if specialize:
-        if world > 1 and rank != 0:
-            dist.barrier()                       # rank 0 fills the cubin cache, the others find it there
+        # every rank may build: the cache is filled with private temporaries and atomic renames, and a hit costs nothing
         spec_built = solver._program(instr, tps).specialize_build()
-        if world > 1 and rank == 0:
-            dist.barrier()
     t_spec = time.perf_counter() - t_spec
     stream = torch.cuda.current_stream().cuda_stream
     dim = 1 << NQ
@@ -311,13 +308,12 @@ def run_gpu(args):
     if clocks:
         clocks.start()            # nvidia-smi starts (and initialises NVML) during the warm-up, samples through the timed region
     # pre-warm: a process on a freshly provisioned box runs its first seconds visibly slower (library pages, NCCL
-    # channels, power state) -- untimed steps until PREWARM_S have passed, then the W warm-up steps of the contract
-    t_pre = time.perf_counter()
-    s_pre = 0
-    while time.perf_counter() - t_pre < PREWARM_S:
+    # channels, power state) -- PREWARM_STEPS untimed steps, then the W warm-up steps of the contract
+    # (a FIXED number of steps: every rank must issue the same collectives -- a time-based loop can differ by one
+    # iteration between ranks and leave them waiting for each other)
+    for s_pre in range(PREWARM_STEPS):
         step(1000 + s_pre)
-        s_pre += 1
-        barrier()
+    barrier()
     for s in range(args.warmup):
         step(s)
     barrier()
