@@ -17,8 +17,10 @@ def main():
     for r in body:
         name = r[kn].split("(")[0].strip()
         ns = float(r[mv].replace(",", ""))
-        if "tile_kernel" in name:
-            name += " [full sweep]" if ns > 1e6 else " [jump-event round]"
+        if name.startswith("ncb_seg_"):
+            name = "ncb_seg_<k> [generated whole-segment sweeps]"
+        elif "tile_kernel" in name:
+            name += " [full sweep]" if ns > 1e6 else " [jump-event piece]"
         tot[name] += ns
         cnt[name] += 1
     total = sum(tot.values())
