@@ -39,7 +39,7 @@ METRIC = "mcwf_trajectories_per_sec"
 UNIT = "trajectories/s"
 NQ, DEPTH, CIRCUIT_SEED = 20, 50, 42
 CPU_SAMPLE_LAYERS = 4        # bounded CPU sample: ~10 s of all-core work per measurement
-PREWARM_STEPS = 10           # untimed pre-warm steps before the warm-up steps (about 3 s)
+PREWARM_STEPS = int(os.environ.get("NCB_BENCH_PREWARM", "10"))   # untimed pre-warm steps before the warm-up steps (about 3 s); reported in the JSON line
 
 
 def workload():

@@ -152,6 +152,9 @@ typedef struct {
     int64_t out_tile_launches; /* launches of the sweep (direct / tile / resident) kernels among out_launches */
     int64_t out_h2d_bytes;     /* bytes copied host -> device during the run (work lists, uniform tables) */
     int64_t out_d2h_bytes;     /* bytes copied device -> host during the run (probabilities, states, counters) */
+    int64_t out_spec_launches; /* sweep launches that ran in a kernel GENERATED for the program (ncb_options.specialize); 0 with
+                                  specialize = 1 means the generated kernels could not be built or loaded and the interpreting
+                                  kernels did the work */
 } ncb_run_params;
 
 int ncb_mcwf_run(ncb_program* program, ncb_run_params* params);
@@ -170,9 +173,11 @@ int ncb_apply_measurement_error_device(double* probabilities_device, const doubl
 /* The tail of QuantumCircuit.execute (QuantumCircuit.py:436-445) without leaving the device:
  *   probabilities_device float64[2^num_qubits], little-endian over all qubits (e.g. the accumulator ncb_mcwf_run filled
  *   with probs_on_device, or the all-reduced sum of the ranks), is multiplied by `scale`, marginalised over `qubits`
- *   (HelperFunctions.py:9-32; kept qubits in ascending order), the read-out error is applied exactly as by
- *   ncb_apply_measurement_error (positional matrices, num_qubits = nq), the index order is reversed to big-endian, and the
- *   float64[2^nq] result is copied to the host buffer `out`.  mats may be NULL (no read-out error). */
+ *   (HelperFunctions.py:9-32; kept qubits in ascending order), the read-out error mats[4k..] of measured qubit qubits[k]
+ *   is applied on that qubit's bit of the marginal (its rank among the kept qubits -- for "all qubits in order" exactly
+ *   what ncb_apply_measurement_error does; the reference strides by the qubit id and is out of bounds for other subsets,
+ *   MeasurementErrorApplicator.cpp:109-112), the index order is reversed to big-endian, and the float64[2^nq] result is
+ *   copied to the host buffer `out`.  mats may be NULL (no read-out error). */
 int ncb_execute_tail_device(const double* probabilities_device, int32_t num_qubits, const int32_t* qubits, int32_t nq,
                             const double* mats, double scale, double* out, void* stream);
 /* Device scratch for callers without a CUDA allocator of their own (the Python mirror's execute()). */

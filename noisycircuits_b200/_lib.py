@@ -36,7 +36,7 @@ class NcbRunParams(C.Structure):
                 ("batch", C.c_int32), ("states", C.c_void_p), ("stream", C.c_void_p),
                 ("out_sweeps", C.c_int64), ("out_events", C.c_int64), ("out_hard_events", C.c_int64),
                 ("out_launches", C.c_int64), ("out_kernel_ms", C.c_double), ("out_tile_launches", C.c_int64),
-                ("out_h2d_bytes", C.c_int64), ("out_d2h_bytes", C.c_int64)]
+                ("out_h2d_bytes", C.c_int64), ("out_d2h_bytes", C.c_int64), ("out_spec_launches", C.c_int64)]
 
 
 # every symbol include/ncb200.h declares

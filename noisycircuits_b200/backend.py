@@ -31,7 +31,14 @@ def postprocess(probs: np.ndarray, num_qubits: int, qubits, measurement_error: d
     if len(qubits) < num_qubits:
         probs = _marginal_little_endian(probs, num_qubits, qubits)
     probs = np.require(probs, dtype=np.float64, requirements=["C", "W", "O"])
-    (apply_measurement_error or simulator.apply_measurement_error)(probs, measurement_error, qubits, len(qubits), num_cores)
+    # The marginal is little-endian over the kept qubits in ascending order, so qubit q sits at bit rank(q); its read-out
+    # matrix is measurement_error[q].  For "all qubits in order" this is literally the reference's call
+    # (QuantumCircuit.py:438-444); for any other subset the reference strides by the qubit id and reads out of bounds
+    # (MeasurementErrorApplicator.cpp:109-112) -- here every subset works.
+    kept = sorted(qubits)
+    ranks = [kept.index(q) for q in qubits]
+    mats = {r: m for r, m in zip(ranks, simulator._matrices_for(measurement_error, qubits))}
+    (apply_measurement_error or simulator.apply_measurement_error)(probs, mats, ranks, len(qubits), num_cores)
     m = len(qubits)
     return probs.reshape([2] * m).transpose(list(range(m))[::-1]).reshape(-1)
 

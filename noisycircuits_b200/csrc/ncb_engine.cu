@@ -184,7 +184,7 @@ struct Engine {
     }
 
     void ensure_device() {
-        if (uploaded) return;
+        if (uploaded) { CK(cudaSetDevice(device)); return; }     // the caller may have switched devices since the upload
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0)
@@ -426,7 +426,8 @@ struct Engine {
         }
         if (verbose) fprintf(stderr, "[ncb] specialised kernels: %d of %d segments loaded\n", loaded, nseg);
     }
-    void launch_step(const LaunchStep& st, cudaStream_t s, const Work* works) {
+    // returns true when the step ran in a kernel generated for the program
+    bool launch_step(const LaunchStep& st, cudaStream_t s, const Work* works) {
         if (st.direct && specialize) {
             ensure_spec();
             void* fn = st.seg < (int)spec_fn.size() ? spec_fn[st.seg] : nullptr;
@@ -438,7 +439,7 @@ struct Engine {
                 long long want = direct_ctas;
                 if (direct_chunk > 0) want = std::max<long long>(want, (total + direct_chunk - 1) / direct_chunk);
                 const int grid = (int)std::min<long long>(total, want);
-                if (grid < 1) return;
+                if (grid < 1) return true;
                 int pool_off, pool_bytes;
                 spec_pool(P, st.seg, &pool_off, &pool_bytes);
                 const unsigned char* pool_g = d_blobs.p + P.blob_off[st.seg] + pool_off;
@@ -449,11 +450,12 @@ struct Engine {
                 const size_t smem = (size_t)spec_pool_cap + (size_t)spec_nbuf * tile_smem();
                 const int rc = g_drv.LaunchKernel(fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (void*)s, args, nullptr);
                 if (rc != 0) throw std::runtime_error("cuLaunchKernel of a specialised kernel failed (" + std::to_string(rc) + ")");
-                return;
+                return true;
             }
         }
         if (st.direct) launch_direct(st.count, s, works + st.begin, st.seg);
         else launch_tile(st.count, s, works + st.begin, st.seg);
+        return false;
     }
     void launch_resident(int grid, cudaStream_t s, const ResidentArgs& a) {
         const int threads = 1 << (P.K - P.R);
@@ -530,7 +532,9 @@ struct Engine {
         long long b = (148ll * 1024 + tiles - 1) / tiles;
         b = ((b + 36) / 37) * 37;
         if (const char* e = getenv("NCB_BATCH")) b = std::max(1, atoi(e));
-        const long long mem_cap = std::max<long long>(1, (16ll << 30) / ((long long)sizeof(cplx) << P.nbits));
+        long long mem_gb = 16;
+        if (const char* e = getenv("NCB_BATCH_MEM_GB")) mem_gb = std::max(1, atoi(e));
+        const long long mem_cap = std::max<long long>(1, (mem_gb << 30) / ((long long)sizeof(cplx) << P.nbits));
         b = std::min(b, mem_cap);
         return (int)std::max<long long>(1, std::min(b, count));
     }
@@ -664,7 +668,7 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             if (overlap && st.seg != cur_seg && cur_seg >= 0) join();
             cur_seg = st.seg;
             cudaStream_t q = overlap && !(st.kind == 0 && st.direct) ? s2 : s;
-            if (st.kind == 0) { launch_step(st, q, d_works[buf].p); ++rp->out_tile_launches; }
+            if (st.kind == 0) { rp->out_spec_launches += launch_step(st, q, d_works[buf].p) ? 1 : 0; ++rp->out_tile_launches; }
             else {
                 decide_kernel<<<st.count, 256, 0, q>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
                 CK(cudaGetLastError());
@@ -710,6 +714,12 @@ void Engine::mcwf_run(ncb_run_params* rp) {
     if (P.mode != MODE_MCWF) throw std::runtime_error("program was not compiled in MCWF mode");
     if (rp->traj_count < 0) throw std::runtime_error("traj_count must be >= 0");
     if (rp->rng == NCB_RNG_EXPLICIT && !rp->uniforms) throw std::runtime_error("rng = EXPLICIT needs uniforms");
+    if (rp->rng == NCB_RNG_MT19937_REFERENCE) {
+        // the reference's stream is consumed in PROGRAM order and its branch decisions see the state of that order
+        // (Simulator.cpp:76-94): a re-ordered program would only be the reference's trajectory in distribution
+        for (int i = 0; i < P.G; ++i)
+            if (P.orig[i] != i) throw std::runtime_error("rng = MT19937_REFERENCE needs a program compiled with strict_order = 1");
+    }
     if (!rp->probs) throw std::runtime_error("probs must not be NULL");
     ensure_device();
     cudaStream_t s = (cudaStream_t)rp->stream;
@@ -717,7 +727,7 @@ void Engine::mcwf_run(ncb_run_params* rp) {
     d_probs.reserve(dim);
     CK(cudaMemsetAsync(d_probs.p, 0, dim * sizeof(double), s));
     rp->out_sweeps = rp->out_events = rp->out_hard_events = rp->out_launches = 0;
-    rp->out_tile_launches = rp->out_h2d_bytes = rp->out_d2h_bytes = 0;
+    rp->out_tile_launches = rp->out_h2d_bytes = rp->out_d2h_bytes = rp->out_spec_launches = 0;
     rp->out_kernel_ms = 0.0;
     CK(cudaEventRecord(t0, s));
     if (rp->traj_count > 0) {
@@ -1048,7 +1058,12 @@ int ncb_execute_tail_device(const double* probabilities_device, int32_t num_qubi
         grid_1d(nout, &g, &bl);
         marginal_kernel<<<g, bl, 0, s>>>(a, probabilities_device, num_qubits, keep, nq, scale);
         CK(cudaGetLastError());
-        if (mats) rc = ncb_apply_measurement_error_device(a, mats, qubits, nq, nq, stream);
+        // the marginal is little-endian over the kept qubits in ascending order: qubit q sits at bit rank(q) of it.  (The
+        // reference strides by the qubit id itself, MeasurementErrorApplicator.cpp:109-112, which reads out of bounds for
+        // any measured set that is not a permutation of 0..nq-1; here every subset works and mats[k] belongs to qubits[k].)
+        std::vector<int32_t> ranks(nq);
+        for (int k = 0; k < nq; ++k) ranks[k] = __builtin_popcount(keep & ((1u << qubits[k]) - 1u));
+        if (mats) rc = ncb_apply_measurement_error_device(a, mats, ranks.data(), nq, nq, stream);
         if (rc == NCB_OK) {
             bit_reverse_kernel<<<g, bl, 0, s>>>(b, a, nq);
             CK(cudaGetLastError());
@@ -1100,12 +1115,22 @@ int ncb_apply_measurement_error(double* probabilities, const double* mats, const
     NCB_CATCH
 }
 
+// The reference's entry points execute strictly in the caller's instruction order (Simulator.cpp:76-94,
+// SimulatorMPI.cpp:40-59): the same mt19937_64 uniform then meets the same state as in the reference.
+static ncb_options reference_options() {
+    ncb_options o;
+    std::memset(&o, 0, sizeof(o));
+    o.low_bits = -1; o.fuse = 1; o.device = -1; o.strict_order = 1;
+    return o;
+}
+
 int ncb_simulate_circuit(const ncb_circuit* circuit, double* statevector, int noisy, uint32_t num_trajectories,
                          int return_state, uint32_t thread_count) {
     (void)thread_count;
     if (!circuit || !statevector) return fail(NCB_E_INVALID, "null argument");
     ncb_program* p = nullptr;
-    int rc = ncb_program_create(circuit, noisy ? NCB_MODE_MCWF : NCB_MODE_PURE, nullptr, &p);
+    const ncb_options opt = reference_options();
+    int rc = ncb_program_create(circuit, noisy ? NCB_MODE_MCWF : NCB_MODE_PURE, &opt, &p);
     if (rc != NCB_OK) return rc;
     const long long dim = 1ll << circuit->num_qubits;
     if (noisy) {
@@ -1135,7 +1160,8 @@ int ncb_run_trajectory(const ncb_circuit* circuit, double* statevector, uint32_t
     (void)thread_count;
     if (!circuit || !statevector) return fail(NCB_E_INVALID, "null argument");
     ncb_program* p = nullptr;
-    int rc = ncb_program_create(circuit, NCB_MODE_MCWF, nullptr, &p);
+    const ncb_options opt = reference_options();
+    int rc = ncb_program_create(circuit, NCB_MODE_MCWF, &opt, &p);
     if (rc != NCB_OK) return rc;
     const long long dim = 1ll << circuit->num_qubits;
     std::vector<double> probs(dim, 0.0);

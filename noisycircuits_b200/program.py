@@ -222,7 +222,7 @@ class Program:
         _lib.check(_lib.lib().ncb_mcwf_run(self._h, C.byref(rp)))
         stats = {"sweeps": rp.out_sweeps, "events": rp.out_events, "hard_events": rp.out_hard_events,
                  "launches": rp.out_launches, "kernel_ms": rp.out_kernel_ms, "tile_launches": rp.out_tile_launches,
-                 "h2d_bytes": rp.out_h2d_bytes, "d2h_bytes": rp.out_d2h_bytes}
+                 "h2d_bytes": rp.out_h2d_bytes, "d2h_bytes": rp.out_d2h_bytes, "specialized_launches": rp.out_spec_launches}
         return (probs, states, stats) if return_states else (probs, stats)
 
     def run_pure(self, want_state=True, want_probs=False, stream=0):

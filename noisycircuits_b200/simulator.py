@@ -56,18 +56,33 @@ def apply_measurement_error(probabilities_array, measurement_noise, qubit_list, 
                                                       C.c_void_p(qubits.ctypes.data), len(qubits), int(num_qubits), int(num_threads)))
 
 
+def _matrices_for(measurement_noise: dict, qubit_list):
+    """The read-out matrix of every listed qubit: ``measurement_noise[q]`` (the dictionary BuildModel produces is keyed by
+    qubit id in ascending order, BuildQubitGateModel.py:843, so for "all qubits in order" this is the reference's positional
+    lookup, MeasurementErrorApplicator.cpp:28-45); a dictionary without that key falls back to the k-th entry."""
+    items = list(measurement_noise.values())
+    out = []
+    for k, q in enumerate(qubit_list):
+        if int(q) in measurement_noise:
+            out.append(np.asarray(measurement_noise[int(q)], np.float64))
+        elif k < len(items):
+            out.append(np.asarray(items[k], np.float64))
+        else:
+            raise IndexError(f"no read-out error matrix for qubit {q}")
+    return out
+
+
 def execute_tail_device(probabilities_device: int, num_qubits: int, qubit_list, measurement_noise=None, scale: float = 1.0,
                         stream: int = 0) -> np.ndarray:
     """The tail of QuantumCircuit.execute (QuantumCircuit.py:436-445) on the device: ``probabilities_device`` is a device
     pointer to float64[2^num_qubits] (little-endian, all qubits); returns scale * marginal over ``qubit_list`` ->
-    read-out error (positional matrices, as apply_measurement_error) -> big-endian order, as a host array."""
+    read-out error (``measurement_noise[q]`` on the bit of qubit q, any subset of qubits) -> big-endian order, as a host
+    array."""
     qubits = np.asarray([int(q) for q in qubit_list], np.int32)
     out = np.empty(1 << len(qubits), np.float64)
     mats = None
     if measurement_noise:
-        mats = np.ascontiguousarray([np.asarray(m, np.float64) for m in measurement_noise.values()], np.float64)
-        if mats.shape[0] < len(qubits):
-            raise IndexError("measurement_noise has fewer entries than measured qubits")
+        mats = np.ascontiguousarray(_matrices_for(measurement_noise, qubits), np.float64)
     _lib.check(_lib.lib().ncb_execute_tail_device(C.c_void_p(int(probabilities_device)), int(num_qubits),
                                                   C.c_void_p(qubits.ctypes.data), len(qubits),
                                                   C.c_void_p(mats.ctypes.data) if mats is not None else None, float(scale),

@@ -60,6 +60,10 @@ class RemoteExecutor:
         self.num_cores = num_cores
         self.rng = rng
         self.seed = seed
+        if rng == "reference":
+            # the reference consumes its mt19937_64 stream in program order and every branch decision sees the state of
+            # that order (Simulator.cpp:76-94): no re-ordering of commuting instructions in this mode
+            engine_options.setdefault("strict_order", True)
         self.engine_options = engine_options
         self.last_stats = None
         self._cache = (None, None)

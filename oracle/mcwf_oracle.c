@@ -6,7 +6,7 @@
  * __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.  The product
  * (noisycircuits_b200/) never links, imports or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every entry point below against
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every entry point below against
  * the reference's own extensions compiled from their sources (oracle/_ref, built by oracle/Makefile)
  * and tests/golden/ holds vectors generated from those extensions.
  *

@@ -12,7 +12,7 @@ Contents
     rho <- sum_k K_k rho K_k^+ with the gate's Kraus list on the gate's qubits; finally diag(rho).
     qiskit-aer is an unpinned, un-vendored dependency (pyproject.toml:28-43), absent here, so this part
     is "parity unpinned" at the third-party boundary; it is pinned statistically to the compiled
-    reference MCWF path by tests/test_oracle_vs_reference.py (TV <= 3/sqrt(N)).
+    reference MCWF path by tests/test_gpu_parity.py::test_mcwf_distribution_matches_density_matrix and tests/test_oracle_golden.py (TV <= 3/sqrt(N)).
   * `reference_modules()`: imports the reference's own pybind11 extensions from oracle/_ref when they
     have been built (they are built from /root/reference sources, never copied).
 """

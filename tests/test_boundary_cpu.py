@@ -131,3 +131,41 @@ def test_specialised_kernel_sources_compile_for_sm_100a(tmp_path, monkeypatch):
     assert prog.specialize_build()                              # second call: cache hit
     small = Program(PackedCircuit(6, circuits.heron_layered(6, 2, circuits.coupled_pairs(tq, 6), seed=1), sq, tq), specialize=True)
     assert small.specialized_source() .count("extern") == 0 and not small.specialize_build()     # resident: nothing to specialise
+
+
+def test_partial_measurement_maps_each_qubit_to_its_bit_of_the_marginal(heron_noise):
+    """backend.postprocess on a measured subset that is NOT a permutation of 0..m-1 (the reference strides by the qubit
+    id and reads out of bounds there, MeasurementErrorApplicator.cpp:109-112): checked against a dense numpy computation."""
+    from noisycircuits_b200.backend import postprocess
+    _sq, _tq, meas, _ = heron_noise
+    n = 4
+    rng = np.random.default_rng(3)
+    p = rng.random(1 << n)
+    p /= p.sum()
+    mdict = {q: meas[q] for q in range(n)}
+
+    def host_meas(probs, noise, qubit_list, num_qubits, num_threads):
+        oracle.measurement_error(probs, noise, qubit_list, num_qubits)
+
+    for qubits in ([2, 3], [1], [0, 2], [3, 1], [0, 1, 2, 3]):
+        got = postprocess(p.copy(), n, qubits, mdict, 1, host_meas)
+        t = p.reshape([2] * n)                                  # axis n-1-q <-> qubit q
+        for q in qubits:                                        # dense: read-out matrix of q on q's axis
+            t = np.moveaxis(np.tensordot(np.asarray(meas[q], float), t, axes=(1, n - 1 - q)), 0, n - 1 - q)
+        kept = sorted(qubits)
+        marg = t.sum(axis=tuple(n - 1 - q for q in range(n) if q not in kept))     # axes now: kept qubits, descending
+        ref = marg.transpose(list(range(len(kept)))[::-1]).reshape(-1)             # big-endian: lowest kept qubit = MSB
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-15, qubits
+
+
+def test_reference_rng_implies_program_order(heron_noise):
+    """rng="reference" (mt19937_64 streams) compiles in strict program order: the reference's branch decisions see the
+    state of that order (Simulator.cpp:76-94), a re-ordered program would only match it in distribution."""
+    from noisycircuits_b200.solvers import RemoteExecutor
+    sq, tq, _, _ = heron_noise
+    n = 14
+    instr = circuits.heron_layered(n, 3, circuits.coupled_pairs(tq, n), seed=3)
+    ex = RemoteExecutor(n, sq, tq, 1, rng="reference")
+    assert list(ex._program(instr).order()) == list(range(len(instr)))
+    free = RemoteExecutor(n, sq, tq, 1)
+    assert list(free._program(instr).order()) != list(range(len(instr)))           # default: tile-friendly order

@@ -369,8 +369,8 @@ def test_execute_tail_on_device_matches_host_chain(heron_noise):
     drop_axes = tuple(ax for ax in range(n) if (n - 1 - ax) not in (1, 3))
     marg = full.sum(axis=drop_axes).reshape(-1)                 # little-endian over (1, 3)
     assert np.abs(no_err - marg.reshape(2, 2).T.reshape(-1)).max() < 1e-14
-    with pytest.raises(Exception):
-        simulator.execute_tail_device(t.data_ptr(), n, [5, 7], {0: meas[0], 1: meas[1]}, 1.0)   # qubit id >= len(qubits)
+    sub = simulator.execute_tail_device(t.data_ptr(), n, [5, 7], {5: meas[5], 7: meas[7]}, 1.0)    # any subset works
+    assert np.abs(sub - postprocess(p.copy(), n, [5, 7], {q: meas[q] for q in range(n)}, 1)).max() < 1e-14
     buf = simulator.DeviceBuffer(16)                     # the C ABI's own scratch allocator
     assert buf.ptr != 0
     buf.free()
@@ -451,3 +451,173 @@ def test_specialised_kernels_are_the_interpreter_written_out(heron_noise):
     ref = oracle.Program(n, [instr[g] for g in order], sq, tq).mcwf(Tq, uniforms=U[:, order], mask_fix=True)
     q, _ = spec.run_mcwf(Tq, seed=seed)
     assert np.abs(q / Tq - ref).max() < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the benchmarked path at BASELINE sizes, in PROGRAM order as well as in the engine's order
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_threads():
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
+def _both_orders(n, instr, sq, tq, prog, U):
+    """Oracle trajectories driven by U (indexed like `instr`) in the caller's order and in the engine's order: returns
+    (mean |psi|^2 in program order, in engine order, per-trajectory flag: same Kraus branch at every instruction)."""
+    order = prog.order()
+    P_prog = oracle.Program(n, instr, sq, tq)
+    P_eng = oracle.Program(n, [instr[g] for g in order], sq, tq)
+    same = []
+    for t in range(U.shape[0]) if n <= 16 else []:
+        _s, c_prog, _p = P_prog.trajectory(U[t], mask_fix=True, diagnostics=True)
+        _s, c_eng, _p = P_eng.trajectory(U[t][order], mask_fix=True, diagnostics=True)
+        same.append(bool(np.array_equal(c_prog[order], c_eng)))
+    from concurrent.futures import ThreadPoolExecutor          # both orders at once (ctypes releases the GIL)
+    Ue = np.ascontiguousarray(U[:, order])
+    th = max(1, _oracle_threads() // 2)
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        fa = pool.submit(P_prog.mcwf, U.shape[0], U, 42, True, th)
+        fb = pool.submit(P_eng.mcwf, U.shape[0], Ue, 42, True, th)
+        a, b = fa.result(), fb.result()
+    return a, b, same
+
+
+@pytest.mark.parametrize("n,depth", [(13, 6), (16, 4)])
+def test_reordered_engine_equals_the_reference_in_program_order(heron_noise, n, depth):
+    """The default (tile-friendly) execution order against the oracle run in the CALLER's order.  Operators on disjoint
+    qubits commute exactly, so a trajectory differs between the two orders only if a uniform falls between the two
+    orders' cumulative branch probabilities (a set of measure ~ noise^2): for every trajectory whose branch sequence is
+    the same in both orders -- all of them here -- the final states agree to rounding."""
+    sq, tq, _, _ = heron_noise
+    instr = circuits.heron_layered(n, depth, circuits.coupled_pairs(tq, n), seed=100 + n)
+    T = 8
+    U = jumpy_uniforms(np.random.default_rng(n), T, len(instr))
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF)
+    order = prog.order()
+    assert list(order) != list(range(len(instr)))
+    _probs, states, stats = prog.run_mcwf(T, uniforms=U, return_states=True)
+    assert stats["hard_events"] > 0
+    P_prog = oracle.Program(n, instr, sq, tq)
+    P_eng = oracle.Program(n, [instr[g] for g in order], sq, tq)
+    agree = 0
+    for t in range(T):
+        ref, c_prog, _ = P_prog.trajectory(U[t], mask_fix=True, diagnostics=True)
+        ref_e, c_eng, _ = P_eng.trajectory(U[t][order], mask_fix=True, diagnostics=True)
+        assert np.abs(states[t] - ref_e).max() < TOL                 # always: the reference algorithm on the engine's order
+        if np.array_equal(c_prog[order], c_eng):
+            agree += 1
+            assert np.abs(states[t] - ref).max() < TOL               # and the reference's own trajectory
+    assert agree == T
+    # strict_order: the caller's order itself
+    strict = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, strict_order=True)
+    _p, st2, _ = strict.run_mcwf(T, uniforms=U, return_states=True)
+    for t in range(T):
+        assert np.abs(st2[t] - P_prog.trajectory(U[t], mask_fix=True)).max() < TOL
+
+
+def test_reference_rng_at_tiled_size_matches_oracle_in_program_order(heron_noise):
+    """ncb_simulate_circuit / ncb_run_trajectory / rng="reference" above the tile size (n = 14): compiled in strict program
+    order, so the mt19937_64(42 + t) streams meet the same states as in the reference (Simulator.cpp:76-94, 118-133)."""
+    sq, tq, _, _ = heron_noise
+    n, T = 14, 6
+    pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)        # adjacent pairs: the verbatim reference is right here
+    instr = circuits.heron_layered(n, 3, pairs, seed=77)
+    O = oracle.Program(n, instr, sq, tq)
+    ref = O.mcwf(T, seed0=42, mask_fix=False, threads=_oracle_threads())
+    buf = np.zeros(1 << n, np.complex128)
+    ncb_simulator.simulate_circuit(instr, buf, sq, tq, n, True, T, False, 2)
+    assert np.abs(buf.real - ref).max() < TOL
+    one = np.zeros(1 << n, np.complex128)
+    ncb_simulator.run_trajectory(instr, one, sq, tq, n, 45, 1)
+    assert np.abs(one.real - np.abs(O.trajectory(O.reference_uniforms(45), mask_fix=False)) ** 2).max() < TOL
+    assert np.abs(RemoteExecutor(n, sq, tq, 2, rng="reference").run(T, instr) - ref).max() < TOL
+    with pytest.raises(_lib.NcbError, match="strict_order"):         # a re-ordered program refuses the reference's streams
+        Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF).run_mcwf(2, rng=_lib.RNG_MT19937_REFERENCE)
+
+
+def test_c5_full_depth_specialised_shared_prefix_vs_oracle(heron_noise):
+    """BASELINE configs[4] exactly as bench.py runs it: 20 qubits, depth 50 (1950 instructions), kernels generated per
+    segment, shared no-jump prefix, in-line jumps, Philox draws -- against the oracle fed the same counter-based uniforms,
+    in the engine's order AND in program order (about 80 s of CPU per oracle trajectory)."""
+    sq, tq, _, _ = heron_noise
+    n, depth, T, seed, begin = 20, 50, 4, 42, 3
+    instr = circuits.heron_layered(n, depth, circuits.coupled_pairs(tq, n), seed=42)
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, specialize=True)
+    got, stats = prog.run_mcwf(T, traj_begin=begin, seed=seed)
+    assert stats["events"] > 0 and abs(got.sum() - T) < 1e-9
+    assert stats.get("specialized_launches", 1) > 0
+    U = np.array([[philox_numpy(seed, begin + t, g) for g in range(len(instr))] for t in range(T)])
+    in_program_order, in_engine_order, _ = _both_orders(n, instr, sq, tq, prog, U)
+    assert np.abs(got / T - in_engine_order).max() < TOL
+    assert np.abs(got / T - in_program_order).max() < TOL
+
+
+def test_c4_eagle16_depth40_vs_oracle(eagle_noise):
+    """BASELINE configs[3] shape: 16-qubit Eagle ecr/sx/x/rz circuit, depth 40, Philox trajectories against the oracle in
+    both orders (non-unitary base operators: the norm is carried and divided out at the end)."""
+    sq, tq, _, _ = eagle_noise
+    n, depth, T, seed = 16, 40, 3, 9
+    instr = circuits.eagle_layered(n, depth, circuits.coupled_pairs(tq, n), seed=42)
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF)
+    got, stats = prog.run_mcwf(T, seed=seed)
+    assert abs(got.sum() - T) < 1e-9
+    U = np.array([[philox_numpy(seed, t, g) for g in range(len(instr))] for t in range(T)])
+    in_program_order, in_engine_order, same = _both_orders(n, instr, sq, tq, prog, U)
+    assert np.abs(got / T - in_engine_order).max() < TOL
+    if all(same):
+        assert np.abs(got / T - in_program_order).max() < TOL
+    else:       # a uniform between the two orders' branch boundaries (measure ~ noise^2): equal in distribution only
+        assert 0.5 * np.abs(got / T - in_program_order).sum() < 1.0
+
+
+def test_c3_qnn12_vs_oracle(heron_noise):
+    """BASELINE configs[2] shape: 12-qubit QNN circuit (RY -> x, sx, rz, sx; CZ chain; RX), 4 layers, resident kernel."""
+    sq, tq, _, _ = heron_noise
+    n = 12
+    instr = circuits.qnn_circuit(n, 4, circuits.coupled_pairs(tq, n, adjacent_only=True), seed=42)
+    replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(12), 6, len(instr)))
+    T, seed = 64, 5
+    U = np.array([[philox_numpy(seed, t, g) for g in range(len(instr))] for t in range(T)])
+    ref = oracle.Program(n, instr, sq, tq).mcwf(T, uniforms=U, mask_fix=True, threads=_oracle_threads())
+    got = RemoteExecutor(n, sq, tq, 1, seed=seed).run(T, instr)
+    assert np.abs(got - ref).max() < TOL
+
+
+@pytest.mark.parametrize("n,depth", [(10, 10), (11, 3)])
+def test_c2_density_matrix_layered_heron_vs_restatement(heron_noise, n, depth):
+    """BASELINE configs[1] shape (layered Heron circuit, 4^n vectorised state) at the largest sizes the numpy restatement
+    finishes in about a minute; 1e-10 per probability (north star check #1).  Parity unpinned at the qiskit-aer boundary."""
+    sq, tq, _, _ = heron_noise
+    instr = circuits.heron_layered(n, depth, circuits.coupled_pairs(tq, n), seed=42)
+    ref = oracle.density_matrix_probs(n, instr, sq, tq)
+    got = DensityMatrixSolver(n, sq, tq, instr, 1).solve(list(range(n)))
+    assert abs(got.sum() - 1) < 1e-10 and np.abs(got - ref).max() < TOL
+
+
+def test_c2_density_matrix_12_qubits_properties_and_mcwf_tv(heron_noise):
+    """configs[1] at its full size (12 qubits, 4^12 state = 268 MB) through size-independent properties: trace 1,
+    non-negative diagonal, and the free-running MCWF distribution of the same circuit within TV <= 3/sqrt(N) of it
+    (north star check #3; N = 10^5 trajectories on the resident kernel)."""
+    sq, tq, _, _ = heron_noise
+    n, N = 12, 100000
+    instr = circuits.heron_layered(n, 10, circuits.coupled_pairs(tq, n), seed=42)
+    dm = DensityMatrixSolver(n, sq, tq, instr, 1).solve(list(range(n)))
+    assert abs(dm.sum() - 1) < 1e-10 and dm.min() > -1e-14
+    mc = RemoteExecutor(n, sq, tq, 1).run(N, instr)
+    assert 0.5 * np.abs(mc - dm).sum() <= 3 / np.sqrt(N)
+
+
+def test_partial_measurement_on_device_any_subset(heron_noise):
+    """ncb_execute_tail_device on measured subsets that are not permutations of 0..m-1 against the dense host chain."""
+    from noisycircuits_b200 import simulator
+    from noisycircuits_b200.backend import postprocess
+    _sq, _tq, meas, _ = heron_noise
+    import torch
+    n = 6
+    p = np.random.default_rng(8).random(1 << n)
+    p /= p.sum()
+    t = torch.from_numpy(p).cuda()
+    mdict = {q: meas[q] for q in range(n)}
+    for qubits in ([2, 3], [5], [0, 2, 4], [4, 1], list(range(n))):
+        dev = simulator.execute_tail_device(t.data_ptr(), n, qubits, mdict, 1.0)
+        ref = postprocess(p.copy(), n, qubits, mdict, 1)
+        assert np.abs(dev - ref).max() < 1e-14, qubits
