@@ -195,9 +195,14 @@ struct SegConst {
     // low thread-index bits of that pass (64-byte runs per 4 lanes).  State offset of thread `tid`, register slot m:
     // apply_runs(gruns_last, tid) | goff_last[m].
     int32_t direct;
-    int32_t pad_[3];
+    // Direct load of the FIRST pass (generated kernels only, ncb_spec.cpp): the same condition and offsets for the first
+    // pass -- its amplitudes come from HBM straight into registers, no shared-memory staging of the tile at all.
+    int32_t direct_first;
+    int32_t pad_[2];
     uint32_t goff_last[1 << MAX_REG_BITS];
     BitRuns gruns_last;
+    uint32_t goff_first[1 << MAX_REG_BITS];
+    BitRuns gruns_first;
     PassHot pass[SC_MAX_PASSES];
     Op ops[SC_MAX_OPS];                // mat: rx1 / dense1 -> index into coef (4 / 8 doubles); other kinds -> as in the blob
     double coef[SC_MAX_COEF];

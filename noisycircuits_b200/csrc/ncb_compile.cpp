@@ -1165,8 +1165,8 @@ static void build_blobs(Program& P) {
             // direct store of the last pass
             if (fits && !passes.empty() && P.nbits > P.K && P.opt.direct && P.R == 3 && !P.has_dense2 && !P.has_dense4) {
                 const int Lb = std::min(std::max(P.opt.low_bits, 0), std::min(P.K - 4, P.nbits));
-                bool ok = Lb >= 2;
-                auto describe_pass = [&](const Pass& ps, uint32_t* goff, BitRuns& gruns) {
+                auto describe_pass = [&](const Pass& ps, uint32_t* goff, BitRuns& gruns) -> bool {
+                    bool ok = Lb >= 2;
                     // every 32-byte sector a warp's store touches must be completed by the same warp: state bits 0 and 1
                     // have to be lane bits (in order) or register bits (the thread writes the neighbours itself)
                     for (int i = 0, lane = 0; i < Lb; ++i) {
@@ -1186,9 +1186,10 @@ static void build_blobs(Program& P) {
                     std::vector<int> gpos;
                     for (int i = 0; i < P.K - P.R; ++i) gpos.push_back(sg.tile_q[ps.tpos[i]]);
                     gruns = make_runs(gpos);
+                    return ok;
                 };
-                describe_pass(passes.back(), sc.goff_last, sc.gruns_last);
-                sc.direct = ok ? 1 : 0;
+                sc.direct = describe_pass(passes.back(), sc.goff_last, sc.gruns_last) ? 1 : 0;
+                sc.direct_first = describe_pass(passes.front(), sc.goff_first, sc.gruns_first) ? 1 : 0;
             }
             P.segconst.push_back(sc);
         }

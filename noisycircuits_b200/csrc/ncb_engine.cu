@@ -95,6 +95,7 @@ struct DriverApi {
     int (*FuncSetAttribute)(void*, int, int) = nullptr;
     int (*LaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**) = nullptr;
     int (*ModuleUnload)(void*) = nullptr;
+    int (*Occupancy)(int*, void*, int, size_t) = nullptr;
     bool load() {
         if (lib) return true;
         lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
@@ -104,7 +105,8 @@ struct DriverApi {
         FuncSetAttribute = (decltype(FuncSetAttribute))dlsym(lib, "cuFuncSetAttribute");
         LaunchKernel = (decltype(LaunchKernel))dlsym(lib, "cuLaunchKernel");
         ModuleUnload = (decltype(ModuleUnload))dlsym(lib, "cuModuleUnload");
-        return ModuleLoadData && ModuleGetFunction && FuncSetAttribute && LaunchKernel && ModuleUnload;
+        Occupancy = (decltype(Occupancy))dlsym(lib, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+        return ModuleLoadData && ModuleGetFunction && FuncSetAttribute && LaunchKernel && ModuleUnload && Occupancy;
     }
 };
 static DriverApi g_drv;
@@ -337,23 +339,32 @@ struct Engine {
     }
     // ---- specialised kernels -----------------------------------------------------------------------------------
     bool specialize = false, spec_tried = false;
-    int spec_nbuf = 2, spec_pool_cap = 0;
-    std::vector<void*> spec_modules, spec_fn;          // CUmodule per part, CUfunction per segment (nullptr: interpreter)
-    // Generates, compiles (nvcc, in parallel, into the cubin cache) and loads the specialised kernels of this program.
-    // Any failure leaves the interpreter in charge (and says so with NCB_VERBOSE).
+    SpecOptions spec_opt;
+    int spec_pool_cap = 0;
+    std::vector<void*> spec_modules;
+    struct SpecFn { void* fn = nullptr; int ctas = 0; };       // CUfunction + resident CTAs per SM (nullptr: interpreter)
+    std::vector<SpecFn> spec_fn, spec_ev_fn;                   // per segment: whole-segment kernel, event-piece kernel
     static constexpr int SPEC_PER_PART = 4;                  // segments per translation unit
-    // host-only part: sources + nvcc into the cache; returns the cache directory of this program ("" on failure)
+    void read_spec_options() {
+        spec_opt = SpecOptions();
+        if (P.K >= 12) spec_opt.nbuf = 1;            // two 64 KB buffers would leave one CTA per SM
+        if (const char* e = getenv("NCB_SPEC_NBUF")) spec_opt.nbuf = atoi(e) == 1 ? 1 : 2;
+        if (const char* e = getenv("NCB_SPEC_LOAD")) spec_opt.load = std::min(std::max(atoi(e), 0), 2);
+        if (const char* e = getenv("NCB_SPEC_EVENTS")) spec_opt.events = atoi(e) != 0;
+    }
+    // Generates and compiles (nvcc, in parallel, into the cubin cache) the specialised kernels of this program; host only.
+    // Returns the cache directory of this program ("" on failure: the interpreter stays in charge, and says so in
+    // ncb_run_params.out_spec_launches).
     std::string spec_build() {
         const bool verbose = getenv("NCB_VERBOSE") != nullptr;
         int nsupported = 0;
         for (int sgi = 0; sgi < (int)P.segs.size(); ++sgi) nsupported += spec_supported(P, sgi);
         if (!nsupported) return "";
+        read_spec_options();
         const std::string libdir = this_library_dir();
         std::string cache = getenv("NCB_SPEC_CACHE") ? getenv("NCB_SPEC_CACHE") : libdir + "/_speccache";
-        spec_nbuf = P.K >= 12 ? 1 : 2;               // two 64 KB buffers would leave one CTA per SM
-        if (const char* e = getenv("NCB_SPEC_NBUF")) spec_nbuf = atoi(e) == 1 ? 1 : 2;
         // (the cubins depend on the kernel headers too: a rebuilt library starts a new cache generation)
-        const std::string dir = cache + "/" + spec_key(P, spec_nbuf) + "-" + build_stamp();
+        const std::string dir = cache + "/" + spec_key(P, spec_opt) + "-" + build_stamp();
         mkdir(cache.c_str(), 0755);
         mkdir(dir.c_str(), 0755);
         const int nseg = (int)P.segs.size();
@@ -374,8 +385,8 @@ struct Engine {
                     const int k = todo[i];
                     // several processes (one per GPU) may build the same cache at once: private temporaries, atomic renames
                     const std::string base = dir + "/part" + std::to_string(k), mine = base + "." + std::to_string((long)getpid());
-                    { std::ofstream f(mine + ".cu"); f << spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_nbuf); }
-                    const std::string cmd = nvcc + " -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -I" + libdir + "/csrc -cubin -o " +
+                    { std::ofstream f(mine + ".cu"); f << spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_opt); }
+                    const std::string cmd = nvcc + " -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -I" + libdir + "/csrc -Xptxas -v -cubin -o " +
                                             mine + ".tmp " + mine + ".cu > " + mine + ".log 2>&1 && mv " + mine + ".tmp " + base + ".cubin && mv " +
                                             mine + ".cu " + base + ".cu && mv " + mine + ".log " + base + ".log";
                     if (system(cmd.c_str()) != 0) failed.fetch_add(1);
@@ -391,10 +402,12 @@ struct Engine {
         }
         return dir;
     }
+    size_t spec_smem(bool ev) const { return (size_t)spec_pool_cap + (size_t)(ev ? 1 : (spec_opt.nbuf == 1 ? 1 : 2)) * tile_smem(); }
     void ensure_spec() {
         if (spec_tried) return;
         spec_tried = true;
-        spec_fn.assign(P.segs.size(), nullptr);
+        spec_fn.assign(P.segs.size(), SpecFn());
+        spec_ev_fn.assign(P.segs.size(), SpecFn());
         const bool verbose = getenv("NCB_VERBOSE") != nullptr;
         if (!g_drv.load()) { if (verbose) fprintf(stderr, "[ncb] specialised kernels: libcuda.so.1 not usable\n"); return; }
         const std::string dir = spec_build();
@@ -406,7 +419,20 @@ struct Engine {
             spec_pool(P, sgi, &off, &bytes);
             spec_pool_cap = std::max(spec_pool_cap, (bytes + 1023) & ~1023);
         }
-        int loaded = 0;
+        const int threads = 1 << (P.K - P.R);
+        int loaded = 0, loaded_ev = 0;
+        auto get = [&](void* mod, const std::string& name, bool ev) {
+            SpecFn f;
+            void* fn = nullptr;
+            if (g_drv.ModuleGetFunction(&fn, mod, name.c_str()) != 0) return f;
+            if (g_drv.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem_optin - 8 * 1024) != 0) return f;
+            g_drv.FuncSetAttribute(fn, 9 /* CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT */, 100);
+            int occ = 0;
+            if (g_drv.Occupancy(&occ, fn, threads, spec_smem(ev)) != 0 || occ < 1) return f;
+            if (const char* e = getenv("NCB_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
+            f.fn = fn; f.ctas = occ;
+            return f;
+        };
         for (int k = 0; k < nparts; ++k) {
             std::ifstream f(dir + "/part" + std::to_string(k) + ".cubin", std::ios::binary);
             std::stringstream ss;
@@ -416,28 +442,26 @@ struct Engine {
             if (image.empty() || g_drv.ModuleLoadData(&mod, image.data()) != 0) continue;
             spec_modules.push_back(mod);
             for (int sgi = k * per; sgi < std::min(nseg, (k + 1) * per); ++sgi) {
-                if (!spec_supported(P, sgi)) continue;
-                void* fn = nullptr;
-                if (g_drv.ModuleGetFunction(&fn, mod, ("ncb_seg_" + std::to_string(sgi)).c_str()) != 0) continue;
-                if (g_drv.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem_optin - 8 * 1024) != 0) continue;
-                spec_fn[sgi] = fn;
-                ++loaded;
+                if (spec_supported(P, sgi)) { spec_fn[sgi] = get(mod, "ncb_seg_" + std::to_string(sgi), false); loaded += spec_fn[sgi].fn != nullptr; }
+                if (spec_opt.events && spec_ev_supported(P, sgi)) {
+                    spec_ev_fn[sgi] = get(mod, "ncb_seg_" + std::to_string(sgi) + "_ev", true);
+                    loaded_ev += spec_ev_fn[sgi].fn != nullptr;
+                }
             }
         }
-        if (verbose) fprintf(stderr, "[ncb] specialised kernels: %d of %d segments loaded\n", loaded, nseg);
+        if (verbose) fprintf(stderr, "[ncb] specialised kernels: %d whole-segment and %d event kernels of %d segments loaded (load mode %d, nbuf %d, %d / %d CTAs per SM)\n",
+                             loaded, loaded_ev, nseg, spec_opt.load, spec_opt.nbuf, nseg && spec_fn[0].fn ? spec_fn[0].ctas : 0, nseg && spec_ev_fn[0].fn ? spec_ev_fn[0].ctas : 0);
     }
     // returns true when the step ran in a kernel generated for the program
     bool launch_step(const LaunchStep& st, cudaStream_t s, const Work* works) {
-        if (st.direct && specialize) {
+        if (specialize) {
             ensure_spec();
-            void* fn = st.seg < (int)spec_fn.size() ? spec_fn[st.seg] : nullptr;
-            if (fn) {
-                configure_tile();
-                if (!direct_ctas) launch_direct(0, s, works, st.seg);            // (configures the launch geometry)
+            const SpecFn f = st.seg < (int)spec_fn.size() ? (st.direct ? spec_fn[st.seg] : spec_ev_fn[st.seg]) : SpecFn();
+            if (f.fn) {
                 const int tile_shift = P.nbits - P.K, threads = 1 << (P.K - P.R);
                 const long long total = (long long)st.count << tile_shift;
-                long long want = direct_ctas;
-                if (direct_chunk > 0) want = std::max<long long>(want, (total + direct_chunk - 1) / direct_chunk);
+                long long want = (long long)sm_count * f.ctas;
+                if (st.direct && direct_chunk > 0) want = std::max<long long>(want, (total + direct_chunk - 1) / direct_chunk);   // CTA turnover lets the event chain in
                 const int grid = (int)std::min<long long>(total, want);
                 if (grid < 1) return true;
                 int pool_off, pool_bytes;
@@ -446,9 +470,16 @@ struct Engine {
                 int pool_cap = spec_pool_cap, nworks = st.count, tshift = tile_shift;
                 const Work* w = works + st.begin;
                 cplx* states = d_states.p;
-                void* args[] = {(void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift};
-                const size_t smem = (size_t)spec_pool_cap + (size_t)spec_nbuf * tile_smem();
-                const int rc = g_drv.LaunchKernel(fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, (void*)s, args, nullptr);
+                int rc;
+                if (st.direct) {
+                    void* args[] = {(void*)P.segconst[st.seg].coef, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift};
+                    rc = g_drv.LaunchKernel(f.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)spec_smem(false), (void*)s, args, nullptr);
+                } else {
+                    double *red = d_red.p, *nrm = d_norm.p;
+                    const Decision* dec = d_dec.p;
+                    void* args[] = {(void*)&d, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift, (void*)&red, (void*)&nrm, (void*)&dec};
+                    rc = g_drv.LaunchKernel(f.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)spec_smem(true), (void*)s, args, nullptr);
+                }
                 if (rc != 0) throw std::runtime_error("cuLaunchKernel of a specialised kernel failed (" + std::to_string(rc) + ")");
                 return true;
             }
@@ -927,7 +958,9 @@ int ncb_program_spec_build(ncb_program* program) {
 int64_t ncb_program_spec_source(const ncb_program* program, int32_t seg_begin, int32_t seg_end, char* buf, int64_t len) {
     if (!program) return -1;
     const Program& P = program->eng.P;
-    const std::string s = spec_source(P, std::max(seg_begin, 0), std::min<int>(seg_end, (int)P.segs.size()));
+    Engine& E = const_cast<ncb_program*>(program)->eng;
+    E.read_spec_options();
+    const std::string s = spec_source(P, std::max(seg_begin, 0), std::min<int>(seg_end, (int)P.segs.size()), E.spec_opt);
     if (buf && len > 0) {
         const size_t n = std::min<size_t>(s.size(), (size_t)len - 1);
         std::memcpy(buf, s.data(), n);

@@ -9,11 +9,6 @@ namespace ncb {
 
 namespace {
 
-std::string lit(double v) {            // exact literal
-    char b[64];
-    std::snprintf(b, sizeof b, "%a", v);
-    return b;
-}
 std::string hex(uint32_t v) {
     char b[32];
     std::snprintf(b, sizeof b, "0x%xu", v);
@@ -36,64 +31,82 @@ std::string runs_expr(const BitRuns& r, const std::string& v) {
     return o.str();
 }
 
-}  // namespace
-
-bool spec_supported(const Program& P, int seg) {
-    if (P.mode == MODE_DENSITY || P.R != 3 || P.has_dense2 || P.has_dense4 || P.nbits <= P.K) return false;
-    if (seg < 0 || seg >= (int)P.segconst.size()) return false;
-    const SegConst& sc = P.segconst[seg];
-    return sc.valid && sc.direct && sc.npass >= 1;
+struct BlobView {
+    const SegBlob* blob;
+    const Segment* sg;
+    const Pass* passes;
+    const Op* ops;
+};
+BlobView view_blob(const Program& P, int seg) {
+    const unsigned char* braw = P.blobs.data() + P.blob_off[seg];
+    BlobView v;
+    v.blob = reinterpret_cast<const SegBlob*>(braw);
+    v.sg = &v.blob->seg;
+    v.passes = reinterpret_cast<const Pass*>(braw + v.blob->pass_off);
+    v.ops = reinterpret_cast<const Op*>(braw + v.blob->op_off);
+    return v;
 }
 
-int spec_ctas_per_sm(const Program& P, int nbuf) {
-    // registers: 64 K per SM; shared memory: nbuf tiles of 16 B x 2^K plus the phase tables (<= 16 KB) within 227 KB
-    const int threads = 1 << (P.K - P.R);
-    int pool_cap = 0;                                  // what the engine stages per CTA beside the tiles (1 KB granules)
-    for (size_t sgi = 0; sgi < P.blob_off.size(); ++sgi) {
-        const SegBlob& blob = *reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[sgi]);
-        pool_cap = std::max(pool_cap, (blob.bytes - blob.pool_off + 1023) & ~1023);
+bool lean_tiled(const Program& P) {
+    return P.mode != MODE_DENSITY && P.R == 3 && !P.has_dense2 && !P.has_dense4 && P.nbits > P.K;
+}
+
+// the constant-bank fast list of pass p (whole pass, no jump inside): coefficients C.c[..], tables in the staged pool
+bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R) {
+    const PassHot& ph = sc.pass[p];
+    for (int i = ph.fop_begin; i < ph.fop_end; ++i) {
+        const Op& op = sc.ops[i];
+        const int ls = op_lean_sel(op);
+        auto rx = [&](int bit, int at) {
+            o << "            spec_rx<" << R << ", " << bit << ">(a, C.c[" << at << "], C.c[" << at + 1 << "], C.c[" << at + 2 << "], C.c[" << at + 3 << "]);\n";
+        };
+        if (ls < 8) {
+            if (op.mat < 0 || (op.mat & 1)) return false;      // (phase tables are complex-aligned entries of the staged pool)
+            o << "            spec_diag<" << R << ", " << ls << ">(a, jb" << p << ", pool + " << op.mat / 2 << ", " << hex(op.rbs & 0xffffu) << ", "
+              << hex(op.midx_lo) << ", " << hex(op.rbs >> 16) << ", " << hex(op.midx_hi) << ", " << (unsigned)op_tmask(op) << "u);\n";
+        } else if (ls < 11) {
+            rx(ls - 8, op.mat);
+        } else if (ls < 14) {
+            o << "            spec_u<" << R << ", " << ls - 11 << ">(a";
+            for (int k = 0; k < 8; ++k) o << ", C.c[" << op.mat + k << "]";
+            o << ");\n";
+        } else if (ls == LSEL_X3) {
+            rx(0, op.mat); rx(1, op.mat + 4); rx(2, op.mat + 8);
+        } else {
+            const int pair = ls - LSEL_X2;                      // (0,1) (0,2) (1,2)
+            rx(pair == 2 ? 1 : 0, op.mat); rx(pair == 0 ? 1 : 2, op.mat + 4);
+        }
     }
-    const int by_smem = (int)((227 * 1024) / ((size_t)nbuf * (16u << P.K) + (size_t)pool_cap + 2048));
-    const int by_regs = 65536 / (threads * 64);
-    return std::max(1, std::min({by_smem, by_regs, 8}));
+    return true;
 }
 
-void spec_pool(const Program& P, int seg, int* offset, int* bytes) {
-    const SegBlob& blob = *reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[seg]);
-    *offset = blob.pool_off;
-    *bytes = blob.bytes - blob.pool_off;
-}
-
-std::string spec_source(const Program& P, int seg_begin, int seg_end, int nbuf) {
-    std::ostringstream o;
-    o << "// generated by ncb_spec.cpp -- do not edit\n#include \"ncb_spec.cuh\"\nusing namespace ncb;\n";
+// ---- whole-segment kernel -----------------------------------------------------------------------------------------
+bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const SpecOptions& opt) {
     const int K = P.K, R = P.R, NA = 1 << R;
-    for (int seg = seg_begin; seg < seg_end; ++seg) {
-        if (!spec_supported(P, seg)) continue;
-        const SegConst& sc = P.segconst[seg];
-        const unsigned char* braw = P.blobs.data() + P.blob_off[seg];
-        const SegBlob& blob = *reinterpret_cast<const SegBlob*>(braw);
-        const Segment& sg = blob.seg;
-        const Pass* passes = reinterpret_cast<const Pass*>(braw + blob.pass_off);
-        // shared memory: [phase tables (pool_cap bytes)] [nbuf tile buffers].  nbuf = 2: tile t+1 streams in while tile t is
-        // processed (three CTAs per SM); nbuf = 1: the next tile is requested as soon as the last pass holds its amplitudes
-        // in registers (four CTAs per SM).
-        o << "extern \"C\" __global__ void __launch_bounds__(" << (1 << (K - R)) << ", " << spec_ctas_per_sm(P, nbuf) << ") ncb_seg_" << seg
-          << "(const unsigned char* __restrict__ pool_g, int pool_bytes, int pool_cap, const Work* __restrict__ works, int nworks,\n"
-             "        cplx* __restrict__ states, int tile_shift) {\n"
-             "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
-             "    const int tid = threadIdx.x, nthreads = blockDim.x;\n"
-             "    const int ntiles = 1 << tile_shift;\n"
-             "    const long long total = (long long)nworks << tile_shift;\n"
-             "    cplx* const buf0 = reinterpret_cast<cplx*>(smem_raw + pool_cap);\n"
-             "    for (int i = tid * 16; i < pool_bytes; i += nthreads * 16) cp_async16(smem_raw + i, pool_g + i);\n"
-             "    cp_async_wait_all();\n    __syncthreads();\n"
-          << "    const cplx* const pool = reinterpret_cast<const cplx*>(smem_raw);\n"
-          << "    const unsigned utid = (unsigned)tid;\n"
-          << "    const unsigned offA = " << runs_expr(sg.eruns, "utid") << ";\n"
-          << "    const unsigned gj_last = " << runs_expr(sc.gruns_last, "utid") << ";\n"
-          << "    const int sA = swz(tid);\n";
-        o << "    auto issue_load = [&](long long tt, cplx* sm) {\n"
+    const SegConst& sc = P.segconst[seg];
+    const BlobView bv = view_blob(P, seg);
+    const Segment& sg = *bv.sg;
+    const int nbuf = opt.nbuf == 1 ? 1 : 2;
+    const int load = sc.direct_first ? std::min(std::max(opt.load, 0), 2) : 0;
+    const int npass = sc.npass;
+    o << "extern \"C\" __global__ void __launch_bounds__(" << (1 << (K - R)) << ", " << spec_ctas_per_sm(P, opt) << ") ncb_seg_" << seg
+      << "(const __grid_constant__ SpecCoef C, const unsigned char* __restrict__ pool_g, int pool_bytes, int pool_cap,\n"
+         "        const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int tile_shift) {\n"
+         "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+         "    const int tid = threadIdx.x, nthreads = blockDim.x;\n"
+         "    const int ntiles = 1 << tile_shift;\n"
+         "    const long long total = (long long)nworks << tile_shift;\n"
+         "    cplx* const buf0 = reinterpret_cast<cplx*>(smem_raw + pool_cap);\n"
+         "    for (int i = tid * 16; i < pool_bytes; i += nthreads * 16) cp_async16(smem_raw + i, pool_g + i);\n"
+         "    cp_async_wait_all();\n    __syncthreads();\n"
+         "    const cplx* const pool = reinterpret_cast<const cplx*>(smem_raw);\n"
+         "    const unsigned utid = (unsigned)tid;\n"
+      << "    const unsigned gj_last = " << runs_expr(sc.gruns_last, "utid") << ";\n";
+    if (load == 0) {
+        // ---- tile staged in shared memory with cp.async (as in the interpreting direct kernel) ----
+        o << "    const unsigned offA = " << runs_expr(sg.eruns, "utid") << ";\n"
+          << "    const int sA = swz(tid);\n"
+          << "    auto issue_load = [&](long long tt, cplx* sm) {\n"
              "        const unsigned tl = (unsigned)(tt & (ntiles - 1));\n"
           << "        const cplx* st = states + ((long long)works[tt >> tile_shift].src << " << P.nbits << ") + " << runs_expr(sg.bruns, "tl") << ";\n";
         for (int it = 0; it < NA; ++it)
@@ -116,38 +129,15 @@ std::string spec_source(const Program& P, int seg_begin, int seg_end, int nbuf) 
         o << "        const unsigned tl = (unsigned)(t & (ntiles - 1));\n"
           << "        cplx* const dst = states + ((long long)works[t >> tile_shift].slot << " << P.nbits << ") + " << runs_expr(sg.bruns, "tl") << ";\n"
           << "        __syncthreads();\n";
-        for (int p = 0; p < sc.npass; ++p) {
+        for (int p = 0; p < npass; ++p) {
             const PassHot& ph = sc.pass[p];
-            const bool last = p == sc.npass - 1;
+            const bool last = p == npass - 1;
             o << "        {   // pass " << p << "\n            cplx a[" << NA << "];\n"
-              << "            const int jb" << p << " = (int)" << runs_expr(passes[p].truns, "utid") << ", jbs" << p << " = swz(jb" << p << ");\n";
+              << "            const int jb" << p << " = (int)" << runs_expr(bv.passes[p].truns, "utid") << ", jbs" << p << " = swz(jb" << p << ");\n";
             for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ph.regoff_swz[m] << "];\n";
             if (last && nbuf == 1) o << "            __syncthreads();\n            if (tn < total) issue_load(tn, buf0);\n";
             if (last && nbuf == 2) o << "            __syncthreads();            // this buffer is refilled at the top of the next iteration\n";
-            for (int i = ph.fop_begin; i < ph.fop_end; ++i) {
-                const Op& op = sc.ops[i];
-                const int ls = op_lean_sel(op);
-                auto rx = [&](int bit, int at) {
-                    o << "            spec_rx<" << bit << ">(a, " << lit(sc.coef[at]) << ", " << lit(sc.coef[at + 1]) << ", " << lit(sc.coef[at + 2]) << ", "
-                      << lit(sc.coef[at + 3]) << ");\n";
-                };
-                if (ls < 8) {
-                    o << "            spec_diag<" << ls << ">(a, jb" << p << ", pool + " << op.mat / 2 << ", " << hex(op.rbs & 0xffffu) << ", " << hex(op.midx_lo)
-                      << ", " << hex(op.rbs >> 16) << ", " << hex(op.midx_hi) << ", " << (unsigned)op_tmask(op) << "u);\n";
-                    if (op.mat < 0 || (op.mat & 1)) return std::string();      // (phase tables are complex-aligned pool entries)
-                } else if (ls < 11) {
-                    rx(ls - 8, op.mat);
-                } else if (ls < 14) {
-                    o << "            spec_u<" << ls - 11 << ">(a";
-                    for (int k = 0; k < 8; ++k) o << ", " << lit(sc.coef[op.mat + k]);
-                    o << ");\n";
-                } else if (ls == LSEL_X3) {
-                    rx(0, op.mat); rx(1, op.mat + 4); rx(2, op.mat + 8);
-                } else {
-                    const int pair = ls - LSEL_X2;                      // (0,1) (0,2) (1,2)
-                    rx(pair == 2 ? 1 : 0, op.mat); rx(pair == 0 ? 1 : 2, op.mat + 4);
-                }
-            }
+            if (!emit_fast_ops(o, sc, p, R)) return false;
             if (last) {
                 for (int m = 0; m < NA; ++m) o << "            st_stream(dst + (gj_last | " << hex(sc.goff_last[m]) << "), a[" << m << "]);\n";
             } else {
@@ -157,22 +147,264 @@ std::string spec_source(const Program& P, int seg_begin, int seg_end, int nbuf) 
             o << "        }\n";
         }
         o << "    }\n}\n\n";
+        return true;
     }
-    (void)K;
+    // ---- first pass loaded from HBM straight into registers ----
+    // Shared memory only carries the exchanges between passes (a thread reads back the slots it wrote within a pass, so one
+    // barrier per pass TRANSITION).  nbuf = 2: tiles alternate between two buffers, so the first store of a tile never meets
+    // the last reads of the previous one; nbuf = 1: one more barrier per tile instead.
+    o << "    const unsigned gj_first = " << runs_expr(sc.gruns_first, "utid") << ";\n"
+      << "    auto gload = [&](long long tt, cplx* r) {\n"
+         "        const unsigned tl = (unsigned)(tt & (ntiles - 1));\n"
+      << "        const cplx* st = states + ((long long)works[tt >> tile_shift].src << " << P.nbits << ") + (" << runs_expr(sg.bruns, "tl") << " | gj_first);\n";
+    for (int m = 0; m < NA; ++m) o << "        r[" << m << "] = ld_stream(st + " << hex(sc.goff_first[m]) << ");\n";
+    o << "    };\n"
+         "    long long t = blockIdx.x;\n    if (t >= total) return;\n"
+      << "    cplx a[" << NA << "];\n    gload(t, a);\n"
+      << "    for (int iter = 0; t < total; t += gridDim.x, ++iter) {\n";
+    if (npass > 1) {
+        if (nbuf == 2) o << "        cplx* const sm = buf0 + ((size_t)(iter & 1) << " << K << ");\n";
+        else o << "        cplx* const sm = buf0;\n";
+    }
+    o << "        const long long tn = t + gridDim.x;\n"
+         "        const unsigned tl = (unsigned)(t & (ntiles - 1));\n"
+      << "        cplx* const dst = states + ((long long)works[t >> tile_shift].slot << " << P.nbits << ") + " << runs_expr(sg.bruns, "tl") << ";\n";
+    if (load == 2) o << "        cplx nx[" << NA << "];\n";
+    for (int p = 0; p < npass; ++p) {
+        const PassHot& ph = sc.pass[p];
+        const bool last = p == npass - 1;
+        o << "        {   // pass " << p << "\n"
+          << "            const int jb" << p << " = (int)" << runs_expr(bv.passes[p].truns, "utid") << ", jbs" << p << " = swz(jb" << p << ");\n"
+          << "            (void)jbs" << p << ";\n";
+        if (p > 0)
+            for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ph.regoff_swz[m] << "];\n";
+        if (last) {
+            if (nbuf == 1 && npass > 1) o << "            __syncthreads();            // every thread holds its amplitudes: the buffer is free for the next tile\n";
+            if (load == 2) o << "            if (tn < total) gload(tn, nx);\n";
+        }
+        if (!emit_fast_ops(o, sc, p, R)) return false;
+        if (last) {
+            for (int m = 0; m < NA; ++m) o << "            st_stream(dst + (gj_last | " << hex(sc.goff_last[m]) << "), a[" << m << "]);\n";
+        } else {
+            for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ph.regoff_swz[m] << "] = a[" << m << "];\n";
+            o << "            __syncthreads();\n";
+        }
+        o << "        }\n";
+    }
+    if (load == 2) {
+        o << "        if (tn < total) {\n";
+        for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = nx[" << m << "];\n";
+        o << "        }\n";
+    } else {
+        o << "        if (tn < total) gload(tn, a);\n";
+    }
+    o << "    }\n}\n\n";
+    return true;
+}
+
+// ---- event kernel ---------------------------------------------------------------------------------------------------
+// One op of the general list (the blob's op array), guarded / selected as the interpreter's fetch() does.
+void emit_general_op(std::ostringstream& o, const Op& op, int p, int R, const std::string& off_expr, const char* ind) {
+    const int kind = op_kind(op);
+    if (kind == OPK_DIAG) {
+        o << ind << "spec_diag<" << R << ", " << op_regmask(op) << ">(a, jb" << p << ", pool + ((" << off_expr << ") >> 1), " << hex(op.rbs & 0xffffu) << ", "
+          << hex(op.midx_lo) << ", " << hex(op.rbs >> 16) << ", " << hex(op.midx_hi) << ", " << (unsigned)op_tmask(op) << "u);\n";
+    } else if (kind == OPK_RX1) {
+        o << ind << "spec_rx_m<" << R << ", " << op_rb(op, 0) << ">(a, pool_d + (" << off_expr << "));\n";
+    } else {
+        o << ind << "spec_u_m<" << R << ", " << op_rb(op, 0) << ">(a, pool_d + (" << off_expr << "));\n";
+    }
+}
+
+bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const SpecOptions& opt) {
+    const int K = P.K, R = P.R, NA = 1 << R;
+    const BlobView bv = view_blob(P, seg);
+    const Segment& sg = *bv.sg;
+    const int npass = bv.blob->npass;
+    for (int i = 0; i < bv.blob->nops; ++i) {
+        const Op& op = bv.ops[i];
+        const int kind = op_kind(op);
+        if (kind != OPK_DIAG && kind != OPK_RX1 && kind != OPK_DENSE1) return false;
+        if (op.mat < 0 || op.mat_bare < 0 || (op.mat & 1) || (op.mat_bare & 1)) return false;
+    }
+    (void)opt;
+    o << "extern \"C\" __global__ void __launch_bounds__(" << (1 << (K - R)) << ", " << spec_ctas_per_sm(P, opt) << ") ncb_seg_" << seg << "_ev"
+      << "(DevProgram P, const unsigned char* __restrict__ pool_g, int pool_bytes, int pool_cap,\n"
+         "        const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int tile_shift,\n"
+         "        double* __restrict__ red_part, double* __restrict__ norm_part, const Decision* __restrict__ decisions) {\n"
+         "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+         "    __shared__ double s_buf[32 * 20];\n"
+         "    __shared__ double s_out[20];\n"
+         "    const int tid = threadIdx.x, nthreads = blockDim.x;\n"
+         "    const int ntiles = 1 << tile_shift;\n"
+         "    const long long total = (long long)nworks << tile_shift;\n"
+         "    cplx* const sm = reinterpret_cast<cplx*>(smem_raw + pool_cap);\n"
+         "    for (int i = tid * 16; i < pool_bytes; i += nthreads * 16) cp_async16(smem_raw + i, pool_g + i);\n"
+         "    cp_async_wait_all();\n    __syncthreads();\n"
+         "    const cplx* const pool = reinterpret_cast<const cplx*>(smem_raw);\n"
+         "    const double* const pool_d = reinterpret_cast<const double*>(smem_raw);\n"
+      << "    const Segment* const sg = P.segs + " << seg << ";\n"
+      << "    const int K = " << K << ";\n"
+         "    const unsigned utid = (unsigned)tid;\n"
+      << "    const unsigned offA = " << runs_expr(sg.eruns, "utid") << ";\n"
+      << "    const int sA = swz(tid);\n";
+    for (int p = 0; p < npass; ++p)
+        o << "    const int jb" << p << " = (int)" << runs_expr(bv.passes[p].truns, "utid") << ", jbs" << p << " = swz(jb" << p << ");\n";
+    o << "    auto issue_load = [&](long long tt, const Work& w) {\n"
+         "        if (w.flags & WF_INIT) return;\n"
+         "        const unsigned tl = (unsigned)(tt & (ntiles - 1));\n"
+      << "        const cplx* st = states + ((long long)w.src << " << P.nbits << ") + " << runs_expr(sg.bruns, "tl") << ";\n";
+    for (int it = 0; it < NA; ++it)
+        o << "        cp_async16(sm + (sA ^ " << sg.it_swz[it] << "), st + (offA | " << hex(sg.it_off[it]) << "));\n";
+    o << "    };\n";
+    // the pass programs, every operator guarded by its instruction index (what run_range + fetch() interpret)
+    o << "    auto run_passes = [&](const int lo, const int hi, const bool bare) {\n";
+    for (int p = 0; p < npass; ++p) {
+        const Pass& ps = bv.passes[p];
+        if (ps.instr_hi <= ps.instr_lo) continue;
+        o << "        if (" << ps.instr_lo << " < hi && " << ps.instr_hi << " > lo) {   // pass " << p << "\n"
+          << "            cplx a[" << NA << "];\n";
+        for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "];\n";
+        auto member = [&](const Op& op, const char* ind) {
+            o << ind << "if (" << op.instr << " >= lo && " << op.instr << " < hi) {\n";
+            std::string off = std::to_string(op.mat);
+            if (op.mat_bare != op.mat) off = "(bare && hi == " + std::to_string(op.instr + 1) + ") ? " + std::to_string(op.mat_bare) + " : " + std::to_string(op.mat);
+            emit_general_op(o, op, p, R, off, (std::string(ind) + "    ").c_str());
+            o << ind << "}\n";
+        };
+        for (int i = ps.op_begin; i < ps.op_end; ++i) {
+            const Op& op = bv.ops[i];
+            if (op.kind_nb >> 31) {
+                const int span = (int)((op.kind_nb >> 25) & 0x3f), last = op.pad;
+                o << "            if (" << op.instr << " >= lo && (" << last + 1 << " < hi || (" << last + 1 << " == hi && !bare))) {\n";
+                emit_general_op(o, op, p, R, std::to_string(op.mat), "                ");
+                o << "            } else {\n";
+                for (int j = 1; j <= span; ++j) member(bv.ops[i + j], "                ");
+                o << "            }\n";
+                i += span;
+            } else {
+                member(op, "            ");
+            }
+        }
+        for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "] = a[" << m << "];\n";
+        o << "            __syncthreads();\n        }\n";
+    }
+    o << "    };\n";
+    o << "    long long t = blockIdx.x;\n    if (t >= total) return;\n"
+         "    Work w = works[t >> tile_shift];\n"
+         "    issue_load(t, w);\n"
+         "    asm volatile(\"cp.async.commit_group;\\n\" ::: \"memory\");\n"
+         "    for (; t < total; t += gridDim.x) {\n"
+         "        const long long tn = t + gridDim.x;\n"
+         "        asm volatile(\"cp.async.wait_group 0;\\n\" ::: \"memory\");\n"
+         "        __syncthreads();\n"
+         "        const int o = (int)(t & (ntiles - 1));\n"
+         "        if (w.flags & WF_INIT) {\n";
+    for (int it = 0; it < NA; ++it) o << "            sm[sA ^ " << sg.it_swz[it] << "] = cplx{0.0, 0.0};\n";
+    o << "            if (o == 0 && tid == 0) sm[swz(0)] = cplx{1.0, 0.0};\n"
+         "            __syncthreads();\n"
+         "        }\n"
+         "        if (w.flags & WF_PRO_STATIC) event_apply(sm, P, sg, w.ev_instr, w.ev_k, 1.0);\n"
+         "        else if (w.flags & WF_PRO_DYNAMIC) event_apply(sm, P, sg, w.ev_instr, decisions[w.slot].k, decisions[w.slot].scale);\n"
+         "        {\n"
+         "            int lo = w.instr_lo;\n"
+         "            for (int part = (w.flags & WF_MID) ? 0 : 1; part < 2; ++part) {\n"
+         "                const int hi = part == 0 ? w.mid_instr + 1 : w.instr_hi;\n"
+         "                const bool bare = part == 0 ? true : (w.flags & WF_BARE_LAST) != 0;\n"
+         "                run_passes(lo, hi, bare);\n"
+         "                if (part == 0) {\n"
+         "                    event_apply(sm, P, sg, w.mid_instr, (int)((unsigned)w.flags >> 16), 1.0);\n"
+         "                    lo = w.mid_instr + 1;\n"
+         "                }\n"
+         "            }\n"
+         "        }\n"
+         "        if (w.flags & WF_REDUCE) {\n"
+         "            const Instr in = P.instrs[w.instr_hi - 1];\n"
+         "            const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;\n"
+         "            event_reduce(sm, K, p0, p1, s_buf, s_out, red_part + ((long long)w.slot * ntiles + o) * RED_VALUES);\n"
+         "        }\n"
+         "        if (w.flags & WF_NORM) {\n"
+         "            double v[1] = {0.0};\n"
+         "            for (int i = tid; i < (1 << K); i += nthreads) v[0] += cnorm2(sm[i]);\n"
+         "            block_reduce<1>(v, s_buf, s_out);\n"
+         "            if (tid == 0) norm_part[(long long)w.slot * ntiles + o] = s_out[0];\n"
+         "        }\n"
+         "        {\n"
+      << "            cplx* st = states + ((long long)w.slot << " << P.nbits << ") + " << runs_expr(sg.bruns, "(unsigned)o") << ";\n";
+    for (int it = 0; it < NA; ++it)
+        o << "            st_stream(st + (offA | " << hex(sg.it_off[it]) << "), sm[sA ^ " << sg.it_swz[it] << "]);\n";
+    o << "        }\n"
+         "        __syncthreads();\n"
+         "        if (tn < total) {\n"
+         "            w = works[tn >> tile_shift];\n"
+         "            issue_load(tn, w);\n"
+         "        }\n"
+         "        asm volatile(\"cp.async.commit_group;\\n\" ::: \"memory\");\n"
+         "    }\n"
+         "    asm volatile(\"cp.async.wait_all;\\n\" ::: \"memory\");\n"
+         "}\n\n";
+    return true;
+}
+
+}  // namespace
+
+bool spec_supported(const Program& P, int seg) {
+    if (!lean_tiled(P)) return false;
+    if (seg < 0 || seg >= (int)P.segconst.size()) return false;
+    const SegConst& sc = P.segconst[seg];
+    return sc.valid && sc.direct && sc.npass >= 1;
+}
+
+bool spec_ev_supported(const Program& P, int seg) {
+    if (!lean_tiled(P) || seg < 0 || seg >= (int)P.blob_off.size()) return false;
+    // every state offset of the tile has to exist (tiles of a state smaller than a tile carry virtual bits)
+    return P.nbits >= P.K;
+}
+
+int spec_ctas_per_sm(const Program& P, const SpecOptions& opt) {
+    // registers: 64 K per SM; shared memory: nbuf tiles of 16 B x 2^K plus the phase tables (<= 16 KB) within 227 KB
+    const int threads = 1 << (P.K - P.R);
+    int pool_cap = 0;                                  // what the engine stages per CTA beside the tiles (1 KB granules)
+    for (size_t sgi = 0; sgi < P.blob_off.size(); ++sgi) {
+        const SegBlob& blob = *reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[sgi]);
+        pool_cap = std::max(pool_cap, (blob.bytes - blob.pool_off + 1023) & ~1023);
+    }
+    const int nbuf = opt.nbuf == 1 ? 1 : 2;
+    const int by_smem = (int)((227 * 1024) / ((size_t)nbuf * (16u << P.K) + (size_t)pool_cap + 2048));
+    const int by_regs = 65536 / (threads * 64);
+    return std::max(1, std::min({by_smem, by_regs, 8}));
+}
+
+void spec_pool(const Program& P, int seg, int* offset, int* bytes) {
+    const SegBlob& blob = *reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[seg]);
+    *offset = blob.pool_off;
+    *bytes = blob.bytes - blob.pool_off;
+}
+
+std::string spec_source(const Program& P, int seg_begin, int seg_end, const SpecOptions& opt) {
+    std::ostringstream o;
+    o << "// generated by ncb_spec.cpp -- do not edit\n#include \"ncb_spec.cuh\"\nusing namespace ncb;\n";
+    for (int seg = seg_begin; seg < seg_end; ++seg) {
+        if (spec_supported(P, seg)) {
+            std::ostringstream k;
+            if (emit_segment_kernel(k, P, seg, opt)) o << k.str();
+        }
+        if (opt.events && spec_ev_supported(P, seg)) {
+            std::ostringstream k;
+            if (emit_event_kernel(k, P, seg, opt)) o << k.str();
+        }
+    }
     return o.str();
 }
 
-std::string spec_key(const Program& P, int nbuf) {
-    // FNV-1a over the staged blobs and the constant-bank programs
+std::string spec_key(const Program& P, const SpecOptions& opt) {
+    // FNV-1a over the generated source of every segment: the source is all the cubins depend on (beside the headers,
+    // which the engine covers with a build stamp)
     uint64_t h = 1469598103934665603ull;
-    auto mix = [&](const void* p, size_t n) {
-        const unsigned char* b = static_cast<const unsigned char*>(p);
-        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
-    };
-    mix(P.blobs.data(), P.blobs.size());
-    if (!P.segconst.empty()) mix(P.segconst.data(), P.segconst.size() * sizeof(SegConst));
-    const int geo[6] = {P.nbits, P.K, P.R, (int)P.segs.size(), nbuf, 3 /* generator version */};
-    mix(geo, sizeof geo);
+    const std::string src = spec_source(P, 0, (int)P.segs.size(), opt);
+    for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
+    const int geo[4] = {P.nbits, P.K, P.R, 5 /* generator version */};
+    for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);
     return b;

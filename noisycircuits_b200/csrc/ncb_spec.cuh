@@ -1,19 +1,28 @@
-// Building blocks of the SPECIALISED sweep kernels (ncb_spec.cpp generates one kernel per segment from them).
+// Building blocks of the SPECIALISED sweep kernels (ncb_spec.cpp generates the kernels of a program from them).
 //
 // The direct kernel interprets a segment's constant-bank program: per operator a dispatch, constant-bank loads of its
 // coefficients and index arithmetic on run-time geometry.  A specialised kernel is the same code with the segment's
 // program written out: every pass is a straight line of the hand-written operator kernels of ncb_common.h called with
-// LITERAL coefficients, masks and offsets, so the compiler folds the interpreter away (no dispatch, no LDCU, address
-// arithmetic with immediates).  Same tile geometry, same shared-memory layout, same phase tables as the direct kernel:
-// results are bit-identical to it.
+// LITERAL masks, offsets and bit positions, so the compiler folds the interpreter away (no dispatch, address arithmetic
+// with immediates).  Gate coefficients are NOT literals: they arrive in a __grid_constant__ kernel parameter, i.e. in the
+// constant bank, where FP64 instructions take them as direct operands -- the generated code, and with it the cubin cache
+// key, depends on the structure of the circuit only, so a parameter sweep over one gate skeleton compiles once.
+//
+//   ncb_seg_<k>      works that run the WHOLE segment k without a jump event: first pass loaded from HBM straight into
+//                    registers, last pass stored from registers straight to HBM, shared memory only for the exchanges
+//                    between passes.
+//   ncb_seg_<k>_ev   works that carry a jump event (pieces [lo, hi) of the segment, in-line jumps, reduced-density
+//                    reductions): the pass programs with every operator guarded by its instruction index.
 #pragma once
 #define NCB_TEMPLATES_ONLY
 #include "ncb_kernels.cuh"
 
 namespace ncb {
 
+struct SpecCoef { double c[SC_MAX_COEF]; };     // SegConst::coef of the segment
+
 // diagonal operator with literal gather parameters (see diag_mask); T: the phase table in the staged pool
-template <int MASK>
+template <int R, int MASK>
 __device__ __forceinline__ void spec_diag(cplx* a, int jb, const cplx* T, unsigned mask_a, unsigned magic_a, unsigned mask_b,
                                           unsigned magic_b, unsigned mult) {
     Op op{};
@@ -21,17 +30,30 @@ __device__ __forceinline__ void spec_diag(cplx* a, int jb, const cplx* T, unsign
     op.rbs = mask_a | (mask_b << 16);
     op.midx_lo = magic_a;
     op.midx_hi = magic_b;
-    diag_mask<3, MASK, true>(op, jb, T, a, a);
+    diag_mask<R, MASK, true>(op, jb, T, a, a);
 }
-template <int B>
+template <int R, int B>
 __device__ __forceinline__ void spec_rx(cplx* a, double c0, double c1, double c2, double c3) {
     const cplx m4[4] = {cplx{c0, 0.0}, cplx{0.0, c1}, cplx{0.0, c2}, cplx{c3, 0.0}};
-    rx1_bit<3, B>(a, a, m4);
+    rx1_bit<R, B>(a, a, m4);
 }
-template <int B>
+template <int R, int B>
 __device__ __forceinline__ void spec_u(cplx* a, double c0, double c1, double c2, double c3, double c4, double c5, double c6, double c7) {
     const cplx m4[4] = {cplx{c0, c1}, cplx{c2, c3}, cplx{c4, c5}, cplx{c6, c7}};
-    dense1_bit<3, B>(a, a, m4);
+    dense1_bit<R, B>(a, a, m4);
+}
+// the same with the 2x2 (row-major, interleaved re/im) read from the staged pool in shared memory (event kernels)
+template <int R, int B>
+__device__ __forceinline__ void spec_rx_m(cplx* a, const double* m) {
+    const cplx* M = reinterpret_cast<const cplx*>(m);
+    const cplx m4[4] = {ld_shared_cplx(M), ld_shared_cplx(M + 1), ld_shared_cplx(M + 2), ld_shared_cplx(M + 3)};
+    rx1_bit<R, B>(a, a, m4);
+}
+template <int R, int B>
+__device__ __forceinline__ void spec_u_m(cplx* a, const double* m) {
+    const cplx* M = reinterpret_cast<const cplx*>(m);
+    const cplx m4[4] = {ld_shared_cplx(M), ld_shared_cplx(M + 1), ld_shared_cplx(M + 2), ld_shared_cplx(M + 3)};
+    dense1_bit<R, B>(a, a, m4);
 }
 
 }  // namespace ncb

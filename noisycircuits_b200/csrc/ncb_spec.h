@@ -6,16 +6,30 @@
 
 namespace ncb {
 
-// true when segment `seg` of P can run in a specialised kernel (lean program, tiled, valid constant-bank program with
-// direct store)
+struct SpecOptions {
+    int nbuf = 2;     // shared-memory tile buffers of a whole-segment kernel (2: a tile's passes never wait for the previous
+                      // tile's last reads)
+    int load = 2;     // how a whole-segment kernel gets its tile: 0 staged in shared memory with cp.async (as the interpreting
+                      // direct kernel does); 1 the first pass loads HBM -> registers (no staging, one barrier and one
+                      // shared-memory round trip less); 2 like 1, and the next tile's loads are issued into a second register
+                      // set when the last pass starts, so they overlap its arithmetic and stores
+    int events = 1;   // 1: also generate ncb_seg_<k>_ev, the kernel of the works that carry a jump event (pieces of a segment)
+};
+
+// true when segment `seg` of P can run in a specialised whole-segment kernel (lean program, tiled, valid constant-bank
+// program with direct store)
 bool spec_supported(const Program& P, int seg);
-// CUDA source of `extern "C" __global__ void ncb_seg_<seg>(...)` for segments [seg_begin, seg_end) of P
-std::string spec_source(const Program& P, int seg_begin, int seg_end, int nbuf = 2);
-// bytes of segment seg's phase-table pool (the only part of the staged blob a specialised kernel needs) and its offset
+// true when the works of segment `seg` that carry jump events can run in a generated kernel (lean program, tiled)
+bool spec_ev_supported(const Program& P, int seg);
+// CUDA source of `extern "C" __global__ void ncb_seg_<seg>(...)` (and ncb_seg_<seg>_ev) for segments [seg_begin, seg_end)
+// of P.  The source depends on the STRUCTURE of the program only (geometry, operator kinds, bit positions, table
+// offsets): gate coefficients come in through a kernel parameter (constant bank), phase tables through the staged pool.
+std::string spec_source(const Program& P, int seg_begin, int seg_end, const SpecOptions& opt = SpecOptions());
+// bytes of segment seg's matrix pool (the only part of the staged blob a specialised kernel needs) and its offset
 void spec_pool(const Program& P, int seg, int* offset, int* bytes);
 // resident CTAs per SM the generated kernels are compiled for (launch bounds)
-int spec_ctas_per_sm(const Program& P, int nbuf);
-// content hash of everything the generated code depends on (cache key)
-std::string spec_key(const Program& P, int nbuf = 2);
+int spec_ctas_per_sm(const Program& P, const SpecOptions& opt);
+// content hash of everything the generated code depends on (cache key): a hash of the source itself
+std::string spec_key(const Program& P, const SpecOptions& opt = SpecOptions());
 
 }  // namespace ncb
