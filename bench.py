@@ -18,8 +18,14 @@ roofline   the sweep ("tile") kernel against the measured HBM copy bandwidth (ME
            algorithmic bytes = sweeps * 2 * 16 B * 2^n; launch duration = device time of the
            timed region / number of tile launches (the small decide / accumulate kernels are charged to it).
 cpu_baseline  the reference's compiled CPU path (oracle/_ref/patched: these circuits have non-adjacent coupled
-           pairs) on all host cores, on a bounded sample (first layer(s) of the same circuit),
-           scaled by instructions (the reference's cost per instruction is flat).
+           pairs) on all host cores, on a bounded sample: 4 consecutive layers of the same circuit
+           run as a circuit of their own, the rate scaled by instructions.  The reference sweeps all 2^n amplitudes
+           (1 + K + 2) times per instruction whatever their values (QuantumGates.hpp:117-144, 360-419), so its cost per
+           instruction does not depend on the state; --impl reference walks the circuit slice by slice (step s times layers
+           4s .. 4s+3, cyclically) and reports the per-slice rates, and profiles/ holds one run of the full circuit.
+parity     untimed, in the same run: 2 Philox trajectories of the FULL benchmarked program (generated kernels, shared
+           prefix) against the CPU oracle in program order (about a minute of two host threads; --no-parity skips it).
+c2_density_matrix / strong_scaling   extra keys, see run_gpu.
 """
 import argparse
 import datetime
@@ -54,7 +60,9 @@ def config(traj_per_step, n_gpus):
     return {"workload": f"{NQ}-qubit depth-{DEPTH} random layered Heron circuit (1q in x/sx/rx/rz, 2q in cz/rzz on the 19 coupled "
                         f"pairs of qubits 0-19), Sample_Noise_Model_Heron_QPU noise (threshold 1e-6), BASELINE configs[4]",
             "instructions": DEPTH * (NQ + 19), "trajectories_per_step_per_gpu": traj_per_step,
-            "target_trajectories": 100000, "parallelism": f"trajectory-sharded x{n_gpus}",
+            "target_trajectories": 100000,
+            "note": "throughput is flat in the trajectory count (measured 592 .. 9472 per step, profiles/r02_batch_sweep.jsonl): the timed region "
+                    "runs steps x trajectories_per_step_per_gpu x n_gpus trajectories, not 10^5", "parallelism": f"trajectory-sharded x{n_gpus}",
             "l2": "inputs larger than L2 (every sweep launch walks a state batch of up to 296 trajectories x 16 MiB = 4.7 GB per GPU)",
             "shared_no_jump_prefix": os.environ.get("NCB_SHARE_PREFIX", "1") != "0",
             "specialized_kernels": os.environ.get("NCB_SPECIALIZE", "1") != "0"}
@@ -192,11 +200,13 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------------------------
 # CPU reference arm
 # -------------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(instr, sq, tq, layers, trajectories, cores):
-    """trajectories/sec of the reference's compiled CPU path on the FULL circuit, measured on its first `layers`
-    layers and scaled by the instruction count.  Returns (rate, kind, sample description, seconds)."""
+def cpu_reference_rate(instr, sq, tq, layers, trajectories, cores, first_layer=0):
+    """trajectories/sec of the reference's compiled CPU path on the FULL circuit, measured on `layers` consecutive layers
+    (from `first_layer`, run as a circuit of their own from |0..0>) and scaled by the instruction count.  Returns (rate,
+    kind, sample description, seconds)."""
     per_layer = NQ + 19
-    sample = instr[:layers * per_layer]
+    first_layer = first_layer % max(DEPTH - layers + 1, 1)
+    sample = instr[first_layer * per_layer:(first_layer + layers) * per_layer]
     n = NQ
     ref_dir = os.path.join(ROOT, "oracle", "_ref", "patched")
     kind = "port"
@@ -228,8 +238,8 @@ def cpu_reference_rate(instr, sq, tq, layers, trajectories, cores):
         raise RuntimeError("CPU reference returned a non-normalised distribution")
     rate_sample = trajectories / dt
     rate_full = rate_sample * len(sample) / len(instr)
-    desc = (f"{trajectories} trajectories of the first {layers} layer(s) ({len(sample)} of {len(instr)} instructions) of the same "
-            f"circuit in {dt:.1f} s on {cores} threads; rate scaled by {len(sample)}/{len(instr)}")
+    desc = (f"{trajectories} trajectories of layers {first_layer}..{first_layer + layers - 1} ({len(sample)} of {len(instr)} instructions) of "
+            f"the same circuit in {dt:.1f} s on {cores} threads; rate scaled by {len(sample)}/{len(instr)}")
     return rate_full, kind, desc, dt
 
 
@@ -240,16 +250,28 @@ def run_reference(args):
     sq, tq, _meas, _pairs, instr = workload()
     cores = os.cpu_count() or 1
     traj = max(cores, 8)
-    rates, descs, kind, secs = [], [], "port", 0.0
-    for s in range(args.warmup + args.steps):
-        r, kind, desc, dt = cpu_reference_rate(instr, sq, tq, CPU_SAMPLE_LAYERS, traj, cores)
+    rates, descs, kind, secs, slices = [], [], "port", 0.0, []
+    if args.full_circuit:
+        # the whole 1950-instruction circuit, `cores` trajectories per step (about two minutes per step on 16 threads)
+        layers, starts = DEPTH, [0] * (args.warmup + args.steps)
+    else:
+        # step s times layers 4s .. 4s+3 (cyclically): 13 steps walk the whole circuit once
+        layers, starts = CPU_SAMPLE_LAYERS, [CPU_SAMPLE_LAYERS * s for s in range(args.warmup + args.steps)]
+    for s, first in enumerate(starts):
+        r, kind, desc, dt = cpu_reference_rate(instr, sq, tq, layers, traj, cores, first)
         if s >= args.warmup:
             rates.append(r); descs.append(desc); secs += dt
+            slices.append({"first_layer": first % max(DEPTH - layers + 1, 1), "layers": layers, "trajectories_per_s_full_circuit": r})
     value = len(rates) / sum(1.0 / r for r in rates)
+    spread = (max(rates) - min(rates)) / value if rates else 0.0
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(traj, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": descs[-1]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": ("the full circuit per step; " if args.full_circuit else
+                                        f"{CPU_SAMPLE_LAYERS}-layer slices of the circuit, one per step, walking the circuit cyclically "
+                                        f"(the reference's cost per instruction does not depend on the state); ") + descs[-1]},
+            "sample_slices": slices, "slice_rate_spread": spread, "extrapolated": not args.full_circuit,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -257,6 +279,68 @@ def run_reference(args):
 # -------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------------------------
+def philox_uniform_host(seed, traj, instr):
+    """Philox4x32-10 with the engine's (counter, key) convention (ncb_common.h:philox_uniform), plain Python."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [int(instr), int(traj) & 0xffffffff, (int(traj) >> 32) & 0xffffffff, 0x6e636232]
+    k0, k1 = seed & 0xffffffff, (seed >> 32) & 0xffffffff
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xffffffff, p1 & 0xffffffff, ((p0 >> 32) ^ c[3] ^ k1) & 0xffffffff, p0 & 0xffffffff]
+        k0, k1 = (k0 + W0) & 0xffffffff, (k1 + W1) & 0xffffffff
+    bits = ((c[0] << 21) ^ (c[1] >> 11)) & ((1 << 53) - 1)
+    return bits / 9007199254740992.0
+
+
+def parity_block(solver, instr, sq, tq, tps):
+    """Untimed: PARITY_TRAJ Philox trajectories of the benchmarked program (same compiled object, generated kernels, shared
+    prefix) against the CPU oracle fed the same counter-based uniforms IN PROGRAM ORDER (the oracle is the checker here,
+    never the thing measured)."""
+    T, seed, begin, tol = 2, 42, 5, 1e-10
+    t0 = time.perf_counter()
+    try:
+        from oracle import oracle
+        prog = solver._program(instr, tps)
+        got, st = prog.run_mcwf(T, traj_begin=begin, seed=seed)
+        U = np.array([[philox_uniform_host(seed, begin + t, g) for g in range(len(instr))] for t in range(T)])
+        ref = oracle.Program(NQ, instr, sq, tq).mcwf(T, uniforms=U, mask_fix=True, threads=T)
+        diff = float(np.abs(got / T - ref).max())
+        return {"trajectories": T, "instructions": len(instr), "order": "program order (the engine runs its tile-friendly order)",
+                "max_abs_diff_probability": diff, "tol": tol, "ok": bool(diff < tol), "events": int(st["events"]),
+                "specialized_launches": int(st["specialized_launches"]), "seconds": time.perf_counter() - t0}
+    except Exception as e:
+        return {"ok": False, "error": repr(e), "seconds": time.perf_counter() - t0}
+
+
+def c2_block(peak):
+    """BASELINE configs[1]: 12-qubit density-matrix path (4^12 vectorised state, 268 MB) on a depth-10 layered Heron
+    circuit, one GPU.  GB/s on the sweeps actually EXECUTED (one read + one write of the 4^n state per segment)."""
+    try:
+        import torch
+        from noisycircuits_b200 import circuits, noise_io, _lib
+        from noisycircuits_b200.solvers import DensityMatrixSolver
+        sq, tq, _m, _ = noise_io.load_noise_tables(os.path.join(ROOT, "tests", "golden", "heron20_noise.npz"))
+        n, depth = 12, 10
+        instr = circuits.heron_layered(n, depth, circuits.coupled_pairs(tq, n), seed=42)
+        dm = DensityMatrixSolver(n, sq, tq, instr, 1)
+        p = dm.solve(list(range(n)))
+        best = None
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            p = dm.solve(list(range(n)))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        sweeps = dm._program.query(_lib.Q_NUM_SEGMENTS)
+        gbs = sweeps * 32.0 * 4 ** n / best / 1e9
+        return {"workload": f"{n}-qubit density matrix, depth-{depth} layered Heron circuit ({len(instr)} instructions)", "seconds": best,
+                "sweeps": int(sweeps), "state_bytes": 16 * 4 ** n, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak,
+                "trace": float(p.sum()), "min_probability": float(p.min()),
+                "parity": "GPU vs the numpy restatement at 1e-10 for n <= 11 in tests/test_gpu_parity.py; unpinned at the qiskit-aer boundary"}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -320,7 +404,7 @@ def run_gpu(args):
     if clocks:
         clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"sweeps": 0, "launches": 0, "tile_launches": 0, "events": 0, "hard_events": 0}
+    agg = {"sweeps": 0, "launches": 0, "tile_launches": 0, "events": 0, "hard_events": 0, "specialized_launches": 0}
     ev0.record()
     for s in range(args.steps):
         _, st = step(args.warmup + s)
@@ -337,26 +421,46 @@ def run_gpu(args):
     value = world * tps * args.steps / (ms * 1e-3)
     check = float(total.sum().item()) / (world * tps)
 
-    # ---- end-to-end arm: public plug-in call with host buffers ----
+    # ---- end-to-end arm: the public call chain with host results ----
+    # N = 1: backend.execute (QuantumCircuit.execute for sim_backend "b200"); N > 1: backend.execute_sharded
+    # (QuantumCircuitMPI.execute: contiguous shards, one NCCL all-reduce, tail on the device, result to every rank's host).
+    # Per step the work lists go host -> device and the float64[2^n] result device -> host inside the timed region.
+    from noisycircuits_b200 import backend
+    meas_all = {q: _meas[q] for q in range(NQ)}
+
+    def public_call(first_traj, count_total):
+        if world == 1:
+            return backend.execute(NQ, instr, sq, tq, meas_all, None, count_total, executor=solver, traj_offset=first_traj)
+        return backend.execute_sharded(NQ, instr, sq, tq, meas_all, None, count_total, executor=solver, traj_offset=first_traj)
+
+    public_call(10 ** 7, world * tps)               # untimed: the tail kernels' first launch
     barrier()
     w0 = time.perf_counter()
     h2d = d2h = 0
     for s in range(args.steps):
-        if world == 1:
-            probs, st = step(args.warmup + args.steps + s, host=True)
-            h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
-        else:
-            # the public multi-GPU call chain (backend.execute_sharded): device accumulation, one NCCL all-reduce,
-            # then the float64[2^n] result to the host
-            _, st = step(args.warmup + args.steps + s)
-            probs = total.cpu().numpy()
-            h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"] + probs.nbytes
+        probs = public_call((args.warmup + args.steps + s) * world * tps, world * tps)
+        st = solver.last_stats
+        h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"] + probs.nbytes
     barrier()
     e2e_s = time.perf_counter() - w0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * tps * args.steps / float(t.item())
+    e2e_norm = float(probs.sum())
+
+    # ---- strong scaling: ONE execute / execute_sharded of a fixed total, split over the ranks (QuantumCircuitMPI.py:329-332) ----
+    strong = None
+    if args.strong_traj > 0:
+        barrier()
+        w0 = time.perf_counter()
+        probs = public_call(2 * 10 ** 7, args.strong_traj)
+        barrier()
+        t = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"total_trajectories": args.strong_traj, "seconds": float(t.item()), "value": args.strong_traj / float(t.item()),
+                  "unit": UNIT, "call": "backend.execute" if world == 1 else "backend.execute_sharded", "norm_check": float(probs.sum())}
 
     if rank == 0:
         peaks = {}
@@ -368,12 +472,12 @@ def run_gpu(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         alg_bytes = agg["sweeps"] * 32.0 * dim                      # one rank's tile launches
         achieved = alg_bytes / (ms * 1e-3) / 1e9
-        # DRAM traffic per launch from the committed ncu --set full capture (profiles/): measured there as a ratio to
-        # the algorithmic bytes of the captured launch, applied to this run's bytes per launch
-        traffic = None
+        # DRAM traffic per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full
+        # capture of this command (profiles/r02_traffic.json, with the algorithmic bytes of the captured launches beside it)
+        traffic, traffic_src = None, None
         try:
-            ratio = json.load(open(os.path.join(ROOT, "profiles", "tile_kernel_traffic.json")))["traffic_over_algorithmic"]
-            traffic = ratio * alg_bytes / max(agg["tile_launches"], 1)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -383,13 +487,20 @@ def run_gpu(args):
                         "d2h_bytes_per_step": d2h // max(args.steps, 1)},
                 "gpu_launches": agg["launches"],
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src,
+                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "kernel": ("ncb_seg_<k> (generated whole-segment sweeps)" if specialize else "ncb::direct_kernel (whole-segment sweeps)") + " + ncb::tile_kernel (jump-event pieces)",
                              "algorithmic_bytes_per_launch": alg_bytes / max(agg["tile_launches"], 1),
                              "avg_launch_ms": ms / max(agg["tile_launches"], 1), "tile_launches": agg["tile_launches"],
                              "sweeps_per_trajectory": agg["sweeps"] / (tps * args.steps)},
-                "clocks": clock_info, "norm_check": check, "specialize_build": {"ok": bool(spec_built), "seconds": t_spec},
+                "clocks": clock_info, "norm_check": check, "e2e_norm_check": e2e_norm,
+                "specialize_build": {"ok": bool(spec_built), "seconds": t_spec},
+                "specialized_launches": agg["specialized_launches"], "prewarm_steps": PREWARM_STEPS,
+                "timed_trajectories": world * tps * args.steps, "strong_scaling": strong,
                 "events_per_trajectory": agg["events"] / (tps * args.steps)}
+        if world == 1 and not args.no_parity:
+            line["parity"] = parity_block(solver, instr, sq, tq, tps)
+        if world == 1 and not args.no_c2:
+            line["c2_density_matrix"] = c2_block(peak)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             try:
@@ -410,6 +521,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--traj-per-step", type=int, default=592)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed in-run parity check against the oracle (about a minute)")
+    ap.add_argument("--no-c2", action="store_true", help="skip the 12-qubit density-matrix extra line")
+    ap.add_argument("--strong-traj", type=int, default=16384, help="total trajectories of the strong-scaling call (0: skip)")
+    ap.add_argument("--full-circuit", action="store_true", help="--impl reference: time the whole circuit per step instead of 4-layer slices")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -85,11 +85,15 @@ typedef struct {
                          /* 0 (default): the batched MCWF run computes the evolution every trajectory shares before its
                             first jump event once per batch (results per trajectory are bit-identical; fewer sweeps).
                             1: every trajectory is swept on its own from |0..0>. */
-    int32_t specialize;  /* 1: the sweeps of whole segments run in kernels GENERATED for this program (one per segment: the
-                            pass programs written out with literal coefficients, compiled with nvcc into a cubin cache next
-                            to the library, loaded through the driver API) instead of the interpreting kernel -- same
-                            arithmetic, ~40 % fewer instructions.  Costs a few seconds at the first run of a new program;
-                            falls back to the interpreter when nvcc or libcuda are not usable.  0 (default): off. */
+    int32_t specialize;  /* 1 or 2: the sweeps run in kernels GENERATED for this program (per segment one kernel for the works that
+                            run the whole segment and one for the works that carry jump events: the pass programs written out,
+                            compiled with nvcc into a cubin cache next to the library, loaded through the driver API) instead
+                            of the interpreting kernels -- same arithmetic, a third of the instructions.  1: gate coefficients
+                            are literals in the generated code (fastest; the cubins belong to this circuit and these angles);
+                            2: coefficients are a kernel parameter, so the generated code -- and the cache key -- depends on
+                            the circuit's STRUCTURE only: a parameter sweep over one gate skeleton compiles once.  Costs a few
+                            seconds at the first run of a new program; when nvcc or libcuda are not usable the interpreter
+                            runs and ncb_run_params.out_spec_launches stays 0.  0 (default): off. */
 } ncb_options;
 
 typedef struct ncb_program ncb_program;

@@ -58,17 +58,20 @@ def _validate(num_qubits, instruction_list, qubits, num_trajectories):
 
 
 def execute(num_qubits, instruction_list, single_qubit_noise, two_qubit_noise, measurement_error, qubits=None,
-            num_trajectories=100, num_cores=1, rng="philox", seed=42, **engine_options) -> np.ndarray:
-    """QuantumCircuit.execute for sim_backend "b200": big-endian probabilities of the measured qubits."""
+            num_trajectories=100, num_cores=1, rng="philox", seed=42, executor=None, traj_offset=0, **engine_options) -> np.ndarray:
+    """QuantumCircuit.execute for sim_backend "b200": big-endian probabilities of the measured qubits.
+
+    executor: a RemoteExecutor to reuse (it keeps the compiled program of the last circuit); traj_offset: global id of
+    the first trajectory (keys the counter-based RNG)."""
     if qubits is None:
         qubits = list(range(num_qubits))
     _validate(num_qubits, instruction_list, qubits, num_trajectories)
-    solver = RemoteExecutor(num_qubits, single_qubit_noise, two_qubit_noise, num_cores, rng=rng, seed=seed, **engine_options)
+    solver = executor or RemoteExecutor(num_qubits, single_qubit_noise, two_qubit_noise, num_cores, rng=rng, seed=seed, **engine_options)
     # the sum over trajectories stays on the device; marginal, read-out error and bit reversal run there too and only the
     # 2^len(qubits) result comes back (SURVEY 8(f) #3)
     acc = simulator.DeviceBuffer(1 << num_qubits)
     try:
-        solver.run_sum(instruction_list, 0, num_trajectories, device_probs=acc.ptr)
+        solver.run_sum(instruction_list, int(traj_offset), num_trajectories, device_probs=acc.ptr)
         return simulator.execute_tail_device(acc.ptr, num_qubits, qubits, measurement_error, 1.0 / float(num_trajectories))
     finally:
         acc.free()
@@ -76,12 +79,13 @@ def execute(num_qubits, instruction_list, single_qubit_noise, two_qubit_noise, m
 
 def execute_sharded(num_qubits, instruction_list, single_qubit_noise, two_qubit_noise, measurement_error, qubits=None,
                     num_trajectories=100, rng="philox", seed=42, group=None, shard_runner=None,
-                    apply_measurement_error=None, **engine_options) -> np.ndarray:
+                    apply_measurement_error=None, executor=None, traj_offset=0, **engine_options) -> np.ndarray:
     """QuantumCircuitMPI.execute over torch.distributed.  Every rank returns the full result (the reference
     broadcasts it, QuantumCircuitMPI.py:367).
 
     shard_runner(local_start, local_count) -> float64[2^n] sum of |psi|^2 over the shard; default: the GPU engine
     writing into a device tensor that is all-reduced in place (NCCL).  Tests inject a CPU runner (gloo).
+    executor: a RemoteExecutor to reuse; traj_offset: global id of the first trajectory of the call.
     """
     import torch
     import torch.distributed as dist
@@ -96,10 +100,10 @@ def execute_sharded(num_qubits, instruction_list, single_qubit_noise, two_qubit_
     start, count = shard_range(num_trajectories, rank, world)
     dim = 1 << num_qubits
     if shard_runner is None:
-        solver = RemoteExecutor(num_qubits, single_qubit_noise, two_qubit_noise, 1, rng=rng, seed=seed, **engine_options)
+        solver = executor or RemoteExecutor(num_qubits, single_qubit_noise, two_qubit_noise, 1, rng=rng, seed=seed, **engine_options)
         total = torch.zeros(dim, dtype=torch.float64, device="cuda")
         if count > 0:
-            solver.run_sum(instruction_list, start, count, device_probs=total.data_ptr(),
+            solver.run_sum(instruction_list, int(traj_offset) + start, count, device_probs=total.data_ptr(),
                            stream=torch.cuda.current_stream().cuda_stream)
     else:
         local = shard_runner(start, count) if count > 0 else np.zeros(dim)

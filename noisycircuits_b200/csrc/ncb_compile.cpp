@@ -1163,7 +1163,7 @@ static void build_blobs(Program& P) {
             sc.valid = fits ? 1 : 0;
             sc.npass = (int)passes.size(); sc.nops = nops; sc.ncoef = ncoef;
             // direct store of the last pass
-            if (fits && !passes.empty() && P.nbits > P.K && P.opt.direct && P.R == 3 && !P.has_dense2 && !P.has_dense4) {
+            if (fits && !passes.empty() && P.nbits > P.K && P.opt.direct && (P.R == 3 || P.R == 4) && P.mode != MODE_DENSITY && !P.has_dense2 && !P.has_dense4) {
                 const int Lb = std::min(std::max(P.opt.low_bits, 0), std::min(P.K - 4, P.nbits));
                 auto describe_pass = [&](const Pass& ps, uint32_t* goff, BitRuns& gruns) -> bool {
                     bool ok = Lb >= 2;

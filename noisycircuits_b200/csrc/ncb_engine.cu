@@ -339,6 +339,7 @@ struct Engine {
     }
     // ---- specialised kernels -----------------------------------------------------------------------------------
     bool specialize = false, spec_tried = false;
+    int specialize_mode = 0;          // ncb_options.specialize: 1 literal coefficients, 2 coefficients through the constant bank
     SpecOptions spec_opt;
     int spec_pool_cap = 0;
     std::vector<void*> spec_modules;
@@ -351,6 +352,8 @@ struct Engine {
         if (const char* e = getenv("NCB_SPEC_NBUF")) spec_opt.nbuf = atoi(e) == 1 ? 1 : 2;
         if (const char* e = getenv("NCB_SPEC_LOAD")) spec_opt.load = std::min(std::max(atoi(e), 0), 2);
         if (const char* e = getenv("NCB_SPEC_EVENTS")) spec_opt.events = atoi(e) != 0;
+        spec_opt.literal = specialize_mode == 2 ? 0 : 1;
+        if (const char* e = getenv("NCB_SPEC_LITERAL")) spec_opt.literal = atoi(e) != 0;
     }
     // Generates and compiles (nvcc, in parallel, into the cubin cache) the specialised kernels of this program; host only.
     // Returns the cache directory of this program ("" on failure: the interpreter stays in charge, and says so in
@@ -484,7 +487,7 @@ struct Engine {
                 return true;
             }
         }
-        if (st.direct) launch_direct(st.count, s, works + st.begin, st.seg);
+        if (st.direct && P.R == 3) launch_direct(st.count, s, works + st.begin, st.seg);      // (the interpreting direct kernel is R = 3)
         else launch_tile(st.count, s, works + st.begin, st.seg);
         return false;
     }
@@ -907,8 +910,9 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     } catch (...) { delete p; throw; }
     p->eng.device = device;
     p->eng.independent = options && options->independent_trajectories != 0;
-    p->eng.specialize = options && options->specialize == 1;
-    if (const char* e = getenv("NCB_SPECIALIZE")) p->eng.specialize = atoi(e) != 0;
+    p->eng.specialize_mode = options ? options->specialize : 0;
+    if (const char* e = getenv("NCB_SPECIALIZE")) p->eng.specialize_mode = atoi(e);
+    p->eng.specialize = p->eng.specialize_mode == 1 || p->eng.specialize_mode == 2;
     *out = p;
     return NCB_OK;
     NCB_CATCH

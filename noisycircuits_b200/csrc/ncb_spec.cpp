@@ -9,6 +9,11 @@ namespace ncb {
 
 namespace {
 
+std::string lit(double v) {            // exact literal
+    char b[64];
+    std::snprintf(b, sizeof b, "%a", v);
+    return b;
+}
 std::string hex(uint32_t v) {
     char b[32];
     std::snprintf(b, sizeof b, "0x%xu", v);
@@ -48,33 +53,36 @@ BlobView view_blob(const Program& P, int seg) {
 }
 
 bool lean_tiled(const Program& P) {
-    return P.mode != MODE_DENSITY && P.R == 3 && !P.has_dense2 && !P.has_dense4 && P.nbits > P.K;
+    return P.mode != MODE_DENSITY && (P.R == 3 || P.R == 4) && !P.has_dense2 && !P.has_dense4 && P.nbits > P.K;
 }
 
-// the constant-bank fast list of pass p (whole pass, no jump inside): coefficients C.c[..], tables in the staged pool
-bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R) {
+// the fast list of pass p (whole pass, no jump inside): coefficients as literals or C.c[..], tables in the staged pool
+bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool literal) {
     const PassHot& ph = sc.pass[p];
+    auto coef = [&](int i) { return literal ? lit(sc.coef[i]) : "C.c[" + std::to_string(i) + "]"; };
     for (int i = ph.fop_begin; i < ph.fop_end; ++i) {
         const Op& op = sc.ops[i];
-        const int ls = op_lean_sel(op);
+        const int kind = op_kind(op), ls = op_lean_sel(op);
         auto rx = [&](int bit, int at) {
-            o << "            spec_rx<" << R << ", " << bit << ">(a, C.c[" << at << "], C.c[" << at + 1 << "], C.c[" << at + 2 << "], C.c[" << at + 3 << "]);\n";
+            o << "            spec_rx<" << R << ", " << bit << ">(a, " << coef(at) << ", " << coef(at + 1) << ", " << coef(at + 2) << ", " << coef(at + 3) << ");\n";
         };
-        if (ls < 8) {
+        if (kind == OPK_DIAG) {
             if (op.mat < 0 || (op.mat & 1)) return false;      // (phase tables are complex-aligned entries of the staged pool)
-            o << "            spec_diag<" << R << ", " << ls << ">(a, jb" << p << ", pool + " << op.mat / 2 << ", " << hex(op.rbs & 0xffffu) << ", "
+            o << "            spec_diag<" << R << ", " << op_regmask(op) << ">(a, jb" << p << ", pool + " << op.mat / 2 << ", " << hex(op.rbs & 0xffffu) << ", "
               << hex(op.midx_lo) << ", " << hex(op.rbs >> 16) << ", " << hex(op.midx_hi) << ", " << (unsigned)op_tmask(op) << "u);\n";
-        } else if (ls < 11) {
-            rx(ls - 8, op.mat);
-        } else if (ls < 14) {
-            o << "            spec_u<" << R << ", " << ls - 11 << ">(a";
-            for (int k = 0; k < 8; ++k) o << ", C.c[" << op.mat + k << "]";
-            o << ");\n";
-        } else if (ls == LSEL_X3) {
+        } else if (kind == OPK_RX1 && R == 3 && ls == LSEL_X3) {      // fused rotations of the lean fast list (R = 3 only)
             rx(0, op.mat); rx(1, op.mat + 4); rx(2, op.mat + 8);
-        } else {
+        } else if (kind == OPK_RX1 && R == 3 && ls >= LSEL_X2 && ls < LSEL_X3) {
             const int pair = ls - LSEL_X2;                      // (0,1) (0,2) (1,2)
             rx(pair == 2 ? 1 : 0, op.mat); rx(pair == 0 ? 1 : 2, op.mat + 4);
+        } else if (kind == OPK_RX1) {
+            rx(op_rb(op, 0), op.mat);
+        } else if (kind == OPK_DENSE1) {
+            o << "            spec_u<" << R << ", " << op_rb(op, 0) << ">(a";
+            for (int k = 0; k < 8; ++k) o << ", " << coef(op.mat + k);
+            o << ");\n";
+        } else {
+            return false;
         }
     }
     return true;
@@ -137,7 +145,7 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
             for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ph.regoff_swz[m] << "];\n";
             if (last && nbuf == 1) o << "            __syncthreads();\n            if (tn < total) issue_load(tn, buf0);\n";
             if (last && nbuf == 2) o << "            __syncthreads();            // this buffer is refilled at the top of the next iteration\n";
-            if (!emit_fast_ops(o, sc, p, R)) return false;
+            if (!emit_fast_ops(o, sc, p, R, opt.literal != 0)) return false;
             if (last) {
                 for (int m = 0; m < NA; ++m) o << "            st_stream(dst + (gj_last | " << hex(sc.goff_last[m]) << "), a[" << m << "]);\n";
             } else {
@@ -182,7 +190,7 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
             if (nbuf == 1 && npass > 1) o << "            __syncthreads();            // every thread holds its amplitudes: the buffer is free for the next tile\n";
             if (load == 2) o << "            if (tn < total) gload(tn, nx);\n";
         }
-        if (!emit_fast_ops(o, sc, p, R)) return false;
+        if (!emit_fast_ops(o, sc, p, R, opt.literal != 0)) return false;
         if (last) {
             for (int m = 0; m < NA; ++m) o << "            st_stream(dst + (gj_last | " << hex(sc.goff_last[m]) << "), a[" << m << "]);\n";
         } else {
@@ -371,7 +379,7 @@ int spec_ctas_per_sm(const Program& P, const SpecOptions& opt) {
     }
     const int nbuf = opt.nbuf == 1 ? 1 : 2;
     const int by_smem = (int)((227 * 1024) / ((size_t)nbuf * (16u << P.K) + (size_t)pool_cap + 2048));
-    const int by_regs = 65536 / (threads * 64);
+    const int by_regs = 65536 / (threads * (P.R == 4 ? 128 : 64));
     return std::max(1, std::min({by_smem, by_regs, 8}));
 }
 

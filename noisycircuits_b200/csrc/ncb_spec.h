@@ -9,11 +9,16 @@ namespace ncb {
 struct SpecOptions {
     int nbuf = 2;     // shared-memory tile buffers of a whole-segment kernel (2: a tile's passes never wait for the previous
                       // tile's last reads)
-    int load = 2;     // how a whole-segment kernel gets its tile: 0 staged in shared memory with cp.async (as the interpreting
+    int load = 0;     // how a whole-segment kernel gets its tile: 0 staged in shared memory with cp.async (as the interpreting
                       // direct kernel does); 1 the first pass loads HBM -> registers (no staging, one barrier and one
                       // shared-memory round trip less); 2 like 1, and the next tile's loads are issued into a second register
                       // set when the last pass starts, so they overlap its arithmetic and stores
     int events = 1;   // 1: also generate ncb_seg_<k>_ev, the kernel of the works that carry a jump event (pieces of a segment)
+    int literal = 1;  // 1: gate coefficients are written into the source as exact literals (ptxas materialises them next to
+                      // their use; the cubin then belongs to this circuit AND these angles); 0: they are read from the
+                      // SpecCoef kernel parameter (constant bank), so the source -- and the cubin cache key -- depends on the
+                      // circuit's structure only and a parameter sweep compiles once (measured 13 % slower: ptxas hoists all
+                      // constant loads out of the tile loop and pays for it in registers)
 };
 
 // true when segment `seg` of P can run in a specialised whole-segment kernel (lean program, tiled, valid constant-bank

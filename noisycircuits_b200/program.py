@@ -132,7 +132,7 @@ class Program:
         self.packed = packed
         self.mode = mode
         opts = _lib.NcbOptions(tile_bits, reg_bits, low_bits, fuse, device, int(bool(strict_order)),
-                               int(bool(independent_trajectories)), int(bool(specialize)))
+                               int(bool(independent_trajectories)), 2 if specialize in (2, "parametric") else int(bool(specialize)))
         _lib.check(_lib.lib().ncb_program_create(C.byref(packed.struct), mode, C.byref(opts), C.byref(self._h)))
         self.num_qubits = packed.num_qubits
         self.num_instructions = packed.num_instructions

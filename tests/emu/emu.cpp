@@ -166,7 +166,7 @@ void run_plan(const Program& P, const BatchPlan& plan, int B, std::vector<cplx>&
         if (st.kind == 0) {
             for (int i = 0; i < st.count; ++i) {
                 const Work& w = plan.works[st.begin + i];
-                if (st.direct) { emulate_direct_work(P, w, st.seg, states); continue; }
+                if (st.direct && P.R == 3) { emulate_direct_work(P, w, st.seg, states); continue; }      // (as Engine::launch_step)
                 if (P.R == 4) emulate_work<4>(P, w, st.seg, states, red_part, norm_part, decisions);
                 else emulate_work<3>(P, w, st.seg, states, red_part, norm_part, decisions);
             }

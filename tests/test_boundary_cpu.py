@@ -120,18 +120,21 @@ def test_specialised_kernel_sources_compile_for_sm_100a(tmp_path, monkeypatch):
     monkeypatch.setenv("NCB_SPEC_CACHE", str(tmp_path))
     n = 13
     instr = circuits.heron_layered(n, 3, circuits.coupled_pairs(tq, n), seed=2)
-    prog = Program(PackedCircuit(n, instr, sq, tq), tile_bits=9, specialize=True)
+    prog = Program(PackedCircuit(n, instr, sq, tq), tile_bits=9, specialize="parametric")
     src = prog.specialized_source()
     nseg = prog.query(4)
     # per segment: the whole-segment kernel and the kernel of the works that carry jump events
     assert src.count('extern "C" __global__') == 2 * nseg and src.count("_ev(DevProgram") == nseg
-    assert "spec_diag<" in src and "st_stream(dst" in src and "ld_stream(st" in src
+    assert "spec_diag<" in src and "st_stream(dst" in src
     assert "switch" not in src and "sc." not in src             # no interpreter left in the generated code
     assert "C.c[" in src and "0x1p" not in src                  # coefficients come from the constant bank, not as literals
     # ... so the source (and the cubin cache key) depends on the circuit's structure only: other angles, same kernels
     instr2 = [[g, q, (t * 0.7 + 0.1 if g in ("rx", "rz", "rzz") else t)] for g, q, t in instr]
-    prog2 = Program(PackedCircuit(n, instr2, sq, tq), tile_bits=9, specialize=True)
+    prog2 = Program(PackedCircuit(n, instr2, sq, tq), tile_bits=9, specialize="parametric")
     assert prog2.specialized_source() == src
+    # specialize=True: coefficients as exact literals (the fastest code; one cubin set per parameter set)
+    lit = Program(PackedCircuit(n, instr, sq, tq), tile_bits=9, specialize=True).specialized_source()
+    assert "C.c[" not in lit and "0x1." in lit and lit != Program(PackedCircuit(n, instr2, sq, tq), tile_bits=9, specialize=True).specialized_source()
     assert prog.specialize_build()
     cubins = [f for d, _, fs in os.walk(tmp_path) for f in fs if f.endswith(".cubin")]
     assert len(cubins) == (nseg + 3) // 4
