@@ -3,8 +3,20 @@
 // code (the product) and as plain C++ (tests/emu: a thread-by-thread emulation used only to test the host planner
 // and the index maps on machines without a GPU).
 #pragma once
+#if defined(__CUDACC_RTC__)
+// in-process compilation of the generated kernels (NVRTC): no host headers
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <math.h>
 #include <stdint.h>
+#endif
 
 #if defined(__CUDACC__)
 #define NCB_HD __host__ __device__ __forceinline__

@@ -111,6 +111,66 @@ struct DriverApi {
 };
 static DriverApi g_drv;
 
+// NVRTC (resolved with dlopen as well): the generated kernels are compiled IN PROCESS -- no nvcc binary, no header files on
+// disk (the device headers are embedded in the library, embed_headers.py), no child processes.
+extern "C" {
+extern const int ncb_embedded_count;
+extern const char* const ncb_embedded_names[];
+extern const char* const ncb_embedded_sources[];
+}
+struct NvrtcApi {
+    void* lib = nullptr;
+    bool tried = false;
+    int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+    int (*GetCUBINSize)(void*, size_t*) = nullptr;
+    int (*GetCUBIN)(void*, char*) = nullptr;
+    int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+    int (*GetProgramLog)(void*, char*) = nullptr;
+    int (*DestroyProgram)(void**) = nullptr;
+    bool load() {
+        if (tried) return lib != nullptr;
+        tried = true;
+        std::vector<std::string> names;
+        if (const char* e = getenv("NCB_NVRTC_LIB")) names.push_back(e);
+        for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.13"}) names.push_back(n);
+        for (const std::string& n : names) {
+            lib = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        CreateProgram = (decltype(CreateProgram))dlsym(lib, "nvrtcCreateProgram");
+        CompileProgram = (decltype(CompileProgram))dlsym(lib, "nvrtcCompileProgram");
+        GetCUBINSize = (decltype(GetCUBINSize))dlsym(lib, "nvrtcGetCUBINSize");
+        GetCUBIN = (decltype(GetCUBIN))dlsym(lib, "nvrtcGetCUBIN");
+        GetProgramLogSize = (decltype(GetProgramLogSize))dlsym(lib, "nvrtcGetProgramLogSize");
+        GetProgramLog = (decltype(GetProgramLog))dlsym(lib, "nvrtcGetProgramLog");
+        DestroyProgram = (decltype(DestroyProgram))dlsym(lib, "nvrtcDestroyProgram");
+        if (!(CreateProgram && CompileProgram && GetCUBINSize && GetCUBIN && GetProgramLogSize && GetProgramLog && DestroyProgram)) {
+            dlclose(lib); lib = nullptr;
+        }
+        return lib != nullptr;
+    }
+    // source -> cubin for sm_100a; returns false (with the compiler's log) on failure.  Thread safe per call.
+    bool compile(const std::string& src, const std::string& name, std::string& cubin, std::string& log) {
+        void* prog = nullptr;
+        if (CreateProgram(&prog, src.c_str(), name.c_str(), ncb_embedded_count, ncb_embedded_sources, ncb_embedded_names) != 0) { log = "nvrtcCreateProgram failed"; return false; }
+        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+        const int rc = CompileProgram(prog, 3, opts);
+        size_t n = 0;
+        if (GetProgramLogSize(prog, &n) == 0 && n > 1) { log.resize(n); GetProgramLog(prog, &log[0]); }
+        bool ok = rc == 0;
+        if (ok) {
+            size_t cn = 0;
+            ok = GetCUBINSize(prog, &cn) == 0 && cn > 0;
+            if (ok) { cubin.resize(cn); ok = GetCUBIN(prog, &cubin[0]) == 0; }
+        }
+        DestroyProgram(&prog);
+        return ok;
+    }
+};
+static NvrtcApi g_nvrtc;
+
 static std::string build_stamp() {
     uint64_t h = 1469598103934665603ull;
     for (const char* c = __DATE__ " " __TIME__; *c; ++c) { h ^= (unsigned char)*c; h *= 1099511628211ull; }
@@ -348,7 +408,8 @@ struct Engine {
     static constexpr int SPEC_PER_PART = 4;                  // segments per translation unit
     void read_spec_options() {
         spec_opt = SpecOptions();
-        if (P.K >= 12) spec_opt.nbuf = 1;            // two 64 KB buffers would leave one CTA per SM
+        if (P.K >= 12 || P.R == 4) spec_opt.nbuf = 1;   // K = 12: two 64 KB buffers would leave one CTA per SM; R = 4 (128-thread
+                                                        // CTAs): four single-buffered CTAs per SM beat three double-buffered ones
         if (const char* e = getenv("NCB_SPEC_NBUF")) spec_opt.nbuf = atoi(e) == 1 ? 1 : 2;
         if (const char* e = getenv("NCB_SPEC_LOAD")) spec_opt.load = std::min(std::max(atoi(e), 0), 2);
         if (const char* e = getenv("NCB_SPEC_EVENTS")) spec_opt.events = atoi(e) != 0;
@@ -378,8 +439,15 @@ struct Engine {
         for (int k = 0; k < nparts; ++k)
             if (!exists(dir + "/part" + std::to_string(k) + ".cubin")) todo.push_back(k);
         if (!todo.empty()) {
+            // compiler: NVRTC in process (default); NCB_SPEC_COMPILER=nvcc runs the nvcc binary instead (needs the toolkit
+            // and this library's csrc/ headers on disk)
+            const char* want = getenv("NCB_SPEC_COMPILER");
+            bool use_nvrtc = !(want && std::string(want) == "nvcc") && g_nvrtc.load();
             const std::string nvcc = getenv("NCB_NVCC") ? getenv("NCB_NVCC") : "/usr/local/cuda/bin/nvcc";
-            if (!exists(nvcc)) { if (verbose) fprintf(stderr, "[ncb] specialised kernels: %s not found\n", nvcc.c_str()); return ""; }
+            if (!use_nvrtc && !exists(nvcc)) {
+                if (verbose) fprintf(stderr, "[ncb] specialised kernels: neither libnvrtc nor %s is usable\n", nvcc.c_str());
+                return "";
+            }
             std::atomic<int> next{0}, failed{0};
             auto worker = [&]() {
                 for (;;) {
@@ -388,19 +456,32 @@ struct Engine {
                     const int k = todo[i];
                     // several processes (one per GPU) may build the same cache at once: private temporaries, atomic renames
                     const std::string base = dir + "/part" + std::to_string(k), mine = base + "." + std::to_string((long)getpid());
-                    { std::ofstream f(mine + ".cu"); f << spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_opt); }
-                    const std::string cmd = nvcc + " -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -I" + libdir + "/csrc -Xptxas -v -cubin -o " +
-                                            mine + ".tmp " + mine + ".cu > " + mine + ".log 2>&1 && mv " + mine + ".tmp " + base + ".cubin && mv " +
-                                            mine + ".cu " + base + ".cu && mv " + mine + ".log " + base + ".log";
-                    if (system(cmd.c_str()) != 0) failed.fetch_add(1);
+                    const std::string src = spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_opt);
+                    { std::ofstream f(mine + ".cu"); f << src; }
+                    bool ok;
+                    if (use_nvrtc) {
+                        std::string cubin, log;
+                        ok = g_nvrtc.compile(src, "part" + std::to_string(k) + ".cu", cubin, log);
+                        { std::ofstream f(mine + ".log"); f << log; }
+                        if (ok) { std::ofstream f(mine + ".tmp", std::ios::binary); f.write(cubin.data(), (std::streamsize)cubin.size()); ok = (bool)f; }
+                        if (ok) ok = rename((mine + ".tmp").c_str(), (base + ".cubin").c_str()) == 0;
+                        rename((mine + ".cu").c_str(), (base + ".cu").c_str());
+                        rename((mine + ".log").c_str(), (base + ".log").c_str());
+                    } else {
+                        const std::string cmd = nvcc + " -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -I" + libdir + "/csrc -Xptxas -v -cubin -o " +
+                                                mine + ".tmp " + mine + ".cu > " + mine + ".log 2>&1 && mv " + mine + ".tmp " + base + ".cubin && mv " +
+                                                mine + ".cu " + base + ".cu && mv " + mine + ".log " + base + ".log";
+                        ok = system(cmd.c_str()) == 0;
+                    }
+                    if (!ok) failed.fetch_add(1);
                 }
             };
             const int nthreads = std::max(1, std::min<int>({(int)todo.size(), plan_threads(), 16}));
             std::vector<std::thread> pool;
             for (int i = 0; i < nthreads; ++i) pool.emplace_back(worker);
             for (auto& t : pool) t.join();
-            if (verbose) fprintf(stderr, "[ncb] specialised kernels: compiled %zu parts with %d threads (%d failed) into %s\n", todo.size(), nthreads,
-                                 failed.load(), dir.c_str());
+            if (verbose) fprintf(stderr, "[ncb] specialised kernels: compiled %zu parts with %s on %d threads (%d failed) into %s\n", todo.size(),
+                                 use_nvrtc ? "NVRTC" : "nvcc", nthreads, failed.load(), dir.c_str());
             if (failed.load()) return "";
         }
         return dir;
@@ -878,8 +959,16 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     // default register bits: 3; 4 when the program carries 3-4 bit dense operators (density-matrix superoperators,
     // 3-4 qubit unitaries)
     opt.reg_bits = mode == NCB_MODE_DENSITY ? 4 : 3;
+    bool need4 = false;
     for (int g = 0; g < circuit->num_instructions; ++g)
-        if (circuit->opcode[g] == NCB_UNITARY && circuit->unitary_nq && circuit->unitary_nq[g] >= 3) opt.reg_bits = 4;
+        if (circuit->opcode[g] == NCB_UNITARY && circuit->unitary_nq && circuit->unitary_nq[g] >= 3) { opt.reg_bits = 4; need4 = true; }
+    // generated kernels (ncb_options.specialize) of lean tiled MCWF programs run best with R = 4 (16 amplitudes per thread,
+    // 128-thread CTAs, a quarter fewer passes: measured +10 % on the 20-qubit workload); the interpreting kernels with R = 3
+    int spec_mode = options ? options->specialize : 0;
+    if (const char* e = getenv("NCB_SPECIALIZE")) spec_mode = atoi(e);
+    const bool reg_explicit = (options && options->reg_bits > 0) || getenv("NCB_REG_BITS") != nullptr;
+    const bool auto4 = mode == NCB_MODE_MCWF && (spec_mode == 1 || spec_mode == 2) && !reg_explicit && !need4;
+    if (auto4) opt.reg_bits = 4;
     if (options) {
         if (options->tile_bits > 0) { opt.tile_bits = options->tile_bits; opt.resident_bits = options->tile_bits; }
         if (options->reg_bits > 0) opt.reg_bits = options->reg_bits;
@@ -902,6 +991,10 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     ncb_program* p = new ncb_program();
     try {
         compile_program(view_of(circuit), mode, opt, p->eng.P);
+        if (auto4 && (p->eng.P.has_dense2 || p->eng.P.has_dense4 || p->eng.P.nbits <= p->eng.P.K)) {
+            opt.reg_bits = 3;                       // not a program the generated kernels cover: back to the default geometry
+            compile_program(view_of(circuit), mode, opt, p->eng.P);
+        }
         if (p->eng.P.R == 3 && p->eng.P.has_dense2 && p->eng.P.K > 11) {     // the dense-4x4 kernels run 256 threads
             opt.tile_bits = 11;
             opt.resident_bits = std::min(opt.resident_bits, 11);             // (a 12-bit state then runs as two tiles)

@@ -13,7 +13,9 @@
 //   decide_kernel    branch decision of the state-dependent jump events from the reduced density matrices.
 //   accumulate / norm / diag / measurement-error kernels: the tail of the path.
 #pragma once
+#if !defined(__CUDACC_RTC__)
 #include <cuda_runtime.h>
+#endif
 
 #include "ncb_common.h"
 
