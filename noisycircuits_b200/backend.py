@@ -118,13 +118,15 @@ def execute_sharded(num_qubits, instruction_list, single_qubit_noise, two_qubit_
     return postprocess(probs, num_qubits, qubits, measurement_error, 1, apply_measurement_error)
 
 
-def install(name: str = "b200") -> bool:
+def install(name: str = "b200", cache_noise_tables: bool = False) -> bool:
     """Registers this package as ``NoisyCircuits.utils.<name>`` and teaches ``QuantumCircuit`` the new
     ``sim_backend``.  Returns False when NoisyCircuits is not importable (nothing is changed then).
 
     The reference selects its in-process (non-Ray) path by string equality with "custom"
     (QuantumCircuit.py:410), so ``execute`` is wrapped: for the new back-end it runs the same call chain with this
     package's RemoteExecutor (see INTEGRATION.md for the three-line upstream patch that makes the wrapper unnecessary).
+
+    cache_noise_tables: also cache the noise operators ``BuildModel`` builds at construction on disk (content addressed).
     """
     try:
         from NoisyCircuits.QuantumCircuit import QuantumCircuit as QC
@@ -132,6 +134,19 @@ def install(name: str = "b200") -> bool:
         return False
     pkg = sys.modules[__package__]
     sys.modules[f"NoisyCircuits.utils.{name}"] = pkg
+    if cache_noise_tables:
+        # QuantumCircuit.__init__ rebuilds the noise operators with joblib on every construction (QuantumCircuit.py:149-157):
+        # put the content-addressed on-disk cache in front of the reference's builder (cache.cached_qubit_gate_model)
+        from NoisyCircuits.utils.BuildQubitGateModel import BuildModel
+        from . import cache
+        if not getattr(BuildModel.build_qubit_gate_model, "_ncb200", False):
+            build = BuildModel.build_qubit_gate_model
+
+            def build_cached(self):
+                return cache.cached_qubit_gate_model(self, build)
+
+            build_cached._ncb200 = True
+            BuildModel.build_qubit_gate_model = build_cached
     if name not in QC.available_sim_backends:
         QC.available_sim_backends.append(name)
     if getattr(QC.execute, "_ncb200", False):

@@ -11,7 +11,9 @@
 #include <thread>
 #include <atomic>
 #include <dlfcn.h>
+#include <dirent.h>
 #include <sys/stat.h>
+#include <sys/time.h>
 #include <unistd.h>
 #include <fstream>
 #include <sstream>
@@ -416,7 +418,51 @@ struct Engine {
         spec_opt.literal = specialize_mode == 2 ? 0 : 1;
         if (const char* e = getenv("NCB_SPEC_LITERAL")) spec_opt.literal = atoi(e) != 0;
     }
-    // Generates and compiles (nvcc, in parallel, into the cubin cache) the specialised kernels of this program; host only.
+    // Cubin cache: $NCB_SPEC_CACHE, else <library dir>/_speccache, else (read-only installation) ~/.cache/noisycircuits_b200/
+    // speccache, else the temporary directory.  One sub-directory per (generated source, library build); the least recently
+    // used ones are removed beyond NCB_SPEC_CACHE_MAX (default 64) entries.
+    static std::string spec_cache_root(const std::string& libdir) {
+        std::vector<std::string> cands;
+        if (const char* e = getenv("NCB_SPEC_CACHE")) cands.push_back(e);
+        else {
+            cands.push_back(libdir + "/_speccache");
+            if (const char* h = getenv("HOME")) cands.push_back(std::string(h) + "/.cache/noisycircuits_b200/speccache");
+            const char* t = getenv("TMPDIR");
+            cands.push_back(std::string(t ? t : "/tmp") + "/noisycircuits_b200_speccache");
+        }
+        for (const std::string& c : cands) {
+            // mkdir -p
+            for (size_t k = 1; k <= c.size(); ++k)
+                if (k == c.size() || c[k] == '/') mkdir(c.substr(0, k).c_str(), 0755);
+            if (access(c.c_str(), W_OK | X_OK) == 0) return c;
+        }
+        return "";
+    }
+    static void spec_cache_evict(const std::string& cache) {
+        size_t keep = 64;
+        if (const char* e = getenv("NCB_SPEC_CACHE_MAX")) keep = (size_t)std::max(1, atoi(e));
+        std::vector<std::pair<time_t, std::string>> dirs;
+        if (DIR* d = opendir(cache.c_str())) {
+            while (dirent* e = readdir(d)) {
+                if (e->d_name[0] == '.') continue;
+                const std::string p = cache + "/" + e->d_name;
+                struct stat st;
+                if (stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) dirs.push_back({st.st_mtime, p});
+            }
+            closedir(d);
+        }
+        if (dirs.size() < keep) return;
+        std::sort(dirs.begin(), dirs.end());
+        for (size_t i = 0; i + keep <= dirs.size(); ++i) {          // oldest first; leaves keep - 1 (a new one is about to be added)
+            if (DIR* d = opendir(dirs[i].second.c_str())) {
+                while (dirent* e = readdir(d))
+                    if (e->d_name[0] != '.') unlink((dirs[i].second + "/" + e->d_name).c_str());
+                closedir(d);
+            }
+            rmdir(dirs[i].second.c_str());
+        }
+    }
+    // Generates and compiles (NVRTC, in parallel, into the cubin cache) the specialised kernels of this program; host only.
     // Returns the cache directory of this program ("" on failure: the interpreter stays in charge, and says so in
     // ncb_run_params.out_spec_launches).
     std::string spec_build() {
@@ -426,11 +472,17 @@ struct Engine {
         if (!nsupported) return "";
         read_spec_options();
         const std::string libdir = this_library_dir();
-        std::string cache = getenv("NCB_SPEC_CACHE") ? getenv("NCB_SPEC_CACHE") : libdir + "/_speccache";
+        const std::string cache = spec_cache_root(libdir);
+        if (cache.empty()) { if (verbose) fprintf(stderr, "[ncb] specialised kernels: no writable cache directory\n"); return ""; }
         // (the cubins depend on the kernel headers too: a rebuilt library starts a new cache generation)
         const std::string dir = cache + "/" + spec_key(P, spec_opt) + "-" + build_stamp();
-        mkdir(cache.c_str(), 0755);
-        mkdir(dir.c_str(), 0755);
+        struct stat st_dir;
+        if (stat(dir.c_str(), &st_dir) != 0) {
+            spec_cache_evict(cache);
+            mkdir(dir.c_str(), 0755);
+        } else {
+            utimes(dir.c_str(), nullptr);            // most recently used
+        }
         const int nseg = (int)P.segs.size();
         const int per = SPEC_PER_PART;
         const int nparts = (nseg + per - 1) / per;

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _lib
+from . import _lib, cache
 from .program import PackedCircuit, Program
 
 _RNG = {"philox": _lib.RNG_PHILOX, "reference": _lib.RNG_MT19937_REFERENCE}
@@ -38,13 +38,13 @@ def _marginal_little_endian(probs: np.ndarray, num_qubits: int, keep) -> np.ndar
 
 
 def _fingerprint(instruction_list):
-    """Content key of an instruction list (recompile only when the circuit changes)."""
+    """Content key of an instruction list (compared as a whole: no hash collisions)."""
     items = []
     for name, qubits, param in instruction_list:
         if isinstance(param, np.ndarray):
             param = param.tobytes()
         items.append((name, tuple(qubits), param))
-    return hash(tuple(items))
+    return tuple(items)
 
 
 class RemoteExecutor:
@@ -74,12 +74,20 @@ class RemoteExecutor:
 
     def _program(self, instruction_list, traj_count: int = 0) -> Program:
         opts = dict(self.engine_options)
-        opts.setdefault("specialize", traj_count >= self.SPECIALIZE_FROM)
-        key = (_fingerprint(instruction_list), bool(opts["specialize"]))
+        # automatic choice: kernels generated for the circuit's STRUCTURE ("parametric": the cubins of a gate skeleton are
+        # shared by every parameter set, so a training loop compiles once); specialize=True asks for literal coefficients
+        opts.setdefault("specialize", "parametric" if traj_count >= self.SPECIALIZE_FROM else False)
+        # fast path: the same list object contents and the same noise dictionaries as last time (in-place edits of the
+        # dictionaries are not seen here -- call invalidate()); otherwise the packed bytes decide (cache.get_program)
+        key = (_fingerprint(instruction_list), str(opts["specialize"]), id(self.single_qubit_noise), id(self.two_qubit_noise))
         if self._cache[0] != key:
             packed = PackedCircuit(self.num_qubits, instruction_list, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
-            self._cache = (key, Program(packed, _lib.MODE_MCWF, **opts))
+            self._cache = (key, cache.get_program(packed, _lib.MODE_MCWF, **opts))
         return self._cache[1]
+
+    def invalidate(self) -> None:
+        """Forget the compiled program (after editing the noise dictionaries in place)."""
+        self._cache = (None, None)
 
     def run_sum(self, instruction_list, traj_begin: int, traj_count: int, uniforms=None, device_probs=None,
                 accumulate=False, stream=0):

@@ -193,3 +193,39 @@ def test_generated_kernels_compile_with_nvcc_too(tmp_path, monkeypatch):
     assert prog.specialize_build()
     logs = [os.path.join(d, f) for d, _, fs in os.walk(tmp_path) for f in fs if f.endswith(".log")]
     assert logs and "ptxas info" in open(logs[0]).read()
+
+
+def test_program_cache_is_content_addressed(heron_noise):
+    """cache.get_program: the packed bytes (gates, angles, the Kraus operators used) are the key -- a fresh RemoteExecutor
+    on the same circuit reuses the compiled program, another angle or another Kraus operator does not."""
+    from noisycircuits_b200 import cache
+    from noisycircuits_b200.solvers import RemoteExecutor
+    sq, tq, _, _ = heron_noise
+    n = 6
+    instr = circuits.heron_layered(n, 2, circuits.coupled_pairs(tq, n), seed=5)
+    cache.clear_programs()
+    a = RemoteExecutor(n, sq, tq, 1)._program(instr)
+    b = RemoteExecutor(n, sq, tq, 1)._program([list(x) for x in instr])              # new executor, equal content
+    assert a is b and cache.stats["program_hits"] >= 1
+    other = [list(x) for x in instr]
+    other[0] = ["rx", other[0][1], 0.123]
+    assert RemoteExecutor(n, sq, tq, 1)._program(other) is not a
+    sq2 = {q: {g: [np.array(k) for k in ops] for g, ops in gates.items()} for q, gates in sq.items()}
+    g0 = instr[0][0]                                     # a gate the circuit really applies on qubit 0
+    sq2[0][g0][0] = sq2[0][g0][0] * 0.999
+    assert RemoteExecutor(n, sq2, tq, 1)._program(instr) is not a
+    assert RemoteExecutor(n, sq, tq, 1, strict_order=True)._program(instr) is not a   # options are part of the key
+
+
+def test_spec_cache_eviction(tmp_path, monkeypatch, heron_noise):
+    """The cubin cache keeps at most NCB_SPEC_CACHE_MAX program directories (least recently used go first)."""
+    sq, tq, _, _ = heron_noise
+    monkeypatch.setenv("NCB_SPEC_CACHE", str(tmp_path))
+    monkeypatch.setenv("NCB_SPEC_CACHE_MAX", "2")
+    n = 13
+    for seed in range(3):
+        instr = circuits.heron_layered(n, 1, circuits.coupled_pairs(tq, n), seed=seed)[:6 + seed]
+        prog = Program(PackedCircuit(n, instr, sq, tq), tile_bits=9, specialize=True)
+        if not prog.specialize_build():
+            pytest.skip("no libnvrtc / nvcc on this machine")
+    assert len([d for d in os.listdir(tmp_path) if os.path.isdir(os.path.join(tmp_path, d))]) == 2

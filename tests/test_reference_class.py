@@ -93,3 +93,40 @@ def test_reference_class_hands_the_golden_inputs_to_the_b200_backend(monkeypatch
     qc2.CX(0, 1)
     ref = qc2.execute(qubits=[0, 1], num_trajectories=50, num_cores=1)
     assert ref.shape == (4,) and abs(ref.sum() - 1) < 1e-9 and not seen.get("n") == 2
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference checkout")
+def test_noise_operator_cache_in_front_of_the_reference_builder(tmp_path, monkeypatch):
+    """install(cache_noise_tables=True): the second construction of a QuantumCircuit on the same noise model takes its
+    noise operators from the content-addressed on-disk cache instead of re-running BuildModel (QuantumCircuit.py:149-157)."""
+    paths = [os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, "oracle", "_ref"), os.path.join(REF, "src")]
+    sys.path[:0] = paths
+    monkeypatch.setenv("PYTHONPATH", os.pathsep.join(paths + [ROOT, os.environ.get("PYTHONPATH", "")]))
+    monkeypatch.setenv("NCB_CACHE_DIR", str(tmp_path))
+    try:
+        from NoisyCircuits.QuantumCircuit import QuantumCircuit
+    except Exception as exc:
+        pytest.skip(f"reference package not importable: {exc}")
+    import noisycircuits_b200
+    from noisycircuits_b200 import cache
+    from noisycircuits_b200.calibration import create_noise_model
+    gates = [["rz", "rx", "sx", "x"], ["cz", "rzz"]]
+    assert noisycircuits_b200.install(cache_noise_tables=True)
+    nm = create_noise_model(os.path.join(REF, "noise_models", "Sample_Noise_Model_Heron_QPU.csv"), gates)
+    before = dict(cache.stats)
+    kw = dict(num_qubits=4, noise_model=nm, backend_qpu_type="heron", basis_gates=gates, sim_backend="b200", threshold=1e-6, verbose=False)
+    a = QuantumCircuit(**kw)
+    b = QuantumCircuit(**kw)
+    assert cache.stats["noise_misses"] == before["noise_misses"] + 1 and cache.stats["noise_hits"] == before["noise_hits"] + 1
+    assert len([f for f in os.listdir(tmp_path) if f.startswith("noise-")]) == 1
+    for q in a.single_qubit_error:
+        for g, ops in a.single_qubit_error[q].items():
+            assert all(np.array_equal(x, y) for x, y in zip(ops, b.single_qubit_error[q][g]))
+    for g in a.two_qubit_error:
+        for pair, ops in a.two_qubit_error[g].items():
+            assert all(np.array_equal(x, y) for x, y in zip(ops, b.two_qubit_error[g][pair]))
+    assert a.connectivity == b.connectivity
+    b.H(0); b.CX(0, 1)                                     # the decomposer got its coupling map from the cached entry
+    assert len(b.instruction_list) > 0
+    c = QuantumCircuit(**dict(kw, threshold=1e-8))         # another threshold: another entry
+    assert cache.stats["noise_misses"] == before["noise_misses"] + 2 and c.threshold == 1e-8
