@@ -104,6 +104,12 @@ int ncb_version(void);
 /* Compilation is host-only (no CUDA call is made until a run function is called). */
 int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* options, ncb_program** out);
 void ncb_program_destroy(ncb_program* program);
+/* Replaces the program's circuit in place (same mode and options): the new circuit is compiled on the host and takes over
+ * the engine object -- device buffers, streams and, when the generated code does not change (ncb_options.specialize = 2: same
+ * gate skeleton, other angles), the loaded kernels are kept, so a parameter sweep (QNN training loop) pays a host compile
+ * and a table upload per circuit instead of a new engine.  Fails with NCB_E_INVALID when the new circuit compiles to another
+ * geometry (number of qubits, tile or register bits). */
+int ncb_program_update(ncb_program* program, const ncb_circuit* circuit);
 /* Human-readable plan (segments, tiles, passes) into buf; returns the number of bytes needed. */
 int64_t ncb_program_describe(const ncb_program* program, char* buf, int64_t len);
 

@@ -40,7 +40,7 @@ class NcbRunParams(C.Structure):
 
 
 # every symbol include/ncb200.h declares
-EXPORTS = ["ncb_last_error", "ncb_version", "ncb_program_create", "ncb_program_destroy", "ncb_program_describe",
+EXPORTS = ["ncb_last_error", "ncb_version", "ncb_program_create", "ncb_program_destroy", "ncb_program_update", "ncb_program_describe",
            "ncb_program_query", "ncb_program_order", "ncb_program_events", "ncb_program_reference_uniforms", "ncb_mcwf_run", "ncb_pure_run",
            "ncb_density_run", "ncb_apply_measurement_error", "ncb_apply_measurement_error_device",
            "ncb_execute_tail_device", "ncb_device_alloc", "ncb_device_free", "ncb_program_spec_build", "ncb_program_spec_source",
@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
         L.ncb_program_create.argtypes = [C.POINTER(NcbCircuit), C.c_int, C.POINTER(NcbOptions), C.POINTER(C.c_void_p)]
         L.ncb_program_destroy.argtypes = [C.c_void_p]
         L.ncb_program_destroy.restype = None
+        L.ncb_program_update.argtypes = [C.c_void_p, C.POINTER(NcbCircuit)]
         L.ncb_program_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.ncb_program_describe.restype = C.c_int64
         L.ncb_program_query.argtypes = [C.c_void_p, C.c_int]

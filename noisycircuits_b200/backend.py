@@ -69,12 +69,22 @@ def execute(num_qubits, instruction_list, single_qubit_noise, two_qubit_noise, m
     solver = executor or RemoteExecutor(num_qubits, single_qubit_noise, two_qubit_noise, num_cores, rng=rng, seed=seed, **engine_options)
     # the sum over trajectories stays on the device; marginal, read-out error and bit reversal run there too and only the
     # 2^len(qubits) result comes back
-    acc = simulator.DeviceBuffer(1 << num_qubits)
-    try:
-        solver.run_sum(instruction_list, int(traj_offset), num_trajectories, device_probs=acc.ptr)
-        return simulator.execute_tail_device(acc.ptr, num_qubits, qubits, measurement_error, 1.0 / float(num_trajectories))
-    finally:
-        acc.free()
+    acc = _accumulator(1 << num_qubits)
+    solver.run_sum(instruction_list, int(traj_offset), num_trajectories, device_probs=acc.ptr)
+    return simulator.execute_tail_device(acc.ptr, num_qubits, qubits, measurement_error, 1.0 / float(num_trajectories))
+
+
+_acc_cache = {}
+
+
+def _accumulator(count: int):
+    """Device accumulator float64[count], kept between calls (a cudaMalloc / cudaFree pair per execute() costs up to
+    100 ms next to a multi-GB state batch)."""
+    buf = _acc_cache.get(count)
+    if buf is None or not buf.ptr:
+        _acc_cache.clear()
+        buf = _acc_cache[count] = simulator.DeviceBuffer(count)
+    return buf
 
 
 def execute_sharded(num_qubits, instruction_list, single_qubit_noise, two_qubit_noise, measurement_error, qubits=None,

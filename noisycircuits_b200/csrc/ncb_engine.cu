@@ -10,6 +10,7 @@
 #include <string>
 #include <thread>
 #include <atomic>
+#include <mutex>
 #include <dlfcn.h>
 #include <dirent.h>
 #include <sys/stat.h>
@@ -247,18 +248,35 @@ struct Engine {
         if (!v.empty()) CK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     }
 
+    bool device_ready = false;       // device chosen, streams and events created (once); `uploaded`: the program's tables are on it
     void ensure_device() {
-        if (uploaded) { CK(cudaSetDevice(device)); return; }     // the caller may have switched devices since the upload
-        int count = 0;
-        cudaError_t e = cudaGetDeviceCount(&count);
-        if (e != cudaSuccess || count == 0)
-            throw CudaError(std::string("no usable CUDA device (") + cudaGetErrorString(e) + "): this engine has no CPU fallback");
-        if (device >= 0) CK(cudaSetDevice(device));
-        CK(cudaGetDevice(&device));
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, device));
-        sm_count = prop.multiProcessorCount;
-        smem_optin = prop.sharedMemPerBlockOptin;
+        if (device_ready) {
+            CK(cudaSetDevice(device));                           // the caller may have switched devices since
+        } else {
+            int count = 0;
+            cudaError_t e = cudaGetDeviceCount(&count);
+            if (e != cudaSuccess || count == 0)
+                throw CudaError(std::string("no usable CUDA device (") + cudaGetErrorString(e) + "): this engine has no CPU fallback");
+            if (device >= 0) CK(cudaSetDevice(device));
+            CK(cudaGetDevice(&device));
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, device));
+            sm_count = prop.multiProcessorCount;
+            smem_optin = prop.sharedMemPerBlockOptin;
+            for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&buf_free[i], cudaEventDisableTiming));
+            CK(cudaEventCreate(&t0));
+            CK(cudaEventCreate(&t1));
+            int lo_pri = 0, hi_pri = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+            CK(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_pri));
+            CK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
+            if (const char* e2 = getenv("NCB_DIRECT_CHUNK")) direct_chunk = atoi(e2);
+            if (const char* e2 = getenv("NCB_OVERLAP")) overlap_streams = atoi(e2) != 0;
+            d_counters.reserve(4);
+            device_ready = true;
+        }
+        if (uploaded) return;
         upload(d_ops, P.ops); upload(d_passes, P.passes); upload(d_segs, P.segs); upload(d_instrs, P.instrs);
         upload(d_chans, P.chans); upload(d_pool, P.pool); upload(d_noisy, P.noisy_instrs); upload(d_orig, P.orig); upload(d_blobs, P.blobs);
         d.ops = d_ops.p; d.passes = d_passes.p; d.segs = d_segs.p; d.instrs = d_instrs.p; d.chans = d_chans.p;
@@ -267,20 +285,24 @@ struct Engine {
         const size_t need = resident() ? resident_smem() : tile_launch_smem();
         if (need + 6 * 1024 > smem_optin)
             throw std::runtime_error("tile does not fit shared memory: need " + std::to_string(need) + " B, device offers " + std::to_string(smem_optin));
-        for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&buf_free[i], cudaEventDisableTiming));
-        CK(cudaEventCreate(&t0));
-        CK(cudaEventCreate(&t1));
-        {
-            int lo_pri = 0, hi_pri = 0;
-            CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-            CK(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_pri));
-            CK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
-            if (const char* e = getenv("NCB_DIRECT_CHUNK")) direct_chunk = atoi(e);
-            if (const char* e = getenv("NCB_OVERLAP")) overlap_streams = atoi(e) != 0;
-        }
-        d_counters.reserve(4);
         uploaded = true;
+    }
+    // A new circuit in the same engine object (ncb_program_update): device buffers, streams and -- when the generated code
+    // does not change (same structure, coefficients through the constant bank) -- the loaded kernels are kept.
+    std::string spec_key_loaded;
+    void replace_program(Program&& np) {
+        if (np.K != P.K || np.R != P.R || np.nbits != P.nbits || np.mode != P.mode)
+            throw std::runtime_error("ncb_program_update: the new circuit compiles to another geometry (qubits / tile / register bits): create a new program");
+        P = std::move(np);
+        uploaded = false;
+        tile_configured = false;
+        direct_ctas = 0;
+        if (spec_tried && (spec_key_loaded.empty() || spec_key(P, spec_opt) != spec_key_loaded)) {
+            for (void* m : spec_modules) if (g_drv.ModuleUnload) g_drv.ModuleUnload(m);
+            spec_modules.clear(); spec_fn.clear(); spec_ev_fn.clear();
+            spec_tried = false;
+            spec_key_loaded.clear();
+        }
     }
 
     // ---- kernel dispatch: three instantiations --------------------------------------------------------------
@@ -374,7 +396,8 @@ struct Engine {
         CK(cudaGetLastError());
     }
     // direct kernel (works that run a whole segment without an event; lean programs only)
-    int direct_ctas = 0, direct_chunk = 16;      // tiles per direct-kernel CTA: CTA turnover lets the (higher-priority) event chain in
+    int direct_ctas = 0, direct_chunk = 8;       // tiles per direct-kernel CTA: CTA turnover lets the (higher-priority) event chain in
+                                                 // (measured on the 20-qubit workload: 8 -> 2612, 16 -> 2557, 32 -> 2531, persistent -> slower)
     size_t direct_smem() const {
         return (size_t)tile_blob_cap + tile_smem() + (size_t)SC_MAX_PASSES * sizeof(unsigned short) * ((size_t)1 << (P.K - P.R));
     }
@@ -548,6 +571,7 @@ struct Engine {
         if (!g_drv.load()) { if (verbose) fprintf(stderr, "[ncb] specialised kernels: libcuda.so.1 not usable\n"); return; }
         const std::string dir = spec_build();
         if (dir.empty()) return;
+        spec_key_loaded = spec_key(P, spec_opt);
         const int nseg = (int)P.segs.size(), per = SPEC_PER_PART, nparts = (nseg + per - 1) / per;
         spec_pool_cap = 0;
         for (int sgi = 0; sgi < nseg; ++sgi) {
@@ -1065,6 +1089,17 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
 
 void ncb_program_destroy(ncb_program* program) { delete program; }
 
+int ncb_program_update(ncb_program* program, const ncb_circuit* circuit) {
+    if (!program || !circuit) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    Engine& E = program->eng;
+    Program np;
+    compile_program(view_of(circuit), E.P.mode, E.P.opt, np);
+    E.replace_program(std::move(np));
+    return NCB_OK;
+    NCB_CATCH
+}
+
 int64_t ncb_program_describe(const ncb_program* program, char* buf, int64_t len) {
     if (!program) return 0;
     const std::string s = describe_program(program->eng.P);
@@ -1231,11 +1266,19 @@ int ncb_execute_tail_device(const double* probabilities_device, int32_t num_qubi
     }
     cudaStream_t s = (cudaStream_t)stream;
     const long long nout = 1ll << nq;
-    double *a = nullptr, *b = nullptr;
-    CK(cudaMalloc(&a, sizeof(double) * nout));
-    if (cudaMalloc(&b, sizeof(double) * nout) != cudaSuccess) { cudaFree(a); throw std::runtime_error("out of device memory"); }
+    // scratch: kept between calls (cudaMalloc / cudaFree cost up to 100 ms each next to a multi-GB state batch -- measured)
+    static std::mutex tail_mutex;
+    static DevBuf<double> tail_scratch[2];
+    static int tail_device = -1;
+    std::lock_guard<std::mutex> lock(tail_mutex);
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev != tail_device) { tail_scratch[0] = DevBuf<double>(); tail_scratch[1] = DevBuf<double>(); tail_device = dev; }   // (per device; the old buffers stay with their device)
+    tail_scratch[0].reserve((size_t)nout);
+    tail_scratch[1].reserve((size_t)nout);
+    double *a = tail_scratch[0].p, *b = tail_scratch[1].p;
     int rc = NCB_OK;
-    try {
+    {
         int g, bl;
         grid_1d(nout, &g, &bl);
         marginal_kernel<<<g, bl, 0, s>>>(a, probabilities_device, num_qubits, keep, nq, scale);
@@ -1252,8 +1295,7 @@ int ncb_execute_tail_device(const double* probabilities_device, int32_t num_qubi
             CK(cudaMemcpyAsync(out, b, sizeof(double) * nout, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
         }
-    } catch (...) { cudaFree(a); cudaFree(b); throw; }
-    cudaFree(a); cudaFree(b);
+    }
     return rc;
     NCB_CATCH
 }

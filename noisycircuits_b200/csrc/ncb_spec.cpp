@@ -2,6 +2,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <algorithm>
 #include <sstream>
 
@@ -64,6 +65,13 @@ bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool
         const Op& op = sc.ops[i];
         const int kind = op_kind(op), ls = op_lean_sel(op);
         auto rx = [&](int bit, int at) {
+            // literal coefficients: a rotation with a vanishing diagonal (x = i rx(pi): cos(pi/2) = 6e-17) is written as the
+            // anti-diagonal operator it is -- half the FP64 instructions; the dropped terms are below 1e-15 of the kept ones
+            const double* c = sc.coef + at;
+            if (literal && std::fabs(c[0]) <= 1e-15 * std::fabs(c[1]) && std::fabs(c[3]) <= 1e-15 * std::fabs(c[2])) {
+                o << "            spec_xl<" << R << ", " << bit << ">(a, " << lit(c[1]) << ", " << lit(c[2]) << ");\n";
+                return;
+            }
             o << "            spec_rx<" << R << ", " << bit << ">(a, " << coef(at) << ", " << coef(at + 1) << ", " << coef(at + 2) << ", " << coef(at + 3) << ");\n";
         };
         if (kind == OPK_DIAG) {
@@ -273,8 +281,10 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
         o << "        if (" << ps.instr_lo << " < hi && " << ps.instr_hi << " > lo) {   // pass " << p << "\n"
           << "            cplx a[" << NA << "];\n";
         for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "];\n";
-        auto member = [&](const Op& op, const char* ind) {
-            o << ind << "if (" << op.instr << " >= lo && " << op.instr << " < hi) {\n";
+        // (hot: the operator stands alone in the list; cold: a member of a merged group, run one by one only when a jump
+        //  cuts the group -- the hints keep the cold code out of the fall-through path and of the instruction cache)
+        auto member = [&](const Op& op, const char* ind, bool hot) {
+            o << ind << "if (" << (hot ? "__builtin_expect(" : "(") << op.instr << " >= lo && " << op.instr << " < hi" << (hot ? ", 1)" : ")") << ") {\n";
             std::string off = std::to_string(op.mat);
             if (op.mat_bare != op.mat) off = "(bare && hi == " + std::to_string(op.instr + 1) + ") ? " + std::to_string(op.mat_bare) + " : " + std::to_string(op.mat);
             emit_general_op(o, op, p, R, off, (std::string(ind) + "    ").c_str());
@@ -284,14 +294,14 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
             const Op& op = bv.ops[i];
             if (op.kind_nb >> 31) {
                 const int span = (int)((op.kind_nb >> 25) & 0x3f), last = op.pad;
-                o << "            if (" << op.instr << " >= lo && (" << last + 1 << " < hi || (" << last + 1 << " == hi && !bare))) {\n";
+                o << "            if (__builtin_expect(" << op.instr << " >= lo && (" << last + 1 << " < hi || (" << last + 1 << " == hi && !bare)), 1)) {\n";
                 emit_general_op(o, op, p, R, std::to_string(op.mat), "                ");
                 o << "            } else {\n";
-                for (int j = 1; j <= span; ++j) member(bv.ops[i + j], "                ");
+                for (int j = 1; j <= span; ++j) member(bv.ops[i + j], "                ", false);
                 o << "            }\n";
                 i += span;
             } else {
-                member(op, "            ");
+                member(op, "            ", true);
             }
         }
         for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "] = a[" << m << "];\n";

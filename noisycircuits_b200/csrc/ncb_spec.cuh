@@ -37,6 +37,18 @@ __device__ __forceinline__ void spec_rx(cplx* a, double c0, double c1, double c2
     const cplx m4[4] = {cplx{c0, 0.0}, cplx{0.0, c1}, cplx{0.0, c2}, cplx{c3, 0.0}};
     rx1_bit<R, B>(a, a, m4);
 }
+// [[0, i b], [i c, 0]]: the x gate (i rx(pi)) merged with a diagonal base operator -- half the arithmetic of spec_rx
+template <int R, int B>
+__device__ __forceinline__ void spec_xl(cplx* a, double b, double c) {
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        const int i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cplx{-b * y.y, b * y.x};
+        a[i1] = cplx{-c * x.y, c * x.x};
+    }
+}
 template <int R, int B>
 __device__ __forceinline__ void spec_u(cplx* a, double c0, double c1, double c2, double c3, double c4, double c5, double c6, double c7) {
     const cplx m4[4] = {cplx{c0, c1}, cplx{c2, c3}, cplx{c4, c5}, cplx{c6, c7}};

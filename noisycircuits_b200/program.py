@@ -116,6 +116,21 @@ class PackedCircuit:
             self.num_channels, _ptr(self.channel_offset), _ptr(self.channel_count), _ptr(self.channel_dim),
             _ptr(self.kraus_pool))
 
+    def with_thetas(self, thetas) -> "PackedCircuit":
+        """The same circuit (gate skeleton, qubits, Kraus lists) with other gate parameters: thetas[g] replaces the
+        parameter of instruction g (entries of parameter-free gates are ignored by the compiler).  No Python loop over the
+        instructions: what a parameter sweep needs per circuit."""
+        import copy
+        other = copy.copy(self)
+        other.theta = np.ascontiguousarray(thetas, np.float64).copy()
+        if other.theta.shape != self.theta.shape:
+            raise ValueError(f"thetas must have shape {self.theta.shape}")
+        other.struct = _lib.NcbCircuit(
+            self.num_qubits, self.num_instructions, _ptr(other.opcode), _ptr(other.q0), _ptr(other.q1), _ptr(other.theta), _ptr(other.channel),
+            _ptr(other.unitary_offset), _ptr(other.unitary_nq), _ptr(other.unitary_qubits), _ptr(other.unitary_pool),
+            other.num_channels, _ptr(other.channel_offset), _ptr(other.channel_count), _ptr(other.channel_dim), _ptr(other.kraus_pool))
+        return other
+
     @property
     def kraus_count(self) -> np.ndarray:
         """Operators in each instruction's Kraus list (0: no noise step)."""
@@ -134,6 +149,14 @@ class Program:
         opts = _lib.NcbOptions(tile_bits, reg_bits, low_bits, fuse, device, int(bool(strict_order)),
                                int(bool(independent_trajectories)), 2 if specialize in (2, "parametric") else int(bool(specialize)))
         _lib.check(_lib.lib().ncb_program_create(C.byref(packed.struct), mode, C.byref(opts), C.byref(self._h)))
+        self.num_qubits = packed.num_qubits
+        self.num_instructions = packed.num_instructions
+
+    def update(self, packed: "PackedCircuit") -> None:
+        """Replaces the circuit in place (``ncb_program_update``): same mode and options, the engine's device buffers and --
+        for ``specialize="parametric"`` programs of the same gate skeleton -- its loaded kernels are kept."""
+        _lib.check(_lib.lib().ncb_program_update(self._h, C.byref(packed.struct)))
+        self.packed = packed
         self.num_qubits = packed.num_qubits
         self.num_instructions = packed.num_instructions
 

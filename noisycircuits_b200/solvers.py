@@ -105,25 +105,53 @@ class RemoteExecutor:
         return probs / float(num_trajectories)
 
     def run_many(self, num_trajectories: int, instruction_lists) -> list:
-        """``run`` for a sequence of circuits (a QNN parameter sweep over one gate skeleton): circuit
-        i + 1 is packed and compiled on a host thread while the GPU runs circuit i.  Same results as calling ``run`` in a
-        loop (trajectory ids 0..N-1 for every circuit)."""
-        from concurrent.futures import ThreadPoolExecutor
-
-        def build(instr):
-            packed = PackedCircuit(self.num_qubits, instr, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
-            return Program(packed, _lib.MODE_MCWF, **self.engine_options)
-
+        """``run`` for a sequence of circuits (a QNN parameter sweep over one gate skeleton).  Two engine
+        objects take turns: while the GPU runs circuit i in one, a host thread packs circuit i + 1 and compiles it INTO the
+        other one in place (``Program.update``: device buffers, streams and -- for one gate skeleton -- the loaded kernels
+        are reused).  Same results as calling ``run`` in a loop (trajectory ids 0..N-1 for every circuit)."""
         lists = list(instruction_lists)
-        out = []
         if not lists:
-            return out
+            return []
+        packs = (PackedCircuit(self.num_qubits, instr, self.single_qubit_noise, self.two_qubit_noise, noisy=True) for instr in lists)
+        return self._run_packed(num_trajectories, packs, len(lists))
+
+    def run_sweep(self, num_trajectories: int, instruction_list: list, thetas) -> list:
+        """``run`` for the gate skeleton ``instruction_list`` with every row of ``thetas`` ([sets][instructions]: the
+        parameter of each instruction; entries of parameter-free gates are ignored) -- the parameter sets of a training
+        loop as a batch: the skeleton is packed once, each set only replaces the angle array."""
+        thetas = np.asarray(thetas, np.float64)
+        if thetas.ndim != 2 or thetas.shape[1] != len(instruction_list):
+            raise ValueError("thetas must have shape [sets][len(instruction_list)]")
+        base = PackedCircuit(self.num_qubits, instruction_list, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
+        pad = np.zeros(base.theta.shape[0] - thetas.shape[1])
+        packs = (base.with_thetas(np.concatenate([row, pad])) for row in thetas)
+        return self._run_packed(num_trajectories, packs, thetas.shape[0])
+
+    def _run_packed(self, num_trajectories, packs, count):
+        from concurrent.futures import ThreadPoolExecutor
+        opts = dict(self.engine_options)
+        opts.setdefault("specialize", "parametric" if num_trajectories >= self.SPECIALIZE_FROM else False)
+        packs = iter(packs)
+        engines = [None, None]
+
+        def prepare(slot):
+            packed = next(packs)
+            if engines[slot] is None:
+                engines[slot] = Program(packed, _lib.MODE_MCWF, **opts)
+            else:
+                try:
+                    engines[slot].update(packed)
+                except _lib.NcbError:                      # another geometry: a new engine object
+                    engines[slot] = Program(packed, _lib.MODE_MCWF, **opts)
+            return engines[slot]
+
+        out = []
         with ThreadPoolExecutor(max_workers=1) as pool:
-            nxt = pool.submit(build, lists[0])
-            for i in range(len(lists)):
+            nxt = pool.submit(prepare, 0)
+            for i in range(count):
                 prog = nxt.result()
-                if i + 1 < len(lists):
-                    nxt = pool.submit(build, lists[i + 1])
+                if i + 1 < count:
+                    nxt = pool.submit(prepare, (i + 1) & 1)
                 probs, stats = prog.run_mcwf(num_trajectories, traj_begin=0, rng=_RNG[self.rng], seed=self.seed)
                 self.last_stats = stats
                 out.append(probs / float(num_trajectories))

@@ -64,13 +64,20 @@ def sweep(name, n, lists, sq, tq, T):
     t0 = time.perf_counter()
     a = [ex.run(T, instr) for instr in lists]
     t_loop = time.perf_counter() - t0
+    ex.run_many(T, lists[:2])                      # (engine objects of the ping-pong created)
     t0 = time.perf_counter()
     b = ex.run_many(T, lists)
     t_many = time.perf_counter() - t0
-    same = all(np.array_equal(x, y) for x, y in zip(a, b))
+    # the same sweep as a parameter batch over one gate skeleton (angles as an array, no Python loop per circuit)
+    thetas = np.array([[0.0 if p is None else float(p) for _g, _q, p in instr] for instr in lists])
+    t0 = time.perf_counter()
+    c = ex.run_sweep(T, lists[0], thetas)
+    t_sweep = time.perf_counter() - t0
+    same = all(np.array_equal(x, y) for x, y in zip(a, b)) and all(np.array_equal(x, y) for x, y in zip(a, c))
     print(json.dumps({"config": name, "qubits": n, "circuits": len(lists), "trajectories_per_circuit": T, "seconds_loop": t_loop,
-                      "seconds_run_many": t_many, "circuits_per_s_loop": len(lists) / t_loop,
-                      "circuits_per_s_run_many": len(lists) / t_many, "identical": same}), flush=True)
+                      "seconds_run_many": t_many, "seconds_run_sweep": t_sweep, "circuits_per_s_loop": len(lists) / t_loop,
+                      "circuits_per_s_run_many": len(lists) / t_many, "circuits_per_s_run_sweep": len(lists) / t_sweep,
+                      "kernel_ms_per_circuit": ex.last_stats["kernel_ms"], "identical": same}), flush=True)
 
 
 _pairs12 = circuits.coupled_pairs(h_tq, 12, adjacent_only=True)
