@@ -99,6 +99,12 @@ enum OpKind : uint8_t {
     OPK_RX1 = 4,      // [[a, i b], [i c, d]] with a, b, c, d real: 8 flops per pair.  rx is of this form, sx and x are up
                       // to a global phase (sx = e^{i pi/4} rx(pi/2), x = i rx(pi)), which the compiler factors out.
                       // (Deliberately few kinds: every extra case of the executor's switch costs register shuffling.)
+    // Density-matrix superoperators sum_k (K_k U) (x) conj(K_k U) of channels whose Kraus operators map computational basis
+    // states to basis states up to a phase / weight (Pauli mixtures, reset, amplitude / phase damping -- every channel of the
+    // reference's noise models) composed with a diagonal or permutation-like gate: an element |r><c| only feeds elements
+    // with the same r XOR c, so the 16x16 (4x4) matrix is four 4x4 (two 2x2) blocks.  Only in the R = 4 dense kernels.
+    OPK_DENSE4BD = 5, // 16x16 on register bits 0..3 (row bits 0,1; column bits 2,3): blocks M[d][r'][r], d = r XOR c; 64 entries
+    OPK_DENSE2BD = 6, // 4x4 on register bits rb[0] (row), rb[1] (column): blocks M[d][r'][r]; 8 entries
 };
 
 // One executable step inside a pass.  `mat`/`mat_bare` are offsets (in doubles) into the matrix pool: `mat` is the
@@ -398,6 +404,43 @@ NCB_HD void dense4(const cplx* in, cplx* out, const cplx* __restrict__ M) {
     }
 }
 
+// Block-diagonal 16x16: amplitude index m = r | (c << 2) (r: row bits = register bits 0,1; c: column bits = register
+// bits 2,3); block d = r ^ c acts on the four amplitudes (r, r ^ d).  A quarter of the arithmetic of dense4.
+template <int R>
+NCB_HD void dense4bd(const cplx* in, cplx* out, const cplx* __restrict__ M) {
+    if (R < 4) return;
+    constexpr int MASK = (1 << R) - 1;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+#pragma unroll
+        for (int r2 = 0; r2 < 4; ++r2) {
+            cplx v = cmul(M[d * 16 + r2 * 4], in[(0 | ((0 ^ d) << 2)) & MASK]);
+#pragma unroll
+            for (int r = 1; r < 4; ++r) v = cfma(M[d * 16 + r2 * 4 + r], in[(r | ((r ^ d) << 2)) & MASK], v);
+            out[(r2 | ((r2 ^ d) << 2)) & MASK] = v;
+        }
+        NCB_NO_HOIST();
+    }
+}
+// Block-diagonal 4x4 on register bits B0 (row bit) and B1 (column bit): block d = r ^ c on the two amplitudes (r, r ^ d).
+template <int R, int B0, int B1>
+NCB_HD void dense2bd_bits(const cplx* in, cplx* out, const cplx* __restrict__ M) {
+    constexpr int LO = B0 < B1 ? B0 : B1, HI = B0 < B1 ? B1 : B0;
+    const cplx m[8] = {M[0], M[1], M[2], M[3], M[4], M[5], M[6], M[7]};
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 2)); ++g) {
+        int base = ((g >> LO) << (LO + 1)) | (g & ((1 << LO) - 1));
+        base = ((base >> HI) << (HI + 1)) | (base & ((1 << HI) - 1));
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const int i0 = base | (d << B1), i1 = base | (1 << B0) | ((1 ^ d) << B1);      // (r, c) = (0, d), (1, 1 ^ d)
+            const cplx x = in[i0], y = in[i1];
+            out[i0] = cfma(m[d * 4 + 1], y, cmul(m[d * 4 + 0], x));
+            out[i1] = cfma(m[d * 4 + 3], y, cmul(m[d * 4 + 2], x));
+        }
+    }
+}
+
 // Diagonal operator.  MASK = the register bits it involves: the 2^popc(MASK) phases a thread needs are adjacent in
 // the table (the host lays the table out as [thread-bit hash][register bits in MASK]), so one index computation and
 // popc(MASK) vector loads serve the 2^R amplitudes.
@@ -451,8 +494,8 @@ NCB_HD void apply_op(const Op& op, int jb, const cplx* __restrict__ M, const cpl
     const int b0 = op_rb(op, 0), b1 = op_rb(op, 1);
     int sel;
     if (kind == OPK_DIAG) sel = (kind << 4) | op_regmask(op);
-    else if (kind == OPK_DENSE4) sel = kind << 4;
-    else if (kind == OPK_DENSE2) sel = (kind << 4) | (b0 << 2) | b1;
+    else if (kind == OPK_DENSE4 || kind == OPK_DENSE4BD) sel = kind << 4;
+    else if (kind == OPK_DENSE2 || kind == OPK_DENSE2BD) sel = (kind << 4) | (b0 << 2) | b1;
     else sel = (kind << 4) | b0;
     (void)NA;
     switch (sel) {
@@ -474,6 +517,15 @@ NCB_HD void apply_op(const Op& op, int jb, const cplx* __restrict__ M, const cpl
         NCB_TWO_BIT(2, 0) NCB_TWO_BIT(2, 1) NCB_TWO_BIT(2, 3) NCB_TWO_BIT(3, 0) NCB_TWO_BIT(3, 1) NCB_TWO_BIT(3, 2)
 #undef NCB_TWO_BIT
     case OPK_DENSE4 << 4: if (FEAT & FEAT_DENSE4) dense4<R>(in, out, M); else NCB_UNREACHABLE(); break;
+    case OPK_DENSE4BD << 4: if (FEAT & FEAT_DENSE4) dense4bd<R>(in, out, M); else NCB_UNREACHABLE(); break;
+#define NCB_TWO_BIT_BD(X, Y)                                                             \
+    case (OPK_DENSE2BD << 4) | (X << 2) | Y:                                             \
+        if ((FEAT & FEAT_DENSE4) && R > X && R > Y) dense2bd_bits<R, (R > X ? X : 0), (R > Y ? Y : 1)>(in, out, M); \
+        else NCB_UNREACHABLE();                                                          \
+        break;
+        NCB_TWO_BIT_BD(0, 1) NCB_TWO_BIT_BD(0, 2) NCB_TWO_BIT_BD(0, 3) NCB_TWO_BIT_BD(1, 0) NCB_TWO_BIT_BD(1, 2) NCB_TWO_BIT_BD(1, 3)
+        NCB_TWO_BIT_BD(2, 0) NCB_TWO_BIT_BD(2, 1) NCB_TWO_BIT_BD(2, 3) NCB_TWO_BIT_BD(3, 0) NCB_TWO_BIT_BD(3, 1) NCB_TWO_BIT_BD(3, 2)
+#undef NCB_TWO_BIT_BD
     default:
         NCB_UNREACHABLE();        // the host compiler only emits the kinds above
 #if !defined(__CUDA_ARCH__)

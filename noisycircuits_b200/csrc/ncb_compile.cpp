@@ -726,7 +726,8 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
         // possible group header, its matrices, a share of a pass record)
         auto blob_cost = [&](const LogicalOp& l) {
             const size_t copies = l.bare == l.mat ? 1 : 2;
-            const size_t mats = l.diag ? ((size_t)16 << l.nb) * copies + 128 : (l.nb <= 2 ? ((size_t)16 << (2 * l.nb)) * copies : 0);
+            const size_t mats = l.diag ? ((size_t)16 << l.nb) * copies + 128
+                                       : (l.nb <= 2 ? ((size_t)16 << (2 * l.nb)) * copies : (mode == MODE_DENSITY && l.nb == 4 ? (size_t)1024 * copies : 0));
             return (size_t)(opt.blob_cost_scale * (double)(2 * sizeof(Op) + sizeof(Op) / 2 + mats + sizeof(Pass) / 3));
         };
         size_t cur_cost = sizeof(SegBlob) + sizeof(Pass);
@@ -886,8 +887,28 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
                 } else if (l.nb <= 2) {
                     for (int i = 0; i < l.nb; ++i) rb[i] = (uint32_t)reg_of[local_of[l.bits[i]]];
                     cmat m = read_complex(l.mat.data(), d * d), mb = read_complex(l.bare.data(), d * d);
-                    if (l.nb == 2) { kind = OPK_DENSE2; P.has_dense2 = true; }
-                    else {
+                    if (l.nb == 2) {
+                        kind = OPK_DENSE2; P.has_dense2 = true;
+                        // density-matrix superoperator on (row bit, column bit) that never mixes different r XOR c: two
+                        // 2x2 blocks (the R = 4 dense kernels carry the block kernel)
+                        auto bd2 = [&](const cmat& a) {
+                            for (int ro = 0; ro < 4; ++ro)
+                                for (int ri = 0; ri < 4; ++ri)
+                                    if ((((ro & 1) ^ (ro >> 1)) != ((ri & 1) ^ (ri >> 1))) && a[ro * 4 + ri] != cd(0, 0)) return false;
+                            return true;
+                        };
+                        if (mode == MODE_DENSITY && R == 4 && opt.fuse && l.bits[1] == l.bits[0] + P.nq && bd2(m) && bd2(mb)) {
+                            kind = OPK_DENSE2BD;
+                            auto blocks = [](const cmat& a) {
+                                cmat b(8);
+                                for (int dl = 0; dl < 2; ++dl)
+                                    for (int r2 = 0; r2 < 2; ++r2)
+                                        for (int r = 0; r < 2; ++r) b[dl * 4 + r2 * 2 + r] = a[(r2 + 2 * (r2 ^ dl)) * 4 + (r + 2 * (r ^ dl))];
+                                return b;
+                            };
+                            m = blocks(m); mb = blocks(mb);
+                        }
+                    } else {
                         const int km = pattern_1q(m, 4e-16), kb = pattern_1q(mb, 4e-16);
                         kind = km == kb ? km : OPK_DENSE1;
                         snap_pattern(m, kind); snap_pattern(mb, kind);
@@ -916,8 +937,33 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
                         return flatten(big);
                     };
                     for (int i = 0; i < 4; ++i) rb[i] = (uint32_t)i;
-                    op.mat = pb.add_doubles(remap(l.mat));
-                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(remap(l.bare));
+                    std::vector<double> big = remap(l.mat), big_bare = remap(l.bare);
+                    // block structure in register coordinates: m = r | (c << 2) with the row bits on registers 0,1 and the
+                    // column bits on 2,3 (true for the density-matrix superoperators: row bits are the lower state bits)
+                    auto bd4 = [&](const std::vector<double>& a) {
+                        for (int ro = 0; ro < 16; ++ro)
+                            for (int ri = 0; ri < 16; ++ri)
+                                if (((ro & 3) ^ (ro >> 2)) != ((ri & 3) ^ (ri >> 2)) && (a[2 * (ro * 16 + ri)] != 0.0 || a[2 * (ro * 16 + ri) + 1] != 0.0)) return false;
+                        return true;
+                    };
+                    const bool rows_low = l.nb == 4 && mode == MODE_DENSITY && rbit[0] < 2 && rbit[1] < 2 && rbit[2] >= 2 && rbit[3] >= 2 &&
+                                          rbit[2] == rbit[0] + 2 && rbit[3] == rbit[1] + 2;
+                    if (rows_low && opt.fuse && bd4(big) && bd4(big_bare)) {
+                        kind = OPK_DENSE4BD;
+                        auto blocks = [](const std::vector<double>& a) {
+                            std::vector<double> b(128);
+                            for (int dl = 0; dl < 4; ++dl)
+                                for (int r2 = 0; r2 < 4; ++r2)
+                                    for (int r = 0; r < 4; ++r) {
+                                        const int ro = r2 | ((r2 ^ dl) << 2), ri = r | ((r ^ dl) << 2), e = dl * 16 + r2 * 4 + r;
+                                        b[2 * e] = a[2 * (ro * 16 + ri)]; b[2 * e + 1] = a[2 * (ro * 16 + ri) + 1];
+                                    }
+                            return b;
+                        };
+                        big = blocks(big); big_bare = blocks(big_bare);
+                    }
+                    op.mat = pb.add_doubles(big);
+                    op.mat_bare = l.bare == l.mat ? op.mat : pb.add_doubles(big_bare);
                 }
                 op.kind_nb = (uint32_t)(kind & 0xf) | ((uint32_t)l.nb << 4) | ((uint32_t)kind & 0x0fff00u);
                 if (R == 3) {   // jump-table case of the lean executor (see ncb_common.h)
@@ -1057,6 +1103,8 @@ static void build_blobs(Program& P) {
                 case OPK_DENSE1: case OPK_RX1: nd = 8; break;
                 case OPK_DENSE2: nd = 32; break;
                 case OPK_DENSE4: nd = 512; break;
+                case OPK_DENSE4BD: nd = 128; break;
+                case OPK_DENSE2BD: nd = 16; break;
                 }
                 const bool big = kind == OPK_DENSE4;
                 const int m = op.mat, mb = op.mat_bare;
@@ -1222,7 +1270,7 @@ std::string describe_program(const Program& P) {
       << " norm_preserving=" << P.norm_preserving << " dense2=" << P.has_dense2 << " dense4=" << P.has_dense4
       << " pool=" << P.pool.size() << " blobs=" << P.blobs.size() << " reorder=" << P.opt.reorder << " attempts=" << P.compile_attempts;
     {
-        static const char* names[] = {"diag", "dense1", "dense2", "dense4", "rx1", "?", "?", "?"};
+        static const char* names[] = {"diag", "dense1", "dense2", "dense4", "rx1", "dense4bd", "dense2bd", "?"};
         int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, groups = 0;
         for (const Op& op : P.ops) { ++cnt[op_kind(op) & 7]; groups += (int)(op.kind_nb >> 31); }
         o << " kinds{";
