@@ -272,6 +272,7 @@ struct Engine {
             CK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
             if (const char* e2 = getenv("NCB_DIRECT_CHUNK")) direct_chunk = atoi(e2);
+            if (const char* e2 = getenv("NCB_EV_CHUNK")) ev_chunk = atoi(e2);
             if (const char* e2 = getenv("NCB_OVERLAP")) overlap_streams = atoi(e2) != 0;
             d_counters.reserve(4);
             device_ready = true;
@@ -396,6 +397,7 @@ struct Engine {
         CK(cudaGetLastError());
     }
     // direct kernel (works that run a whole segment without an event; lean programs only)
+    int ev_chunk = 0;
     int direct_ctas = 0, direct_chunk = 8;       // tiles per direct-kernel CTA: CTA turnover lets the (higher-priority) event chain in
                                                  // (measured on the 20-qubit workload: 8 -> 2612, 16 -> 2557, 32 -> 2531, persistent -> slower)
     size_t direct_smem() const {
@@ -622,6 +624,9 @@ struct Engine {
                 const long long total = (long long)st.count << tile_shift;
                 long long want = (long long)sm_count * f.ctas;
                 if (st.direct && direct_chunk > 0) want = std::max<long long>(want, (total + direct_chunk - 1) / direct_chunk);   // CTA turnover lets the event chain in
+                // event launches are small (a few trajectories): with ev_chunk > 0 a CTA takes at least that many tiles, so a
+                // launch occupies fewer CTA slots for longer -- its latency hides behind the segment's whole-segment launch
+                if (!st.direct && ev_chunk > 0) want = std::min<long long>(want, std::max<long long>(sm_count, (total + ev_chunk - 1) / ev_chunk));
                 const int grid = (int)std::min<long long>(total, want);
                 if (grid < 1) return true;
                 int pool_off, pool_bytes;
@@ -632,7 +637,8 @@ struct Engine {
                 cplx* states = d_states.p;
                 int rc;
                 if (st.direct) {
-                    void* args[] = {(void*)P.segconst[st.seg].coef, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift};
+                    double* nrm = d_norm.p;
+                    void* args[] = {(void*)P.segconst[st.seg].coef, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift, (void*)&nrm};
                     rc = g_drv.LaunchKernel(f.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)spec_smem(false), (void*)s, args, nullptr);
                 } else {
                     double *red = d_red.p, *nrm = d_norm.p;
@@ -814,6 +820,12 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
     std::vector<cplx> host_states;
     int buf = 0;
     const bool want_norm = !P.norm_preserving;
+    // generated kernels: the whole-segment kernel of the last segment accumulates the squared norm itself
+    bool direct_norm = false;
+    if (specialize && want_norm) {
+        ensure_spec();
+        direct_norm = !spec_fn.empty() && spec_fn.back().fn != nullptr;
+    }
     CK(cudaMemsetAsync(d_red.p, 0, (size_t)SL * ntiles * RED_VALUES * sizeof(double), s));
     for (long long b0 = 0; b0 < count; b0 += B) {
         const int nb = (int)std::min<long long>(B, count - b0);
@@ -829,7 +841,7 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             const long long tl = mt ? b : b0 + b;
             plan_events(P, [&](int i) { return us.get(tl, i); }, events[b]);
         }
-        schedule_batch(P, events, true, want_norm, plan, share);
+        schedule_batch(P, events, true, want_norm, plan, share, true, direct_norm);
         for (int b = 0; b < nb; ++b) {
             rp->out_events += (int64_t)events[b].size();
             for (const Event& e : events[b]) rp->out_hard_events += e.kmin != e.kmax;

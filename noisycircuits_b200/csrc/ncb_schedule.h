@@ -40,8 +40,9 @@ struct BatchPlan {
 // the trunk's state at the start of that segment (Work::src) and written to its own slot; trajectories without any
 // event are the trunk (weight = their number).  The numbers produced per trajectory are bit-identical to the unshared
 // schedule: the same kernels run on the same data, fewer times.
+// direct_norm: works of the last segment that only carry WF_NORM count as "whole segment, no event" too.
 inline void schedule_batch(const Program& P, const std::vector<std::vector<Event>>& events, bool init, bool want_norm,
-                           BatchPlan& out, bool share_prefix = false, bool inline_certain = true) {
+                           BatchPlan& out, bool share_prefix = false, bool inline_certain = true, bool direct_norm = false) {
     out.works.clear(); out.decides.clear(); out.steps.clear(); out.sweeps = 0;
     const int B = (int)events.size(), S = (int)P.segs.size();
     share_prefix = share_prefix && init && B > 1 && S > 0;
@@ -121,8 +122,9 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
         const bool seg_direct = (size_t)s < P.segconst.size() && P.segconst[s].valid && P.segconst[s].direct;
         if (seg_direct && st.count) {
             auto first = out.works.begin() + st.begin;
+            // (direct_norm: the whole-segment kernel of the LAST segment also accumulates the squared norm -- generated kernels)
             auto mid = std::stable_partition(first, out.works.end(), [&](const Work& w) {
-                return w.flags == 0 && w.instr_lo <= sg.instr_lo && w.instr_hi >= sg.instr_hi; });
+                return (w.flags == 0 || (direct_norm && last && w.flags == WF_NORM)) && w.instr_lo <= sg.instr_lo && w.instr_hi >= sg.instr_hi; });
             const int nd = (int)(mid - first);
             if (nd) out.steps.push_back(LaunchStep{0, st.begin, nd, s, 1});
             if (st.count - nd) out.steps.push_back(LaunchStep{0, st.begin + nd, st.count - nd, s, 0});

@@ -105,14 +105,35 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
     const int nbuf = opt.nbuf == 1 ? 1 : 2;
     const int load = sc.direct_first ? std::min(std::max(opt.load, 0), 2) : 0;
     const int npass = sc.npass;
+    // the last segment of a program whose operators do not preserve the norm also accumulates the squared norm of every
+    // tile (WF_NORM; what the event-capable kernel does for works that carry events): the amplitudes are in registers then
+    const bool with_norm = seg == (int)P.segs.size() - 1 && !P.norm_preserving;
+    auto emit_norm = [&](std::ostringstream& os) {
+        if (!with_norm) return;
+        os << "            {   // squared norm of the tile: fixed shuffle tree per warp, warps added in order (deterministic)\n"
+              "                double nrm = 0.0;\n";
+        for (int m = 0; m < NA; ++m) os << "                nrm += cnorm2(a[" << m << "]);\n";
+        os << "                nrm = warp_sum(nrm);\n"
+              "                if ((tid & 31) == 0) s_nrm[tid >> 5] = nrm;\n"
+              "                __syncthreads();\n"
+              "                if (tid == 0) {\n"
+              "                    double t2 = 0.0;\n"
+              "                    for (int wv = 0; wv < (nthreads >> 5); ++wv) t2 += s_nrm[wv];\n"
+              "                    norm_part[(long long)works[t >> tile_shift].slot * ntiles + tl] = t2;\n"
+              "                }\n"
+              "                __syncthreads();\n"
+              "            }\n";
+    };
     o << "extern \"C\" __global__ void __launch_bounds__(" << (1 << (K - R)) << ", " << spec_ctas_per_sm(P, opt) << ") ncb_seg_" << seg
       << "(const __grid_constant__ SpecCoef C, const unsigned char* __restrict__ pool_g, int pool_bytes, int pool_cap,\n"
-         "        const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int tile_shift) {\n"
+         "        const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int tile_shift, double* __restrict__ norm_part) {\n"
          "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
          "    const int tid = threadIdx.x, nthreads = blockDim.x;\n"
          "    const int ntiles = 1 << tile_shift;\n"
          "    const long long total = (long long)nworks << tile_shift;\n"
          "    cplx* const buf0 = reinterpret_cast<cplx*>(smem_raw + pool_cap);\n"
+      << (with_norm ? "    __shared__ double s_nrm[32];\n" : "    (void)norm_part;\n")
+      << "    (void)nthreads;\n"
          "    for (int i = tid * 16; i < pool_bytes; i += nthreads * 16) cp_async16(smem_raw + i, pool_g + i);\n"
          "    cp_async_wait_all();\n    __syncthreads();\n"
          "    const cplx* const pool = reinterpret_cast<const cplx*>(smem_raw);\n"
@@ -155,6 +176,7 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
             if (last && nbuf == 2) o << "            __syncthreads();            // this buffer is refilled at the top of the next iteration\n";
             if (!emit_fast_ops(o, sc, p, R, opt.literal != 0)) return false;
             if (last) {
+                emit_norm(o);
                 for (int m = 0; m < NA; ++m) o << "            st_stream(dst + (gj_last | " << hex(sc.goff_last[m]) << "), a[" << m << "]);\n";
             } else {
                 for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ph.regoff_swz[m] << "] = a[" << m << "];\n";
@@ -200,6 +222,7 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
         }
         if (!emit_fast_ops(o, sc, p, R, opt.literal != 0)) return false;
         if (last) {
+            emit_norm(o);
             for (int m = 0; m < NA; ++m) o << "            st_stream(dst + (gj_last | " << hex(sc.goff_last[m]) << "), a[" << m << "]);\n";
         } else {
             for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ph.regoff_swz[m] << "] = a[" << m << "];\n";
@@ -421,7 +444,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 5 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 6 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);

@@ -623,3 +623,21 @@ def test_partial_measurement_on_device_any_subset(heron_noise):
         dev = simulator.execute_tail_device(t.data_ptr(), n, qubits, mdict, 1.0)
         ref = postprocess(p.copy(), n, qubits, mdict, 1)
         assert np.abs(dev - ref).max() < 1e-14, qubits
+
+
+def test_execute_sharded_gpu_branch(heron_noise):
+    """backend.execute_sharded on a device (QuantumCircuitMPI.execute: shard -> device accumulator -> all-reduce -> tail on
+    the device); with one rank (no process group) it must return what execute() returns, and a trajectory offset must be
+    the same as sharding by hand.  The multi-rank NCCL path is the N > 1 end-to-end arm of bench.py."""
+    from noisycircuits_b200.backend import execute, execute_sharded
+    sq, tq, meas, _ = heron_noise
+    n = 13
+    instr = circuits.heron_layered(n, 2, circuits.coupled_pairs(tq, n), seed=6)
+    mdict = {q: meas[q] for q in range(n)}
+    a = execute(n, instr, sq, tq, mdict, None, 96, seed=5)
+    b = execute_sharded(n, instr, sq, tq, mdict, None, 96, seed=5)
+    assert np.abs(a - b).max() < 1e-14 and abs(b.sum() - 1) < 1e-9
+    ex = RemoteExecutor(n, sq, tq, 1, seed=5)
+    c = execute_sharded(n, instr, sq, tq, mdict, [0, 5, 7], 40, executor=ex, traj_offset=56)
+    d = execute(n, instr, sq, tq, mdict, [0, 5, 7], 40, executor=ex, traj_offset=56)
+    assert np.abs(c - d).max() < 1e-14 and c.shape == (8,)
