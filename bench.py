@@ -14,9 +14,10 @@ count, so the 10^5-trajectory configuration is reported as trajectories/sec.
 value      device-timed (CUDA events, max over ranks) whole-job trajectories/sec, program resident on the GPU.
 e2e        the same metric through the public plug-in call (RemoteExecutor.run_sum) returning HOST probabilities:
            per step the work lists go host->device and the float64[2^n] result device->host inside the timed region.
-roofline   the sweep ("tile") kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json):
-           algorithmic bytes = sweeps * 2 * 16 B * 2^n; launch duration = device time of the
-           timed region / number of tile launches (the small decide / accumulate kernels are charged to it).
+roofline   the sweep kernels (generated per segment: ncb_seg_<k>, ncb_seg_<k>_ev) against the measured HBM copy bandwidth
+           (MEASURED_PEAKS.json): algorithmic bytes = sweeps * 2 * 16 B * 2^n; launch duration = device
+           time of the timed region / number of sweep launches (the small decide / accumulate kernels are charged to it).
+           traffic = DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture.
 cpu_baseline  the reference's compiled CPU path (oracle/_ref/patched: these circuits have non-adjacent coupled
            pairs) on all host cores, on a bounded sample: 4 consecutive layers of the same circuit
            run as a circuit of their own, the rate scaled by instructions.  The reference sweeps all 2^n amplitudes
@@ -488,7 +489,10 @@ def run_gpu(args):
                 "gpu_launches": agg["launches"],
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                             "kernel": ("ncb_seg_<k> (generated whole-segment sweeps)" if specialize else "ncb::direct_kernel (whole-segment sweeps)") + " + ncb::tile_kernel (jump-event pieces)",
+                             "kernel": ("ncb_seg_<k> (generated whole-segment sweeps) + ncb_seg_<k>_ev (generated, works with jump events)" if specialize
+                                        else "ncb::direct_kernel (whole-segment sweeps) + ncb::tile_kernel (works with jump events)"),
+                             "definition": "achieved = sweeps x 2 x 16 B x 2^n (SURVEY 8(d)) / device time of the timed region: the sweep kernels are charged "
+                                           "with the whole step (event pieces, decide and accumulate kernels, launch gaps); per-kernel figures: profiles/",
                              "algorithmic_bytes_per_launch": alg_bytes / max(agg["tile_launches"], 1),
                              "avg_launch_ms": ms / max(agg["tile_launches"], 1), "tile_launches": agg["tile_launches"],
                              "sweeps_per_trajectory": agg["sweeps"] / (tps * args.steps)},

@@ -1079,9 +1079,16 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     ncb_program* p = new ncb_program();
     try {
         compile_program(view_of(circuit), mode, opt, p->eng.P);
-        if (auto4 && (p->eng.P.has_dense2 || p->eng.P.has_dense4 || p->eng.P.nbits <= p->eng.P.K)) {
-            opt.reg_bits = 3;                       // not a program the generated kernels cover: back to the default geometry
-            compile_program(view_of(circuit), mode, opt, p->eng.P);
+        if (auto4) {
+            // R = 4 pays for rotation / diagonal programs (Heron: +10 %); programs full of generic 2x2 operators (Eagle: the
+            // one-qubit factors of the decomposed ecr) run 7 % faster with R = 3 (measured, profiles/r02_variants.jsonl)
+            long long rx = 0, u = 0;
+            for (const Op& op : p->eng.P.ops) { rx += op_kind(op) == OPK_RX1; u += op_kind(op) == OPK_DENSE1; }
+            const bool generic_heavy = 4 * u > rx + u;
+            if (p->eng.P.has_dense2 || p->eng.P.has_dense4 || p->eng.P.nbits <= p->eng.P.K || generic_heavy) {
+                opt.reg_bits = 3;                   // (or not a program the generated kernels cover at all: the default geometry)
+                compile_program(view_of(circuit), mode, opt, p->eng.P);
+            }
         }
         if (p->eng.P.R == 3 && p->eng.P.has_dense2 && p->eng.P.K > 11) {     // the dense-4x4 kernels run 256 threads
             opt.tile_bits = 11;

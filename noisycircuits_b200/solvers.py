@@ -68,15 +68,23 @@ class RemoteExecutor:
         self.last_stats = None
         self._cache = (None, None)
 
-    # from this many trajectories on, a few seconds spent on kernels generated for the circuit (ncb_options.specialize)
-    # pay for themselves; an explicit specialize=True / False in the engine options overrides it
+    # Generated kernels (ncb_options.specialize) cost a few seconds of compilation per new kernel set.  Without an explicit
+    # specialize=... in the engine options: from SPECIALIZE_FROM trajectories per call the "parametric" kernels are used
+    # (coefficients as a kernel parameter: one kernel set per gate SKELETON, so a parameter sweep compiles once), and calls
+    # so long that the compilation is noise -- trajectories x 2^n >= LITERAL_FROM_AMPLITUDES, e.g. 65536 trajectories of 20
+    # qubits -- get the literal-coefficient kernels (10-35 % faster, one kernel set per parameter set; the on-disk cache
+    # keeps the 64 most recently used sets).
     SPECIALIZE_FROM = 4096
+    LITERAL_FROM_AMPLITUDES = 1 << 36
+
+    def _auto_specialize(self, traj_count: int):
+        if traj_count < self.SPECIALIZE_FROM:
+            return False
+        return True if (int(traj_count) << self.num_qubits) >= self.LITERAL_FROM_AMPLITUDES else "parametric"
 
     def _program(self, instruction_list, traj_count: int = 0) -> Program:
         opts = dict(self.engine_options)
-        # automatic choice: kernels generated for the circuit's STRUCTURE ("parametric": the cubins of a gate skeleton are
-        # shared by every parameter set, so a training loop compiles once); specialize=True asks for literal coefficients
-        opts.setdefault("specialize", "parametric" if traj_count >= self.SPECIALIZE_FROM else False)
+        opts.setdefault("specialize", self._auto_specialize(traj_count))
         # fast path: the same list object contents and the same noise dictionaries as last time (in-place edits of the
         # dictionaries are not seen here -- call invalidate()); otherwise the packed bytes decide (cache.get_program)
         key = (_fingerprint(instruction_list), str(opts["specialize"]), id(self.single_qubit_noise), id(self.two_qubit_noise))
@@ -130,7 +138,7 @@ class RemoteExecutor:
     def _run_packed(self, num_trajectories, packs, count):
         from concurrent.futures import ThreadPoolExecutor
         opts = dict(self.engine_options)
-        opts.setdefault("specialize", "parametric" if num_trajectories >= self.SPECIALIZE_FROM else False)
+        opts.setdefault("specialize", "parametric" if num_trajectories >= self.SPECIALIZE_FROM else False)   # a sweep: one kernel set
         packs = iter(packs)
         engines = [None, None]
 

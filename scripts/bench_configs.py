@@ -19,8 +19,8 @@ h_sq, h_tq, _hm, _ = noise_io.load_noise_tables(os.path.join(G, "heron20_noise.n
 e_sq, e_tq, _em, _ = noise_io.load_noise_tables(os.path.join(G, "eagle16_noise.npz"))
 
 
-def mcwf(name, n, instr, sq, tq, T, reps=2):
-    ex = RemoteExecutor(n, sq, tq, 1)
+def mcwf(name, n, instr, sq, tq, T, reps=2, **opts):
+    ex = RemoteExecutor(n, sq, tq, 1, **opts)
     ex.run(min(T, 64), instr)                      # compile + upload + warm-up
     best = None
     for _ in range(reps):
@@ -52,9 +52,10 @@ dm("C2 12q density matrix depth 10", 12, circuits.heron_layered(12, 4 if quick e
 # C3: 12-qubit QNN-style circuit, 10^4 trajectories
 mcwf("C3 12q QNN x1e4", 12, circuits.qnn_circuit(12, 4, circuits.coupled_pairs(h_tq, 12, adjacent_only=True), seed=42), h_sq, h_tq, 2000 if quick else 10000)
 # C4: 16-qubit Eagle ECR/SX/RZ depth 40
-mcwf("C4 16q Eagle depth 40", 16, circuits.eagle_layered(16, 40, circuits.coupled_pairs(e_tq, 16), seed=42), e_sq, e_tq, 1184 if quick else 4736)
+# (C4 / C5 stand for 10^5-trajectory runs: RemoteExecutor would pick the literal-coefficient generated kernels there by itself)
+mcwf("C4 16q Eagle depth 40", 16, circuits.eagle_layered(16, 40, circuits.coupled_pairs(e_tq, 16), seed=42), e_sq, e_tq, 1184 if quick else 4736, specialize=True)
 # C5: 20-qubit Heron depth 50
-mcwf("C5 20q Heron depth 50", 20, circuits.heron_layered(20, 50, circuits.coupled_pairs(h_tq, 20), seed=42), h_sq, h_tq, 296 if quick else 1184)
+mcwf("C5 20q Heron depth 50", 20, circuits.heron_layered(20, 50, circuits.coupled_pairs(h_tq, 20), seed=42), h_sq, h_tq, 296 if quick else 1184, specialize=True)
 
 
 # C3 sweep: 20 parameter sets of the QNN skeleton (a training loop's inner evaluation): loop of run() vs run_many()
