@@ -277,7 +277,8 @@ LogicalOp make_lop(int instr, const std::vector<int>& bits, const cmat& merged, 
     l.nb = (int)bits.size();
     for (int i = 0; i < 8; ++i) l.bits[i] = i < l.nb ? bits[i] : -1;
     const int d = 1 << l.nb;
-    l.diag = is_diagonal(merged, d) && is_diagonal(bare, d);
+    l.generic = l.nb > 4;
+    l.diag = !l.generic && is_diagonal(merged, d) && is_diagonal(bare, d);
     if (l.diag) { l.mat = flatten(diag_of(merged, d)); l.bare = flatten(diag_of(bare, d)); }
     else { l.mat = flatten(merged); l.bare = flatten(bare); }
     return l;
@@ -467,7 +468,7 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
         cmat U;
         if (opc == G_UNITARY) {
             const int k = c.unitary_nq[g];
-            if (k < 1 || k > 4) throw std::runtime_error("instruction " + std::to_string(g) + ": unitary on " + std::to_string(k) + " qubits is not supported (1..4)");
+            if (k < 1 || k > 8) throw std::runtime_error("instruction " + std::to_string(g) + ": unitary on " + std::to_string(k) + " qubits is not supported (1..8)");
             for (int b = 0; b < k; ++b) qb.push_back(c.unitary_qubits[8 * g + b]);
             U = read_complex(c.unitary_pool + 2 * c.unitary_offset[g], (1 << k) * (1 << k));
         } else {
@@ -571,6 +572,8 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
             for (int b = 0; b < L; ++b) low |= 1ull << b;
             int max_seg_ops = 50;        // keeps a segment's program inside the shared-memory staging area
             if (const char* e = getenv("NCB_MAX_SEG_OPS")) max_seg_ops = std::max(1, atoi(e));
+            std::vector<char> generic_ptr(P.G, 0);
+            for (const LogicalOp& l : lops) if (l.generic) generic_ptr[l.instr] = 1;
             // runs every ready instruction inside tile S from heads h (modified); returns the executed list
             auto run = [&](uint64_t S, std::vector<size_t>& h, std::vector<int>* out) {
                 int count = 0;
@@ -583,6 +586,7 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
                         if (!((S >> b) & 1) || h[b] >= queue[b].size()) continue;
                         const int g = queue[b][h[b]];
                         if (ubits[g] & ~S) continue;
+                        if (generic_ptr[g]) continue;                          // (never part of a tile)
                         bool ok = true;
                         for (int c = 0; c < nb && ok; ++c)
                             if (((ubits[g] >> c) & 1) && (h[c] >= queue[c].size() || queue[c][h[c]] != g)) ok = false;
@@ -666,10 +670,19 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
                 }
                 list.swap(out);
             };
-            std::vector<char> done(P.G, 0);
+            std::vector<char> done(P.G, 0), generic_instr(P.G, 0);
+            for (const LogicalOp& l : lops) if (l.generic) generic_instr[l.instr] = 1;
             int next_undone = 0;
             while ((int)order.size() < P.G) {
                 while (next_undone < P.G && done[next_undone]) ++next_undone;
+                if (generic_instr[next_undone]) {
+                    // a 5..8-bit unitary is a segment of its own; as the oldest pending instruction it is ready
+                    for (int c = 0; c < nb; ++c)
+                        if ((ubits[next_undone] >> c) & 1) ++head[c];
+                    done[next_undone] = 1;
+                    order.push_back(next_undone);
+                    continue;
+                }
                 // seed: the oldest pending instruction (it is ready: everything before it on its bits is done)
                 uint64_t S = low | ubits[next_undone];
                 if (__builtin_popcountll(S) > kfit) throw std::runtime_error("an operation does not fit a tile; increase tile_bits");
@@ -713,7 +726,7 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
     }
 
     // ---- segmentation: maximal runs of consecutive logical ops whose bits fit one tile --------------------------
-    struct SegBuild { std::vector<int> tile; size_t lop_begin, lop_end; };
+    struct SegBuild { std::vector<int> tile; size_t lop_begin, lop_end; bool generic = false; };
     std::vector<SegBuild> sb;
     auto fresh_tile = [&]() { std::vector<int> t; for (int b = 0; b < L; ++b) t.push_back(b); return t; };
     auto tile_union = [&](std::vector<int> t, const LogicalOp& l) {
@@ -733,6 +746,16 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
         size_t cur_cost = sizeof(SegBlob) + sizeof(Pass);
         SegBuild cur{fresh_tile(), 0, 0};
         for (size_t i = 0; i < lops.size(); ++i) {
+            if (lops[i].generic) {
+                // a 5..8-bit unitary: close the running segment, a segment of its own, start afresh
+                if (cur.lop_end > cur.lop_begin) sb.push_back(cur);
+                SegBuild gs{fresh_tile(), i, i + 1};
+                gs.generic = true;
+                sb.push_back(gs);
+                cur = SegBuild{fresh_tile(), i + 1, i + 1};
+                cur_cost = sizeof(SegBlob) + sizeof(Pass);
+                continue;
+            }
             const bool new_instr = i == 0 || lops[i].instr != lops[i - 1].instr;
             // an instruction's lops stay in one segment (a jump event reduces over the instruction's qubits right after
             // its last lop): the tile has to take all of them
@@ -754,6 +777,11 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
             cur_cost += blob_cost(lops[i]);
         }
         if (cur.lop_end > cur.lop_begin || sb.empty()) sb.push_back(cur);
+        if (sb.back().generic && mode == MODE_MCWF && !P.norm_preserving) {
+            // the squared norm is accumulated by the last sweep of a register-blocked segment: close with an empty one
+            SegBuild tail{fresh_tile(), lops.size(), lops.size()};
+            sb.push_back(tail);
+        }
     }
 
     // ---- passes and ops -----------------------------------------------------------------------------------------
@@ -784,9 +812,22 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
             seg.bruns = make_runs(bpos);
         }
         seg.pass_begin = (int)P.passes.size();
-        seg.instr_lo = s.lop_end > s.lop_begin ? lops[s.lop_begin].instr : 0;
-        seg.instr_hi = s.lop_end > s.lop_begin ? lops[s.lop_end - 1].instr + 1 : 0;
+        seg.instr_lo = s.lop_end > s.lop_begin ? lops[s.lop_begin].instr : (s.lop_begin > 0 ? P.G : 0);
+        seg.instr_hi = s.lop_end > s.lop_begin ? lops[s.lop_end - 1].instr + 1 : (s.lop_begin > 0 ? P.G : 0);
         const int seg_id = (int)P.segs.size();
+        if (s.generic) {
+            const LogicalOp& l = lops[s.lop_begin];
+            GenericOp go;
+            go.seg = seg_id; go.nb = l.nb;
+            for (int i = 0; i < 8; ++i) go.bits[i] = i < l.nb ? l.bits[i] : -1;
+            go.mat = pb.add_doubles(l.mat);
+            P.generics.push_back(go);
+            P.instrs[l.instr].seg = seg_id;
+            seg.pad[0] = 1;
+            seg.pass_end = seg.pass_begin;
+            P.segs.push_back(seg);
+            continue;
+        }
 
         std::vector<PassBuild> pbs(1);
         for (size_t i = s.lop_begin; i < s.lop_end; ++i) {

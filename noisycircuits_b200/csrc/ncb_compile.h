@@ -54,6 +54,16 @@ struct LogicalOp {
     bool diag;
     std::vector<double> mat;      // merged (2^nb x 2^nb complex, interleaved) or, if diag, 2^nb phases
     std::vector<double> bare;
+    bool generic = false;         // dense operator on 5..8 bits (a user-supplied `unitary`): a segment of its own, run by
+                                  // generic_unitary_kernel (gather -> shared-memory mat-vec -> scatter)
+};
+
+// A k-bit (5 <= k <= 8) dense unitary: does not fit the register-blocked passes (2^R amplitudes per thread, R <= 4).
+struct GenericOp {
+    int seg;                      // the segment that consists of this operator alone (Segment::pad[0] == 1)
+    int nb;
+    int bits[8];                  // matrix bit i <-> state bit bits[i]
+    int mat;                      // offset (doubles) of the 2^nb x 2^nb row-major complex matrix in the program's pool
 };
 
 struct Program {
@@ -73,6 +83,7 @@ struct Program {
     std::vector<Segment> segs;
     std::vector<Instr> instrs;
     std::vector<Channel> chans;
+    std::vector<GenericOp> generics;    // segments that are one 5..8-bit unitary (reference: apply_unitary_gate takes any k)
     std::vector<int32_t> draw_pos;      // position of the instruction's draw in the reference's MT stream, -1: none
     int num_draws = 0;
     std::vector<int32_t> noisy_instrs;  // execution positions that have a channel with >= 2 operators

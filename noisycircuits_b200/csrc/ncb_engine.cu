@@ -236,7 +236,7 @@ struct Engine {
         if (t1) cudaEventDestroy(t1);
     }
 
-    bool resident() const { return P.nbits <= P.K; }
+    bool resident() const { return P.nbits <= P.K && P.generics.empty(); }     // (a 5..8-bit unitary is a launch of its own)
     size_t tile_smem() const { return ((size_t)1 << P.K) * sizeof(cplx); }
     size_t resident_smem() const {
         return tile_smem() + ((size_t)1 << P.nbits) * sizeof(double) + (((size_t)P.G + 31) / 32 + 1) * sizeof(unsigned);
@@ -654,6 +654,19 @@ struct Engine {
         else launch_tile(st.count, s, works + st.begin, st.seg);
         return false;
     }
+    // a segment that is one 5..8-bit unitary
+    void launch_generic(const LaunchStep& st, cudaStream_t s, const Work* works) {
+        const GenericOp* go = nullptr;
+        for (const GenericOp& g : P.generics) if (g.seg == st.seg) go = &g;
+        if (!go) throw std::runtime_error("internal: generic launch on an ordinary segment");
+        GenericArgs ga;
+        ga.nb = go->nb;
+        for (int i = 0; i < 8; ++i) ga.bits[i] = go->bits[i];
+        const long long groups = ((long long)st.count << (P.nbits - go->nb)) >> (8 - go->nb);      // block iterations
+        const int grid = (int)std::max<long long>(1, std::min<long long>(groups, (long long)sm_count * 8));
+        generic_unitary_kernel<<<grid, 256, 0, s>>>(works + st.begin, st.count, d_states.p, P.nbits, ga, reinterpret_cast<const cplx*>(d_pool.p + go->mat));
+        CK(cudaGetLastError());
+    }
     void launch_resident(int grid, cudaStream_t s, const ResidentArgs& a) {
         const int threads = 1 << (P.K - P.R);
         if (!resident_configured) {
@@ -802,7 +815,7 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
 
 void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
     const long long dim = 1ll << P.nbits, count = rp->traj_count;
-    const int ntiles = 1 << (P.nbits - P.K);
+    const int ntiles = 1 << (P.nbits > P.K ? P.nbits - P.K : 0);     // (a small state with a 5..8-bit unitary runs as one tile)
     const int B = rp->batch > 0 ? (int)std::min<long long>(rp->batch, count) : auto_batch(count);
     // trajectories are one and the same evolution until their first jump: computed once per batch (ncb_schedule.h)
     bool share = !rp->states && !independent;
@@ -870,8 +883,9 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
         for (const LaunchStep& st : plan.steps) {
             if (overlap && st.seg != cur_seg && cur_seg >= 0) join();
             cur_seg = st.seg;
-            cudaStream_t q = overlap && !(st.kind == 0 && st.direct) ? s2 : s;
+            cudaStream_t q = overlap && !(st.kind == 0 && st.direct) && st.kind != 2 ? s2 : s;
             if (st.kind == 0) { rp->out_spec_launches += launch_step(st, q, d_works[buf].p) ? 1 : 0; ++rp->out_tile_launches; }
+            else if (st.kind == 2) { launch_generic(st, q, d_works[buf].p); ++rp->out_tile_launches; }
             else {
                 decide_kernel<<<st.count, 256, 0, q>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
                 CK(cudaGetLastError());
@@ -991,14 +1005,17 @@ void Engine::run_deterministic(cudaStream_t s) {
         a.states_out = d_states.p; a.normalize = 0; a.counters = nullptr;
         launch_resident(1, s, a);
     } else {
-        d_red.reserve(RED_VALUES); d_norm.reserve((size_t)1 << (P.nbits - P.K)); d_dec.reserve(1);
+        d_red.reserve(RED_VALUES); d_norm.reserve((size_t)1 << (P.nbits > P.K ? P.nbits - P.K : 0)); d_dec.reserve(1);
         std::vector<std::vector<Event>> events(1);
         BatchPlan plan;
         schedule_batch(P, events, true, false, plan);
         d_works[0].reserve(plan.works.size() + 1);
         CK(cudaMemcpyAsync(d_works[0].p, plan.works.data(), plan.works.size() * sizeof(Work), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
-        for (const LaunchStep& st : plan.steps) launch_step(st, s, d_works[0].p);
+        for (const LaunchStep& st : plan.steps) {
+            if (st.kind == 2) launch_generic(st, s, d_works[0].p);
+            else launch_step(st, s, d_works[0].p);
+        }
     }
 }
 

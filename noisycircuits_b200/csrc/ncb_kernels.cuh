@@ -370,6 +370,54 @@ decide_kernel(DevProgram P, const DecideItem* __restrict__ items, int nitems, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// generic k-bit unitary (5 <= k <= 8): gather -> shared-memory mat-vec -> scatter (QuantumGates.hpp:968-1064 takes any k;
+// the register-blocked passes stop at 4 bits).  One thread per (group, row); a block works on 256 >> k groups at a time.
+// ---------------------------------------------------------------------------------------------------------------
+struct GenericArgs {
+    int nb;
+    int bits[8];               // matrix bit i <-> state bit bits[i]
+};
+__global__ void __launch_bounds__(256)
+generic_unitary_kernel(const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int nbits, GenericArgs ga,
+                       const cplx* __restrict__ U) {
+    __shared__ cplx g_in[256];
+    const int k = ga.nb, dimk = 1 << k, gpb = 256 >> k;
+    const int lg = threadIdx.x >> k, row = threadIdx.x & (dimk - 1);
+    const long long ngroups = 1ll << (nbits - k), total = (long long)nworks * ngroups;
+    unsigned tmask = 0;
+    for (int i = 0; i < k; ++i) tmask |= 1u << ga.bits[i];
+    unsigned spread = 0;                                       // this thread's row, spread over the target bits
+    for (int i = 0; i < k; ++i) spread |= (unsigned)((row >> i) & 1) << ga.bits[i];
+    for (long long it = (long long)blockIdx.x * gpb; it < total; it += (long long)gridDim.x * gpb) {
+        const long long gi = it + lg;
+        const bool active = gi < total;
+        Work w{};
+        long long off = 0;
+        if (active) {
+            w = works[gi / ngroups];
+            long long g = gi % ngroups;
+            unsigned base = 0;                                  // deposit g into the non-target bits
+            for (int b = 0; b < nbits; ++b)
+                if (!((tmask >> b) & 1u)) { base |= (unsigned)(g & 1) << b; g >>= 1; }
+            off = (long long)(base | spread);
+            cplx v;
+            if (w.flags & WF_INIT) v = cplx{off == 0 ? 1.0 : 0.0, 0.0};
+            else v = states[((long long)w.src << nbits) + off];
+            g_in[lg * dimk + row] = v;
+        }
+        __syncthreads();
+        if (active) {
+            const cplx* Ur = U + (size_t)row * dimk;
+            const cplx* x = g_in + lg * dimk;
+            cplx acc = cmul(Ur[0], x[0]);
+            for (int c = 1; c < dimk; ++c) acc = cfma(Ur[c], x[c], acc);
+            states[((long long)w.slot << nbits) + off] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // tail kernels
 // ---------------------------------------------------------------------------------------------------------------
 // scale[slot] = weight[slot] / sum_tiles norm_part[slot][tile]   (weight: how many trajectories end in this slot's state)

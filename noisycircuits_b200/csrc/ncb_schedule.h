@@ -15,7 +15,8 @@
 namespace ncb {
 
 struct LaunchStep {
-    int kind;          // 0: tile launch over works[begin, begin+count); 1: decide launch over decides[begin, begin+count)
+    int kind;          // 0: tile launch over works[begin, begin+count); 1: decide launch over decides[begin, begin+count);
+                       // 2: generic-unitary launch over works[begin, begin+count) (a segment that is one 5..8-bit unitary)
     int begin, count;
     int seg;           // tile launches: segment (all works of a launch share it)
     int direct;        // tile launches: 1 = every work runs the whole segment without an event (direct kernel)
@@ -103,7 +104,7 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
             return false;
         };
         // main launch
-        LaunchStep st{0, (int)out.works.size(), 0, s, 0};
+        LaunchStep st{sg.pad[0] ? 2 : 0, (int)out.works.size(), 0, s, 0};
         live.clear();
         if (share_prefix && s < trunk_until) {
             Work w{tout, tin, sg.instr_lo, sg.instr_hi, first ? WF_INIT : 0, -1, -1, -1};

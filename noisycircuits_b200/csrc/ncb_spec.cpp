@@ -399,7 +399,7 @@ bool spec_supported(const Program& P, int seg) {
 bool spec_ev_supported(const Program& P, int seg) {
     if (!lean_tiled(P) || seg < 0 || seg >= (int)P.blob_off.size()) return false;
     // every state offset of the tile has to exist (tiles of a state smaller than a tile carry virtual bits)
-    return P.nbits >= P.K;
+    return P.nbits >= P.K && P.segs[seg].pad[0] == 0;          // (not for a segment that is one 5..8-bit unitary)
 }
 
 int spec_ctas_per_sm(const Program& P, const SpecOptions& opt) {

@@ -157,13 +157,46 @@ void emulate_direct_work(const Program& P, const Work& w, int seg, std::vector<c
     }
 }
 
+// a segment that is one 5..8-bit unitary (generic_unitary_kernel): gather, mat-vec, scatter per group
+void emulate_generic(const Program& P, const Work& w, int seg, std::vector<cplx>& states) {
+    const GenericOp* go = nullptr;
+    for (const GenericOp& g : P.generics) if (g.seg == seg) go = &g;
+    if (!go) throw std::runtime_error("generic launch on an ordinary segment");
+    const int k = go->nb, dimk = 1 << k;
+    const cplx* U = reinterpret_cast<const cplx*>(P.pool.data() + go->mat);
+    unsigned tmask = 0;
+    for (int i = 0; i < k; ++i) tmask |= 1u << go->bits[i];
+    std::vector<cplx> in(dimk), out(dimk);
+    for (long long g = 0; g < (1ll << (P.nbits - k)); ++g) {
+        long long gg = g;
+        unsigned base = 0;
+        for (int b = 0; b < P.nbits; ++b)
+            if (!((tmask >> b) & 1u)) { base |= (unsigned)(gg & 1) << b; gg >>= 1; }
+        std::vector<long long> off(dimk);
+        for (int r = 0; r < dimk; ++r) {
+            unsigned sp = 0;
+            for (int i = 0; i < k; ++i) sp |= (unsigned)((r >> i) & 1) << go->bits[i];
+            off[r] = (long long)(base | sp);
+            in[r] = (w.flags & WF_INIT) ? cplx{off[r] == 0 ? 1.0 : 0.0, 0.0} : states[((size_t)w.src << P.nbits) + off[r]];
+        }
+        for (int r = 0; r < dimk; ++r) {
+            cplx acc = cmul(U[(size_t)r * dimk], in[0]);
+            for (int c = 1; c < dimk; ++c) acc = cfma(U[(size_t)r * dimk + c], in[c], acc);
+            out[r] = acc;
+        }
+        for (int r = 0; r < dimk; ++r) states[((size_t)w.slot << P.nbits) + off[r]] = out[r];
+    }
+}
+
 void run_plan(const Program& P, const BatchPlan& plan, int B, std::vector<cplx>& states, std::vector<double>& norm_part) {
     const int tile_shift = P.nbits > P.K ? P.nbits - P.K : 0, ntiles = 1 << tile_shift;
     std::vector<double> red_part((size_t)B * ntiles * 32, 0.0);
     norm_part.assign((size_t)B * ntiles, 0.0);
     std::vector<Decision> decisions(B);
     for (const LaunchStep& st : plan.steps) {
-        if (st.kind == 0) {
+        if (st.kind == 2) {
+            for (int i = 0; i < st.count; ++i) emulate_generic(P, plan.works[st.begin + i], st.seg, states);
+        } else if (st.kind == 0) {
             for (int i = 0; i < st.count; ++i) {
                 const Work& w = plan.works[st.begin + i];
                 if (st.direct && P.R == 3) { emulate_direct_work(P, w, st.seg, states); continue; }      // (as Engine::launch_step)

@@ -641,3 +641,33 @@ def test_execute_sharded_gpu_branch(heron_noise):
     c = execute_sharded(n, instr, sq, tq, mdict, [0, 5, 7], 40, executor=ex, traj_offset=56)
     d = execute(n, instr, sq, tq, mdict, [0, 5, 7], 40, executor=ex, traj_offset=56)
     assert np.abs(c - d).max() < 1e-14 and c.shape == (8,)
+
+
+@pytest.mark.parametrize("n", [7, 14])
+def test_unitaries_on_five_to_eight_qubits_gpu(heron_noise, n):
+    """`unitary` on 5..8 qubits (QuantumGates.hpp:968-1064 takes any k): generic_unitary_kernel segments between ordinary
+    ones -- pure state against the oracle (1e-12), noisy replay state by state, density matrix at 5 qubits."""
+    sq, tq, _, _ = heron_noise
+    rng = np.random.default_rng(40 + n)
+
+    def haar(k):
+        d = 1 << k
+        return np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))[0]
+    layer = circuits.heron_layered(n, 1, circuits.coupled_pairs(tq, n, adjacent_only=True), seed=n)
+    instr = []
+    for k in (5, 6, min(8, n), 7):
+        instr += [["unitary", [int(q) for q in rng.choice(n, size=k, replace=False)], haar(k)]] + layer
+    instr += [["unitary", [int(q) for q in rng.choice(n, size=5, replace=False)], haar(5)]]
+    ref = oracle.Program(n, instr, noisy=False).pure_state()
+    assert np.abs(PureStateSolver(n, instr, 1, True).solve() - ref).max() < 1e-12
+    assert np.abs(PureStateSolver(n, instr, 1, True, strict_order=True).solve() - ref).max() < 1e-12
+    stats, prog = replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(n), 4, len(instr)))
+    assert prog.query(_lib.Q_RESIDENT) == 0 and stats["events"] > 0
+    got, _ = prog.run_mcwf(32, seed=3)                              # free running, shared prefix
+    assert abs(got.sum() - 32) < 1e-9
+    if n == 7:
+        m = 5
+        dinstr = circuits.heron_layered(m, 1, circuits.coupled_pairs(tq, m), seed=1) + [["unitary", [3, 0, 4, 1, 2], haar(5)]] + \
+            circuits.heron_layered(m, 1, circuits.coupled_pairs(tq, m), seed=2)
+        dm = DensityMatrixSolver(m, sq, tq, dinstr, 1).solve(list(range(m)))
+        assert np.abs(dm - oracle.density_matrix_probs(m, dinstr, sq, tq)).max() < TOL

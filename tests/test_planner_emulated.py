@@ -227,3 +227,49 @@ def test_random_circuits_all_gates_random_channels(case):
     U = jumpy_uniforms(rng, 4, len(instr))
     stats, _E = check_replay(n, instr, sq, tq, U, tile_bits=tile_bits, reg_bits=reg_bits, low_bits=2, fuse=1, reorder=1)
     assert stats["events"] > 0
+
+
+def _haar(rng, k):
+    d = 1 << k
+    return np.linalg.qr(rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d)))[0]
+
+
+@pytest.mark.parametrize("n,tile_bits,reg_bits", [(7, 12, 3), (9, 12, 4), (13, 9, 3), (14, 11, 4)])
+def test_unitaries_on_five_to_eight_qubits(heron_noise, n, tile_bits, reg_bits):
+    """`unitary` on k = 5..8 qubits (the reference's apply_unitary_gate takes any k, QuantumGates.hpp:968-1064): a segment
+    of its own, run as gather -> mat-vec -> scatter.  Pure state (reordered and strict), with noise around it (the
+    instruction itself is noise free, FunctionMapper.hpp:77), first and last in the circuit, against the oracle."""
+    sq, tq, _, _ = heron_noise
+    rng = np.random.default_rng(n)
+    pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)
+    layer = circuits.heron_layered(n, 1, pairs, seed=n)
+    instr = []
+    for k in (5, 6, min(8, n), 7 if n >= 7 else 5):
+        qs = [int(q) for q in rng.choice(n, size=k, replace=False)]
+        instr += [["unitary", qs, _haar(rng, k)]] + layer
+    instr += [["unitary", [int(q) for q in rng.choice(n, size=5, replace=False)], _haar(rng, 5)]]      # last instruction
+    ref = oracle.Program(n, instr, noisy=False).pure_state()
+    for reorder in (1, 0):
+        E = EmuProgram(PackedCircuit(n, instr, noisy=False), 2, tile_bits=tile_bits, reg_bits=reg_bits, reorder=reorder)
+        assert np.abs(E.run_deterministic() - ref).max() < 1e-12
+    # noisy trajectories: replay with explicit uniforms (the engine's order; the uniforms stay with their instructions)
+    E = EmuProgram(PackedCircuit(n, instr, sq, tq), 0, tile_bits=tile_bits, reg_bits=reg_bits)
+    order = E.order()
+    U = np.random.default_rng(1).random((3, len(instr)))
+    U[1:] = 1 - 0.03 * np.random.default_rng(2).random((2, len(instr))) ** 2
+    states, stats = E.mcwf_states(U)
+    O = oracle.Program(n, [instr[g] for g in order], sq, tq)
+    for t in range(3):
+        assert np.abs(states[t] - O.trajectory(U[t][order], mask_fix=True)).max() < TOL
+    assert stats["events"] > 0
+
+
+def test_density_matrix_with_a_five_qubit_unitary(heron_noise):
+    sq, tq, _, _ = heron_noise
+    n = 5
+    rng = np.random.default_rng(3)
+    instr = circuits.heron_layered(n, 1, circuits.coupled_pairs(tq, n), seed=1) + [["unitary", [3, 0, 4, 1, 2], _haar(rng, 5)]] + \
+        circuits.heron_layered(n, 1, circuits.coupled_pairs(tq, n), seed=2)
+    E = EmuProgram(PackedCircuit(n, instr, sq, tq), 1, tile_bits=9, reg_bits=4)
+    rho = E.run_deterministic().reshape(1 << n, 1 << n).T
+    assert np.abs(rho - oracle.density_matrix(n, instr, sq, tq)).max() < TOL
