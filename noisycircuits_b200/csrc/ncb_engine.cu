@@ -211,6 +211,11 @@ struct Engine {
     DevBuf<DecideItem> d_decides[2];
     PinnedBuf<Work> h_works[2];
     PinnedBuf<DecideItem> h_decides[2];
+    // generated event kernels decide in the kernel (last CTA of a state): per work the event's uniform, per slot a ticket
+    DevBuf<double> d_work_u[2];
+    PinnedBuf<double> h_work_u[2];
+    DevBuf<int> d_tickets;
+    const double* cur_work_u = nullptr;
     cudaEvent_t buf_free[2] = {nullptr, nullptr};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     // second stream: a segment's jump-event chain (first pieces, decide, rounds) runs beside the direct launch of the
@@ -223,9 +228,10 @@ struct Engine {
     ~Engine() {
         d_ops.release(); d_passes.release(); d_segs.release(); d_instrs.release(); d_chans.release(); d_pool.release();
         d_noisy.release(); d_orig.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_weight.release(); d_trunk.release(); d_probs.release();
-        d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release();
+        d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release(); d_tickets.release();
         for (int i = 0; i < 2; ++i) {
             d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
+            d_work_u[i].release(); h_work_u[i].release();
             if (buf_free[i]) cudaEventDestroy(buf_free[i]);
         }
         for (void* m : spec_modules) if (g_drv.ModuleUnload) g_drv.ModuleUnload(m);
@@ -642,8 +648,11 @@ struct Engine {
                     rc = g_drv.LaunchKernel(f.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)spec_smem(false), (void*)s, args, nullptr);
                 } else {
                     double *red = d_red.p, *nrm = d_norm.p;
-                    const Decision* dec = d_dec.p;
-                    void* args[] = {(void*)&d, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift, (void*)&red, (void*)&nrm, (void*)&dec};
+                    Decision* dec = d_dec.p;
+                    const double* wu = cur_work_u ? cur_work_u + st.begin : nullptr;
+                    int* tk = d_tickets.p;
+                    void* args[] = {(void*)&d, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift, (void*)&red, (void*)&nrm,
+                                    (void*)&dec, (void*)&wu, (void*)&tk};
                     rc = g_drv.LaunchKernel(f.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)spec_smem(true), (void*)s, args, nullptr);
                 }
                 if (rc != 0) throw std::runtime_error("cuLaunchKernel of a specialised kernel failed (" + std::to_string(rc) + ")");
@@ -840,6 +849,9 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
         direct_norm = !spec_fn.empty() && spec_fn.back().fn != nullptr;
     }
     CK(cudaMemsetAsync(d_red.p, 0, (size_t)SL * ntiles * RED_VALUES * sizeof(double), s));
+    d_tickets.reserve(SL);
+    CK(cudaMemsetAsync(d_tickets.p, 0, (size_t)SL * sizeof(int), s));
+    const bool fused_decide_on = specialize && (ensure_spec(), !spec_ev_fn.empty());
     for (long long b0 = 0; b0 < count; b0 += B) {
         const int nb = (int)std::min<long long>(B, count - b0);
         if (rp->rng == NCB_RNG_MT19937_REFERENCE) {
@@ -871,6 +883,22 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             std::memcpy(h_decides[buf].p, plan.decides.data(), plan.decides.size() * sizeof(DecideItem));
             CK(cudaMemcpyAsync(d_decides[buf].p, h_decides[buf].p, plan.decides.size() * sizeof(DecideItem), cudaMemcpyHostToDevice, s));
         }
+        cur_work_u = nullptr;
+        if (fused_decide_on) {
+            // the uniform of the event each reducing work ends in (the generated event kernels decide in the kernel)
+            h_work_u[buf].reserve_growing(plan.works.size() + 1); d_work_u[buf].reserve_growing(plan.works.size() + 1);
+            for (size_t i = 0; i < plan.works.size(); ++i) {
+                const Work& w = plan.works[i];
+                double u = 0.0;
+                if ((w.flags & WF_REDUCE) && w.slot < nb)
+                    for (const Event& e : events[w.slot])
+                        if (e.instr == w.instr_hi - 1) { u = e.u; break; }
+                h_work_u[buf].p[i] = u;
+            }
+            CK(cudaMemcpyAsync(d_work_u[buf].p, h_work_u[buf].p, plan.works.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+            rp->out_h2d_bytes += (int64_t)(plan.works.size() * sizeof(double));
+            cur_work_u = d_work_u[buf].p;
+        }
         const bool overlap = overlap_streams && share;
         auto join = [&]() {          // both streams wait for each other
             CK(cudaEventRecord(ev_a, s));
@@ -887,6 +915,8 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
             if (st.kind == 0) { rp->out_spec_launches += launch_step(st, q, d_works[buf].p) ? 1 : 0; ++rp->out_tile_launches; }
             else if (st.kind == 2) { launch_generic(st, q, d_works[buf].p); ++rp->out_tile_launches; }
             else {
+                // (the generated event kernel of this segment has decided already: last CTA of every reducing state)
+                if (fused_decide_on && st.seg < (int)spec_ev_fn.size() && spec_ev_fn[st.seg].fn) continue;
                 decide_kernel<<<st.count, 256, 0, q>>>(d, d_decides[buf].p + st.begin, st.count, d_red.p, ntiles, d_dec.p);
                 CK(cudaGetLastError());
             }

@@ -142,6 +142,34 @@ static __device__ __noinline__ void event_reduce(const cplx* sm, int K, int p0, 
     __syncthreads();
 }
 
+// Branch decision by the CTA that delivered the LAST partial of a state (generated event kernels: no decide launch).
+// src: the state's ntiles x RED_VALUES partials (written by other CTAs: read around L1); the sum runs in a fixed order --
+// warp w adds the tiles o = w (mod nwarps), warp 0 adds the warps' sums in order -- so it does not depend on which CTA
+// happens to be last.  s_buf: >= (nwarps + 1) * 32 doubles of shared memory.
+static __device__ __noinline__ void fused_decide(const DevProgram& P, const double* src, int ntiles, int instr, double u,
+                                                 Decision* out, double* s_buf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double s = 0.0;
+    for (int o = warp; o < ntiles; o += nwarps) s += __ldcg(src + (long long)o * RED_VALUES + lane);
+    s_buf[warp * RED_VALUES + lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double* rho = s_buf + nwarps * RED_VALUES;
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += s_buf[w * RED_VALUES + lane];
+        rho[lane] = t;
+        __syncwarp();
+        if (lane == 0) {
+            const Channel ch = P.chans[P.instrs[instr].channel];
+            mirror_rho(rho, ch.dim);
+            double scale;
+            out->k = decide_branch(rho, ch, P.pool, u, &scale);
+            out->scale = scale;
+        }
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // tile kernel
 // ---------------------------------------------------------------------------------------------------------------

@@ -270,10 +270,12 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
     o << "extern \"C\" __global__ void __launch_bounds__(" << (1 << (K - R)) << ", " << spec_ctas_per_sm(P, opt) << ") ncb_seg_" << seg << "_ev"
       << "(DevProgram P, const unsigned char* __restrict__ pool_g, int pool_bytes, int pool_cap,\n"
          "        const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int tile_shift,\n"
-         "        double* __restrict__ red_part, double* __restrict__ norm_part, const Decision* __restrict__ decisions) {\n"
+         "        double* __restrict__ red_part, double* __restrict__ norm_part, Decision* decisions,\n"
+         "        const double* __restrict__ work_u, int* tickets) {\n"
          "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
          "    __shared__ double s_buf[32 * 20];\n"
          "    __shared__ double s_out[20];\n"
+         "    __shared__ int s_last;\n"
          "    const int tid = threadIdx.x, nthreads = blockDim.x;\n"
          "    const int ntiles = 1 << tile_shift;\n"
          "    const long long total = (long long)nworks << tile_shift;\n"
@@ -363,6 +365,15 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
          "            const Instr in = P.instrs[w.instr_hi - 1];\n"
          "            const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;\n"
          "            event_reduce(sm, K, p0, p1, s_buf, s_out, red_part + ((long long)w.slot * ntiles + o) * RED_VALUES);\n"
+         "            // the CTA that delivers the last partial of this state decides the branch: no decide launch in the chain\n"
+         "            __threadfence();\n"
+         "            if (tid == 0) s_last = atomicAdd(&tickets[w.slot], 1) == ntiles - 1;\n"
+         "            __syncthreads();\n"
+         "            if (s_last) {\n"
+         "                __threadfence();\n"
+         "                fused_decide(P, red_part + (long long)w.slot * ntiles * RED_VALUES, ntiles, w.instr_hi - 1, work_u[t >> tile_shift], decisions + w.slot, s_buf);\n"
+         "                if (tid == 0) tickets[w.slot] = 0;\n"
+         "            }\n"
          "        }\n"
          "        if (w.flags & WF_NORM) {\n"
          "            double v[1] = {0.0};\n"
@@ -444,7 +455,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 6 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 7 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);
