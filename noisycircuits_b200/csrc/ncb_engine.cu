@@ -531,12 +531,22 @@ struct Engine {
                 if (verbose) fprintf(stderr, "[ncb] specialised kernels: neither libnvrtc nor %s is usable\n", nvcc.c_str());
                 return "";
             }
+            // several processes (one per GPU) build the same cache at once: each starts at another part and skips what a
+            // neighbour has finished meanwhile
+            {
+                int rot = 0;
+                if (const char* e = getenv("LOCAL_RANK")) rot = atoi(e);
+                int ranks = 1;
+                if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+                std::rotate(todo.begin(), todo.begin() + (size_t)((long long)rot * (long long)todo.size() / ranks) % todo.size(), todo.end());
+            }
             std::atomic<int> next{0}, failed{0};
             auto worker = [&]() {
                 for (;;) {
                     const int i = next.fetch_add(1);
                     if (i >= (int)todo.size()) break;
                     const int k = todo[i];
+                    if (exists(dir + "/part" + std::to_string(k) + ".cubin")) continue;
                     // several processes (one per GPU) may build the same cache at once: private temporaries, atomic renames
                     const std::string base = dir + "/part" + std::to_string(k), mine = base + "." + std::to_string((long)getpid());
                     const std::string src = spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_opt);
