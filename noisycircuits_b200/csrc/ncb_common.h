@@ -256,6 +256,10 @@ enum WorkFlags : int32_t {
     WF_NORM = 32,          // finally accumulate the squared norm
     WF_MID = 64,           // a jump whose branch is known from u alone happens INSIDE the range: run [instr_lo, mid_instr]
                            // with the bare gate, apply Kraus operator (flags >> 16) of mid_instr, go on with the rest
+    WF_PULL = 128,         // (with WF_MID) that in-line jump is the trajectory's ONLY event in this segment: a merged operator
+                           // group that does not touch the jump's qubits may run as a whole on one side of the jump (operators
+                           // on disjoint qubits commute exactly, the branch does not depend on the state) instead of being
+                           // split into its members around it.  Honoured by the generated event kernels, ignored elsewhere.
 };
 struct Work {
     int32_t slot, src, instr_lo, instr_hi;     // src: slot the tiles are READ from (== slot except when a trajectory

@@ -279,6 +279,7 @@ struct Engine {
             CK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
             if (const char* e2 = getenv("NCB_DIRECT_CHUNK")) direct_chunk = atoi(e2);
             if (const char* e2 = getenv("NCB_EV_CHUNK")) ev_chunk = atoi(e2);
+            if (const char* e2 = getenv("NCB_EV_PULL")) ev_pull = atoi(e2) != 0;
             if (const char* e2 = getenv("NCB_OVERLAP")) overlap_streams = atoi(e2) != 0;
             d_counters.reserve(4);
             device_ready = true;
@@ -404,6 +405,7 @@ struct Engine {
     }
     // direct kernel (works that run a whole segment without an event; lean programs only)
     int ev_chunk = 0;
+    bool ev_pull = true;          // generated event kernels keep merged groups whole around an in-line jump they do not touch (WF_PULL)
     int direct_ctas = 0, direct_chunk = 8;       // tiles per direct-kernel CTA: CTA turnover lets the (higher-priority) event chain in
                                                  // (measured on the 20-qubit workload: 8 -> 2612, 16 -> 2557, 32 -> 2531, persistent -> slower)
     size_t direct_smem() const {
@@ -661,8 +663,9 @@ struct Engine {
                     Decision* dec = d_dec.p;
                     const double* wu = cur_work_u ? cur_work_u + st.begin : nullptr;
                     int* tk = d_tickets.p;
+                    int pull_on = ev_pull ? 1 : 0;
                     void* args[] = {(void*)&d, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift, (void*)&red, (void*)&nrm,
-                                    (void*)&dec, (void*)&wu, (void*)&tk};
+                                    (void*)&dec, (void*)&wu, (void*)&tk, &pull_on};
                     rc = g_drv.LaunchKernel(f.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)spec_smem(true), (void*)s, args, nullptr);
                 }
                 if (rc != 0) throw std::runtime_error("cuLaunchKernel of a specialised kernel failed (" + std::to_string(rc) + ")");

@@ -90,6 +90,7 @@ inline void schedule_batch(const Program& P, const std::vector<std::vector<Event
             if (inline_certain && cur[b] < end[b] && events[b][cur[b]].kmin == events[b][cur[b]].kmax && events[b][cur[b]].kmin < 0x8000) {
                 const Event& m = events[b][cur[b]];
                 w.flags |= WF_MID | (m.kmin << 16);
+                if (end[b] - cur[b] == 1 && w.instr_lo == sg.instr_lo) w.flags |= WF_PULL;      // the only event of the segment
                 w.mid_instr = m.instr;
                 ++cur[b];
             }

@@ -271,7 +271,7 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
       << "(DevProgram P, const unsigned char* __restrict__ pool_g, int pool_bytes, int pool_cap,\n"
          "        const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int tile_shift,\n"
          "        double* __restrict__ red_part, double* __restrict__ norm_part, Decision* decisions,\n"
-         "        const double* __restrict__ work_u, int* tickets) {\n"
+         "        const double* __restrict__ work_u, int* tickets, int pull_on) {\n"
          "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
          "    __shared__ double s_buf[32 * 20];\n"
          "    __shared__ double s_out[20];\n"
@@ -299,7 +299,9 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
         o << "        cp_async16(sm + (sA ^ " << sg.it_swz[it] << "), st + (offA | " << hex(sg.it_off[it]) << "));\n";
     o << "    };\n";
     // the pass programs, every operator guarded by its instruction index (what run_range + fetch() interpret)
-    o << "    auto run_passes = [&](const int lo, const int hi, const bool bare) {\n";
+    // qb / qe: tile positions of the qubits of the in-line jump this range begins after / ends in when merged groups that do
+    // not touch them may stay whole (WF_PULL); ~0u otherwise (every group "touches": strict splitting by instruction index)
+    o << "    auto run_passes = [&](const int lo, const int hi, const bool bare, const unsigned qb, const unsigned qe) {\n";
     for (int p = 0; p < npass; ++p) {
         const Pass& ps = bv.passes[p];
         if (ps.instr_hi <= ps.instr_lo) continue;
@@ -319,9 +321,20 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
             const Op& op = bv.ops[i];
             if (op.kind_nb >> 31) {
                 const int span = (int)((op.kind_nb >> 25) & 0x3f), last = op.pad;
-                o << "            if (__builtin_expect(" << op.instr << " >= lo && (" << last + 1 << " < hi || (" << last + 1 << " == hi && !bare)), 1)) {\n";
+                // tile positions the merged operator touches
+                unsigned gm = 0;
+                if (op_kind(op) == OPK_DIAG) {
+                    gm = (op.rbs & 0xffffu) | (op.rbs >> 16);
+                    for (int r = 0; r < R; ++r) if ((op_regmask(op) >> r) & 1) gm |= 1u << ps.regpos[r];
+                } else {
+                    gm = 1u << ps.regpos[op_rb(op, 0)];
+                }
+                o << "            if (__builtin_expect(" << op.instr << " >= lo && ((" << last + 1 << " < hi || (" << last + 1 << " == hi && !bare)) || ("
+                  << op.instr << " < hi && !(" << hex(gm) << " & qe))), 1)) {\n";
                 emit_general_op(o, op, p, R, std::to_string(op.mat), "                ");
-                o << "            } else {\n";
+                o << "            } else if (" << op.instr << " < lo && !(" << hex(gm) << " & qb)) {\n"
+                     "                // ran as a whole before the jump this range begins after\n"
+                     "            } else {\n";
                 for (int j = 1; j <= span; ++j) member(bv.ops[i + j], "                ", false);
                 o << "            }\n";
                 i += span;
@@ -351,10 +364,17 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
          "        else if (w.flags & WF_PRO_DYNAMIC) event_apply(sm, P, sg, w.ev_instr, decisions[w.slot].k, decisions[w.slot].scale);\n"
          "        {\n"
          "            int lo = w.instr_lo;\n"
+         "            unsigned qmid = ~0u;\n"
+         "            if ((w.flags & WF_PULL) && pull_on) {\n"
+         "                const Instr in = P.instrs[w.mid_instr];\n"
+         "                qmid = 1u << tile_pos(*sg, K, in.q0);\n"
+         "                if (in.q1 >= 0) qmid |= 1u << tile_pos(*sg, K, in.q1);\n"
+         "            }\n"
          "            for (int part = (w.flags & WF_MID) ? 0 : 1; part < 2; ++part) {\n"
          "                const int hi = part == 0 ? w.mid_instr + 1 : w.instr_hi;\n"
          "                const bool bare = part == 0 ? true : (w.flags & WF_BARE_LAST) != 0;\n"
-         "                run_passes(lo, hi, bare);\n"
+         "                const bool after_mid = part == 1 && (w.flags & WF_MID);\n"
+         "                run_passes(lo, hi, bare, after_mid ? qmid : ~0u, part == 0 ? qmid : ~0u);\n"
          "                if (part == 0) {\n"
          "                    event_apply(sm, P, sg, w.mid_instr, (int)((unsigned)w.flags >> 16), 1.0);\n"
          "                    lo = w.mid_instr + 1;\n"
@@ -366,11 +386,16 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
          "            const int p0 = tile_pos(*sg, K, in.q0), p1 = in.q1 >= 0 ? tile_pos(*sg, K, in.q1) : -1;\n"
          "            event_reduce(sm, K, p0, p1, s_buf, s_out, red_part + ((long long)w.slot * ntiles + o) * RED_VALUES);\n"
          "            // the CTA that delivers the last partial of this state decides the branch: no decide launch in the chain\n"
-         "            __threadfence();\n"
-         "            if (tid == 0) s_last = atomicAdd(&tickets[w.slot], 1) == ntiles - 1;\n"
+         "            // (thread 0 wrote the partial: its fence publishes it before the ticket, the second fence orders the last\n"
+         "            //  CTA's reads after it; a fence by every thread of every reducing tile cost 2-3x on these launches)\n"
+         "            if (tid == 0) {\n"
+         "                __threadfence();\n"
+         "                const int last = atomicAdd(&tickets[w.slot], 1) == ntiles - 1;\n"
+         "                __threadfence();\n"
+         "                s_last = last;\n"
+         "            }\n"
          "            __syncthreads();\n"
          "            if (s_last) {\n"
-         "                __threadfence();\n"
          "                fused_decide(P, red_part + (long long)w.slot * ntiles * RED_VALUES, ntiles, w.instr_hi - 1, work_u[t >> tile_shift], decisions + w.slot, s_buf);\n"
          "                if (tid == 0) tickets[w.slot] = 0;\n"
          "            }\n"
@@ -455,7 +480,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 7 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 8 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);

@@ -671,3 +671,41 @@ def test_unitaries_on_five_to_eight_qubits_gpu(heron_noise, n):
             circuits.heron_layered(m, 1, circuits.coupled_pairs(tq, m), seed=2)
         dm = DensityMatrixSolver(m, sq, tq, dinstr, 1).solve(list(range(m)))
         assert np.abs(dm - oracle.density_matrix_probs(m, dinstr, sq, tq)).max() < TOL
+
+
+def test_generated_event_kernels_single_inline_jump(heron_noise):
+    """Generated event kernels, the WF_PULL path: a trajectory whose only event in a segment is a jump known from the
+    uniform alone keeps the merged operator groups that do not touch the jump's qubits whole around it.  One certain jump
+    per trajectory at 48 different instructions (and a few trajectories with a state-dependent one), replayed state by
+    state against the oracle; the same with the pull switched off gives the same states."""
+    sq, tq, _, _ = heron_noise
+    n = 15
+    instr = circuits.heron_layered(n, 5, circuits.coupled_pairs(tq, n), seed=31)
+    prog = Program(PackedCircuit(n, instr, sq, tq), _lib.MODE_MCWF, specialize=True)
+    order = prog.order()
+    G = len(instr)
+    rng = np.random.default_rng(4)
+    rows, kinds = [], []
+    for g in rng.permutation(G):
+        if len(rows) >= 56:
+            break
+        for trial in range(40):
+            u = np.full(G, 0.5)
+            u[g] = 1.0 - 10.0 ** (-rng.uniform(0.5, 5.0))
+            ev = prog.events(u)
+            if len(ev) == 1 and int(ev[0][0]) == g:
+                certain = int(ev[0][1]) == int(ev[0][2])
+                if certain and kinds.count("certain") < 48 or (not certain and kinds.count("hard") < 8):
+                    rows.append(u); kinds.append("certain" if certain else "hard")
+                    break
+    assert kinds.count("certain") >= 30 and kinds.count("hard") >= 2
+    U = np.array(rows)
+    O = oracle.Program(n, [instr[g] for g in order], sq, tq)
+    _p, states, stats = prog.run_mcwf(U.shape[0], uniforms=U, return_states=True)
+    assert stats["events"] == U.shape[0] and stats["specialized_launches"] == stats["tile_launches"] > 0
+    worst = max(float(np.abs(states[t] - O.trajectory(U[t][order], mask_fix=True)).max()) for t in range(U.shape[0]))
+    assert worst < TOL, worst
+    # batched (shared prefix: every trajectory forks from the trunk at the segment of its jump)
+    probs, _ = prog.run_mcwf(U.shape[0], rng=_lib.RNG_EXPLICIT, uniforms=U)
+    ref = sum(np.abs(O.trajectory(U[t][order], mask_fix=True)) ** 2 for t in range(U.shape[0]))
+    assert np.abs(probs - ref).max() < TOL * U.shape[0]
