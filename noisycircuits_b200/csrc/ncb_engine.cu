@@ -662,7 +662,7 @@ struct Engine {
                     double *red = d_red.p, *nrm = d_norm.p;
                     Decision* dec = d_dec.p;
                     const double* wu = cur_work_u ? cur_work_u + st.begin : nullptr;
-                    int* tk = d_tickets.p;
+                    int* tk = cur_work_u ? d_tickets.p : nullptr;          // (null: a decide launch follows, NCB_FUSED_DECIDE=0)
                     int pull_on = ev_pull ? 1 : 0;
                     void* args[] = {(void*)&d, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift, (void*)&red, (void*)&nrm,
                                     (void*)&dec, (void*)&wu, (void*)&tk, &pull_on};
@@ -864,7 +864,12 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
     CK(cudaMemsetAsync(d_red.p, 0, (size_t)SL * ntiles * RED_VALUES * sizeof(double), s));
     d_tickets.reserve(SL);
     CK(cudaMemsetAsync(d_tickets.p, 0, (size_t)SL * sizeof(int), s));
-    const bool fused_decide_on = specialize && (ensure_spec(), !spec_ev_fn.empty());
+    // NCB_FUSED_DECIDE=1: the generated event kernels decide the branch themselves (last CTA of a state) instead of a decide
+    // launch between the pieces.  Off by default: measured 3 % slower (the chain's latency is hidden behind the segment's
+    // whole-segment launch anyway, while the deciding CTA's sum over 512 partials sits in the event launch's tail).
+    bool fused_decide_on = false;
+    if (const char* e = getenv("NCB_FUSED_DECIDE")) fused_decide_on = atoi(e) != 0;
+    fused_decide_on = fused_decide_on && specialize && (ensure_spec(), !spec_ev_fn.empty());
     for (long long b0 = 0; b0 < count; b0 += B) {
         const int nb = (int)std::min<long long>(B, count - b0);
         if (rp->rng == NCB_RNG_MT19937_REFERENCE) {

@@ -149,8 +149,17 @@ static __device__ __noinline__ void event_reduce(const cplx* sm, int K, int p0, 
 static __device__ __noinline__ void fused_decide(const DevProgram& P, const double* src, int ntiles, int instr, double u,
                                                  Decision* out, double* s_buf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double s = 0.0;
-    for (int o = warp; o < ntiles; o += nwarps) s += __ldcg(src + (long long)o * RED_VALUES + lane);
+    // eight independent accumulators per lane (the loads are L2 round trips: a single dependent chain took ~60 us for 512
+    // tiles and sat in the launch's tail), added in a fixed order
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int o = warp; o < ntiles; o += 8 * nwarps) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int oo = o + j * nwarps;
+            if (oo < ntiles) acc[j] += __ldcg(src + (long long)oo * RED_VALUES + lane);
+        }
+    }
+    const double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     s_buf[warp * RED_VALUES + lane] = s;
     __syncthreads();
     if (warp == 0) {

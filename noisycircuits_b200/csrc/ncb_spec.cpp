@@ -388,6 +388,7 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
          "            // the CTA that delivers the last partial of this state decides the branch: no decide launch in the chain\n"
          "            // (thread 0 wrote the partial: its fence publishes it before the ticket, the second fence orders the last\n"
          "            //  CTA's reads after it; a fence by every thread of every reducing tile cost 2-3x on these launches)\n"
+         "            if (tickets != nullptr) {\n"
          "            if (tid == 0) {\n"
          "                __threadfence();\n"
          "                const int last = atomicAdd(&tickets[w.slot], 1) == ntiles - 1;\n"
@@ -398,6 +399,7 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
          "            if (s_last) {\n"
          "                fused_decide(P, red_part + (long long)w.slot * ntiles * RED_VALUES, ntiles, w.instr_hi - 1, work_u[t >> tile_shift], decisions + w.slot, s_buf);\n"
          "                if (tid == 0) tickets[w.slot] = 0;\n"
+         "            }\n"
          "            }\n"
          "        }\n"
          "        if (w.flags & WF_NORM) {\n"
@@ -480,7 +482,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 8 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 9 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);
