@@ -448,6 +448,7 @@ struct Engine {
         if (const char* e = getenv("NCB_SPEC_NBUF")) spec_opt.nbuf = atoi(e) == 1 ? 1 : 2;
         if (const char* e = getenv("NCB_SPEC_LOAD")) spec_opt.load = std::min(std::max(atoi(e), 0), 2);
         if (const char* e = getenv("NCB_SPEC_EVENTS")) spec_opt.events = atoi(e) != 0;
+        if (const char* e = getenv("NCB_SPEC_CTAS")) spec_opt.ctas = std::max(0, atoi(e));
         spec_opt.literal = specialize_mode == 2 ? 0 : 1;
         if (const char* e = getenv("NCB_SPEC_LITERAL")) spec_opt.literal = atoi(e) != 0;
     }

@@ -449,6 +449,7 @@ int spec_ctas_per_sm(const Program& P, const SpecOptions& opt) {
         pool_cap = std::max(pool_cap, (blob.bytes - blob.pool_off + 1023) & ~1023);
     }
     const int nbuf = opt.nbuf == 1 ? 1 : 2;
+    if (opt.ctas > 0) return opt.ctas;
     const int by_smem = (int)((227 * 1024) / ((size_t)nbuf * (16u << P.K) + (size_t)pool_cap + 2048));
     const int by_regs = 65536 / (threads * (P.R == 4 ? 128 : 64));
     return std::max(1, std::min({by_smem, by_regs, 8}));
