@@ -229,3 +229,25 @@ def test_spec_cache_eviction(tmp_path, monkeypatch, heron_noise):
         if not prog.specialize_build():
             pytest.skip("no libnvrtc / nvcc on this machine")
     assert len([d for d in os.listdir(tmp_path) if os.path.isdir(os.path.join(tmp_path, d))]) == 2
+
+
+def test_execute_argument_errors_match_the_reference(heron_noise):
+    """backend.execute / execute_sharded raise what QuantumCircuit.execute raises, before anything touches a device
+    (QuantumCircuit.py:391-409; the reference's tests/test_QuantumCircuit_error_handling.py pins these)."""
+    from noisycircuits_b200.backend import execute, execute_sharded
+    sq, tq, meas, _ = heron_noise
+    n = 3
+    instr = circuits.heron_layered(n, 1, circuits.coupled_pairs(tq, n), seed=1)
+    for fn in (execute, execute_sharded):
+        with pytest.raises(TypeError, match="Qubits must be a list of integers"):
+            fn(n, instr, sq, tq, meas, "012", 10)
+        with pytest.raises(TypeError, match="Qubits must be a list of integers"):
+            fn(n, instr, sq, tq, meas, [0, 1.5], 10)
+        with pytest.raises(ValueError, match="out of range"):
+            fn(n, instr, sq, tq, meas, [0, 3], 10)
+        with pytest.raises(ValueError, match="No instructions"):
+            fn(n, [], sq, tq, meas, [0], 10)
+        with pytest.raises(TypeError, match="num_trajectories must be an integer"):
+            fn(n, instr, sq, tq, meas, [0], 10.0)
+        with pytest.raises(ValueError, match="positive integer"):
+            fn(n, instr, sq, tq, meas, [0], 0)
