@@ -58,7 +58,9 @@ bool lean_tiled(const Program& P) {
 }
 
 // the fast list of pass p (whole pass, no jump inside): coefficients as literals or C.c[..], tables in the staged pool
-bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool literal) {
+// scalar: the product of the real factors taken out of the rotations so far (literal mode, factor_scalars); the caller
+// multiplies it back in once, in the segment's last pass
+bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool literal, double* scalar = nullptr) {
     const PassHot& ph = sc.pass[p];
     auto coef = [&](int i) { return literal ? lit(sc.coef[i]) : "C.c[" + std::to_string(i) + "]"; };
     for (int i = ph.fop_begin; i < ph.fop_end; ++i) {
@@ -67,8 +69,30 @@ bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool
         auto rx = [&](int bit, int at) {
             // literal coefficients: a rotation with a vanishing diagonal (x = i rx(pi): cos(pi/2) = 6e-17) is written as the
             // anti-diagonal operator it is -- half the FP64 instructions; the dropped terms are below 1e-15 of the kept ones
-            const double* c = sc.coef + at;
-            if (literal && std::fabs(c[0]) <= 1e-15 * std::fabs(c[1]) && std::fabs(c[3]) <= 1e-15 * std::fabs(c[2])) {
+            const double* c = sc.coef + at;          // [[c0, i c1], [i c2, c3]]
+            const bool xlike = std::fabs(c[0]) <= 1e-15 * std::fabs(c[1]) && std::fabs(c[3]) <= 1e-15 * std::fabs(c[2]);
+            if (literal && scalar && std::isfinite(c[0] + c[1] + c[2] + c[3])) {
+                // one real coefficient factored out: half the FP64 instructions for the symmetric forms, none for x
+                const std::string hd = "<" + std::to_string(R) + ", " + std::to_string(bit) + ">(a";
+                const bool sym = std::fabs(c[0] - c[3]) <= 1e-15 * std::fabs(c[0]) && std::fabs(c[1] - c[2]) <= 1e-15 * std::fabs(c[1]);
+                if (xlike && c[1] != 0.0) {
+                    *scalar *= c[1];
+                    if (std::fabs(c[1] - c[2]) <= 1e-15 * std::fabs(c[1])) o << "            spec_xs" << hd << ");\n";
+                    else o << "            spec_xl2" << hd << ", " << lit(c[2] / c[1]) << ");\n";
+                    return;
+                }
+                if (sym && (c[0] != 0.0 || c[1] != 0.0)) {
+                    if (std::fabs(c[0]) >= std::fabs(c[1])) { *scalar *= c[0]; o << "            spec_rx_s1" << hd << ", " << lit(c[1] / c[0]) << ");\n"; }
+                    else { *scalar *= c[1]; o << "            spec_rx_s2" << hd << ", " << lit(c[0] / c[1]) << ");\n"; }
+                    return;
+                }
+                if (std::fabs(c[0]) >= 0.25 * std::max(std::fabs(c[1]), std::max(std::fabs(c[2]), std::fabs(c[3])))) {
+                    *scalar *= c[0];
+                    o << "            spec_rx_a" << hd << ", " << lit(c[1] / c[0]) << ", " << lit(c[2] / c[0]) << ", " << lit(c[3] / c[0]) << ");\n";
+                    return;
+                }
+            }
+            if (literal && xlike) {
                 o << "            spec_xl<" << R << ", " << bit << ">(a, " << lit(c[1]) << ", " << lit(c[2]) << ");\n";
                 return;
             }
@@ -108,7 +132,14 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
     // the last segment of a program whose operators do not preserve the norm also accumulates the squared norm of every
     // tile (WF_NORM; what the event-capable kernel does for works that carry events): the amplitudes are in registers then
     const bool with_norm = seg == (int)P.segs.size() - 1 && !P.norm_preserving;
+    double scalar = 1.0;
+    double* const sp = (opt.literal && opt.factor) ? &scalar : nullptr;
     auto emit_norm = [&](std::ostringstream& os) {
+        if (scalar != 1.0) {      // the real factors taken out of this segment's rotations, multiplied back in once
+            os << "            {\n                const double S = " << lit(scalar) << ";\n";
+            for (int m = 0; m < NA; ++m) os << "                a[" << m << "].x *= S; a[" << m << "].y *= S;\n";
+            os << "            }\n";
+        }
         if (!with_norm) return;
         os << "            {   // squared norm of the tile: fixed shuffle tree per warp, warps added in order (deterministic)\n"
               "                double nrm = 0.0;\n";
@@ -174,7 +205,7 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
             for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ph.regoff_swz[m] << "];\n";
             if (last && nbuf == 1) o << "            __syncthreads();\n            if (tn < total) issue_load(tn, buf0);\n";
             if (last && nbuf == 2) o << "            __syncthreads();            // this buffer is refilled at the top of the next iteration\n";
-            if (!emit_fast_ops(o, sc, p, R, opt.literal != 0)) return false;
+            if (!emit_fast_ops(o, sc, p, R, opt.literal != 0, sp)) return false;
             if (last) {
                 emit_norm(o);
                 for (int m = 0; m < NA; ++m) o << "            st_stream(dst + (gj_last | " << hex(sc.goff_last[m]) << "), a[" << m << "]);\n";
@@ -220,7 +251,7 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
             if (nbuf == 1 && npass > 1) o << "            __syncthreads();            // every thread holds its amplitudes: the buffer is free for the next tile\n";
             if (load == 2) o << "            if (tn < total) gload(tn, nx);\n";
         }
-        if (!emit_fast_ops(o, sc, p, R, opt.literal != 0)) return false;
+        if (!emit_fast_ops(o, sc, p, R, opt.literal != 0, sp)) return false;
         if (last) {
             emit_norm(o);
             for (int m = 0; m < NA; ++m) o << "            st_stream(dst + (gj_last | " << hex(sc.goff_last[m]) << "), a[" << m << "]);\n";
@@ -483,7 +514,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 9 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 10 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);

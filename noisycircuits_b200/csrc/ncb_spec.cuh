@@ -49,6 +49,63 @@ __device__ __forceinline__ void spec_xl(cplx* a, double b, double c) {
         a[i1] = cplx{-c * x.y, c * x.x};
     }
 }
+// Rotations with ONE real coefficient factored out (the generator multiplies the factors of a segment into one scalar that
+// the last pass applies once): half the FP64 instructions of spec_rx for the symmetric forms.
+//   spec_rx_s1: [[1, i t], [i t, 1]]      (a = d, b = c, |a| >= |b|: factor a, t = b / a)
+//   spec_rx_s2: [[t, i], [i, t]]          (a = d, b = c, |a| <  |b|: factor b, t = a / b)
+//   spec_rx_a:  [[1, i tb], [i tc, td]]   (general: factor a)
+//   spec_xs:    [[0, i], [i, 0]]          (x-like with b = c: no arithmetic at all)
+//   spec_xl2:   [[0, i], [i t, 0]]        (x-like, factor b, t = c / b)
+template <int R, int B>
+__device__ __forceinline__ void spec_rx_s1(cplx* a, double t) {
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1)), i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cplx{x.x - t * y.y, x.y + t * y.x};
+        a[i1] = cplx{y.x - t * x.y, y.y + t * x.x};
+    }
+}
+template <int R, int B>
+__device__ __forceinline__ void spec_rx_s2(cplx* a, double t) {
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1)), i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cplx{t * x.x - y.y, t * x.y + y.x};
+        a[i1] = cplx{t * y.x - x.y, t * y.y + x.x};
+    }
+}
+template <int R, int B>
+__device__ __forceinline__ void spec_rx_a(cplx* a, double tb, double tc, double td) {
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1)), i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cplx{x.x - tb * y.y, x.y + tb * y.x};
+        a[i1] = cplx{td * y.x - tc * x.y, td * y.y + tc * x.x};
+    }
+}
+template <int R, int B>
+__device__ __forceinline__ void spec_xs(cplx* a) {
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1)), i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cplx{-y.y, y.x};
+        a[i1] = cplx{-x.y, x.x};
+    }
+}
+template <int R, int B>
+__device__ __forceinline__ void spec_xl2(cplx* a, double t) {
+#pragma unroll
+    for (int g = 0; g < (1 << (R - 1)); ++g) {
+        const int i0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1)), i1 = i0 | (1 << B);
+        const cplx x = a[i0], y = a[i1];
+        a[i0] = cplx{-y.y, y.x};
+        a[i1] = cplx{-t * x.y, t * x.x};
+    }
+}
 template <int R, int B>
 __device__ __forceinline__ void spec_u(cplx* a, double c0, double c1, double c2, double c3, double c4, double c5, double c6, double c7) {
     const cplx m4[4] = {cplx{c0, c1}, cplx{c2, c3}, cplx{c4, c5}, cplx{c6, c7}};

@@ -14,6 +14,8 @@ struct SpecOptions {
                       // shared-memory round trip less); 2 like 1, and the next tile's loads are issued into a second register
                       // set when the last pass starts, so they overlap its arithmetic and stores
     int events = 1;   // 1: also generate ncb_seg_<k>_ev, the kernel of the works that carry a jump event (pieces of a segment)
+    int factor = 1;   // 1 (literal mode): one real coefficient is factored out of every rotation and the product is multiplied
+                      // back in once per segment -- half the FP64 instructions of the symmetric rotations, none for x
     int ctas = 0;     // > 0: resident CTAs per SM the kernels are compiled for (launch bounds; 0: from registers and shared memory)
     int literal = 1;  // 1: gate coefficients are written into the source as exact literals (ptxas materialises them next to
                       // their use; the cubin then belongs to this circuit AND these angles); 0: they are read from the
