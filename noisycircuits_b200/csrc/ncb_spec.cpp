@@ -60,7 +60,11 @@ bool lean_tiled(const Program& P) {
 // the fast list of pass p (whole pass, no jump inside): coefficients as literals or C.c[..], tables in the staged pool
 // scalar: the product of the real factors taken out of the rotations so far (literal mode, factor_scalars); the caller
 // multiplies it back in once, in the segment's last pass
-bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool literal, double* scalar = nullptr) {
+bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool literal, double* scalar = nullptr /* re, im */) {
+    auto scale_by = [&](double re, double im) {
+        const double x = scalar[0] * re - scalar[1] * im, y = scalar[0] * im + scalar[1] * re;
+        scalar[0] = x; scalar[1] = y;
+    };
     const PassHot& ph = sc.pass[p];
     auto coef = [&](int i) { return literal ? lit(sc.coef[i]) : "C.c[" + std::to_string(i) + "]"; };
     for (int i = ph.fop_begin; i < ph.fop_end; ++i) {
@@ -76,18 +80,18 @@ bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool
                 const std::string hd = "<" + std::to_string(R) + ", " + std::to_string(bit) + ">(a";
                 const bool sym = std::fabs(c[0] - c[3]) <= 1e-15 * std::fabs(c[0]) && std::fabs(c[1] - c[2]) <= 1e-15 * std::fabs(c[1]);
                 if (xlike && c[1] != 0.0) {
-                    *scalar *= c[1];
+                    scale_by(c[1], 0.0);
                     if (std::fabs(c[1] - c[2]) <= 1e-15 * std::fabs(c[1])) o << "            spec_xs" << hd << ");\n";
                     else o << "            spec_xl2" << hd << ", " << lit(c[2] / c[1]) << ");\n";
                     return;
                 }
                 if (sym && (c[0] != 0.0 || c[1] != 0.0)) {
-                    if (std::fabs(c[0]) >= std::fabs(c[1])) { *scalar *= c[0]; o << "            spec_rx_s1" << hd << ", " << lit(c[1] / c[0]) << ");\n"; }
-                    else { *scalar *= c[1]; o << "            spec_rx_s2" << hd << ", " << lit(c[0] / c[1]) << ");\n"; }
+                    if (std::fabs(c[0]) >= std::fabs(c[1])) { scale_by(c[0], 0.0); o << "            spec_rx_s1" << hd << ", " << lit(c[1] / c[0]) << ");\n"; }
+                    else { scale_by(c[1], 0.0); o << "            spec_rx_s2" << hd << ", " << lit(c[0] / c[1]) << ");\n"; }
                     return;
                 }
                 if (std::fabs(c[0]) >= 0.25 * std::max(std::fabs(c[1]), std::max(std::fabs(c[2]), std::fabs(c[3])))) {
-                    *scalar *= c[0];
+                    scale_by(c[0], 0.0);
                     o << "            spec_rx_a" << hd << ", " << lit(c[1] / c[0]) << ", " << lit(c[2] / c[0]) << ", " << lit(c[3] / c[0]) << ");\n";
                     return;
                 }
@@ -110,6 +114,21 @@ bool emit_fast_ops(std::ostringstream& o, const SegConst& sc, int p, int R, bool
         } else if (kind == OPK_RX1) {
             rx(op_rb(op, 0), op.mat);
         } else if (kind == OPK_DENSE1) {
+            const double* c = sc.coef + op.mat;      // u00, u01, u10, u11 (re, im)
+            const double m0 = std::hypot(c[0], c[1]), mx = std::max(std::hypot(c[2], c[3]), std::max(std::hypot(c[4], c[5]), std::hypot(c[6], c[7])));
+            if (literal && scalar && std::isfinite(m0 + mx) && m0 >= 0.25 * mx && m0 > 0.0) {
+                // first entry factored out (a complex scalar this time): [[1, p], [q, r]]
+                auto div = [&](int i, double* re, double* im) {
+                    const double d = c[0] * c[0] + c[1] * c[1];
+                    *re = (c[i] * c[0] + c[i + 1] * c[1]) / d; *im = (c[i + 1] * c[0] - c[i] * c[1]) / d;
+                };
+                double pr, pi, qr, qi, rr, ri;
+                div(2, &pr, &pi); div(4, &qr, &qi); div(6, &rr, &ri);
+                scale_by(c[0], c[1]);
+                o << "            spec_u1<" << R << ", " << op_rb(op, 0) << ">(a, " << lit(pr) << ", " << lit(pi) << ", " << lit(qr) << ", " << lit(qi) << ", "
+                  << lit(rr) << ", " << lit(ri) << ");\n";
+                continue;
+            }
             o << "            spec_u<" << R << ", " << op_rb(op, 0) << ">(a";
             for (int k = 0; k < 8; ++k) o << ", " << coef(op.mat + k);
             o << ");\n";
@@ -132,11 +151,15 @@ bool emit_segment_kernel(std::ostringstream& o, const Program& P, int seg, const
     // the last segment of a program whose operators do not preserve the norm also accumulates the squared norm of every
     // tile (WF_NORM; what the event-capable kernel does for works that carry events): the amplitudes are in registers then
     const bool with_norm = seg == (int)P.segs.size() - 1 && !P.norm_preserving;
-    double scalar = 1.0;
-    double* const sp = (opt.literal && opt.factor) ? &scalar : nullptr;
+    double scalar[2] = {1.0, 0.0};
+    double* const sp = (opt.literal && opt.factor) ? scalar : nullptr;
     auto emit_norm = [&](std::ostringstream& os) {
-        if (scalar != 1.0) {      // the real factors taken out of this segment's rotations, multiplied back in once
-            os << "            {\n                const double S = " << lit(scalar) << ";\n";
+        if (scalar[1] != 0.0) {   // the factors taken out of this segment's one-qubit operators, multiplied back in once
+            os << "            {\n                const cplx S{" << lit(scalar[0]) << ", " << lit(scalar[1]) << "};\n";
+            for (int m = 0; m < NA; ++m) os << "                a[" << m << "] = cmul(a[" << m << "], S);\n";
+            os << "            }\n";
+        } else if (scalar[0] != 1.0) {
+            os << "            {\n                const double S = " << lit(scalar[0]) << ";\n";
             for (int m = 0; m < NA; ++m) os << "                a[" << m << "].x *= S; a[" << m << "].y *= S;\n";
             os << "            }\n";
         }
@@ -514,7 +537,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 10 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 11 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);
