@@ -438,7 +438,7 @@ def test_specialised_kernels_are_the_interpreter_written_out(heron_noise):
     if not spec.specialize_build():
         pytest.skip("nvcc not usable on this box: the interpreter is the only path")
     src = spec.specialized_source(0, 1)
-    assert "ncb_seg_0" in src and "spec_rx<" in src and "switch" not in src
+    assert "ncb_seg_0" in src and "spec_rx" in src and "switch" not in src
     plain = Program(pk, _lib.MODE_MCWF)
     T, seed = 300, 21
     a, sa = spec.run_mcwf(T, seed=seed)
