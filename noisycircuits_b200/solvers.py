@@ -140,7 +140,12 @@ class RemoteExecutor:
         opts = dict(self.engine_options)
         opts.setdefault("specialize", "parametric" if num_trajectories >= self.SPECIALIZE_FROM else False)   # a sweep: one kernel set
         packs = iter(packs)
-        engines = [None, None]
+        # the two engine objects live as long as the executor: a training loop calls this every step, and creating an engine
+        # means a dozen device allocations (each can stall for tens of milliseconds next to a large state batch)
+        key = tuple(sorted((k, str(v)) for k, v in opts.items()))
+        if getattr(self, "_sweep_key", None) != key:
+            self._sweep_key, self._sweep_engines = key, [None, None]
+        engines = self._sweep_engines
 
         def prepare(slot):
             packed = next(packs)
