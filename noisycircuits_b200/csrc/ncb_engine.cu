@@ -229,6 +229,8 @@ struct Engine {
         d_ops.release(); d_passes.release(); d_segs.release(); d_instrs.release(); d_chans.release(); d_pool.release();
         d_noisy.release(); d_orig.release(); d_blobs.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_weight.release(); d_trunk.release(); d_probs.release();
         d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release(); d_tickets.release();
+        d_thresh.release(); d_seg_pool.release(); d_block_count.release(); d_nitems.release(); d_ckpt_for.release(); d_items.release();
+        d_items_tmp.release(); d_ckpt.release();
         for (int i = 0; i < 2; ++i) {
             d_works[i].release(); d_decides[i].release(); h_works[i].release(); h_decides[i].release();
             d_work_u[i].release(); h_work_u[i].release();
@@ -303,11 +305,13 @@ struct Engine {
             throw std::runtime_error("ncb_program_update: the new circuit compiles to another geometry (qubits / tile / register bits): create a new program");
         P = std::move(np);
         uploaded = false;
+        res_tables = false;
         tile_configured = false;
         direct_ctas = 0;
         if (spec_tried && (spec_key_loaded.empty() || spec_key(P, spec_opt) != spec_key_loaded)) {
             for (void* m : spec_modules) if (g_drv.ModuleUnload) g_drv.ModuleUnload(m);
             spec_modules.clear(); spec_fn.clear(); spec_ev_fn.clear();
+            res_fn = res_trunk_fn = nullptr;
             spec_tried = false;
             spec_key_loaded.clear();
         }
@@ -504,8 +508,14 @@ struct Engine {
         const bool verbose = getenv("NCB_VERBOSE") != nullptr;
         int nsupported = 0;
         for (int sgi = 0; sgi < (int)P.segs.size(); ++sgi) nsupported += spec_supported(P, sgi);
-        if (!nsupported) return "";
+        const bool res = resident() && spec_resident_supported(P);       // one more part: the resident kernels
+        if (!nsupported && !res) return "";
         read_spec_options();
+        if (res && verbose) {
+            const ResidentLayout lay = spec_resident_layout(P, spec_opt);
+            fprintf(stderr, "[ncb] generated resident kernels: %d B of staged tables, %zu B shared memory, accumulator in %s memory, %d CTAs/SM planned\n",
+                    lay.pool_bytes, lay.smem, lay.acc_global ? "global" : "shared", lay.ctas);
+        }
         const std::string libdir = this_library_dir();
         const std::string cache = spec_cache_root(libdir);
         if (cache.empty()) { if (verbose) fprintf(stderr, "[ncb] specialised kernels: no writable cache directory\n"); return ""; }
@@ -520,11 +530,12 @@ struct Engine {
         }
         const int nseg = (int)P.segs.size();
         const int per = SPEC_PER_PART;
-        const int nparts = (nseg + per - 1) / per;
+        const int nparts = nsupported ? (nseg + per - 1) / per : 0;
         auto exists = [](const std::string& f) { struct stat st; return stat(f.c_str(), &st) == 0 && st.st_size > 0; };
+        auto part_name = [&](int k) { return k == nparts ? std::string("resident") : "part" + std::to_string(k); };
         std::vector<int> todo;
-        for (int k = 0; k < nparts; ++k)
-            if (!exists(dir + "/part" + std::to_string(k) + ".cubin")) todo.push_back(k);
+        for (int k = 0; k < nparts + (res ? 1 : 0); ++k)
+            if (!exists(dir + "/" + part_name(k) + ".cubin")) todo.push_back(k);
         if (!todo.empty()) {
             // compiler: NVRTC in process (default); NCB_SPEC_COMPILER=nvcc runs the nvcc binary instead (needs the toolkit
             // and this library's csrc/ headers on disk)
@@ -550,15 +561,15 @@ struct Engine {
                     const int i = next.fetch_add(1);
                     if (i >= (int)todo.size()) break;
                     const int k = todo[i];
-                    if (exists(dir + "/part" + std::to_string(k) + ".cubin")) continue;
+                    if (exists(dir + "/" + part_name(k) + ".cubin")) continue;
                     // several processes (one per GPU) may build the same cache at once: private temporaries, atomic renames
-                    const std::string base = dir + "/part" + std::to_string(k), mine = base + "." + std::to_string((long)getpid());
-                    const std::string src = spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_opt);
+                    const std::string base = dir + "/" + part_name(k), mine = base + "." + std::to_string((long)getpid());
+                    const std::string src = k == nparts ? spec_resident_source(P, spec_opt) : spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_opt);
                     { std::ofstream f(mine + ".cu"); f << src; }
                     bool ok;
                     if (use_nvrtc) {
                         std::string cubin, log;
-                        ok = g_nvrtc.compile(src, "part" + std::to_string(k) + ".cu", cubin, log);
+                        ok = g_nvrtc.compile(src, part_name(k) + ".cu", cubin, log);
                         { std::ofstream f(mine + ".log"); f << log; }
                         if (ok) { std::ofstream f(mine + ".tmp", std::ios::binary); f.write(cubin.data(), (std::streamsize)cubin.size()); ok = (bool)f; }
                         if (ok) ok = rename((mine + ".tmp").c_str(), (base + ".cubin").c_str()) == 0;
@@ -594,7 +605,12 @@ struct Engine {
         const std::string dir = spec_build();
         if (dir.empty()) return;
         spec_key_loaded = spec_key(P, spec_opt);
-        const int nseg = (int)P.segs.size(), per = SPEC_PER_PART, nparts = (nseg + per - 1) / per;
+        const int nseg = (int)P.segs.size(), per = SPEC_PER_PART;
+        int nparts = (nseg + per - 1) / per;
+        if (resident()) {
+            nparts = 0;
+            load_resident_module(dir, verbose);
+        }
         spec_pool_cap = 0;
         for (int sgi = 0; sgi < nseg; ++sgi) {
             int off, bytes;
@@ -634,6 +650,65 @@ struct Engine {
         if (verbose) fprintf(stderr, "[ncb] specialised kernels: %d whole-segment and %d event kernels of %d segments loaded (load mode %d, nbuf %d, %d / %d CTAs per SM)\n",
                              loaded, loaded_ev, nseg, spec_opt.load, spec_opt.nbuf, nseg && spec_fn[0].fn ? spec_fn[0].ctas : 0, nseg && spec_ev_fn[0].fn ? spec_ev_fn[0].ctas : 0);
     }
+    // ---- generated resident kernels (ncb_res_trunk / ncb_res, see ncb_spec.cpp) ----------------------------------------
+    void* res_fn = nullptr;
+    void* res_trunk_fn = nullptr;
+    ResidentLayout res_lay;
+    int res_ctas = 0;
+    DevBuf<double> d_thresh;
+    DevBuf<int32_t> d_seg_pool, d_block_count, d_nitems;
+    DevBuf<ResCkpt> d_ckpt_for;
+    DevBuf<ResItem> d_items, d_items_tmp;
+    DevBuf<cplx> d_ckpt;
+    bool res_tables = false;
+    void load_resident_module(const std::string& dir, bool verbose) {
+        res_fn = res_trunk_fn = nullptr;
+        if (!spec_resident_supported(P)) return;
+        res_lay = spec_resident_layout(P, spec_opt);
+        std::ifstream f(dir + "/resident.cubin", std::ios::binary);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        const std::string image = ss.str();
+        void* mod = nullptr;
+        if (image.empty() || g_drv.ModuleLoadData(&mod, image.data()) != 0) return;
+        spec_modules.push_back(mod);
+        void *fr = nullptr, *ft = nullptr;
+        if (g_drv.ModuleGetFunction(&fr, mod, "ncb_res") != 0 || g_drv.ModuleGetFunction(&ft, mod, "ncb_res_trunk") != 0) return;
+        for (void* fn : {fr, ft}) {
+            if (g_drv.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem_optin - 8 * 1024) != 0) return;
+            g_drv.FuncSetAttribute(fn, 9 /* CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT */, 100);
+        }
+        int occ = 0;
+        if (g_drv.Occupancy(&occ, fr, 1 << (P.K - P.R), res_lay.smem) != 0 || occ < 1) return;
+        if (const char* e = getenv("NCB_CTAS_PER_SM")) occ = std::max(1, std::min(occ, atoi(e)));
+        res_ctas = occ;
+        res_fn = fr; res_trunk_fn = ft;
+        if (verbose) fprintf(stderr, "[ncb] generated resident kernels loaded: %d threads, %zu B shared memory (%d B of tables), accumulator in %s memory, %d CTAs/SM\n",
+                             1 << (P.K - P.R), res_lay.smem, res_lay.pool_bytes, res_lay.acc_global ? "global" : "shared", occ);
+    }
+    // tables of the generated resident kernels (per program: uploaded again after ncb_program_update)
+    void ensure_res_tables() {
+        if (res_tables) return;
+        std::vector<double> th(2 * std::max<size_t>(P.noisy_instrs.size(), 1));
+        for (size_t a = 0; a < P.noisy_instrs.size(); ++a) {
+            const Channel& ch = P.chans[P.instrs[P.noisy_instrs[a]].channel];
+            const double* lo = P.pool.data() + ch.bounds;
+            const double* hi = lo + (ch.count - 1);
+            th[2 * a] = ch.base == 0 ? -1.0 : hi[ch.base - 1] + EVENT_MARGIN;             // (plan_events' fast test)
+            th[2 * a + 1] = ch.base == ch.count - 1 ? 2.0 : lo[ch.base] - EVENT_MARGIN;
+        }
+        upload(d_thresh, th);
+        std::vector<int32_t> sp;
+        for (size_t k = 0; k < res_lay.pool_src.size(); ++k) { sp.push_back(res_lay.pool_src[k]); sp.push_back(res_lay.pool_len[k]); }
+        upload(d_seg_pool, sp);
+        const std::vector<int32_t> ck = spec_resident_ckpts(P);
+        d_ckpt_for.reserve(ck.size() / 2);
+        CK(cudaMemcpy(d_ckpt_for.p, ck.data(), ck.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        d_ckpt.reserve(((size_t)P.passes.size() + 1) << P.K);
+        d_nitems.reserve(1);
+        res_tables = true;
+    }
+
     // returns true when the step ran in a kernel generated for the program
     bool launch_step(const LaunchStep& st, cudaStream_t s, const Work* works) {
         if (specialize) {
@@ -802,8 +877,6 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
         rp->out_h2d_bytes += (int64_t)(table.size() * sizeof(double));
         a.uniforms = d_uniforms.p;
     }
-    d_partial.reserve((size_t)grid * dim);
-    a.partial_probs = d_partial.p;
     if (rp->states) { d_states.reserve((size_t)count * dim); a.states_out = d_states.p; }
     CK(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(unsigned long long), s));
     a.counters = d_counters.p;
@@ -811,11 +884,51 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
     if (const char* e = getenv("NCB_SHARE_PREFIX")) a.share = a.share && atoi(e) != 0;
     d_trunk.reserve(dim);
     a.trunk_probs = d_trunk.p;
-    launch_resident(grid, s, a);
     int g, b;
     grid_1d(dim, &g, &b);
-    sum_partials_kernel<<<g, b, 0, s>>>(d_probs.p, d_partial.p, dim, grid, a.share ? d_trunk.p : nullptr, d_counters.p + 2);
-    CK(cudaGetLastError());
+    bool generated = false;
+    if (specialize && !independent) {
+        ensure_spec();
+        generated = res_fn != nullptr;
+    }
+    if (generated) {
+        // generated kernels: the trunk once (second stream) beside the planning kernels, then the trajectories that leave it
+        ensure_res_tables();
+        const int nblk = (int)((count + RES_PLAN_THREADS - 1) / RES_PLAN_THREADS);
+        d_items.reserve((size_t)count); d_items_tmp.reserve((size_t)nblk * RES_PLAN_THREADS); d_block_count.reserve(nblk);
+        const int rgrid = (int)std::max<long long>(1, std::min<long long>(count, (long long)sm_count * res_ctas));
+        d_partial.reserve((size_t)rgrid * dim);
+        ResArgs ra{};
+        ra.traj_begin = rp->traj_begin; ra.seed = rp->seed; ra.uniforms = a.uniforms; ra.thresh = d_thresh.p; ra.blobs = d_blobs.p;
+        ra.seg_pool = d_seg_pool.p; ra.items = d_items.p; ra.n_items = d_nitems.p; ra.ckpt_for = d_ckpt_for.p; ra.ckpt = d_ckpt.p;
+        ra.partial = d_partial.p; ra.states_out = a.states_out; ra.trunk_probs = d_trunk.p; ra.counters = d_counters.p;
+        ra.normalize = a.normalize; ra.acc_global = res_lay.acc_global;
+        const unsigned threads = 1u << (P.K - P.R);
+        void* args[] = {(void*)&d, (void*)&ra};
+        CK(cudaEventRecord(ev_a, s));
+        CK(cudaStreamWaitEvent(s2, ev_a, 0));
+        int rc = g_drv.LaunchKernel(res_trunk_fn, 1, 1, 1, threads, 1, 1, (unsigned)res_lay.smem, (void*)s2, args, nullptr);
+        if (rc != 0) throw std::runtime_error("cuLaunchKernel of the generated trunk kernel failed (" + std::to_string(rc) + ")");
+        CK(cudaEventRecord(ev_b, s2));
+        res_plan_kernel<<<nblk, RES_PLAN_THREADS, 0, s>>>(d_thresh.p, d_noisy.p, d_orig.p, (int)P.noisy_instrs.size(), P.G, rp->seed, rp->traj_begin, (int)count,
+                                                          a.uniforms, rp->states ? 1 : 0, d_items_tmp.p, d_block_count.p);
+        CK(cudaGetLastError());
+        res_scatter_kernel<<<nblk, RES_PLAN_THREADS, 0, s>>>(d_items_tmp.p, d_block_count.p, d_items.p, d_nitems.p, d_counters.p, (int)count);
+        CK(cudaGetLastError());
+        CK(cudaStreamWaitEvent(s, ev_b, 0));
+        rc = g_drv.LaunchKernel(res_fn, (unsigned)rgrid, 1, 1, threads, 1, 1, (unsigned)res_lay.smem, (void*)s, args, nullptr);
+        if (rc != 0) throw std::runtime_error("cuLaunchKernel of the generated resident kernel failed (" + std::to_string(rc) + ")");
+        sum_partials_kernel<<<g, b, 0, s>>>(d_probs.p, d_partial.p, dim, rgrid, d_trunk.p, d_counters.p + 2);
+        CK(cudaGetLastError());
+        rp->out_spec_launches += 2;
+        rp->out_launches += 3;
+    } else {
+        d_partial.reserve((size_t)grid * dim);
+        a.partial_probs = d_partial.p;
+        launch_resident(grid, s, a);
+        sum_partials_kernel<<<g, b, 0, s>>>(d_probs.p, d_partial.p, dim, grid, a.share ? d_trunk.p : nullptr, d_counters.p + 2);
+        CK(cudaGetLastError());
+    }
     unsigned long long cnt[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(cnt, d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
     rp->out_d2h_bytes += (int64_t)sizeof(cnt);
@@ -1000,7 +1113,8 @@ void Engine::mcwf_run(ncb_run_params* rp) {
     if (rp->traj_count > 0) {
         if (resident()) {
             // chunk so the optional tables / states stay bounded
-            const long long chunk = rp->states || rp->rng != NCB_RNG_PHILOX ? std::max<long long>(1, (1ll << 28) / std::max<long long>(dim * 2, (long long)P.G)) : rp->traj_count;
+            const long long chunk = rp->states || rp->rng != NCB_RNG_PHILOX ? std::max<long long>(1, (1ll << 28) / std::max<long long>(dim * 2, (long long)P.G))
+                                                                            : std::min<long long>(rp->traj_count, 1ll << 24);
             ncb_run_params sub = *rp;
             for (long long b0 = 0; b0 < rp->traj_count; b0 += chunk) {
                 sub.traj_begin = rp->traj_begin + b0;
@@ -1011,7 +1125,7 @@ void Engine::mcwf_run(ncb_run_params* rp) {
             }
             rp->out_sweeps = sub.out_sweeps; rp->out_events = sub.out_events; rp->out_hard_events = sub.out_hard_events;
             rp->out_launches = sub.out_launches; rp->out_tile_launches = sub.out_tile_launches;
-            rp->out_h2d_bytes = sub.out_h2d_bytes; rp->out_d2h_bytes = sub.out_d2h_bytes;
+            rp->out_h2d_bytes = sub.out_h2d_bytes; rp->out_d2h_bytes = sub.out_d2h_bytes; rp->out_spec_launches = sub.out_spec_launches;
         } else {
             mcwf_tiled(rp, s);
         }
@@ -1152,7 +1266,9 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
             long long rx = 0, u = 0;
             for (const Op& op : p->eng.P.ops) { rx += op_kind(op) == OPK_RX1; u += op_kind(op) == OPK_DENSE1; }
             const bool generic_heavy = 4 * u > rx + u;
-            if (p->eng.P.has_dense2 || p->eng.P.has_dense4 || p->eng.P.nbits <= p->eng.P.K || generic_heavy) {
+            // states that fit one CTA (generated resident kernels): R = 4 from 2^11 amplitudes (>= 128 threads per CTA)
+            const bool small = p->eng.P.nbits <= p->eng.P.K;
+            if (p->eng.P.has_dense2 || p->eng.P.has_dense4 || (small && p->eng.P.K < 11) || generic_heavy) {
                 opt.reg_bits = 3;                   // (or not a program the generated kernels cover at all: the default geometry)
                 compile_program(view_of(circuit), mode, opt, p->eng.P);
             }
@@ -1230,7 +1346,9 @@ int64_t ncb_program_spec_source(const ncb_program* program, int32_t seg_begin, i
     const Program& P = program->eng.P;
     Engine& E = const_cast<ncb_program*>(program)->eng;
     E.read_spec_options();
-    const std::string s = spec_source(P, std::max(seg_begin, 0), std::min<int>(seg_end, (int)P.segs.size()), E.spec_opt);
+    // (a program whose state fits one CTA has one module: the generated resident kernels)
+    const std::string s = E.resident() ? spec_resident_source(P, E.spec_opt)
+                                       : spec_source(P, std::max(seg_begin, 0), std::min<int>(seg_end, (int)P.segs.size()), E.spec_opt);
     if (buf && len > 0) {
         const size_t n = std::min<size_t>(s.size(), (size_t)len - 1);
         std::memcpy(buf, s.data(), n);

@@ -582,6 +582,84 @@ struct ResidentArgs {
     double* trunk_probs;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// generated resident kernels (ncb_spec.cpp: ncb_res_trunk / ncb_res): arguments and the two planning kernels
+// ---------------------------------------------------------------------------------------------------------------
+// A trajectory is the jump-free evolution (the "trunk") up to its first flagged draw.  The trunk runs ONCE (ncb_res_trunk,
+// one CTA) and leaves its state at every pass boundary in global memory (2^K amplitudes each: L2 resident); the planning
+// kernels list the trajectories that leave the trunk, in trajectory order (deterministic), and ncb_res runs each of them
+// from the last checkpoint before its first flagged draw -- the others are only counted and weighted with the trunk's result.
+struct ResItem { int32_t tl, first; };      // trajectory (index within the call) and execution position of its first flagged draw (G: none)
+struct ResCkpt { int32_t pass, instr; };    // checkpoint to start from (global pass index; -1: |0...0>) and the first instruction still to run
+struct ResArgs {
+    long long traj_begin;
+    unsigned long long seed;
+    const double* uniforms;          // NULL: Philox; else [traj_count][G], by execution position
+    const double* thresh;            // [n_noisy][2]: a draw u with thresh[0] < u <= thresh[1] selects the base branch for sure
+    const unsigned char* blobs;      // the program's segment blobs (phase tables and 2x2 coefficients are staged from their pools)
+    const int32_t* seg_pool;         // [nseg][2]: byte offset of segment s's pool in blobs, bytes
+    const ResItem* items;
+    const int32_t* n_items;
+    const ResCkpt* ckpt_for;         // [G + 1], by execution position of the first flagged draw
+    cplx* ckpt;                      // [npass + 1][2^K]: trunk states in the shared-memory (swizzled) layout; [npass] = final state
+    double* partial;                 // [gridDim.x][2^nbits]
+    cplx* states_out;                // optional [traj_count][2^nbits]
+    double* trunk_probs;             // [2^nbits] normalised |psi|^2 of the trunk
+    unsigned long long* counters;    // [0] events, [1] state-dependent events, [2] trajectories that never leave the trunk
+    int32_t normalize, acc_global;
+};
+
+#ifndef NCB_TEMPLATES_ONLY
+constexpr int RES_PLAN_THREADS = 128;
+// first flagged draw of every trajectory; the flagged ones (all of them with `all`) compacted per block, in order
+__global__ void __launch_bounds__(RES_PLAN_THREADS)
+res_plan_kernel(const double* __restrict__ thresh, const int32_t* __restrict__ noisy, const int32_t* __restrict__ orig, int n_noisy, int G,
+                unsigned long long seed, long long traj_begin, int count, const double* __restrict__ uniforms, int all,
+                ResItem* __restrict__ tmp, int32_t* __restrict__ block_count) {
+    __shared__ int wcount[RES_PLAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.x * RES_PLAN_THREADS + tid;
+    int first = G;
+    if (t < count) {
+        const double* utab = uniforms ? uniforms + (long long)t * G : nullptr;
+        for (int a = 0; a < n_noisy; ++a) {
+            const int i = noisy[a];
+            const double u = utab ? utab[i] : philox_uniform(seed, (unsigned long long)(traj_begin + t), (uint32_t)orig[i]);
+            if (!(u > thresh[2 * a] && u <= thresh[2 * a + 1])) { first = i; break; }
+        }
+    }
+    const bool flag = t < count && (all || first < G);
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) wcount[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < RES_PLAN_THREADS / 32; ++w) { if (w < warp) off += wcount[w]; total += wcount[w]; }
+    if (flag) tmp[blockIdx.x * RES_PLAN_THREADS + off + __popc(m & ((1u << lane) - 1u))] = ResItem{t, first};
+    if (tid == 0) block_count[blockIdx.x] = total;
+}
+// the blocks' lists back to back; the last block leaves the totals
+__global__ void __launch_bounds__(RES_PLAN_THREADS)
+res_scatter_kernel(const ResItem* __restrict__ tmp, const int32_t* __restrict__ block_count, ResItem* __restrict__ items,
+                   int32_t* __restrict__ n_items, unsigned long long* __restrict__ counters, int count) {
+    __shared__ int wsum[RES_PLAN_THREADS / 32];
+    const int tid = threadIdx.x;
+    int s = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += RES_PLAN_THREADS) s += block_count[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) wsum[tid >> 5] = s;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < RES_PLAN_THREADS / 32; ++w) base += wsum[w];
+    const int cnt = block_count[blockIdx.x];
+    if (tid < cnt) items[base + tid] = tmp[blockIdx.x * RES_PLAN_THREADS + tid];
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        n_items[0] = base + cnt;
+        counters[2] = (unsigned long long)(count - (base + cnt));
+    }
+}
+#endif  // NCB_TEMPLATES_ONLY
+
 template <int R, int FEAT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 resident_kernel(DevProgram P, ResidentArgs A) {

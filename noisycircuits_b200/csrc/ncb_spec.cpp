@@ -309,6 +309,61 @@ void emit_general_op(std::ostringstream& o, const Op& op, int p, int R, const st
     }
 }
 
+// The pass programs of a segment with every operator guarded by its instruction index (what run_range + fetch() interpret):
+// the body of a function / lambda with (lo, hi, bare, qb, qe) in scope, jb<p> / jbs<p>, pool and pool_d declared by the caller.
+// qb / qe: tile positions of the qubits of the in-line jump this range begins after / ends in when merged groups that do
+// not touch them may stay whole (WF_PULL); ~0u otherwise (every group "touches": strict splitting by instruction index).
+// ckpt_pass0 >= 0 (resident trunk): before pass p the tile is copied to ckpt + ((ckpt_pass0 + p) << K) when ckpt != nullptr.
+void emit_guarded_passes(std::ostringstream& o, const BlobView& bv, int R, int K = 0, int ckpt_pass0 = -1) {
+    const int NA = 1 << R, npass = bv.blob->npass;
+    for (int p = 0; p < npass; ++p) {
+        const Pass& ps = bv.passes[p];
+        if (ps.instr_hi <= ps.instr_lo) continue;
+        o << "        if (" << ps.instr_lo << " < hi && " << ps.instr_hi << " > lo) {   // pass " << p << "\n";
+        if (ckpt_pass0 >= 0)
+            o << "            if (ckpt != nullptr) {\n                cplx* const c = ckpt + ((size_t)" << ckpt_pass0 + p << " << " << K << ");\n"
+              << "                for (int i = (int)threadIdx.x; i < " << (1 << K) << "; i += (int)blockDim.x) c[i] = sm[i];\n            }\n";
+        o << "            cplx a[" << NA << "];\n";
+        for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "];\n";
+        // (hot: the operator stands alone in the list; cold: a member of a merged group, run one by one only when a jump
+        //  cuts the group -- the hints keep the cold code out of the fall-through path and of the instruction cache)
+        auto member = [&](const Op& op, const char* ind, bool hot) {
+            o << ind << "if (" << (hot ? "__builtin_expect(" : "(") << op.instr << " >= lo && " << op.instr << " < hi" << (hot ? ", 1)" : ")") << ") {\n";
+            std::string off = std::to_string(op.mat);
+            if (op.mat_bare != op.mat) off = "(bare && hi == " + std::to_string(op.instr + 1) + ") ? " + std::to_string(op.mat_bare) + " : " + std::to_string(op.mat);
+            emit_general_op(o, op, p, R, off, (std::string(ind) + "    ").c_str());
+            o << ind << "}\n";
+        };
+        for (int i = ps.op_begin; i < ps.op_end; ++i) {
+            const Op& op = bv.ops[i];
+            if (op.kind_nb >> 31) {
+                const int span = (int)((op.kind_nb >> 25) & 0x3f), last = op.pad;
+                // tile positions the merged operator touches
+                unsigned gm = 0;
+                if (op_kind(op) == OPK_DIAG) {
+                    gm = (op.rbs & 0xffffu) | (op.rbs >> 16);
+                    for (int r = 0; r < R; ++r) if ((op_regmask(op) >> r) & 1) gm |= 1u << ps.regpos[r];
+                } else {
+                    gm = 1u << ps.regpos[op_rb(op, 0)];
+                }
+                o << "            if (__builtin_expect(" << op.instr << " >= lo && ((" << last + 1 << " < hi || (" << last + 1 << " == hi && !bare)) || ("
+                  << op.instr << " < hi && !(" << hex(gm) << " & qe))), 1)) {\n";
+                emit_general_op(o, op, p, R, std::to_string(op.mat), "                ");
+                o << "            } else if (" << op.instr << " < lo && !(" << hex(gm) << " & qb)) {\n"
+                     "                // ran as a whole before the jump this range begins after\n"
+                     "            } else {\n";
+                for (int j = 1; j <= span; ++j) member(bv.ops[i + j], "                ", false);
+                o << "            }\n";
+                i += span;
+            } else {
+                member(op, "            ", true);
+            }
+        }
+        for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "] = a[" << m << "];\n";
+        o << "            __syncthreads();\n        }\n";
+    }
+}
+
 bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const SpecOptions& opt) {
     const int K = P.K, R = P.R, NA = 1 << R;
     const BlobView bv = view_blob(P, seg);
@@ -352,53 +407,8 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
     for (int it = 0; it < NA; ++it)
         o << "        cp_async16(sm + (sA ^ " << sg.it_swz[it] << "), st + (offA | " << hex(sg.it_off[it]) << "));\n";
     o << "    };\n";
-    // the pass programs, every operator guarded by its instruction index (what run_range + fetch() interpret)
-    // qb / qe: tile positions of the qubits of the in-line jump this range begins after / ends in when merged groups that do
-    // not touch them may stay whole (WF_PULL); ~0u otherwise (every group "touches": strict splitting by instruction index)
     o << "    auto run_passes = [&](const int lo, const int hi, const bool bare, const unsigned qb, const unsigned qe) {\n";
-    for (int p = 0; p < npass; ++p) {
-        const Pass& ps = bv.passes[p];
-        if (ps.instr_hi <= ps.instr_lo) continue;
-        o << "        if (" << ps.instr_lo << " < hi && " << ps.instr_hi << " > lo) {   // pass " << p << "\n"
-          << "            cplx a[" << NA << "];\n";
-        for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "];\n";
-        // (hot: the operator stands alone in the list; cold: a member of a merged group, run one by one only when a jump
-        //  cuts the group -- the hints keep the cold code out of the fall-through path and of the instruction cache)
-        auto member = [&](const Op& op, const char* ind, bool hot) {
-            o << ind << "if (" << (hot ? "__builtin_expect(" : "(") << op.instr << " >= lo && " << op.instr << " < hi" << (hot ? ", 1)" : ")") << ") {\n";
-            std::string off = std::to_string(op.mat);
-            if (op.mat_bare != op.mat) off = "(bare && hi == " + std::to_string(op.instr + 1) + ") ? " + std::to_string(op.mat_bare) + " : " + std::to_string(op.mat);
-            emit_general_op(o, op, p, R, off, (std::string(ind) + "    ").c_str());
-            o << ind << "}\n";
-        };
-        for (int i = ps.op_begin; i < ps.op_end; ++i) {
-            const Op& op = bv.ops[i];
-            if (op.kind_nb >> 31) {
-                const int span = (int)((op.kind_nb >> 25) & 0x3f), last = op.pad;
-                // tile positions the merged operator touches
-                unsigned gm = 0;
-                if (op_kind(op) == OPK_DIAG) {
-                    gm = (op.rbs & 0xffffu) | (op.rbs >> 16);
-                    for (int r = 0; r < R; ++r) if ((op_regmask(op) >> r) & 1) gm |= 1u << ps.regpos[r];
-                } else {
-                    gm = 1u << ps.regpos[op_rb(op, 0)];
-                }
-                o << "            if (__builtin_expect(" << op.instr << " >= lo && ((" << last + 1 << " < hi || (" << last + 1 << " == hi && !bare)) || ("
-                  << op.instr << " < hi && !(" << hex(gm) << " & qe))), 1)) {\n";
-                emit_general_op(o, op, p, R, std::to_string(op.mat), "                ");
-                o << "            } else if (" << op.instr << " < lo && !(" << hex(gm) << " & qb)) {\n"
-                     "                // ran as a whole before the jump this range begins after\n"
-                     "            } else {\n";
-                for (int j = 1; j <= span; ++j) member(bv.ops[i + j], "                ", false);
-                o << "            }\n";
-                i += span;
-            } else {
-                member(op, "            ", true);
-            }
-        }
-        for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "] = a[" << m << "];\n";
-        o << "            __syncthreads();\n        }\n";
-    }
+    emit_guarded_passes(o, bv, R);
     o << "    };\n";
     o << "    long long t = blockIdx.x;\n    if (t >= total) return;\n"
          "    Work w = works[t >> tile_shift];\n"
@@ -479,6 +489,187 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
     return true;
 }
 
+// ---- resident kernels -----------------------------------------------------------------------------------------------
+// States of <= 2^K amplitudes (one tile, identity index map): the whole trajectory lives in one CTA's shared memory.  The
+// module holds the segments' guarded pass programs as device functions (the same text the event kernels are made of,
+// coefficients and phase tables read from the staged pools: structure-only source) and two kernels around them:
+//   ncb_res_trunk   one CTA: the jump-free evolution from |0...0>, its state left in global memory at every pass boundary
+//   ncb_res         persistent CTAs over the trajectories that leave the trunk: start from the last checkpoint before the
+//                   first flagged draw, events handled in line (reduced density matrix, branch decision, Kraus operator)
+bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOptions& opt) {
+    const int K = P.K, R = P.R, nseg = (int)P.segs.size(), NT = 1 << (K - R);
+    const ResidentLayout lay = spec_resident_layout(P, opt);
+    for (int seg = 0; seg < nseg; ++seg) {
+        const BlobView bv = view_blob(P, seg);
+        for (int i = 0; i < bv.blob->nops; ++i) {
+            const Op& op = bv.ops[i];
+            const int kind = op_kind(op);
+            if (kind != OPK_DIAG && kind != OPK_RX1 && kind != OPK_DENSE1) return false;
+            if (op.mat < 0 || op.mat_bare < 0 || (op.mat & 1) || (op.mat_bare & 1)) return false;
+        }
+        o << "static __device__ __noinline__ void res_seg_" << seg << "(cplx* __restrict__ sm, const unsigned char* __restrict__ poolb, const int lo, const int hi,\n"
+             "        const bool bare, cplx* __restrict__ ckpt) {\n"
+             "    const cplx* const pool = reinterpret_cast<const cplx*>(poolb);\n"
+             "    const double* const pool_d = reinterpret_cast<const double*>(poolb);\n"
+             "    const unsigned utid = threadIdx.x;\n"
+             "    const unsigned qb = ~0u, qe = ~0u;\n"
+             "    (void)pool; (void)pool_d; (void)qb; (void)qe; (void)ckpt;\n";
+        for (int p = 0; p < bv.blob->npass; ++p)
+            o << "    const int jb" << p << " = (int)" << runs_expr(bv.passes[p].truns, "utid") << ", jbs" << p << " = swz(jb" << p << ");\n"
+              << "    (void)jb" << p << "; (void)jbs" << p << ";\n";
+        emit_guarded_passes(o, bv, R, K, P.segs[seg].pass_begin);
+        o << "}\n\n";
+    }
+    // [lo, hi) across the segments
+    o << "static __device__ __forceinline__ void res_run(cplx* sm, const unsigned char* poolb, const int lo, const int hi, const bool bare, cplx* ckpt) {\n";
+    for (int seg = 0; seg < nseg; ++seg)
+        o << "    if (" << P.segs[seg].instr_lo << " < hi && " << P.segs[seg].instr_hi << " > lo) res_seg_" << seg << "(sm, poolb + " << lay.pool_off[seg]
+          << ", lo, hi, bare, ckpt);\n";
+    o << "}\n\n";
+    const int nwords = (P.G + 31) / 32;
+    o << "namespace {\n"
+         "constexpr int RK = " << K << ", RNB = " << P.nbits << ", RDIM = 1 << RNB, RNT = " << NT << ", RG = " << P.G << ", RNPASS = " << (int)P.passes.size()
+      << ", RNWORDS = " << nwords << ", RPOOL = " << lay.pool_bytes << ";\n"
+         "__device__ __forceinline__ void res_stage(unsigned char* poolb, const ResArgs& A) {\n"
+         "    const int tid = threadIdx.x;\n";
+    for (int seg = 0; seg < nseg; ++seg)
+        o << "    for (int i = tid * 16; i < " << lay.pool_len[seg] << "; i += RNT * 16) cp_async16(poolb + " << lay.pool_off[seg] << " + i, A.blobs + A.seg_pool[" << 2 * seg
+          << "] + i);\n";
+    o << "    cp_async_wait_all();\n"
+         "}\n"
+         "__device__ __forceinline__ double res_inv_norm(const cplx* sm, double* s_buf, double* s_out) {\n"
+         "    double v[1] = {0.0};\n"
+         "    for (int j = threadIdx.x; j < (1 << RK); j += RNT) v[0] += cnorm2(sm[j]);\n"
+         "    block_reduce<1>(v, s_buf, s_out);\n"
+         "    const double inv = 1.0 / s_out[0];\n"
+         "    __syncthreads();\n"
+         "    return inv;\n"
+         "}\n"
+         "}  // namespace\n\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", 1) ncb_res_trunk(DevProgram P, ResArgs A) {\n"
+         "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+         "    __shared__ double s_buf[32 * 20];\n"
+         "    __shared__ double s_out[RED_VALUES];\n"
+         "    cplx* const sm = reinterpret_cast<cplx*>(smem_raw);\n"
+         "    unsigned char* const poolb = smem_raw + ((size_t)16 << RK);\n"
+         "    const int tid = threadIdx.x;\n"
+         "    (void)P;\n"
+         "    res_stage(poolb, A);\n"
+         "    for (int j = tid; j < (1 << RK); j += RNT) sm[j] = cplx{0.0, 0.0};\n"
+         "    __syncthreads();\n"
+         "    if (tid == 0) sm[swz(0)] = cplx{1.0, 0.0};\n"
+         "    __syncthreads();\n"
+         "    res_run(sm, poolb, 0, RG, false, A.ckpt);\n"
+         "    {\n"
+         "        cplx* const c = A.ckpt + ((size_t)RNPASS << RK);\n"
+         "        for (int i = tid; i < (1 << RK); i += RNT) c[i] = sm[i];\n"
+         "    }\n"
+         "    const double inv = A.normalize ? res_inv_norm(sm, s_buf, s_out) : 1.0;\n"
+         "    for (int j = tid; j < RDIM; j += RNT) A.trunk_probs[j] = cnorm2(sm[swz(j)]) * inv;\n"
+         "}\n\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << lay.ctas << ") ncb_res(DevProgram P, ResArgs A) {\n"
+         "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+         "    __shared__ double s_buf[32 * 20];\n"
+         "    __shared__ double s_out[RED_VALUES];\n"
+         "    __shared__ double s_red[20];\n"
+         "    __shared__ int s_k;\n"
+         "    __shared__ double s_scale;\n"
+         "    cplx* const sm = reinterpret_cast<cplx*>(smem_raw);\n"
+         "    unsigned char* const poolb = smem_raw + ((size_t)16 << RK);\n"
+         "    unsigned* const evmask = reinterpret_cast<unsigned*>(poolb + RPOOL);\n"
+         "    const int tid = threadIdx.x;\n"
+         "    double* const acc = A.acc_global ? A.partial + (long long)blockIdx.x * RDIM : reinterpret_cast<double*>(evmask + ((RNWORDS + 3) & ~3));\n"
+         "    res_stage(poolb, A);\n"
+         "    for (int j = tid; j < RDIM; j += RNT) acc[j] = 0.0;\n"
+         "    __syncthreads();\n"
+         "    const int n_items = A.n_items[0];\n"
+         "    unsigned long long n_events = 0, n_hard = 0;\n"
+         "    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {\n"
+         "        const ResItem item = A.items[it];\n"
+         "        const long long tl = item.tl;\n"
+         "        const unsigned long long traj = (unsigned long long)(A.traj_begin + tl);\n"
+         "        const double* utab = A.uniforms ? A.uniforms + tl * RG : nullptr;\n"
+         "        const ResCkpt ck = A.ckpt_for[item.first];\n"
+         "        // the trunk's state at the last pass boundary before the first flagged draw\n"
+         "        if (ck.pass >= 0) {\n"
+         "            const cplx* src = A.ckpt + ((size_t)ck.pass << RK);\n"
+         "            for (int i = tid; i < (1 << RK); i += RNT) cp_async16(sm + i, src + i);\n"
+         "        } else {\n"
+         "            for (int j = tid; j < (1 << RK); j += RNT) sm[j] = cplx{0.0, 0.0};\n"
+         "        }\n"
+         "        for (int i = tid; i < RNWORDS; i += RNT) evmask[i] = 0u;\n"
+         "        __syncthreads();\n"
+         "        if (ck.pass < 0 && tid == 0) sm[swz(0)] = cplx{1.0, 0.0};\n"
+         "        // which of the later draws leave their base branch?\n"
+         "        for (int a = tid; a < P.n_noisy; a += RNT) {\n"
+         "            const int i = P.noisy[a];\n"
+         "            if (i < item.first) continue;\n"
+         "            const double u = utab ? utab[i] : philox_uniform(A.seed, traj, (uint32_t)P.orig[i]);\n"
+         "            if (!(u > A.thresh[2 * a] && u <= A.thresh[2 * a + 1])) atomicOr(&evmask[i >> 5], 1u << (i & 31));\n"
+         "        }\n"
+         "        cp_async_wait_all();\n"
+         "        __syncthreads();\n"
+         "        int cur = ck.instr;\n"
+         "        while (true) {\n"
+         "            int e = RG;\n"
+         "            for (int wd = cur >> 5; wd < RNWORDS; ++wd) {\n"
+         "                unsigned m = evmask[wd];\n"
+         "                if (wd == (cur >> 5)) m &= ~0u << (cur & 31);\n"
+         "                if (m) { e = (wd << 5) + __ffs(m) - 1; break; }\n"
+         "            }\n"
+         "            const bool ev = e < RG;\n"
+         "            res_run(sm, poolb, cur, ev ? e + 1 : RG, ev, nullptr);\n"
+         "            if (!ev) break;\n"
+         "            const Instr in = P.instrs[e];\n"
+         "            const Channel ch = P.chans[in.channel];\n"
+         "            const double u = utab ? utab[e] : philox_uniform(A.seed, traj, (uint32_t)P.orig[e]);\n"
+         "            int kmin, kmax;\n"
+         "            classify_uniform(P.pool + ch.bounds, P.pool + ch.bounds + (ch.count - 1), ch.count, u, &kmin, &kmax);\n"
+         "            int k = kmin;\n"
+         "            double scale = 1.0;\n"
+         "            bool base_after_all = false;\n"
+         "            if (kmin != kmax) {\n"
+         "                ++n_hard;\n"
+         "                event_reduce(sm, RK, in.q0, ch.dim == 4 ? in.q1 : -1, s_buf, s_red, s_out);\n"
+         "                if (tid == 0) {\n"
+         "                    mirror_rho(s_out, ch.dim);\n"
+         "                    double sc;\n"
+         "                    s_k = decide_branch(s_out, ch, P.pool, u, &sc);\n"
+         "                    s_scale = sc;\n"
+         "                }\n"
+         "                __syncthreads();\n"
+         "                k = s_k; scale = s_scale;\n"
+         "            } else if (k == ch.base) {\n"
+         "                base_after_all = true;     // flagged by the cheap test only (u within the margin): base branch\n"
+         "            }\n"
+         "            if (!base_after_all) ++n_events;\n"
+         "            const cplx* M = reinterpret_cast<const cplx*>(P.pool + ch.kraus) + k * ch.dim * ch.dim;\n"
+         "            tile_apply_dense(sm, RK, tid, RNT, ch.dim, in.q0, in.q1, M, scale);\n"
+         "            __syncthreads();\n"
+         "            cur = e + 1;\n"
+         "        }\n"
+         "        const double inv = A.normalize ? res_inv_norm(sm, s_buf, s_out) : 1.0;\n"
+         "        for (int j = tid; j < RDIM; j += RNT) acc[j] += cnorm2(sm[swz(j)]) * inv;\n"
+         "        if (A.states_out) {\n"
+         "            const double f = sqrt(inv);\n"
+         "            for (int j = tid; j < RDIM; j += RNT) {\n"
+         "                cplx a = sm[swz(j)];\n"
+         "                a.x *= f; a.y *= f;\n"
+         "                A.states_out[tl * RDIM + j] = a;\n"
+         "            }\n"
+         "        }\n"
+         "        __syncthreads();\n"
+         "    }\n"
+         "    if (!A.acc_global)\n"
+         "        for (int j = tid; j < RDIM; j += RNT) A.partial[(long long)blockIdx.x * RDIM + j] = acc[j];\n"
+         "    if (tid == 0 && A.counters) {\n"
+         "        atomicAdd(&A.counters[0], n_events);\n"
+         "        atomicAdd(&A.counters[1], n_hard);\n"
+         "    }\n"
+         "}\n";
+    return true;
+}
+
 }  // namespace
 
 bool spec_supported(const Program& P, int seg) {
@@ -531,13 +722,94 @@ std::string spec_source(const Program& P, int seg_begin, int seg_end, const Spec
     return o.str();
 }
 
+bool spec_resident_supported(const Program& P) {
+    if (P.mode != MODE_MCWF || (P.R != 3 && P.R != 4) || P.has_dense2 || P.has_dense4) return false;
+    if (P.nbits > P.K || !P.generics.empty() || P.segs.empty()) return false;
+    if (P.blob_off.size() != P.segs.size()) return false;
+    for (const Segment& sg : P.segs)
+        for (int p = 0; p < P.K; ++p)
+            if (sg.tile_q[p] != p) return false;                   // (the resident kernels address the state bits directly)
+    return spec_resident_layout(P, SpecOptions()).ctas >= 1;
+}
+
+ResidentLayout spec_resident_layout(const Program& P, const SpecOptions& opt) {
+    ResidentLayout lay;
+    int at = 0;
+    for (size_t sgi = 0; sgi < P.blob_off.size(); ++sgi) {
+        const SegBlob& blob = *reinterpret_cast<const SegBlob*>(P.blobs.data() + P.blob_off[sgi]);
+        lay.pool_src.push_back((int)P.blob_off[sgi] + blob.pool_off);
+        lay.pool_len.push_back((blob.bytes - blob.pool_off + 15) & ~15);
+        lay.pool_off.push_back(at);
+        at += lay.pool_len.back();
+    }
+    lay.pool_bytes = at;
+    const int threads = 1 << (P.K - P.R);
+    const size_t fixed = ((size_t)16 << P.K) + (size_t)at + (size_t)((((P.G + 31) / 32) + 3) & ~3) * 4;
+    const size_t acc = (size_t)8 << P.nbits, budget = 227 * 1024, stat = 6 * 1024 + 1024;   // static arrays + per-CTA reservation
+    const int by_regs = std::max(1, 65536 / (threads * (P.R == 4 ? 128 : 64)));
+    auto fit = [&](size_t per) { return (int)std::min<size_t>({budget / (per + stat), (size_t)by_regs, (size_t)8}); };
+    // the probability accumulator stays in shared memory unless moving it to global memory (L2) buys another CTA per SM
+    const int with_acc = fit(fixed + acc), without = fit(fixed);
+    lay.acc_global = without > with_acc ? 1 : 0;
+    lay.ctas = lay.acc_global ? without : with_acc;
+    if (opt.ctas > 0 && opt.ctas <= lay.ctas) lay.ctas = opt.ctas;
+    lay.smem = fixed + (lay.acc_global ? 0 : acc);
+    return lay;
+}
+
+std::vector<int32_t> spec_resident_ckpts(const Program& P) {
+    // checkpoint before (global) pass p: valid when every instruction of the passes before p precedes every instruction of
+    // the passes from p on; then it is the state after instructions [0, L_p).  Table: execution position e -> (pass, L) of the
+    // last valid checkpoint with L <= e; e = G -> the final state (pass = number of passes).
+    const int np = (int)P.passes.size();
+    std::vector<int> lo_min(np + 1, P.G), hi_max(np + 1, 0);
+    std::vector<char> nonempty(np, 0);
+    for (size_t sgi = 0; sgi < P.segs.size(); ++sgi) {
+        const BlobView bv = view_blob(P, (int)sgi);
+        for (int p = 0; p < bv.blob->npass; ++p) {
+            const Pass& ps = bv.passes[p];
+            const int gp = P.segs[sgi].pass_begin + p;
+            if (gp >= np) continue;
+            int mn = P.G, mx = -1;
+            for (int i = ps.op_begin; i < ps.op_end; ++i) {
+                const Op& op = bv.ops[i];
+                mn = std::min(mn, (int)op.instr);
+                mx = std::max(mx, (op.kind_nb >> 31) ? (int)op.pad : (int)op.instr);
+            }
+            nonempty[gp] = ps.instr_hi > ps.instr_lo && mx >= 0;
+            lo_min[gp] = nonempty[gp] ? mn : P.G;
+            hi_max[gp] = nonempty[gp] ? mx + 1 : 0;
+        }
+    }
+    std::vector<int> suf(np + 1, P.G), pre(np + 1, 0);         // min instruction of passes >= p, 1 + max instruction of passes < p
+    for (int p = np - 1; p >= 0; --p) suf[p] = std::min(suf[p + 1], lo_min[p]);
+    for (int p = 0; p < np; ++p) pre[p + 1] = std::max(pre[p], hi_max[p]);
+    std::vector<int32_t> out(2 * (size_t)(P.G + 1));
+    int best_pass = -1, best_L = 0, p = 0;
+    for (int e = 0; e <= P.G; ++e) {
+        for (; p < np && suf[p] <= e; ++p)
+            if (nonempty[p] && pre[p] <= suf[p]) { best_pass = p; best_L = suf[p]; }
+        if (e == P.G) { best_pass = np; best_L = P.G; }
+        out[2 * e] = best_pass; out[2 * e + 1] = best_L;
+    }
+    return out;
+}
+
+std::string spec_resident_source(const Program& P, const SpecOptions& opt) {
+    std::ostringstream o, k;
+    o << "// generated by ncb_spec.cpp -- do not edit\n#include \"ncb_spec.cuh\"\nusing namespace ncb;\n";
+    if (!spec_resident_supported(P) || !emit_resident_module(k, P, opt)) return "";
+    o << k.str();
+    return o.str();
+}
+
 std::string spec_key(const Program& P, const SpecOptions& opt) {
     // FNV-1a over the generated source of every segment: the source is all the cubins depend on (beside the headers,
     // which the engine covers with a build stamp)
     uint64_t h = 1469598103934665603ull;
-    const std::string src = spec_source(P, 0, (int)P.segs.size(), opt);
+    const std::string src = spec_source(P, 0, (int)P.segs.size(), opt) + spec_resident_source(P, opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 11 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 12 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);

@@ -1,6 +1,7 @@
 // Source generator of the specialised sweep kernels (see ncb_spec.cuh).
 #pragma once
 #include <string>
+#include <vector>
 
 #include "ncb_compile.h"
 
@@ -37,6 +38,21 @@ std::string spec_source(const Program& P, int seg_begin, int seg_end, const Spec
 void spec_pool(const Program& P, int seg, int* offset, int* bytes);
 // resident CTAs per SM the generated kernels are compiled for (launch bounds)
 int spec_ctas_per_sm(const Program& P, const SpecOptions& opt);
+// ---- resident programs (the whole state in one CTA's shared memory) ----
+struct ResidentLayout {
+    std::vector<int> pool_src, pool_len, pool_off;   // per segment: byte offset of its pool in Program::blobs, bytes (16-byte
+                                                     // multiple), byte offset of its copy in the kernel's staged pool area
+    int pool_bytes = 0;
+    int acc_global = 0;   // 1: the CTA's probability accumulator lives in global memory (buys another CTA per SM)
+    int ctas = 0;         // resident CTAs per SM (launch bounds)
+    size_t smem = 0;      // dynamic shared memory of ncb_res (ncb_res_trunk uses the same amount)
+};
+bool spec_resident_supported(const Program& P);
+ResidentLayout spec_resident_layout(const Program& P, const SpecOptions& opt = SpecOptions());
+// [G + 1][2]: (checkpoint pass, first instruction still to run) by execution position of a trajectory's first flagged draw
+std::vector<int32_t> spec_resident_ckpts(const Program& P);
+// CUDA source of ncb_res_trunk / ncb_res ("" when the program is not resident or carries operators they do not cover)
+std::string spec_resident_source(const Program& P, const SpecOptions& opt = SpecOptions());
 // content hash of everything the generated code depends on (cache key): a hash of the source itself
 std::string spec_key(const Program& P, const SpecOptions& opt = SpecOptions());
 

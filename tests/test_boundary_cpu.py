@@ -137,8 +137,15 @@ def test_specialised_kernel_sources_compile_for_sm_100a(tmp_path, monkeypatch):
     cubins = [f for d, _, fs in os.walk(tmp_path) for f in fs if f.endswith(".cubin")]
     assert len(cubins) == (nseg + 3) // 4
     assert prog.specialize_build()                              # second call: cache hit
-    small = Program(PackedCircuit(6, circuits.heron_layered(6, 2, circuits.coupled_pairs(tq, 6), seed=1), sq, tq), specialize=True)
-    assert small.specialized_source() .count("extern") == 0 and not small.specialize_build()     # resident: nothing to specialise
+    # a state that fits one CTA: one module with the generated resident kernels (trunk + trajectories), structure-only source
+    si = circuits.heron_layered(6, 2, circuits.coupled_pairs(tq, 6), seed=1)
+    small = Program(PackedCircuit(6, si, sq, tq), specialize=True)
+    ssrc = small.specialized_source()
+    assert ssrc.count('extern "C" __global__') == 2 and "ncb_res_trunk" in ssrc and "ncb_res(" in ssrc and "0x1." not in ssrc
+    si2 = [[g, q, (t * 0.7 + 0.1 if g in ("rx", "rz", "rzz") else t)] for g, q, t in si]
+    assert Program(PackedCircuit(6, si2, sq, tq), specialize="parametric").specialized_source() == ssrc
+    assert small.specialize_build()
+    assert any(f == "resident.cubin" for d, _, fs in os.walk(tmp_path) for f in fs)
 
 
 def test_partial_measurement_maps_each_qubit_to_its_bit_of_the_marginal(heron_noise):

@@ -709,3 +709,60 @@ def test_generated_event_kernels_single_inline_jump(heron_noise):
     probs, _ = prog.run_mcwf(U.shape[0], rng=_lib.RNG_EXPLICIT, uniforms=U)
     ref = sum(np.abs(O.trajectory(U[t][order], mask_fix=True)) ** 2 for t in range(U.shape[0]))
     assert np.abs(probs - ref).max() < TOL * U.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# generated resident kernels (states that fit one CTA: trunk with checkpoints, trajectories resumed from them)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,opts", [(5, {}), (9, {}), (10, {"reg_bits": 4}), (11, {}), (12, {}), (12, {"reg_bits": 3}),
+                                    (12, {"strict_order": True})])
+def test_replay_generated_resident_kernels(heron_noise, n, opts):
+    """The replay harness on the generated resident kernels (ncb_res_trunk / ncb_res): every trajectory starts from the trunk's
+    checkpoint before its first flagged draw and has to end in the oracle's state."""
+    sq, tq, _, _ = heron_noise
+    instr = circuits.heron_layered(n, 4, circuits.coupled_pairs(tq, n), seed=n)
+    U = jumpy_uniforms(np.random.default_rng(n), 10, len(instr))
+    U[0] = 0.5                                   # a trajectory that never leaves the trunk
+    stats, prog = replay(n, instr, sq, tq, U, specialize="parametric", **opts)
+    assert prog.query(_lib.Q_RESIDENT) == 1
+    assert stats["specialized_launches"] == 2 and stats["events"] > 0 and stats["hard_events"] > 0
+
+
+def test_replay_generated_resident_kernels_eagle(eagle_noise):
+    """Eagle at a resident size: generic 2x2 factors of the decomposed ecr, norm tracking."""
+    sq, tq, _, _ = eagle_noise
+    n = 10
+    instr = circuits.eagle_layered(n, 3, circuits.coupled_pairs(tq, n), seed=5)
+    stats, prog = replay(n, instr, sq, tq, jumpy_uniforms(np.random.default_rng(1), 8, len(instr)), specialize="parametric")
+    assert stats["specialized_launches"] == 2 and prog.query(_lib.Q_NORM_PRESERVING) == 0
+
+
+@pytest.mark.parametrize("n,layers", [(12, 4), (7, 3)])
+def test_generated_resident_kernels_equal_the_interpreter(heron_noise, n, layers):
+    """Probability path (no states): Philox draws, trajectories that stay on the trunk are only counted; the same sum as the
+    interpreting resident kernel and as the oracle, and independent of how the call is split."""
+    sq, tq, _, _ = heron_noise
+    instr = circuits.qnn_circuit(n, layers, circuits.coupled_pairs(tq, n, adjacent_only=True), seed=7)
+    pk = PackedCircuit(n, instr, sq, tq)
+    gen = Program(pk, _lib.MODE_MCWF, specialize="parametric")
+    interp = Program(pk, _lib.MODE_MCWF)
+    T, seed = 3000, 9
+    a, sa = gen.run_mcwf(T, seed=seed)
+    b, sb = interp.run_mcwf(T, seed=seed)
+    assert sa["specialized_launches"] == 2 and sb["specialized_launches"] == 0
+    assert sa["events"] == sb["events"] and sa["hard_events"] == sb["hard_events"] and sa["events"] > 0
+    assert np.abs(a - b).max() < 1e-12 * T and abs(a.sum() - T) < 1e-8
+    c1, _ = gen.run_mcwf(1000, traj_begin=0, seed=seed)
+    c2, _ = gen.run_mcwf(2000, traj_begin=1000, seed=seed)
+    assert np.abs(c1 + c2 - a).max() < 1e-12 * T
+    Tq = 48
+    U = np.array([[philox_numpy(seed, t, g) for g in range(len(instr))] for t in range(Tq)])
+    ref = oracle.Program(n, instr, sq, tq).mcwf(Tq, uniforms=U, mask_fix=True, threads=_oracle_threads())
+    q, _ = gen.run_mcwf(Tq, seed=seed)
+    assert np.abs(q / Tq - ref).max() < TOL
+    # an in-place update (parameter sweep) keeps the loaded kernels and uploads the new tables
+    instr2 = circuits.qnn_circuit(n, layers, circuits.coupled_pairs(tq, n, adjacent_only=True), seed=8)
+    gen.update(PackedCircuit(n, instr2, sq, tq))
+    d, sd = gen.run_mcwf(T, seed=seed)
+    e, _ = Program(PackedCircuit(n, instr2, sq, tq), _lib.MODE_MCWF).run_mcwf(T, seed=seed)
+    assert sd["specialized_launches"] == 2 and np.abs(d - e).max() < 1e-12 * T
