@@ -1,4 +1,6 @@
 // Host-side compiler of the B200 noisy-circuit engine (see ncb_compile.h).
+#include <memory>
+#include <mutex>
 #include "ncb_compile.h"
 
 #include <algorithm>
@@ -451,10 +453,43 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
     PoolBuilder pb{P.pool};
 
     // ---- channels -------------------------------------------------------------------------------------------
-    std::vector<ChannelInfo> cinfo(std::max(c.num_channels, 0));
+    std::vector<ChannelInfo> cinfo_own(std::max(c.num_channels, 0));
+    std::shared_ptr<const void> cinfo_keep;                 // (a cached analysis stays alive while it is read)
+    const std::vector<ChannelInfo>* cinfo_p = &cinfo_own;
     const bool use_noise = mode != MODE_PURE;
-    if (use_noise)
-        for (int ch = 0; ch < c.num_channels; ++ch) P.chans.push_back(analyse_channel(c, ch, pb, cinfo[ch]));
+    if (use_noise && c.num_channels > 0) {
+        // The analysis of the Kraus lists (operators, M_k, eigenvalue bounds of the cumulative sums) depends on the noise model
+        // only: a parameter sweep re-compiles one gate skeleton with the same channels thousands of times (ncb_program_update),
+        // so the last few analysed channel sets are kept, keyed by the channel data itself.
+        struct Entry { std::vector<unsigned char> key; std::vector<Channel> chans; std::vector<ChannelInfo> info; std::vector<double> pool; };
+        static std::mutex mu;
+        static std::vector<std::shared_ptr<const Entry>> cache;
+        std::vector<unsigned char> key;
+        {
+            const int nch = c.num_channels;
+            const long long elems = c.channel_offset[nch - 1] + (long long)c.channel_count[nch - 1] * c.channel_dim[nch - 1] * c.channel_dim[nch - 1];
+            auto put = [&](const void* ptr, size_t n) { const unsigned char* b = (const unsigned char*)ptr; key.insert(key.end(), b, b + n); };
+            put(&nch, sizeof nch);
+            put(c.channel_offset, sizeof(int64_t) * nch); put(c.channel_count, sizeof(int32_t) * nch); put(c.channel_dim, sizeof(int32_t) * nch);
+            put(c.kraus_pool, sizeof(double) * 2 * (size_t)elems);
+        }
+        std::shared_ptr<const Entry> hit;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (const auto& e : cache) if (e->key == key) { hit = e; break; }
+        }
+        if (!hit) {
+            auto e = std::make_shared<Entry>();
+            for (int ch = 0; ch < c.num_channels; ++ch) P.chans.push_back(analyse_channel(c, ch, pb, cinfo_own[ch]));
+            e->key = std::move(key); e->chans = P.chans; e->info = cinfo_own; e->pool = P.pool;
+            std::lock_guard<std::mutex> lk(mu);
+            cache.insert(cache.begin(), e);
+            if (cache.size() > 4) cache.pop_back();
+        } else {
+            P.chans = hit->chans; cinfo_p = &hit->info; cinfo_keep = hit; P.pool = hit->pool;
+        }
+    }
+    const std::vector<ChannelInfo>& cinfo = *cinfo_p;
 
     // ---- logical ops ----------------------------------------------------------------------------------------
     std::vector<LogicalOp> lops;

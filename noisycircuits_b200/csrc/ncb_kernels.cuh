@@ -179,6 +179,46 @@ static __device__ __noinline__ void fused_decide(const DevProgram& P, const doub
     __syncthreads();
 }
 
+// decide_branch with the block's threads: thread k computes p_k = Re tr(M_k rho) (the same expression, term by term, as
+// decide_branch), thread 0 adds them up and picks in order.  rho: shared memory (mirrored), s_p: >= ch.count doubles of shared
+// memory.  Result in *k_out / *scale_out (shared) after the closing barrier.  Serial fall-back when s_p is too small.
+static __device__ __noinline__ void decide_branch_block(const double* rho, const Channel& ch, const double* __restrict__ pool, double u,
+                                                        double* s_p, int s_p_len, int* k_out, double* scale_out) {
+    const int tid = threadIdx.x;
+    if (ch.count > s_p_len) {
+        if (tid == 0) { double sc; *k_out = decide_branch(rho, ch, pool, u, &sc); *scale_out = sc; }
+        __syncthreads();
+        return;
+    }
+    const int d = ch.dim, dd = d * d;
+    const double* mk = pool + ch.mk;
+    for (int k = tid; k < ch.count; k += blockDim.x) {
+        double p = 0.0;
+        for (int r = 0; r < d; ++r)
+            for (int c = 0; c < d; ++c)
+                p += mk[2 * (k * dd + r * d + c)] * rho[2 * (c * d + r)] - mk[2 * (k * dd + r * d + c) + 1] * rho[2 * (c * d + r) + 1];
+        s_p[k] = p;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int k = 0; k < ch.count; ++k) sum += s_p[k] > 0.0 ? s_p[k] : 0.0;
+        int pick = ch.count - 1;
+        double cp = 0.0, ppick = 0.0;
+        for (int k = 0; k < ch.count; ++k) {
+            double p = s_p[k];
+            if (p < 0.0) p = 0.0;
+            cp += p / sum;
+            ppick = p;
+            if (k == ch.count - 1 || !(cp < u)) { pick = k; break; }
+        }
+        const double st = pool[ch.scale + pick];
+        *scale_out = ppick > 0.0 ? 1.0 / (st * sqrt(ppick)) : 0.0;
+        *k_out = pick;
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // tile kernel
 // ---------------------------------------------------------------------------------------------------------------
@@ -587,9 +627,9 @@ struct ResidentArgs {
 // ---------------------------------------------------------------------------------------------------------------
 // A trajectory is the jump-free evolution (the "trunk") up to its first flagged draw.  The trunk runs ONCE (ncb_res_trunk,
 // one CTA) and leaves its state at every pass boundary in global memory (2^K amplitudes each: L2 resident); the planning
-// kernels list the trajectories that leave the trunk, in trajectory order (deterministic), and ncb_res runs each of them
-// from the last checkpoint before its first flagged draw -- the others are only counted and weighted with the trunk's result.
-struct ResItem { int32_t tl, first; };      // trajectory (index within the call) and execution position of its first flagged draw (G: none)
+// kernel finds every trajectory's first flagged draw; the trajectories that leave the trunk are sorted by it (stable radix sort:
+// deterministic, longest remaining work first, so that dealing them out round-robin balances the CTAs) and ncb_res runs each
+// of them from the last checkpoint before that draw -- the others are only counted and weighted with the trunk's result.
 struct ResCkpt { int32_t pass, instr; };    // checkpoint to start from (global pass index; -1: |0...0>) and the first instruction still to run
 struct ResArgs {
     long long traj_begin;
@@ -598,8 +638,10 @@ struct ResArgs {
     const double* thresh;            // [n_noisy][2]: a draw u with thresh[0] < u <= thresh[1] selects the base branch for sure
     const unsigned char* blobs;      // the program's segment blobs (phase tables and 2x2 coefficients are staged from their pools)
     const int32_t* seg_pool;         // [nseg][2]: byte offset of segment s's pool in blobs, bytes
-    const ResItem* items;
+    const uint32_t* item_first;      // [count] execution position of the first flagged draw, ascending (longest work first);
+    const int32_t* item_traj;        // [count] its trajectory (index within the call); only the first n_items[0] entries are run
     const int32_t* n_items;
+    int32_t count;                   // trajectories of this call
     const ResCkpt* ckpt_for;         // [G + 1], by execution position of the first flagged draw
     cplx* ckpt;                      // [npass + 1][2^K]: trunk states in the shared-memory (swizzled) layout; [npass] = final state
     double* partial;                 // [gridDim.x][2^nbits]
@@ -611,51 +653,62 @@ struct ResArgs {
 
 #ifndef NCB_TEMPLATES_ONLY
 constexpr int RES_PLAN_THREADS = 128;
-// first flagged draw of every trajectory; the flagged ones (all of them with `all`) compacted per block, in order
+// One warp per trajectory: key[t] = execution position of trajectory t's first flagged draw (G: none; G + 1: none and not wanted
+// as an item), val[t] = t; n_items counts the wanted ones.  The lanes test 32 draws at a time (noisy[] ascends, so the first
+// set lane of the first non-empty ballot is the first flagged draw).
 __global__ void __launch_bounds__(RES_PLAN_THREADS)
 res_plan_kernel(const double* __restrict__ thresh, const int32_t* __restrict__ noisy, const int32_t* __restrict__ orig, int n_noisy, int G,
                 unsigned long long seed, long long traj_begin, int count, const double* __restrict__ uniforms, int all,
-                ResItem* __restrict__ tmp, int32_t* __restrict__ block_count) {
-    __shared__ int wcount[RES_PLAN_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = blockIdx.x * RES_PLAN_THREADS + tid;
-    int first = G;
+                uint32_t* __restrict__ key, int32_t* __restrict__ val, int32_t* __restrict__ n_items) {
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (RES_PLAN_THREADS / 32) + (threadIdx.x >> 5);
     if (t < count) {
         const double* utab = uniforms ? uniforms + (long long)t * G : nullptr;
-        for (int a = 0; a < n_noisy; ++a) {
-            const int i = noisy[a];
-            const double u = utab ? utab[i] : philox_uniform(seed, (unsigned long long)(traj_begin + t), (uint32_t)orig[i]);
-            if (!(u > thresh[2 * a] && u <= thresh[2 * a + 1])) { first = i; break; }
+        int first = G;
+        for (int a0 = 0; a0 < n_noisy; a0 += 32) {
+            const int a = a0 + lane;
+            bool flagged = false;
+            if (a < n_noisy) {
+                const int i = noisy[a];
+                const double u = utab ? utab[i] : philox_uniform(seed, (unsigned long long)(traj_begin + t), (uint32_t)orig[i]);
+                flagged = !(u > thresh[2 * a] && u <= thresh[2 * a + 1]);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, flagged);
+            if (m) { first = noisy[a0 + __ffs(m) - 1]; break; }
+        }
+        if (lane == 0) {
+            const bool want = all || first < G;
+            key[t] = (uint32_t)(want ? first : G + 1);
+            val[t] = t;
+            if (want) atomicAdd(&s_cnt, 1);
         }
     }
-    const bool flag = t < count && (all || first < G);
-    const unsigned m = __ballot_sync(0xffffffffu, flag);
-    if (lane == 0) wcount[warp] = __popc(m);
     __syncthreads();
-    int off = 0, total = 0;
-    for (int w = 0; w < RES_PLAN_THREADS / 32; ++w) { if (w < warp) off += wcount[w]; total += wcount[w]; }
-    if (flag) tmp[blockIdx.x * RES_PLAN_THREADS + off + __popc(m & ((1u << lane) - 1u))] = ResItem{t, first};
-    if (tid == 0) block_count[blockIdx.x] = total;
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(n_items, s_cnt);
 }
-// the blocks' lists back to back; the last block leaves the totals
-__global__ void __launch_bounds__(RES_PLAN_THREADS)
-res_scatter_kernel(const ResItem* __restrict__ tmp, const int32_t* __restrict__ block_count, ResItem* __restrict__ items,
-                   int32_t* __restrict__ n_items, unsigned long long* __restrict__ counters, int count) {
-    __shared__ int wsum[RES_PLAN_THREADS / 32];
-    const int tid = threadIdx.x;
-    int s = 0;
-    for (int b = tid; b < (int)blockIdx.x; b += RES_PLAN_THREADS) s += block_count[b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((tid & 31) == 0) wsum[tid >> 5] = s;
+
+// probs[j] += sum_c partial[c][j] (+ n_trunk * trunk[j]) with 8 threads per column: thread (j, g) adds the partials g, g + 8, ...
+// in order, thread (j, 0) the eight sums in order -- deterministic for a given number of partials
+__global__ void __launch_bounds__(256)
+sum_partials_wide_kernel(double* __restrict__ probs, const double* __restrict__ partial, long long dim, int nparts,
+                         const double* __restrict__ trunk, const unsigned long long* __restrict__ n_trunk) {
+    __shared__ double s[8][33];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long long j = (long long)blockIdx.x * 32 + c;
+    double v = 0.0;
+    if (j < dim)
+        for (int p = g; p < nparts; p += 8) v += partial[(long long)p * dim + j];
+    s[g][c] = v;
     __syncthreads();
-    int base = 0;
-    for (int w = 0; w < RES_PLAN_THREADS / 32; ++w) base += wsum[w];
-    const int cnt = block_count[blockIdx.x];
-    if (tid < cnt) items[base + tid] = tmp[blockIdx.x * RES_PLAN_THREADS + tid];
-    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
-        n_items[0] = base + cnt;
-        counters[2] = (unsigned long long)(count - (base + cnt));
+    if (g == 0 && j < dim) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s[k][c];
+        if (trunk) { const double wt = (double)n_trunk[0]; if (wt != 0.0) t += wt * trunk[j]; }
+        probs[j] += t;
     }
 }
 #endif  // NCB_TEMPLATES_ONLY

@@ -1,5 +1,6 @@
 #include "ncb_spec.h"
 
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -322,7 +323,8 @@ void emit_guarded_passes(std::ostringstream& o, const BlobView& bv, int R, int K
         o << "        if (" << ps.instr_lo << " < hi && " << ps.instr_hi << " > lo) {   // pass " << p << "\n";
         if (ckpt_pass0 >= 0)
             o << "            if (ckpt != nullptr) {\n                cplx* const c = ckpt + ((size_t)" << ckpt_pass0 + p << " << " << K << ");\n"
-              << "                for (int i = (int)threadIdx.x; i < " << (1 << K) << "; i += (int)blockDim.x) c[i] = sm[i];\n            }\n";
+              << "                for (int i = (int)threadIdx.x; i < " << (1 << K) << "; i += (int)blockDim.x) c[i] = sm[i];\n"
+              << "                __syncthreads();      // (the copy reads every thread's slots: nobody may store this pass' results before it is done)\n            }\n";
         o << "            cplx a[" << NA << "];\n";
         for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "];\n";
         // (hot: the operator stands alone in the list; cold: a member of a merged group, run one by one only when a jump
@@ -583,9 +585,10 @@ bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOpt
          "    for (int j = tid; j < RDIM; j += RNT) acc[j] = 0.0;\n"
          "    __syncthreads();\n"
          "    const int n_items = A.n_items[0];\n"
+         "    if (blockIdx.x == 0 && tid == 0 && A.counters) A.counters[2] = (unsigned long long)(A.count - n_items);\n"
          "    unsigned long long n_events = 0, n_hard = 0;\n"
          "    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {\n"
-         "        const ResItem item = A.items[it];\n"
+         "        struct { long long tl; int first; } item = {A.item_traj[it], (int)A.item_first[it]};\n"
          "        const long long tl = item.tl;\n"
          "        const unsigned long long traj = (unsigned long long)(A.traj_begin + tl);\n"
          "        const double* utab = A.uniforms ? A.uniforms + tl * RG : nullptr;\n"
@@ -624,20 +627,26 @@ bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOpt
          "            const Channel ch = P.chans[in.channel];\n"
          "            const double u = utab ? utab[e] : philox_uniform(A.seed, traj, (uint32_t)P.orig[e]);\n"
          "            int kmin, kmax;\n"
-         "            classify_uniform(P.pool + ch.bounds, P.pool + ch.bounds + (ch.count - 1), ch.count, u, &kmin, &kmax);\n"
+         "            {   // the channel's bounds through shared memory: one parallel fetch instead of a chain of dependent global loads\n"
+         "                const int nb = 2 * (ch.count - 1);\n"
+         "                const bool staged = nb <= 32 * 20;\n"
+         "                if (staged) {\n"
+         "                    for (int i = tid; i < nb; i += RNT) s_buf[i] = P.pool[ch.bounds + i];\n"
+         "                    __syncthreads();\n"
+         "                }\n"
+         "                const double* bnd = staged ? s_buf : P.pool + ch.bounds;\n"
+         "                classify_uniform(bnd, bnd + (ch.count - 1), ch.count, u, &kmin, &kmax);\n"
+         "                __syncthreads();\n"
+         "            }\n"
          "            int k = kmin;\n"
          "            double scale = 1.0;\n"
          "            bool base_after_all = false;\n"
          "            if (kmin != kmax) {\n"
          "                ++n_hard;\n"
          "                event_reduce(sm, RK, in.q0, ch.dim == 4 ? in.q1 : -1, s_buf, s_red, s_out);\n"
-         "                if (tid == 0) {\n"
-         "                    mirror_rho(s_out, ch.dim);\n"
-         "                    double sc;\n"
-         "                    s_k = decide_branch(s_out, ch, P.pool, u, &sc);\n"
-         "                    s_scale = sc;\n"
-         "                }\n"
+         "                if (tid == 0) mirror_rho(s_out, ch.dim);\n"
          "                __syncthreads();\n"
+         "                decide_branch_block(s_out, ch, P.pool, u, s_buf, 32 * 20, &s_k, &s_scale);\n"
          "                k = s_k; scale = s_scale;\n"
          "            } else if (k == ch.base) {\n"
          "                base_after_all = true;     // flagged by the cheap test only (u within the margin): base branch\n"
@@ -803,13 +812,38 @@ std::string spec_resident_source(const Program& P, const SpecOptions& opt) {
     return o.str();
 }
 
+uint64_t spec_structure_hash(const Program& P, const SpecOptions& opt) {
+    // everything the generators read, without generating: geometry, the segments' blobs up to their pools (headers, passes,
+    // operator records with their table offsets), the pools' sizes, the constant-bank programs (with the coefficients only
+    // when they are written out as literals)
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* ptr, size_t n) {
+        const unsigned char* b = (const unsigned char*)ptr;
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    const int geo[8] = {P.nbits, P.K, P.R, P.G, P.mode, (int)P.segs.size(), (int)P.passes.size(), opt.literal};
+    mix(geo, sizeof geo);
+    const int o2[5] = {opt.nbuf, opt.load, opt.events, opt.factor, opt.ctas};
+    mix(o2, sizeof o2);
+    for (size_t sgi = 0; sgi < P.blob_off.size(); ++sgi) {
+        const unsigned char* braw = P.blobs.data() + P.blob_off[sgi];
+        const SegBlob& blob = *reinterpret_cast<const SegBlob*>(braw);
+        mix(braw, (size_t)blob.pool_off);
+        mix(&blob.bytes, sizeof blob.bytes);
+    }
+    const bool tiled = lean_tiled(P);
+    for (size_t sgi = 0; tiled && sgi < P.segconst.size(); ++sgi)
+        mix(&P.segconst[sgi], opt.literal ? sizeof(SegConst) : offsetof(SegConst, coef));
+    return h;
+}
+
 std::string spec_key(const Program& P, const SpecOptions& opt) {
     // FNV-1a over the generated source of every segment: the source is all the cubins depend on (beside the headers,
     // which the engine covers with a build stamp)
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt) + spec_resident_source(P, opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 12 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 14 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);

@@ -53,6 +53,9 @@ ResidentLayout spec_resident_layout(const Program& P, const SpecOptions& opt = S
 std::vector<int32_t> spec_resident_ckpts(const Program& P);
 // CUDA source of ncb_res_trunk / ncb_res ("" when the program is not resident or carries operators they do not cover)
 std::string spec_resident_source(const Program& P, const SpecOptions& opt = SpecOptions());
+// cheap hash of the records the generators read (no source is generated): equal hashes <=> the same kernels; used to see that
+// an updated program (parameter sweep) keeps its loaded kernels.  A mismatch is re-checked with spec_key.
+uint64_t spec_structure_hash(const Program& P, const SpecOptions& opt = SpecOptions());
 // content hash of everything the generated code depends on (cache key): a hash of the source itself
 std::string spec_key(const Program& P, const SpecOptions& opt = SpecOptions());
 

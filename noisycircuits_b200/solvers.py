@@ -113,15 +113,16 @@ class RemoteExecutor:
         return probs / float(num_trajectories)
 
     def run_many(self, num_trajectories: int, instruction_lists) -> list:
-        """``run`` for a sequence of circuits (a QNN parameter sweep over one gate skeleton).  Two engine
-        objects take turns: while the GPU runs circuit i in one, a host thread packs circuit i + 1 and compiles it INTO the
-        other one in place (``Program.update``: device buffers, streams and -- for one gate skeleton -- the loaded kernels
+        """``run`` for a sequence of circuits (a QNN parameter sweep over one gate skeleton).  A few engine
+        objects take turns: while the GPU runs circuit i in one, host threads pack the next circuits and compile them INTO the
+        others in place (``Program.update``: device buffers, streams and -- for one gate skeleton -- the loaded kernels
         are reused).  Same results as calling ``run`` in a loop (trajectory ids 0..N-1 for every circuit)."""
         lists = list(instruction_lists)
         if not lists:
             return []
-        packs = (PackedCircuit(self.num_qubits, instr, self.single_qubit_noise, self.two_qubit_noise, noisy=True) for instr in lists)
-        return self._run_packed(num_trajectories, packs, len(lists))
+        makers = ((lambda instr=instr: PackedCircuit(self.num_qubits, instr, self.single_qubit_noise, self.two_qubit_noise, noisy=True))
+                  for instr in lists)
+        return self._run_packed(num_trajectories, makers, len(lists))
 
     def run_sweep(self, num_trajectories: int, instruction_list: list, thetas) -> list:
         """``run`` for the gate skeleton ``instruction_list`` with every row of ``thetas`` ([sets][instructions]: the
@@ -132,23 +133,37 @@ class RemoteExecutor:
             raise ValueError("thetas must have shape [sets][len(instruction_list)]")
         base = PackedCircuit(self.num_qubits, instruction_list, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
         pad = np.zeros(base.theta.shape[0] - thetas.shape[1])
-        packs = (base.with_thetas(np.concatenate([row, pad])) for row in thetas)
-        return self._run_packed(num_trajectories, packs, thetas.shape[0])
+        makers = ((lambda row=row: base.with_thetas(np.concatenate([row, pad]))) for row in thetas)
+        return self._run_packed(num_trajectories, makers, thetas.shape[0])
 
-    def _run_packed(self, num_trajectories, packs, count):
+    PREPARE_THREADS = 2          # host threads that pack / compile the next circuits of a sweep while the GPU runs one
+
+    def _run_packed(self, num_trajectories, makers, count):
+        import threading
+        from collections import deque
         from concurrent.futures import ThreadPoolExecutor
         opts = dict(self.engine_options)
         opts.setdefault("specialize", "parametric" if num_trajectories >= self.SPECIALIZE_FROM else False)   # a sweep: one kernel set
-        packs = iter(packs)
-        # the two engine objects live as long as the executor: a training loop calls this every step, and creating an engine
+        makers = iter(makers)
+        depth = max(1, int(self.PREPARE_THREADS))
+        # the engine objects live as long as the executor: a training loop calls this every step, and creating an engine
         # means a dozen device allocations (each can stall for tens of milliseconds next to a large state batch)
-        key = tuple(sorted((k, str(v)) for k, v in opts.items()))
+        key = (depth,) + tuple(sorted((k, str(v)) for k, v in opts.items()))
         if getattr(self, "_sweep_key", None) != key:
-            self._sweep_key, self._sweep_engines = key, [None, None]
+            self._sweep_key, self._sweep_engines = key, [None] * (depth + 1)
         engines = self._sweep_engines
+        lock = threading.Lock()
+        taken = [0]
 
-        def prepare(slot):
-            packed = next(packs)
+        def prepare():
+            # circuit idx goes into engine idx % (depth + 1); the caller only has `depth` preparations outstanding, so that
+            # engine's previous circuit (idx - depth - 1) has been run and collected
+            with lock:
+                idx = taken[0]
+                taken[0] += 1
+                make = next(makers)
+            packed = make()
+            slot = idx % (depth + 1)
             if engines[slot] is None:
                 engines[slot] = Program(packed, _lib.MODE_MCWF, **opts)
             else:
@@ -156,15 +171,21 @@ class RemoteExecutor:
                     engines[slot].update(packed)
                 except _lib.NcbError:                      # another geometry: a new engine object
                     engines[slot] = Program(packed, _lib.MODE_MCWF, **opts)
-            return engines[slot]
+            return idx, engines[slot]
 
-        out = []
-        with ThreadPoolExecutor(max_workers=1) as pool:
-            nxt = pool.submit(prepare, 0)
+        out, ready, futs = [], {}, deque()
+        with ThreadPoolExecutor(max_workers=depth) as pool:
+            for _ in range(min(depth, count)):
+                futs.append(pool.submit(prepare))
+            submitted = len(futs)
             for i in range(count):
-                prog = nxt.result()
-                if i + 1 < count:
-                    nxt = pool.submit(prepare, (i + 1) & 1)
+                while i not in ready:
+                    idx, prog = futs.popleft().result()
+                    ready[idx] = prog
+                prog = ready.pop(i)
+                if submitted < count:
+                    futs.append(pool.submit(prepare))
+                    submitted += 1
                 probs, stats = prog.run_mcwf(num_trajectories, traj_begin=0, rng=_RNG[self.rng], seed=self.seed)
                 self.last_stats = stats
                 out.append(probs / float(num_trajectories))

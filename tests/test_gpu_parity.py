@@ -766,3 +766,24 @@ def test_generated_resident_kernels_equal_the_interpreter(heron_noise, n, layers
     d, sd = gen.run_mcwf(T, seed=seed)
     e, _ = Program(PackedCircuit(n, instr2, sq, tq), _lib.MODE_MCWF).run_mcwf(T, seed=seed)
     assert sd["specialized_launches"] == 2 and np.abs(d - e).max() < 1e-12 * T
+
+
+def test_generated_resident_kernels_are_deterministic_across_updates(heron_noise):
+    """Two circuits taking turns in ONE engine object (the parameter-sweep path: tables re-uploaded, trunk re-run beside the
+    planning kernels): every repeat returns the same bits.  (A missing barrier after the trunk's checkpoint copy once let a
+    fast warp's results into a checkpoint in 2 % of the runs.)"""
+    sq, tq, _, _ = heron_noise
+    n, T = 12, 4000
+    pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)
+    pk = [PackedCircuit(n, circuits.qnn_circuit(n, 4, pairs, seed=100 + k), sq, tq) for k in range(2)]
+    prog = Program(pk[0], _lib.MODE_MCWF, specialize="parametric")
+    refs = []
+    for k in range(2):
+        prog.update(pk[k])
+        refs.append(prog.run_mcwf(T)[0])
+    fresh = Program(pk[1], _lib.MODE_MCWF, specialize="parametric").run_mcwf(T)[0]
+    assert np.array_equal(fresh, refs[1])
+    for r in range(120):
+        prog.update(pk[r & 1])
+        p, st = prog.run_mcwf(T)
+        assert st["specialized_launches"] == 2 and np.array_equal(p, refs[r & 1]), r
