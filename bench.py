@@ -26,7 +26,7 @@ cpu_baseline  the reference's compiled CPU path (oracle/_ref/patched: these circ
            4s .. 4s+3, cyclically) and reports the per-slice rates, and profiles/ holds one run of the full circuit.
 parity     untimed, in the same run: 2 Philox trajectories of the FULL benchmarked program (generated kernels, shared
            prefix) against the CPU oracle in program order (about a minute of two host threads; --no-parity skips it).
-c2_density_matrix / strong_scaling   extra keys, see run_gpu.
+c2_density_matrix / c3_qnn_sweep / strong_scaling   extra keys, see run_gpu.
 """
 import argparse
 import datetime
@@ -342,6 +342,41 @@ def c2_block(peak):
         return {"error": repr(e)}
 
 
+def c3_block():
+    """BASELINE configs[2]: 12-qubit QNN-style Heron circuit, 10^4 trajectories per circuit, one GPU (the state fits one CTA:
+    generated resident kernels), and the training loop's inner evaluation -- 32 parameter sets of the gate skeleton through
+    run_sweep (host threads re-compile the next circuits into idle engine objects while the GPU runs one)."""
+    try:
+        from noisycircuits_b200 import circuits, noise_io
+        from noisycircuits_b200.solvers import RemoteExecutor
+        sq, tq, _m, _ = noise_io.load_noise_tables(os.path.join(ROOT, "tests", "golden", "heron20_noise.npz"))
+        n, layers, T, sets = 12, 4, 10000, 32
+        pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)
+        lists = [circuits.qnn_circuit(n, layers, pairs, seed=100 + i) for i in range(sets)]
+        ex = RemoteExecutor(n, sq, tq, 1)
+        ex.run(T, lists[0])
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            p = ex.run(T, lists[0])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        st = ex.last_stats
+        thetas = np.array([[0.0 if q is None else float(q) for _g, _q, q in l] for l in lists])
+        ex.run_sweep(T, lists[0], thetas[:4])
+        t0 = time.perf_counter()
+        out = ex.run_sweep(T, lists[0], thetas)
+        t_sweep = time.perf_counter() - t0
+        return {"workload": f"{n}-qubit QNN circuit ({len(lists[0])} instructions), {T} trajectories per circuit", "seconds_per_circuit": best,
+                "trajectories_per_s": T / best, "kernel_ms": st["kernel_ms"], "generated_kernel_launches": int(st["specialized_launches"]),
+                "events_per_trajectory": st["events"] / T, "norm_check": float(p.sum()),
+                "sweep": {"parameter_sets": sets, "seconds": t_sweep, "circuits_per_s": sets / t_sweep,
+                          "first_equals_single_run": bool(np.array_equal(out[0], p))},
+                "parity": "tests/test_gpu_parity.py::test_c3_qnn12_vs_oracle, test_generated_resident_kernels_equal_the_interpreter (oracle, 1e-10)"}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -505,6 +540,7 @@ def run_gpu(args):
             line["parity"] = parity_block(solver, instr, sq, tq, tps)
         if world == 1 and not args.no_c2:
             line["c2_density_matrix"] = c2_block(peak)
+            line["c3_qnn_sweep"] = c3_block()
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             try:
@@ -526,7 +562,7 @@ def main():
     ap.add_argument("--traj-per-step", type=int, default=592)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed in-run parity check against the oracle (about a minute)")
-    ap.add_argument("--no-c2", action="store_true", help="skip the 12-qubit density-matrix extra line")
+    ap.add_argument("--no-c2", action="store_true", help="skip the extra lines of the 12-qubit configurations (density matrix, QNN sweep)")
     ap.add_argument("--strong-traj", type=int, default=16384, help="total trajectories of the strong-scaling call (0: skip)")
     ap.add_argument("--full-circuit", action="store_true", help="--impl reference: time the whole circuit per step instead of 4-layer slices")
     args = ap.parse_args()

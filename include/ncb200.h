@@ -168,6 +168,15 @@ typedef struct {
 } ncb_run_params;
 
 int ncb_mcwf_run(ncb_program* program, ncb_run_params* params);
+/* ncb_mcwf_run in two phases, for callers that keep several programs in flight (a parameter sweep: the reference's training
+ * loops call QuantumCircuit.execute once per parameter set, examples/quantum_neural_networks.ipynb cells 20-27):
+ * ncb_mcwf_launch enqueues the run -- with stream = 0 on a stream of the program's own, so that launches of different programs
+ * overlap on the device -- and returns without waiting where the path allows it (programs whose state fits one CTA running
+ * generated kernels with Philox draws: their planning happens on the device; every other program has finished its kernels when
+ * the call returns); ncb_mcwf_collect, with the SAME params object, waits, fills probs (host buffers are written only here) and
+ * the out_* statistics.  One run in flight per program; the buffers of params stay alive in between. */
+int ncb_mcwf_launch(ncb_program* program, ncb_run_params* params);
+int ncb_mcwf_collect(ncb_program* program, ncb_run_params* params);
 /* Noise-free run from |0..0>: state (complex, 2^n) and/or probs (2^n) may be NULL. */
 int ncb_pure_run(ncb_program* program, double* state, double* probs, void* stream);
 /* Density-matrix run: probs[r] = rho[r][r], r over all 2^n basis states (little-endian). */

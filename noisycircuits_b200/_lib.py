@@ -41,7 +41,8 @@ class NcbRunParams(C.Structure):
 
 # every symbol include/ncb200.h declares
 EXPORTS = ["ncb_last_error", "ncb_version", "ncb_program_create", "ncb_program_destroy", "ncb_program_update", "ncb_program_describe",
-           "ncb_program_query", "ncb_program_order", "ncb_program_events", "ncb_program_reference_uniforms", "ncb_mcwf_run", "ncb_pure_run",
+           "ncb_program_query", "ncb_program_order", "ncb_program_events", "ncb_program_reference_uniforms", "ncb_mcwf_run", "ncb_mcwf_launch",
+           "ncb_mcwf_collect", "ncb_pure_run",
            "ncb_density_run", "ncb_apply_measurement_error", "ncb_apply_measurement_error_device",
            "ncb_execute_tail_device", "ncb_device_alloc", "ncb_device_free", "ncb_program_spec_build", "ncb_program_spec_source",
            "ncb_simulate_circuit", "ncb_run_trajectory"]
@@ -78,6 +79,8 @@ def lib() -> C.CDLL:
         L.ncb_program_events.restype = C.c_int64
         L.ncb_program_reference_uniforms.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.ncb_mcwf_run.argtypes = [C.c_void_p, C.POINTER(NcbRunParams)]
+        L.ncb_mcwf_launch.argtypes = [C.c_void_p, C.POINTER(NcbRunParams)]
+        L.ncb_mcwf_collect.argtypes = [C.c_void_p, C.POINTER(NcbRunParams)]
         L.ncb_pure_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ncb_density_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ncb_apply_measurement_error.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32]

@@ -233,7 +233,8 @@ struct Engine {
     int tile_ctas = 148;
 
     ~Engine() {
-        d_prog.release(); h_prog.release(); d_states.release(); d_red.release(); d_norm.release(); d_invnorm.release(); d_weight.release(); d_trunk.release(); d_probs.release();
+        d_prog.release(); h_prog.release(); h_cnt.release(); h_probs.release(); d_states.release();
+        if (s_own) cudaStreamDestroy(s_own); d_red.release(); d_norm.release(); d_invnorm.release(); d_weight.release(); d_trunk.release(); d_probs.release();
         d_partial.release(); d_uniforms.release(); d_dec.release(); d_counters.release(); d_tickets.release();
         d_nitems.release(); d_ckpt.release(); d_sort_tmp.release();
         for (int i = 0; i < 2; ++i) { d_item_key[i].release(); d_item_val[i].release(); }
@@ -259,7 +260,12 @@ struct Engine {
 
     bool device_ready = false;       // device chosen, streams and events created (once); `uploaded`: the program's tables are on it
     cudaEvent_t upload_done = nullptr;
+    cudaStream_t upload_stream_used = nullptr;
     void ensure_device(cudaStream_t upload_stream = nullptr) {
+        init_device();
+        upload_program(upload_stream);
+    }
+    void init_device() {
         if (device_ready) {
             CK(cudaSetDevice(device));                           // the caller may have switched devices since
         } else {
@@ -285,9 +291,12 @@ struct Engine {
             if (const char* e2 = getenv("NCB_EV_CHUNK")) ev_chunk = atoi(e2);
             if (const char* e2 = getenv("NCB_EV_PULL")) ev_pull = atoi(e2) != 0;
             if (const char* e2 = getenv("NCB_OVERLAP")) overlap_streams = atoi(e2) != 0;
+            CK(cudaStreamCreateWithFlags(&s_own, cudaStreamNonBlocking));
             d_counters.reserve(4);
             device_ready = true;
         }
+    }
+    void upload_program(cudaStream_t upload_stream) {
         if (uploaded) return;
         {
             // image: every table at a 256-byte aligned offset
@@ -332,6 +341,7 @@ struct Engine {
             //  waited for; runs on other streams are ordered behind the copy by the event)
             if (!upload_done) CK(cudaEventCreateWithFlags(&upload_done, cudaEventDisableTiming));
             CK(cudaEventRecord(upload_done, upload_stream));
+            upload_stream_used = upload_stream;
         }
         d.ops = d_ops.p; d.passes = d_passes.p; d.segs = d_segs.p; d.instrs = d_instrs.p; d.chans = d_chans.p;
         d.pool = d_pool.p; d.noisy = d_noisy.p; d.orig = d_orig.p; d.n_noisy = (int)P.noisy_instrs.size(); d.G = P.G; d.nbits = P.nbits;
@@ -882,8 +892,17 @@ struct Engine {
         return (int)std::max<long long>(1, std::min(b, count));
     }
 
-    void mcwf_run(ncb_run_params* rp);
-    void mcwf_resident(ncb_run_params* rp, cudaStream_t s);
+    // Two-phase run: mcwf_begin enqueues, mcwf_finish waits and delivers (ncb_mcwf_run = both; ncb_mcwf_launch / _collect let
+    // a caller keep several programs in flight).  `deferred`: nothing has been waited for yet -- only the generated resident path
+    // can do that (its planning happens on the device); every other path has finished its kernels when mcwf_begin returns.
+    bool pending = false, deferred = false;
+    cudaStream_t s_own = nullptr, s_run = nullptr;     // the program's own stream (two-phase runs with stream = 0); stream of the pending run
+    PinnedBuf<unsigned long long> h_cnt;
+    PinnedBuf<double> h_probs;
+    void mcwf_begin(ncb_run_params* rp, bool may_defer);
+    void mcwf_finish(ncb_run_params* rp);
+    void mcwf_run(ncb_run_params* rp) { mcwf_begin(rp, false); mcwf_finish(rp); }
+    void mcwf_resident(ncb_run_params* rp, cudaStream_t s, bool defer = false);
     void mcwf_tiled(ncb_run_params* rp, cudaStream_t s);
     void run_deterministic(cudaStream_t s);       // one slot, no events (pure / density modes); leaves the state in d_states
 };
@@ -894,7 +913,7 @@ static void grid_1d(long long n, int* grid, int* block) {
     if (*grid < 1) *grid = 1;
 }
 
-void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
+void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s, bool defer) {
     const long long dim = 1ll << P.nbits, count = rp->traj_count;
     const int grid = (int)std::min<long long>(count, (long long)sm_count * resident_ctas_per_sm());
     UniformSource us{rp->rng, rp->seed, rp->traj_begin, rp->uniforms, P.G};
@@ -935,7 +954,8 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
         size_t tmp_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_item_key[0].p, d_item_key[1].p, d_item_val[0].p, d_item_val[1].p, (int)count, 0, key_bits, s));
         d_sort_tmp.reserve_growing(tmp_bytes + 16);
-        const int rgrid = (int)std::max<long long>(1, std::min<long long>(count, (long long)sm_count * res_ctas));
+        // (one CTA slot of the device stays free: the trunk of the NEXT program of a sweep runs beside this launch)
+        const int rgrid = (int)std::max<long long>(1, std::min<long long>(count, (long long)sm_count * res_ctas - 1));
         d_partial.reserve((size_t)rgrid * dim);
         ResArgs ra{};
         ra.traj_begin = rp->traj_begin; ra.seed = rp->seed; ra.uniforms = a.uniforms; ra.thresh = d_thresh.p; ra.blobs = d_blobs.p;
@@ -972,9 +992,13 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
         sum_partials_kernel<<<g, b, 0, s>>>(d_probs.p, d_partial.p, dim, grid, a.share ? d_trunk.p : nullptr, d_counters.p + 2);
         CK(cudaGetLastError());
     }
-    unsigned long long cnt[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(cnt, d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
-    rp->out_d2h_bytes += (int64_t)sizeof(cnt);
+    h_cnt.reserve(4);
+    unsigned long long* cnt = h_cnt.p;
+    CK(cudaMemcpyAsync(cnt, d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    rp->out_d2h_bytes += (int64_t)(4 * sizeof(unsigned long long));
+    rp->out_tile_launches += 1;
+    rp->out_launches += 2;
+    if (defer && generated && !rp->states) { deferred = true; return; }       // (mcwf_finish adds the event counts)
     if (rp->states) {
         CK(cudaMemcpyAsync(rp->states, d_states.p, (size_t)count * dim * sizeof(cplx), cudaMemcpyDeviceToHost, s));
         rp->out_d2h_bytes += (int64_t)((size_t)count * dim * sizeof(cplx));
@@ -986,11 +1010,8 @@ void Engine::mcwf_resident(ncb_run_params* rp, cudaStream_t s) {
             rp->states[2 * j] = x * P.global_phase[0] - y * P.global_phase[1];
             rp->states[2 * j + 1] = x * P.global_phase[1] + y * P.global_phase[0];
         }
-    rp->out_tile_launches += 1;
     rp->out_events += (int64_t)cnt[0];
     rp->out_hard_events += (int64_t)cnt[1];
-    rp->out_launches += 2;
-    rp->out_sweeps += 0;
 }
 
 void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
@@ -1133,7 +1154,8 @@ void Engine::mcwf_tiled(ncb_run_params* rp, cudaStream_t s) {
     CK(cudaStreamSynchronize(s));
 }
 
-void Engine::mcwf_run(ncb_run_params* rp) {
+void Engine::mcwf_begin(ncb_run_params* rp, bool may_defer) {
+    if (pending) throw std::runtime_error("a run of this program is still in flight: call ncb_mcwf_collect first");
     if (P.mode != MODE_MCWF) throw std::runtime_error("program was not compiled in MCWF mode");
     if (rp->traj_count < 0) throw std::runtime_error("traj_count must be >= 0");
     if (rp->rng == NCB_RNG_EXPLICIT && !rp->uniforms) throw std::runtime_error("rng = EXPLICIT needs uniforms");
@@ -1145,26 +1167,31 @@ void Engine::mcwf_run(ncb_run_params* rp) {
     }
     if (!rp->probs) throw std::runtime_error("probs must not be NULL");
     cudaStream_t s = (cudaStream_t)rp->stream;
+    init_device();
+    if (may_defer && !s) s = s_own;      // two-phase runs without a caller's stream use the program's own: several programs overlap on the device
     ensure_device(s);
+    if (upload_done && s != upload_stream_used) CK(cudaStreamWaitEvent(s, upload_done, 0));
     const long long dim = 1ll << P.nbits;
     d_probs.reserve(dim);
     CK(cudaMemsetAsync(d_probs.p, 0, dim * sizeof(double), s));
     rp->out_sweeps = rp->out_events = rp->out_hard_events = rp->out_launches = 0;
     rp->out_tile_launches = rp->out_h2d_bytes = rp->out_d2h_bytes = rp->out_spec_launches = 0;
     rp->out_kernel_ms = 0.0;
+    deferred = false;
     CK(cudaEventRecord(t0, s));
     if (rp->traj_count > 0) {
         if (resident()) {
             // chunk so the optional tables / states stay bounded
             const long long chunk = rp->states || rp->rng != NCB_RNG_PHILOX ? std::max<long long>(1, (1ll << 28) / std::max<long long>(dim * 2, (long long)P.G))
                                                                             : std::min<long long>(rp->traj_count, 1ll << 24);
+            const bool one = chunk >= rp->traj_count;
             ncb_run_params sub = *rp;
             for (long long b0 = 0; b0 < rp->traj_count; b0 += chunk) {
                 sub.traj_begin = rp->traj_begin + b0;
                 sub.traj_count = std::min(chunk, rp->traj_count - b0);
                 sub.uniforms = rp->uniforms ? rp->uniforms + b0 * P.G : nullptr;
                 sub.states = rp->states ? rp->states + 2 * b0 * dim : nullptr;
-                mcwf_resident(&sub, s);
+                mcwf_resident(&sub, s, may_defer && one && rp->rng == NCB_RNG_PHILOX);
             }
             rp->out_sweeps = sub.out_sweeps; rp->out_events = sub.out_events; rp->out_hard_events = sub.out_hard_events;
             rp->out_launches = sub.out_launches; rp->out_tile_launches = sub.out_tile_launches;
@@ -1174,13 +1201,7 @@ void Engine::mcwf_run(ncb_run_params* rp) {
         }
     }
     CK(cudaEventRecord(t1, s));
-    CK(cudaEventSynchronize(t1));
-    {
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, t0, t1));
-        rp->out_kernel_ms = ms;
-    }
-    // deliver
+    // deliver (the host copy is issued here and read in mcwf_finish)
     if (rp->probs_on_device) {
         if (rp->accumulate) {
             // probs += d_probs
@@ -1191,14 +1212,34 @@ void Engine::mcwf_run(ncb_run_params* rp) {
         } else {
             CK(cudaMemcpyAsync(rp->probs, d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToDevice, s));
         }
-        CK(cudaStreamSynchronize(s));
     } else {
-        std::vector<double> tmp(dim);
-        CK(cudaMemcpyAsync(tmp.data(), d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        h_probs.reserve((size_t)dim);
+        CK(cudaMemcpyAsync(h_probs.p, d_probs.p, dim * sizeof(double), cudaMemcpyDeviceToHost, s));
         rp->out_d2h_bytes += (int64_t)(dim * sizeof(double));
-        if (rp->accumulate) for (long long j = 0; j < dim; ++j) rp->probs[j] += tmp[j];
-        else std::memcpy(rp->probs, tmp.data(), dim * sizeof(double));
+    }
+    s_run = s;
+    pending = true;
+}
+
+void Engine::mcwf_finish(ncb_run_params* rp) {
+    if (!pending) throw std::runtime_error("no run of this program is in flight");
+    pending = false;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamSynchronize(s_run));
+    {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, t0, t1));
+        rp->out_kernel_ms = ms;
+    }
+    if (deferred) {
+        rp->out_events += (int64_t)h_cnt.p[0];
+        rp->out_hard_events += (int64_t)h_cnt.p[1];
+        deferred = false;
+    }
+    if (!rp->probs_on_device) {
+        const long long dim = 1ll << P.nbits;
+        if (rp->accumulate) for (long long j = 0; j < dim; ++j) rp->probs[j] += h_probs.p[j];
+        else std::memcpy(rp->probs, h_probs.p, dim * sizeof(double));
     }
 }
 
@@ -1432,6 +1473,22 @@ int ncb_mcwf_run(ncb_program* program, ncb_run_params* params) {
     if (!program || !params) return fail(NCB_E_INVALID, "null argument");
     NCB_TRY
     program->eng.mcwf_run(params);
+    return NCB_OK;
+    NCB_CATCH
+}
+
+int ncb_mcwf_launch(ncb_program* program, ncb_run_params* params) {
+    if (!program || !params) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    program->eng.mcwf_begin(params, true);
+    return NCB_OK;
+    NCB_CATCH
+}
+
+int ncb_mcwf_collect(ncb_program* program, ncb_run_params* params) {
+    if (!program || !params) return fail(NCB_E_INVALID, "null argument");
+    NCB_TRY
+    program->eng.mcwf_finish(params);
     return NCB_OK;
     NCB_CATCH
 }

@@ -213,7 +213,7 @@ class Program:
         return u[:self.num_instructions]
 
     def run_mcwf(self, traj_count, traj_begin=0, rng=_lib.RNG_PHILOX, seed=42, uniforms=None, return_states=False,
-                 batch=0, stream=0, device_probs=None, accumulate=False):
+                 batch=0, stream=0, device_probs=None, accumulate=False, _launch_only=False):
         """Sum over trajectories [traj_begin, traj_begin + traj_count) of |psi|^2 (NOT divided by the count).
 
         Returns (probs, stats) or (probs, states, stats).  ``device_probs``: a device pointer (int) to float64[2^n]
@@ -242,11 +242,32 @@ class Program:
         if return_states:
             states = np.empty((traj_count, dim), np.complex128)
             rp.states = _ptr(states)
+        if _launch_only:
+            _lib.check(_lib.lib().ncb_mcwf_launch(self._h, C.byref(rp)))
+            return rp, probs, keep                      # (everything the pending run points into)
         _lib.check(_lib.lib().ncb_mcwf_run(self._h, C.byref(rp)))
-        stats = {"sweeps": rp.out_sweeps, "events": rp.out_events, "hard_events": rp.out_hard_events,
-                 "launches": rp.out_launches, "kernel_ms": rp.out_kernel_ms, "tile_launches": rp.out_tile_launches,
-                 "h2d_bytes": rp.out_h2d_bytes, "d2h_bytes": rp.out_d2h_bytes, "specialized_launches": rp.out_spec_launches}
+        stats = self._stats(rp)
         return (probs, states, stats) if return_states else (probs, stats)
+
+    @staticmethod
+    def _stats(rp):
+        return {"sweeps": rp.out_sweeps, "events": rp.out_events, "hard_events": rp.out_hard_events,
+                "launches": rp.out_launches, "kernel_ms": rp.out_kernel_ms, "tile_launches": rp.out_tile_launches,
+                "h2d_bytes": rp.out_h2d_bytes, "d2h_bytes": rp.out_d2h_bytes, "specialized_launches": rp.out_spec_launches}
+
+    def launch_mcwf(self, traj_count, traj_begin=0, rng=_lib.RNG_PHILOX, seed=42, stream=0, device_probs=None, accumulate=False):
+        """First half of ``run_mcwf`` (``ncb_mcwf_launch``): enqueues the run -- on a stream of this program's own when
+        ``stream`` is 0 -- and returns a handle for ``collect_mcwf``.  Programs whose state fits one CTA (generated kernels,
+        Philox draws) return without waiting for the GPU, so a caller can keep several programs in flight; the others have
+        finished their kernels on return."""
+        return self.run_mcwf(traj_count, traj_begin=traj_begin, rng=rng, seed=seed, stream=stream, device_probs=device_probs,
+                             accumulate=accumulate, _launch_only=True)
+
+    def collect_mcwf(self, handle):
+        """Second half (``ncb_mcwf_collect``): waits for the run ``launch_mcwf`` started and returns (probs, stats)."""
+        rp, probs, _keep = handle
+        _lib.check(_lib.lib().ncb_mcwf_collect(self._h, C.byref(rp)))
+        return probs, self._stats(rp)
 
     def run_pure(self, want_state=True, want_probs=False, stream=0):
         dim = 1 << self.num_qubits

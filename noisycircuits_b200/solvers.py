@@ -149,21 +149,23 @@ class RemoteExecutor:
         # the engine objects live as long as the executor: a training loop calls this every step, and creating an engine
         # means a dozen device allocations (each can stall for tens of milliseconds next to a large state batch)
         key = (depth,) + tuple(sorted((k, str(v)) for k, v in opts.items()))
+        # engines: one in flight on the GPU, one launched behind it, `depth` being prepared
+        n_eng = depth + 2
         if getattr(self, "_sweep_key", None) != key:
-            self._sweep_key, self._sweep_engines = key, [None] * (depth + 1)
+            self._sweep_key, self._sweep_engines = key, [None] * n_eng
         engines = self._sweep_engines
         lock = threading.Lock()
         taken = [0]
 
         def prepare():
-            # circuit idx goes into engine idx % (depth + 1); the caller only has `depth` preparations outstanding, so that
-            # engine's previous circuit (idx - depth - 1) has been run and collected
+            # circuit idx goes into engine idx % n_eng; the caller submits a preparation only when that engine's previous
+            # circuit (idx - n_eng) has been collected
             with lock:
                 idx = taken[0]
                 taken[0] += 1
                 make = next(makers)
             packed = make()
-            slot = idx % (depth + 1)
+            slot = idx % n_eng
             if engines[slot] is None:
                 engines[slot] = Program(packed, _lib.MODE_MCWF, **opts)
             else:
@@ -173,22 +175,35 @@ class RemoteExecutor:
                     engines[slot] = Program(packed, _lib.MODE_MCWF, **opts)
             return idx, engines[slot]
 
-        out, ready, futs = [], {}, deque()
+        # circuit i is launched (ncb_mcwf_launch: programs whose planning happens on the device return at once) before circuit
+        # i - 1 is collected, so the GPU always has the next circuit's kernels queued behind -- or, the trunk, beside -- the
+        # current one's; a preparation is only submitted once the engine it will overwrite has been collected
+        out, ready, futs, inflight = [], {}, deque(), None
         with ThreadPoolExecutor(max_workers=depth) as pool:
-            for _ in range(min(depth, count)):
+            for _ in range(min(depth + 1, count)):
                 futs.append(pool.submit(prepare))
             submitted = len(futs)
+
+            def collect(item):
+                prog, handle = item
+                probs, stats = prog.collect_mcwf(handle)
+                self.last_stats = stats
+                out.append(probs / float(num_trajectories))
+
             for i in range(count):
                 while i not in ready:
                     idx, prog = futs.popleft().result()
                     ready[idx] = prog
                 prog = ready.pop(i)
-                if submitted < count:
+                handle = prog.launch_mcwf(num_trajectories, traj_begin=0, rng=_RNG[self.rng], seed=self.seed)
+                if inflight is not None:
+                    collect(inflight)
+                inflight = (prog, handle)
+                if submitted < count:                    # (goes into the engine of circuit i - 1, collected just now)
                     futs.append(pool.submit(prepare))
                     submitted += 1
-                probs, stats = prog.run_mcwf(num_trajectories, traj_begin=0, rng=_RNG[self.rng], seed=self.seed)
-                self.last_stats = stats
-                out.append(probs / float(num_trajectories))
+            if inflight is not None:
+                collect(inflight)
         return out
 
 

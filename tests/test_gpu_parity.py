@@ -787,3 +787,27 @@ def test_generated_resident_kernels_are_deterministic_across_updates(heron_noise
         prog.update(pk[r & 1])
         p, st = prog.run_mcwf(T)
         assert st["specialized_launches"] == 2 and np.array_equal(p, refs[r & 1]), r
+
+
+def test_two_phase_run_keeps_several_programs_in_flight(heron_noise):
+    """ncb_mcwf_launch / ncb_mcwf_collect: two resident programs launched back to back and collected afterwards return what
+    ncb_mcwf_run returns, bit for bit; a tiled program goes through the same calls (it runs to completion in the launch); a
+    second launch on a program that has one in flight is refused."""
+    sq, tq, _, _ = heron_noise
+    n, T = 11, 3000
+    pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)
+    progs = [Program(PackedCircuit(n, circuits.qnn_circuit(n, 3, pairs, seed=40 + k), sq, tq), _lib.MODE_MCWF, specialize="parametric") for k in range(2)]
+    ref = [p.run_mcwf(T, seed=3)[0] for p in progs]
+    handles = [p.launch_mcwf(T, seed=3) for p in progs]
+    with pytest.raises(_lib.NcbError):
+        progs[0].launch_mcwf(T, seed=3)
+    for p, h, r in zip(progs, handles, ref):
+        got, st = p.collect_mcwf(h)
+        assert np.array_equal(got, r) and st["specialized_launches"] == 2 and st["events"] > 0
+    with pytest.raises(_lib.NcbError):
+        progs[0].collect_mcwf(handles[0])
+    nt = 14
+    tiled = Program(PackedCircuit(nt, circuits.heron_layered(nt, 2, circuits.coupled_pairs(tq, nt), seed=4), sq, tq), _lib.MODE_MCWF)
+    a, sa = tiled.run_mcwf(64, seed=1)
+    b, sb = tiled.collect_mcwf(tiled.launch_mcwf(64, seed=1))
+    assert np.array_equal(a, b) and sa["events"] == sb["events"]
