@@ -41,7 +41,13 @@ def packed_digest(packed, mode: int, options: dict) -> str:
 
 
 def get_program(packed, mode: int = _lib.MODE_MCWF, **options):
-    """The compiled ``Program`` of this packed circuit (compiled on the first request, LRU of PROGRAM_CAPACITY)."""
+    """The compiled ``Program`` of this packed circuit (compiled on the first request, LRU of PROGRAM_CAPACITY).
+
+    ``prog.digest`` names the circuit the object holds.  When the cache is full, a miss RECYCLES the least recently used
+    program of the same kind (mode, options, qubits) with ``Program.update`` instead of building a new engine object: a
+    training loop that calls ``execute`` once per parameter set then pays a re-compilation (under a millisecond) per call, not
+    device allocations and a module load.  Holders of a program from an earlier call check ``digest`` before reusing it
+    (``RemoteExecutor._program`` does)."""
     from .program import Program
     key = packed_digest(packed, mode, options)
     prog = _programs.get(key)
@@ -50,7 +56,23 @@ def get_program(packed, mode: int = _lib.MODE_MCWF, **options):
         stats["program_hits"] += 1
         return prog
     stats["program_misses"] += 1
-    prog = Program(packed, mode, **options)
+    kind = (int(mode), repr(sorted((k, repr(v)) for k, v in options.items())), int(packed.num_qubits))
+    prog = None
+    if len(_programs) >= max(PROGRAM_CAPACITY, 1):
+        for old_key, cand in _programs.items():              # oldest first
+            if getattr(cand, "kind", None) == kind:
+                try:
+                    cand.update(packed)
+                except _lib.NcbError:                         # another geometry (tile / register bits): a new object after all
+                    break
+                del _programs[old_key]
+                prog = cand
+                stats["program_recycled"] = stats.get("program_recycled", 0) + 1
+                break
+    if prog is None:
+        prog = Program(packed, mode, **options)
+        prog.kind = kind
+    prog.digest = key
     _programs[key] = prog
     while len(_programs) > max(PROGRAM_CAPACITY, 1):
         _programs.popitem(last=False)          # (dropped, not closed: an executor may still hold it)

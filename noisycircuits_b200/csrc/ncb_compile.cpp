@@ -314,6 +314,42 @@ double dephase_1q(cmat& merged, cmat& bare) {
     return 0.0;
 }
 
+// One-qubit operator M as D1 . X . D2 with D1, D2 diagonal phases and X of the cheap pattern [[a, i b], [i c, d]] (a, b, c, d
+// real): possible when M00 M11 / (M01 M10) is real -- every unitary, and a unitary times a diagonal Kraus operator.  The
+// phases then move into neighbouring phase tables (diagonal operators commute) and what stays costs half (a quarter with one
+// coefficient factored out) of the generic 2x2.  Gauge: D2 = diag(1, e^{i psi}).  Returns false when M has no such form.
+bool split_dxd(const cmat& M, cd d1[2], cmat& X, cd d2[2]) {
+    const double s = max_abs(M);
+    if (!(s > 0.0)) return false;
+    const double tiny = 1e-14 * s;
+    auto ph = [&](const cd& z) { return std::abs(z) > tiny ? z / std::abs(z) : cd(1, 0); };
+    const cd I(0, 1);
+    cd f0, f1, g1;                    // e^{i phi0}, e^{i phi1}, e^{i psi1}; e^{i psi0} = 1
+    const bool z00 = std::abs(M[0]) <= tiny, z01 = std::abs(M[1]) <= tiny, z10 = std::abs(M[2]) <= tiny, z11 = std::abs(M[3]) <= tiny;
+    if (!z00) {
+        f0 = ph(M[0]);
+        g1 = !z01 ? ph(M[1]) / (I * f0) : cd(1, 0);
+        if (!z10) f1 = ph(M[2]) / I;
+        else f1 = !z11 ? ph(M[3]) / g1 : cd(1, 0);
+        if (z01 && !z10 && !z11) g1 = ph(M[3]) / f1;
+    } else {
+        // M00 = 0: phi0 is free unless M01 pins phi0 + psi1
+        f1 = !z10 ? ph(M[2]) / I : cd(1, 0);
+        g1 = !z11 ? ph(M[3]) / f1 : cd(1, 0);
+        f0 = !z01 ? ph(M[1]) / (I * g1) : cd(1, 0);
+    }
+    d1[0] = f0; d1[1] = f1; d2[0] = cd(1, 0); d2[1] = g1;
+    X.assign(4, cd(0, 0));
+    X[0] = M[0] / (d1[0] * d2[0]); X[1] = M[1] / (d1[0] * d2[1]); X[2] = M[2] / (d1[1] * d2[0]); X[3] = M[3] / (d1[1] * d2[1]);
+    if (pattern_1q(X, 4e-16) != OPK_RX1) return false;
+    snap_pattern(X, OPK_RX1);
+    // verify: D1 X D2 == M to rounding
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 2; ++c)
+            if (std::abs(d1[r] * X[r * 2 + c] * d2[c] - M[r * 2 + c]) > 4e-16 * std::max(1.0, s)) return false;
+    return true;
+}
+
 // Two-qubit gate U (index = b0 + 2 b1) as (A1 x A0) . D . (B1 x B0) with D diagonal, for gates that map each basis
 // state of one "control" bit to a basis state of it (controlled-V, ecr, cx, cy, ...):
 //   U = P_c . sum_b |b><b|_c (x) V_b,   V_0^+ V_1 = Q L Q^+   =>   A_c = P_c (1 or X), A_t = V_0 Q, B_t = Q^+, B_c = 1,
@@ -1136,6 +1172,72 @@ static void compile_program_once(const CircuitView& c, int mode, const CompileOp
                     P.ops.push_back(o1);
                     fast_ops.push_back(o1);
                 }
+            }
+            // Fast list only (whole passes without a jump event; the general list above keeps instruction granularity):
+            // a generic one-bit product M = D1 . X . D2 hands its phases to the nearest phase tables it can reach through
+            // operators it commutes with -- D2 backwards, D1 forwards -- and stays behind as the rx-like X: 8 (4 with its
+            // coefficient factored out) instead of 16 (12) FP64 instructions per amplitude pair.  Only when BOTH phases
+            // find a table (a new table would cost what the split saves).
+            if (mode != MODE_DENSITY && opt.fuse && opt.split_generic) {
+                std::vector<LogicalOp> fl;
+                for (const Group& g : groups) fl.push_back(g.members.size() > 1 ? g.merged : *g.members[0]);
+                std::vector<char> changed(fl.size(), 0);
+                auto merge_phase = [&](LogicalOp& a, int bit, const cd ph[2]) -> bool {      // a (diagonal) *= diag(ph) on `bit`
+                    std::vector<int> bits(a.bits, a.bits + a.nb);
+                    int at = (int)(std::find(bits.begin(), bits.end(), bit) - bits.begin());
+                    if (at == (int)bits.size()) {
+                        if ((int)bits.size() + 1 > max_diag_bits(R)) return false;
+                        // (a wider table is a bigger blob: stay within what the segmenter budgeted, one more bit at most once)
+                        if ((int)bits.size() + 1 > 3) return false;
+                        bits.push_back(bit);
+                        std::vector<double> tab(4 << a.nb);
+                        for (int idx = 0; idx < (2 << a.nb); ++idx) { tab[2 * idx] = a.mat[2 * (idx & ((1 << a.nb) - 1))]; tab[2 * idx + 1] = a.mat[2 * (idx & ((1 << a.nb) - 1)) + 1]; }
+                        a.mat = tab;
+                        a.nb += 1;
+                        for (int i = 0; i < 8; ++i) a.bits[i] = i < a.nb ? bits[i] : -1;
+                    }
+                    for (int idx = 0; idx < (1 << a.nb); ++idx) {
+                        const cd v = cd(a.mat[2 * idx], a.mat[2 * idx + 1]) * ph[(idx >> at) & 1];
+                        a.mat[2 * idx] = v.real(); a.mat[2 * idx + 1] = v.imag();
+                    }
+                    a.bare = a.mat;
+                    return true;
+                };
+                auto is_one2 = [](const cd ph[2]) { return std::abs(ph[0] - cd(1, 0)) < 1e-15 && std::abs(ph[1] - cd(1, 0)) < 1e-15; };
+                for (size_t i = 0; i < fl.size(); ++i) {
+                    if (fl[i].diag || fl[i].nb != 1) continue;
+                    const cmat M = read_complex(fl[i].mat.data(), 4);
+                    if (pattern_1q(M, 4e-16) == OPK_RX1) continue;
+                    cd d1[2], d2[2];
+                    cmat X;
+                    if (!split_dxd(M, d1, X, d2)) continue;
+                    const int bit = fl[i].bits[0];
+                    auto touches = [&](const LogicalOp& o) { for (int k = 0; k < o.nb; ++k) if (o.bits[k] == bit) return true; return false; };
+                    int jb = -1, jf = -1;
+                    for (int j = (int)i - 1; j >= 0 && !is_one2(d2); --j) {
+                        if (fl[j].diag) { if (touches(fl[j]) || fl[j].nb < 3) { jb = j; break; } continue; }
+                        if (touches(fl[j])) break;
+                    }
+                    for (size_t j = i + 1; j < fl.size() && !is_one2(d1); ++j) {
+                        if (fl[j].diag) { if (touches(fl[j]) || fl[j].nb < 3) { jf = (int)j; break; } continue; }
+                        if (touches(fl[j])) break;
+                    }
+                    if ((!is_one2(d2) && jb < 0) || (!is_one2(d1) && jf < 0)) continue;
+                    LogicalOp back = jb >= 0 ? fl[jb] : LogicalOp(), fwd = jf >= 0 ? fl[jf] : LogicalOp();
+                    if (jb >= 0 && !merge_phase(back, bit, d2)) continue;
+                    if (jf >= 0 && !merge_phase(fwd, bit, d1)) continue;
+                    if (jb >= 0) { fl[jb] = back; changed[jb] = 1; }
+                    if (jf >= 0) { fl[jf] = fwd; changed[jf] = 1; }
+                    fl[i] = make_lop(fl[i].instr, {bit}, X, X);
+                    changed[i] = 1;
+                }
+                for (size_t i = 0; i < fl.size(); ++i)
+                    if (changed[i]) {
+                        const Op keep = fast_ops[i];
+                        Op o = emit(fl[i]);
+                        o.instr = keep.instr; o.pad = keep.pad; o.mat_bare = o.mat;
+                        fast_ops[i] = o;
+                    }
             }
             ps.op_end = (int)P.ops.size();
             ps.fop_begin = (int)P.ops.size();

@@ -42,6 +42,8 @@ struct CompileOptions {
     int fuse_rotations = 1; // 1: commuting rx-like rotations of a pass are grouped and dispatched as one op (constant-bank fast list)
     int direct = 1;         // 1: first / last pass of a segment exchange their amplitudes with HBM directly where possible
     int decompose = 1;      // 1: controlled-type two-qubit gates (ecr, cx) run as one-qubit factors + a diagonal table
+    int split_generic = 1;  // 1: in the fast lists a generic one-bit 2x2 hands its phases to neighbouring phase tables and runs as
+                            // the rx-like operator that is left (compile_program: "D1 . X . D2")
     int reorder = 1;        // 1: execute commuting instructions in a tile-friendly (dependency-respecting) order;
                             // 0: strictly in program order
 };

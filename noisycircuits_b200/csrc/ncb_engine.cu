@@ -1338,6 +1338,7 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
     if (const char* e = getenv("NCB_DECOMPOSE")) opt.decompose = atoi(e);
     if (const char* e = getenv("NCB_DIRECT")) opt.direct = atoi(e);
     if (const char* e = getenv("NCB_FUSE_ROT")) opt.fuse_rotations = atoi(e);
+    if (const char* e = getenv("NCB_SPLIT_U")) opt.split_generic = atoi(e);
     if (const char* e = getenv("NCB_PASS_ORDER")) opt.pass_order = atoi(e);
     if (auto4 && mode == NCB_MODE_MCWF && circuit->num_qubits <= std::max(std::min(opt.tile_bits, 12), std::min(opt.resident_bits, MAX_TILE_BITS - 1)))
         opt.reg_bits = 3;                       // the state fits one CTA: R = 3 (see below), known before compiling
@@ -1349,8 +1350,12 @@ int ncb_program_create(const ncb_circuit* circuit, int mode, const ncb_options* 
         if (auto4) {
             // R = 4 pays for rotation / diagonal programs (Heron: +10 %); programs full of generic 2x2 operators (Eagle: the
             // one-qubit factors of the decomposed ecr) run 7 % faster with R = 3 (measured, profiles/r02_variants.jsonl)
+            // (counted on the fast lists, what the whole-segment kernels run: the one-qubit factors that hand their phases to
+            //  a neighbouring table run as rotations there, CompileOptions::split_generic -- with it Eagle is R = 4 too: 19.3 k
+            //  against 17.7 k trajectories/s)
             long long rx = 0, u = 0;
-            for (const Op& op : p->eng.P.ops) { rx += op_kind(op) == OPK_RX1; u += op_kind(op) == OPK_DENSE1; }
+            for (const Pass& ps : p->eng.P.passes)
+                for (int o = ps.fop_begin; o < ps.fop_end; ++o) { rx += op_kind(p->eng.P.ops[o]) == OPK_RX1; u += op_kind(p->eng.P.ops[o]) == OPK_DENSE1; }
             const bool generic_heavy = 4 * u > rx + u;
             // (states that fit one CTA -- generated resident kernels -- run faster with R = 3: twice the threads per state,
             //  0.90 against 1.21 ms on the 12-qubit QNN circuit)

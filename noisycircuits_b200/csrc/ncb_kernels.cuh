@@ -439,19 +439,23 @@ decide_kernel(DevProgram P, const DecideItem* __restrict__ items, int nitems, co
     const double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     part[warp][lane] = s;
     __syncthreads();
+    const Channel ch = P.chans[P.instrs[d.instr].channel];
     if (warp == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += part[w][lane];
         rho[lane] = t;
         __syncwarp();
-        if (lane == 0) {
-            const Channel ch = P.chans[P.instrs[d.instr].channel];
-            mirror_rho(rho, ch.dim);
-            double scale;
-            const int k = decide_branch(rho, ch, P.pool, d.u, &scale);
-            decisions[d.slot].k = k;
-            decisions[d.slot].scale = scale;
-        }
+        if (lane == 0) mirror_rho(rho, ch.dim);
+    }
+    __syncthreads();
+    // p_k = tr(M_k rho) by thread k (Eagle's two-qubit channels keep up to 144 operators: a single lane walking them made
+    // this launch -- it sits between the pieces of every state-dependent event -- 170 us long), the pick in order by thread 0
+    __shared__ int s_k;
+    __shared__ double s_scale;
+    decide_branch_block(rho, ch, P.pool, d.u, &part[0][0], 8 * RED_VALUES, &s_k, &s_scale);
+    if (threadIdx.x == 0) {
+        decisions[d.slot].k = s_k;
+        decisions[d.slot].scale = s_scale;
     }
 }
 

@@ -66,7 +66,7 @@ class RemoteExecutor:
             engine_options.setdefault("strict_order", True)
         self.engine_options = engine_options
         self.last_stats = None
-        self._cache = (None, None)
+        self._cache, self._cache_digest = (None, None), None
 
     # Generated kernels (ncb_options.specialize) cost a few seconds of compilation per new kernel set.  Without an explicit
     # specialize=... in the engine options: from SPECIALIZE_FROM trajectories per call the "parametric" kernels are used
@@ -88,14 +88,16 @@ class RemoteExecutor:
         # fast path: the same list object contents and the same noise dictionaries as last time (in-place edits of the
         # dictionaries are not seen here -- call invalidate()); otherwise the packed bytes decide (cache.get_program)
         key = (_fingerprint(instruction_list), str(opts["specialize"]), id(self.single_qubit_noise), id(self.two_qubit_noise))
-        if self._cache[0] != key:
+        # (the cache may have recycled the object for another circuit meanwhile: its digest says what it holds now)
+        if self._cache[0] != key or getattr(self._cache[1], "digest", None) != self._cache_digest:
             packed = PackedCircuit(self.num_qubits, instruction_list, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
-            self._cache = (key, cache.get_program(packed, _lib.MODE_MCWF, **opts))
+            prog = cache.get_program(packed, _lib.MODE_MCWF, **opts)
+            self._cache, self._cache_digest = (key, prog), prog.digest
         return self._cache[1]
 
     def invalidate(self) -> None:
         """Forget the compiled program (after editing the noise dictionaries in place)."""
-        self._cache = (None, None)
+        self._cache, self._cache_digest = (None, None), None
 
     def run_sum(self, instruction_list, traj_begin: int, traj_count: int, uniforms=None, device_probs=None,
                 accumulate=False, stream=0):

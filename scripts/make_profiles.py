@@ -161,6 +161,30 @@ def launch_summary(src, tag, chunk):
     print(open(os.path.join(ROOT, "profiles", f"{tag}_launch_list_summary.csv")).read())
 
 
+def simple_launch_summary(src, out_path, last=None):
+    """kernel, launches, total, share, average of an ncu launch list (generated per-segment kernels grouped); last: only the
+    last `last` launches (one call of the profiled script)."""
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    h = next(i for i, r in enumerate(rows) if r[0] == "ID")
+    hdr, body = rows[h], rows[h + 1:]
+    if last:
+        body = body[-last:]
+    kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    tot, cnt = collections.Counter(), collections.Counter()
+    for r in body:
+        name = re.sub(r"ncb_seg_\d+", "ncb_seg_<k>", r[kn].split("(")[0].strip())
+        name = re.sub(r"<.*", "<...>", name) if name.startswith("void cub::") else name
+        tot[name] += float(r[mv].replace(",", ""))
+        cnt[name] += 1
+    total = sum(tot.values())
+    with open(out_path, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "launches", "total_us", "share_pct", "avg_us"])
+        for name, ns in tot.most_common():
+            w.writerow([name, cnt[name], f"{ns / 1e3:.1f}", f"{100 * ns / total:.2f}", f"{ns / cnt[name] / 1e3:.1f}"])
+    print(open(out_path).read())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("tag")
@@ -169,6 +193,9 @@ def main():
     ap.add_argument("--seg")
     ap.add_argument("--ev")
     ap.add_argument("--dm")
+    ap.add_argument("--res", help="ncu-rep of ncb_res (generated resident kernel, scripts/prof_c3.py)")
+    ap.add_argument("--c3-launches", help="ncu launch list of scripts/prof_c3.py")
+    ap.add_argument("--c4-launches", help="ncu launch list of scripts/prof_c4.py")
     ap.add_argument("--command", default="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --no-c2 --strong-traj 0")
     a = ap.parse_args()
     P = os.path.join(ROOT, "profiles")
@@ -195,6 +222,18 @@ def main():
                   "ncu --set full --clock-control none --import-source on -k regex:tile_kernel -s 31 -c 4 python scripts/prof_dm.py",
                   "BASELINE configs[1]: 12-qubit density matrix (4^12 vectorised state, 268 MB), depth-10 layered Heron circuit; "
                   "tile_kernel<4, DENSE2|DENSE4, 256, 1>.", os.path.join(P, f"{a.tag}_dm_kernel_ncu_full.md"))
+
+    if a.res:
+        ncu_table(a.res, r"ncb_res$", f"ncu --set full capture of the generated resident kernel ({a.tag})",
+                  "ncu --set full --clock-control none --import-source on -k 'regex:ncb_res$' -s 3 -c 1 python scripts/prof_c3.py",
+                  "BASELINE configs[2]: 12-qubit QNN circuit (284 instructions), 10^4 trajectories per call; the 19 % of the trajectories that "
+                  "leave the jump-free trunk run from the trunk's checkpoint before their first flagged draw, one CTA (512 threads, 2^12 "
+                  "amplitudes in shared memory) per trajectory at a time, two CTAs per SM.  The state never touches HBM: the kernel is bound by "
+                  "the FP64 pipe and the shared-memory exchanges between passes.", os.path.join(P, f"{a.tag}_res_kernel_ncu_full.md"))
+    if a.c3_launches:
+        simple_launch_summary(a.c3_launches, os.path.join(P, f"{a.tag}_c3_launch_list.csv"), last=8)
+    if a.c4_launches:
+        simple_launch_summary(a.c4_launches, os.path.join(P, f"{a.tag}_c4_launch_list.csv"))
 
 
 if __name__ == "__main__":

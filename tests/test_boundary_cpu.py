@@ -224,6 +224,32 @@ def test_program_cache_is_content_addressed(heron_noise):
     assert RemoteExecutor(n, sq, tq, 1, strict_order=True)._program(instr) is not a   # options are part of the key
 
 
+def test_program_cache_recycles_engine_objects_for_new_parameter_sets(heron_noise):
+    """A training loop calls execute once per parameter set: every call is a cache miss.  Once the cache is full a miss
+    recycles the least recently used program of the same kind in place (Program.update) instead of creating an engine object;
+    an executor that still holds the recycled object notices by its digest and asks the cache again."""
+    from noisycircuits_b200 import cache
+    from noisycircuits_b200.solvers import RemoteExecutor
+    sq, tq, _, _ = heron_noise
+    n = 6
+    pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)
+    sets = [circuits.qnn_circuit(n, 2, pairs, seed=s) for s in range(cache.PROGRAM_CAPACITY + 3)]
+    cache.clear_programs()
+    cache.stats["program_recycled"] = 0
+    first_holder = RemoteExecutor(n, sq, tq, 1)
+    p0 = first_holder._program(sets[0])
+    d0 = p0.digest
+    ex = RemoteExecutor(n, sq, tq, 1)
+    progs = [ex._program(s) for s in sets[1:]]
+    assert cache.stats["program_recycled"] == 3 and len({id(p) for p in progs} | {id(p0)}) == cache.PROGRAM_CAPACITY
+    assert p0.digest != d0                                   # sets[0]'s object now holds another circuit ...
+    again = first_holder._program(sets[0])                   # ... and its first holder does not use it blindly
+    assert again.digest == d0 and again.packed.theta.tobytes() == PackedCircuit(n, sets[0], sq, tq).theta.tobytes()
+    # the recycled object is the updated program, not a stale one: its order / description belong to the new circuit
+    fresh = Program(PackedCircuit(n, sets[-1], sq, tq))
+    assert progs[-1].describe() == fresh.describe() and list(progs[-1].order()) == list(fresh.order())
+
+
 def test_spec_cache_eviction(tmp_path, monkeypatch, heron_noise):
     """The cubin cache keeps at most NCB_SPEC_CACHE_MAX program directories (least recently used go first)."""
     sq, tq, _, _ = heron_noise
