@@ -514,6 +514,7 @@ struct Engine {
         if (const char* e = getenv("NCB_SPEC_EVENTS")) spec_opt.events = atoi(e) != 0;
         if (const char* e = getenv("NCB_SPEC_CTAS")) spec_opt.ctas = std::max(0, atoi(e));
         if (const char* e = getenv("NCB_SPEC_FACTOR")) spec_opt.factor = atoi(e) != 0;
+        if (const char* e = getenv("NCB_RES_FAST")) spec_opt.resident_fast = atoi(e) != 0;
         spec_opt.literal = specialize_mode == 2 ? 0 : 1;
         if (const char* e = getenv("NCB_SPEC_LITERAL")) spec_opt.literal = atoi(e) != 0;
     }

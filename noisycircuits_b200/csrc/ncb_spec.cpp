@@ -503,7 +503,7 @@ bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOpt
     const ResidentLayout lay = spec_resident_layout(P, opt);
     for (int seg = 0; seg < nseg; ++seg) {
         const BlobView bv = view_blob(P, seg);
-        for (int i = 0; i < bv.blob->nops; ++i) {
+        for (int i = 0; i < bv.blob->nops; ++i) {          // (general lists and fast lists)
             const Op& op = bv.ops[i];
             const int kind = op_kind(op);
             if (kind != OPK_DIAG && kind != OPK_RX1 && kind != OPK_DENSE1) return false;
@@ -519,6 +519,25 @@ bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOpt
         for (int p = 0; p < bv.blob->npass; ++p)
             o << "    const int jb" << p << " = (int)" << runs_expr(bv.passes[p].truns, "utid") << ", jbs" << p << " = swz(jb" << p << ");\n"
               << "    (void)jb" << p << "; (void)jbs" << p << ";\n";
+        if (opt.resident_fast) {
+            // the whole segment without a bare operator (no jump event inside, the trunk): the passes' FAST lists -- merged groups
+            // only, generic products with their phases handed to the tables -- without any guard
+            o << "    if (lo <= " << P.segs[seg].instr_lo << " && hi >= " << P.segs[seg].instr_hi << " && !(bare && hi == " << P.segs[seg].instr_hi << ")) {\n";
+            for (int p = 0; p < bv.blob->npass; ++p) {
+                const Pass& ps = bv.passes[p];
+                if (ps.instr_hi <= ps.instr_lo) continue;
+                o << "        {   // pass " << p << "\n"
+                  << "            if (ckpt != nullptr) {\n                cplx* const c = ckpt + ((size_t)" << P.segs[seg].pass_begin + p << " << " << K << ");\n"
+                  << "                for (int i = (int)threadIdx.x; i < " << (1 << K) << "; i += (int)blockDim.x) c[i] = sm[i];\n"
+                  << "                __syncthreads();\n            }\n"
+                  << "            cplx a[" << (1 << R) << "];\n";
+                for (int m = 0; m < (1 << R); ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "];\n";
+                for (int i = ps.fop_begin; i < ps.fop_end; ++i) emit_general_op(o, bv.ops[i], p, R, std::to_string(bv.ops[i].mat), "            ");
+                for (int m = 0; m < (1 << R); ++m) o << "            sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "] = a[" << m << "];\n";
+                o << "            __syncthreads();\n        }\n";
+            }
+            o << "        return;\n    }\n";
+        }
         emit_guarded_passes(o, bv, R, K, P.segs[seg].pass_begin);
         o << "}\n\n";
     }
@@ -823,7 +842,7 @@ uint64_t spec_structure_hash(const Program& P, const SpecOptions& opt) {
     };
     const int geo[8] = {P.nbits, P.K, P.R, P.G, P.mode, (int)P.segs.size(), (int)P.passes.size(), opt.literal};
     mix(geo, sizeof geo);
-    const int o2[5] = {opt.nbuf, opt.load, opt.events, opt.factor, opt.ctas};
+    const int o2[6] = {opt.nbuf, opt.load, opt.events, opt.factor, opt.ctas, opt.resident_fast};
     mix(o2, sizeof o2);
     for (size_t sgi = 0; sgi < P.blob_off.size(); ++sgi) {
         const unsigned char* braw = P.blobs.data() + P.blob_off[sgi];
@@ -843,7 +862,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt) + spec_resident_source(P, opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 14 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 15 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);

@@ -65,7 +65,7 @@ def sweep(name, n, lists, sq, tq, T):
     t0 = time.perf_counter()
     a = [ex.run(T, instr) for instr in lists]
     t_loop = time.perf_counter() - t0
-    ex.run_many(T, lists[:2])                      # (engine objects of the ping-pong created)
+    ex.run_many(T, lists[:6])                      # (the engine objects of the pipeline created)
     t0 = time.perf_counter()
     b = ex.run_many(T, lists)
     t_many = time.perf_counter() - t0

@@ -11,7 +11,7 @@ sq, tq, _m, _ = noise_io.load_noise_tables(os.path.join(ROOT, "tests", "golden",
 
 
 def one(tag, n, instr, T, lists=None, env=None, **opts):
-    for k in ("NCB_REG_BITS", "NCB_CTAS_PER_SM"):
+    for k in ("NCB_REG_BITS", "NCB_CTAS_PER_SM", "NCB_RES_FAST"):
         os.environ.pop(k, None)
     os.environ.update(env or {})
     cache.clear_programs()
@@ -25,7 +25,7 @@ def one(tag, n, instr, T, lists=None, env=None, **opts):
     out = {"variant": tag, "qubits": n, "trajectories": T, "first_call_s": first, "seconds": best, "kernel_ms": st["kernel_ms"],
            "spec_launches": st["specialized_launches"], "events": st["events"], "hard": st["hard_events"], "norm": float(p.sum())}
     if lists:
-        ex.run_many(T, lists[:2])
+        ex.run_many(T, lists[:6])
         t0 = time.perf_counter(); a = ex.run_many(T, lists); out["run_many_circuits_per_s"] = len(lists) / (time.perf_counter() - t0)
         thetas = np.array([[0.0 if q is None else float(q) for _g, _q, q in l] for l in lists])
         t0 = time.perf_counter(); b = ex.run_sweep(T, lists[0], thetas); out["run_sweep_circuits_per_s"] = len(lists) / (time.perf_counter() - t0)
@@ -39,7 +39,7 @@ n, T = 12, 10000
 pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)
 lists = [circuits.qnn_circuit(n, 4, pairs, seed=100 + i) for i in range(40)]
 ref = one("C3 interpreter", n, lists[0], T, lists, specialize=False)
-for tag, env in (("C3 generated R=4", {}), ("C3 generated R=3", {"NCB_REG_BITS": "3"}), ("C3 generated R=4 1 CTA/SM", {"NCB_CTAS_PER_SM": "1"})):
+for tag, env in (("C3 generated", {}), ("C3 generated, no fast path", {"NCB_RES_FAST": "0"}), ("C3 generated again", {}), ("C3 generated 1 CTA/SM", {"NCB_CTAS_PER_SM": "1"})):
     p = one(tag, n, lists[0], T, lists, env=env, specialize="parametric")
     print(json.dumps({"variant": tag, "max_abs_diff_vs_interpreter": float(np.abs(p - ref).max())}), flush=True)
 for T2 in (1000, 100000):

@@ -44,3 +44,11 @@ for threads in (1,):
     b = ex.run_many(T, lists)
     d = [i for i in range(len(lists)) if not np.array_equal(a[i], b[i])]
     print("run_many with", threads, "prepare thread: differing circuits:", d, [float(np.abs(a[i] - b[i]).max()) for i in d], flush=True)
+
+# tiled generated kernels (whole-segment + event kernels, shared prefix, two streams): the same bits every time
+nt, Tt = 15, 600
+it = circuits.heron_layered(nt, 6, circuits.coupled_pairs(tq, nt), seed=9)
+pt = Program(PackedCircuit(nt, it, sq, tq), _lib.MODE_MCWF, specialize=True)
+ref_t, st_t = pt.run_mcwf(Tt, seed=2)
+bad = sum(0 if np.array_equal(pt.run_mcwf(Tt, seed=2)[0], ref_t) else 1 for _ in range(30))
+print("tiled generated kernels: repeats differing:", bad, "of 30; events", st_t["events"], "hard", st_t["hard_events"], "spec launches", st_t["specialized_launches"])
