@@ -356,6 +356,7 @@ struct Engine {
     std::string spec_key_loaded;
     uint64_t spec_hash_loaded = 0;
     void replace_program(Program&& np) {
+        if (pending) throw std::runtime_error("ncb_program_update: a run of this program is in flight (ncb_mcwf_collect first)");
         if (np.K != P.K || np.R != P.R || np.nbits != P.nbits || np.mode != P.mode)
             throw std::runtime_error("ncb_program_update: the new circuit compiles to another geometry (qubits / tile / register bits): create a new program");
         P = std::move(np);

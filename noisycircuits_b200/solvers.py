@@ -192,20 +192,33 @@ class RemoteExecutor:
                 self.last_stats = stats
                 out.append(probs / float(num_trajectories))
 
-            for i in range(count):
-                while i not in ready:
-                    idx, prog = futs.popleft().result()
-                    ready[idx] = prog
-                prog = ready.pop(i)
-                handle = prog.launch_mcwf(num_trajectories, traj_begin=0, rng=_RNG[self.rng], seed=self.seed)
+            try:
+                for i in range(count):
+                    while i not in ready:
+                        idx, prog = futs.popleft().result()
+                        ready[idx] = prog
+                    prog = ready.pop(i)
+                    handle = prog.launch_mcwf(num_trajectories, traj_begin=0, rng=_RNG[self.rng], seed=self.seed)
+                    previous, inflight = inflight, (prog, handle)
+                    if previous is not None:
+                        collect(previous)
+                    if submitted < count:                    # (goes into the engine of circuit i - 1, collected just now)
+                        futs.append(pool.submit(prepare))
+                        submitted += 1
+                last, inflight = inflight, None
+                if last is not None:
+                    collect(last)
+            except BaseException:
+                # leave no run in flight and no half-prepared engine behind: the next sweep starts with fresh engine objects
                 if inflight is not None:
-                    collect(inflight)
-                inflight = (prog, handle)
-                if submitted < count:                    # (goes into the engine of circuit i - 1, collected just now)
-                    futs.append(pool.submit(prepare))
-                    submitted += 1
-            if inflight is not None:
-                collect(inflight)
+                    try:
+                        inflight[0].collect_mcwf(inflight[1])
+                    except Exception:
+                        pass
+                for f in futs:
+                    f.cancel()
+                self._sweep_key, self._sweep_engines = None, []
+                raise
         return out
 
 
