@@ -594,9 +594,9 @@ struct Engine {
         const int per = SPEC_PER_PART;
         const int nparts = nsupported ? (nseg + per - 1) / per : 0;
         auto exists = [](const std::string& f) { struct stat st; return stat(f.c_str(), &st) == 0 && st.st_size > 0; };
-        auto part_name = [&](int k) { return k == nparts ? std::string("resident") : "part" + std::to_string(k); };
+        auto part_name = [&](int k) { return k == nparts ? std::string("resident") : k == nparts + 1 ? std::string("restrunk") : "part" + std::to_string(k); };
         std::vector<int> todo;
-        for (int k = 0; k < nparts + (res ? 1 : 0); ++k)
+        for (int k = 0; k < nparts + (res ? 2 : 0); ++k)
             if (!exists(dir + "/" + part_name(k) + ".cubin")) todo.push_back(k);
         if (!todo.empty()) {
             // compiler: NVRTC in process (default); NCB_SPEC_COMPILER=nvcc runs the nvcc binary instead (needs the toolkit
@@ -626,7 +626,7 @@ struct Engine {
                     if (exists(dir + "/" + part_name(k) + ".cubin")) continue;
                     // several processes (one per GPU) may build the same cache at once: private temporaries, atomic renames
                     const std::string base = dir + "/" + part_name(k), mine = base + "." + std::to_string((long)getpid());
-                    const std::string src = k == nparts ? spec_resident_source(P, spec_opt) : spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_opt);
+                    const std::string src = k >= nparts ? spec_resident_source(P, spec_opt, k == nparts ? 1 : 2) : spec_source(P, k * per, std::min(nseg, (k + 1) * per), spec_opt);
                     { std::ofstream f(mine + ".cu"); f << src; }
                     bool ok;
                     if (use_nvrtc) {
@@ -727,15 +727,19 @@ struct Engine {
         res_fn = res_trunk_fn = nullptr;
         if (!spec_resident_supported(P)) return;
         res_lay = spec_resident_layout(P, spec_opt);
-        std::ifstream f(dir + "/resident.cubin", std::ios::binary);
-        std::stringstream ss;
-        ss << f.rdbuf();
-        const std::string image = ss.str();
-        void* mod = nullptr;
-        if (image.empty() || g_drv.ModuleLoadData(&mod, image.data()) != 0) return;
-        spec_modules.push_back(mod);
-        void *fr = nullptr, *ft = nullptr;
-        if (g_drv.ModuleGetFunction(&fr, mod, "ncb_res") != 0 || g_drv.ModuleGetFunction(&ft, mod, "ncb_res_trunk") != 0) return;
+        auto load = [&](const char* file, const char* name) -> void* {
+            std::ifstream f(dir + "/" + file, std::ios::binary);
+            std::stringstream ss;
+            ss << f.rdbuf();
+            const std::string image = ss.str();
+            void *mod = nullptr, *fn = nullptr;
+            if (image.empty() || g_drv.ModuleLoadData(&mod, image.data()) != 0) return nullptr;
+            spec_modules.push_back(mod);
+            return g_drv.ModuleGetFunction(&fn, mod, name) == 0 ? fn : nullptr;
+        };
+        void* fr = load("resident.cubin", "ncb_res");
+        void* ft = load("restrunk.cubin", "ncb_res_trunk");
+        if (!fr || !ft) return;
         for (void* fn : {fr, ft}) {
             if (g_drv.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem_optin - 8 * 1024) != 0) return;
             g_drv.FuncSetAttribute(fn, 9 /* CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT */, 100);

@@ -498,7 +498,9 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
 //   ncb_res_trunk   one CTA: the jump-free evolution from |0...0>, its state left in global memory at every pass boundary
 //   ncb_res         persistent CTAs over the trajectories that leave the trunk: start from the last checkpoint before the
 //                   first flagged draw, events handled in line (reduced density matrix, branch decision, Kraus operator)
-bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOptions& opt) {
+// which: 0 both kernels (cache key, source query), 1 ncb_res only, 2 ncb_res_trunk only (two translation units compile in parallel;
+// the trunk takes the fast path of every segment, so its unit leaves the guarded programs out)
+bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOptions& opt, int which = 0) {
     const int K = P.K, R = P.R, nseg = (int)P.segs.size(), NT = 1 << (K - R);
     const ResidentLayout lay = spec_resident_layout(P, opt);
     for (int seg = 0; seg < nseg; ++seg) {
@@ -538,7 +540,7 @@ bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOpt
             }
             o << "        return;\n    }\n";
         }
-        emit_guarded_passes(o, bv, R, K, P.segs[seg].pass_begin);
+        if (!(which == 2 && opt.resident_fast)) emit_guarded_passes(o, bv, R, K, P.segs[seg].pass_begin);
         o << "}\n\n";
     }
     // [lo, hi) across the segments
@@ -567,6 +569,7 @@ bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOpt
          "    return inv;\n"
          "}\n"
          "}  // namespace\n\n";
+    if (which != 1)
     o << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", 1) ncb_res_trunk(DevProgram P, ResArgs A) {\n"
          "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
          "    __shared__ double s_buf[32 * 20];\n"
@@ -588,6 +591,7 @@ bool emit_resident_module(std::ostringstream& o, const Program& P, const SpecOpt
          "    const double inv = A.normalize ? res_inv_norm(sm, s_buf, s_out) : 1.0;\n"
          "    for (int j = tid; j < RDIM; j += RNT) A.trunk_probs[j] = cnorm2(sm[swz(j)]) * inv;\n"
          "}\n\n";
+    if (which == 2) return true;
     o << "extern \"C\" __global__ void __launch_bounds__(" << NT << ", " << lay.ctas << ") ncb_res(DevProgram P, ResArgs A) {\n"
          "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
          "    __shared__ double s_buf[32 * 20];\n"
@@ -823,10 +827,10 @@ std::vector<int32_t> spec_resident_ckpts(const Program& P) {
     return out;
 }
 
-std::string spec_resident_source(const Program& P, const SpecOptions& opt) {
+std::string spec_resident_source(const Program& P, const SpecOptions& opt, int which) {
     std::ostringstream o, k;
     o << "// generated by ncb_spec.cpp -- do not edit\n#include \"ncb_spec.cuh\"\nusing namespace ncb;\n";
-    if (!spec_resident_supported(P) || !emit_resident_module(k, P, opt)) return "";
+    if (!spec_resident_supported(P) || !emit_resident_module(k, P, opt, which)) return "";
     o << k.str();
     return o.str();
 }
@@ -862,7 +866,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt) + spec_resident_source(P, opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 15 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 16 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);

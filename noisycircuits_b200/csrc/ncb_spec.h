@@ -53,7 +53,8 @@ ResidentLayout spec_resident_layout(const Program& P, const SpecOptions& opt = S
 // [G + 1][2]: (checkpoint pass, first instruction still to run) by execution position of a trajectory's first flagged draw
 std::vector<int32_t> spec_resident_ckpts(const Program& P);
 // CUDA source of ncb_res_trunk / ncb_res ("" when the program is not resident or carries operators they do not cover)
-std::string spec_resident_source(const Program& P, const SpecOptions& opt = SpecOptions());
+// which: 0 both kernels, 1 ncb_res only, 2 ncb_res_trunk only (the engine compiles them as two translation units in parallel)
+std::string spec_resident_source(const Program& P, const SpecOptions& opt = SpecOptions(), int which = 0);
 // cheap hash of the records the generators read (no source is generated): equal hashes <=> the same kernels; used to see that
 // an updated program (parameter sweep) keeps its loaded kernels.  A mismatch is re-checked with spec_key.
 uint64_t spec_structure_hash(const Program& P, const SpecOptions& opt = SpecOptions());
