@@ -516,6 +516,7 @@ struct Engine {
         if (const char* e = getenv("NCB_SPEC_CTAS")) spec_opt.ctas = std::max(0, atoi(e));
         if (const char* e = getenv("NCB_SPEC_FACTOR")) spec_opt.factor = atoi(e) != 0;
         if (const char* e = getenv("NCB_RES_FAST")) spec_opt.resident_fast = atoi(e) != 0;
+        if (const char* e = getenv("NCB_EV_FAST")) spec_opt.ev_fast = atoi(e) != 0;
         spec_opt.literal = specialize_mode == 2 ? 0 : 1;
         if (const char* e = getenv("NCB_SPEC_LITERAL")) spec_opt.literal = atoi(e) != 0;
     }
@@ -791,8 +792,8 @@ struct Engine {
                     const double* wu = cur_work_u ? cur_work_u + st.begin : nullptr;
                     int* tk = cur_work_u ? d_tickets.p : nullptr;          // (null: a decide launch follows, NCB_FUSED_DECIDE=0)
                     int pull_on = ev_pull ? 1 : 0;
-                    void* args[] = {(void*)&d, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift, (void*)&red, (void*)&nrm,
-                                    (void*)&dec, (void*)&wu, (void*)&tk, &pull_on};
+                    void* args[] = {(void*)P.segconst[st.seg].coef, (void*)&d, (void*)&pool_g, &pool_bytes, &pool_cap, (void*)&w, &nworks, (void*)&states, &tshift,
+                                    (void*)&red, (void*)&nrm, (void*)&dec, (void*)&wu, (void*)&tk, &pull_on};
                     rc = g_drv.LaunchKernel(f.fn, (unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)spec_smem(true), (void*)s, args, nullptr);
                 }
                 if (rc != 0) throw std::runtime_error("cuLaunchKernel of a specialised kernel failed (" + std::to_string(rc) + ")");

@@ -315,7 +315,11 @@ void emit_general_op(std::ostringstream& o, const Op& op, int p, int R, const st
 // qb / qe: tile positions of the qubits of the in-line jump this range begins after / ends in when merged groups that do
 // not touch them may stay whole (WF_PULL); ~0u otherwise (every group "touches": strict splitting by instruction index).
 // ckpt_pass0 >= 0 (resident trunk): before pass p the tile is copied to ckpt + ((ckpt_pass0 + p) << K) when ckpt != nullptr.
-void emit_guarded_passes(std::ostringstream& o, const BlobView& bv, int R, int K = 0, int ckpt_pass0 = -1) {
+// sc / fopt (event kernels of tiled programs): a pass that lies entirely inside the range and holds no bare operator runs its
+// FAST list -- the text of the whole-segment kernel (merged groups, literal / factored coefficients, generic products split) --
+// with the factors taken out of its rotations multiplied back at the end of the pass; only the pass a jump cuts is guarded.
+void emit_guarded_passes(std::ostringstream& o, const BlobView& bv, int R, int K = 0, int ckpt_pass0 = -1, const SegConst* sc = nullptr,
+                         const SpecOptions* fopt = nullptr) {
     const int NA = 1 << R, npass = bv.blob->npass;
     for (int p = 0; p < npass; ++p) {
         const Pass& ps = bv.passes[p];
@@ -325,6 +329,29 @@ void emit_guarded_passes(std::ostringstream& o, const BlobView& bv, int R, int K
             o << "            if (ckpt != nullptr) {\n                cplx* const c = ckpt + ((size_t)" << ckpt_pass0 + p << " << " << K << ");\n"
               << "                for (int i = (int)threadIdx.x; i < " << (1 << K) << "; i += (int)blockDim.x) c[i] = sm[i];\n"
               << "                __syncthreads();      // (the copy reads every thread's slots: nobody may store this pass' results before it is done)\n            }\n";
+        bool with_fast = false;
+        if (sc && fopt && sc->valid && p < sc->npass) {
+            std::ostringstream f;
+            double scalar[2] = {1.0, 0.0};
+            if (emit_fast_ops(f, *sc, p, R, fopt->literal != 0, (fopt->literal && fopt->factor) ? scalar : nullptr)) {
+                with_fast = true;
+                o << "            if (lo <= " << ps.instr_lo << " && hi >= " << ps.instr_hi << " && !(bare && hi == " << ps.instr_hi << ")) {\n"
+                  << "            cplx a[" << NA << "];\n";
+                for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "];\n";
+                o << f.str();
+                if (scalar[1] != 0.0) {
+                    o << "            {\n                const cplx S{" << lit(scalar[0]) << ", " << lit(scalar[1]) << "};\n";
+                    for (int m = 0; m < NA; ++m) o << "                a[" << m << "] = cmul(a[" << m << "], S);\n";
+                    o << "            }\n";
+                } else if (scalar[0] != 1.0) {
+                    o << "            {\n                const double S = " << lit(scalar[0]) << ";\n";
+                    for (int m = 0; m < NA; ++m) o << "                a[" << m << "].x *= S; a[" << m << "].y *= S;\n";
+                    o << "            }\n";
+                }
+                for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "] = a[" << m << "];\n";
+                o << "            __syncthreads();\n            } else {\n";
+            }
+        }
         o << "            cplx a[" << NA << "];\n";
         for (int m = 0; m < NA; ++m) o << "            a[" << m << "] = sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "];\n";
         // (hot: the operator stands alone in the list; cold: a member of a merged group, run one by one only when a jump
@@ -362,7 +389,9 @@ void emit_guarded_passes(std::ostringstream& o, const BlobView& bv, int R, int K
             }
         }
         for (int m = 0; m < NA; ++m) o << "            sm[jbs" << p << " ^ " << ps.regoff_swz[m] << "] = a[" << m << "];\n";
-        o << "            __syncthreads();\n        }\n";
+        o << "            __syncthreads();\n";
+        if (with_fast) o << "            }\n";
+        o << "        }\n";
     }
 }
 
@@ -377,9 +406,8 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
         if (kind != OPK_DIAG && kind != OPK_RX1 && kind != OPK_DENSE1) return false;
         if (op.mat < 0 || op.mat_bare < 0 || (op.mat & 1) || (op.mat_bare & 1)) return false;
     }
-    (void)opt;
     o << "extern \"C\" __global__ void __launch_bounds__(" << (1 << (K - R)) << ", " << spec_ctas_per_sm(P, opt) << ") ncb_seg_" << seg << "_ev"
-      << "(DevProgram P, const unsigned char* __restrict__ pool_g, int pool_bytes, int pool_cap,\n"
+      << "(const __grid_constant__ SpecCoef C, DevProgram P, const unsigned char* __restrict__ pool_g, int pool_bytes, int pool_cap,\n"
          "        const Work* __restrict__ works, int nworks, cplx* __restrict__ states, int tile_shift,\n"
          "        double* __restrict__ red_part, double* __restrict__ norm_part, Decision* decisions,\n"
          "        const double* __restrict__ work_u, int* tickets, int pull_on) {\n"
@@ -395,6 +423,7 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
          "    cp_async_wait_all();\n    __syncthreads();\n"
          "    const cplx* const pool = reinterpret_cast<const cplx*>(smem_raw);\n"
          "    const double* const pool_d = reinterpret_cast<const double*>(smem_raw);\n"
+         "    (void)C;\n"
       << "    const Segment* const sg = P.segs + " << seg << ";\n"
       << "    const int K = " << K << ";\n"
          "    const unsigned utid = (unsigned)tid;\n"
@@ -410,7 +439,7 @@ bool emit_event_kernel(std::ostringstream& o, const Program& P, int seg, const S
         o << "        cp_async16(sm + (sA ^ " << sg.it_swz[it] << "), st + (offA | " << hex(sg.it_off[it]) << "));\n";
     o << "    };\n";
     o << "    auto run_passes = [&](const int lo, const int hi, const bool bare, const unsigned qb, const unsigned qe) {\n";
-    emit_guarded_passes(o, bv, R);
+    emit_guarded_passes(o, bv, R, 0, -1, opt.ev_fast ? &P.segconst[seg] : nullptr, &opt);
     o << "    };\n";
     o << "    long long t = blockIdx.x;\n    if (t >= total) return;\n"
          "    Work w = works[t >> tile_shift];\n"
@@ -846,7 +875,7 @@ uint64_t spec_structure_hash(const Program& P, const SpecOptions& opt) {
     };
     const int geo[8] = {P.nbits, P.K, P.R, P.G, P.mode, (int)P.segs.size(), (int)P.passes.size(), opt.literal};
     mix(geo, sizeof geo);
-    const int o2[6] = {opt.nbuf, opt.load, opt.events, opt.factor, opt.ctas, opt.resident_fast};
+    const int o2[7] = {opt.nbuf, opt.load, opt.events, opt.factor, opt.ctas, opt.resident_fast, opt.ev_fast};
     mix(o2, sizeof o2);
     for (size_t sgi = 0; sgi < P.blob_off.size(); ++sgi) {
         const unsigned char* braw = P.blobs.data() + P.blob_off[sgi];
@@ -866,7 +895,7 @@ std::string spec_key(const Program& P, const SpecOptions& opt) {
     uint64_t h = 1469598103934665603ull;
     const std::string src = spec_source(P, 0, (int)P.segs.size(), opt) + spec_resident_source(P, opt);
     for (unsigned char ch : src) { h ^= ch; h *= 1099511628211ull; }
-    const int geo[4] = {P.nbits, P.K, P.R, 16 /* generator version */};
+    const int geo[4] = {P.nbits, P.K, P.R, 17 /* generator version */};
     for (size_t i = 0; i < sizeof geo; ++i) { h ^= reinterpret_cast<const unsigned char*>(geo)[i]; h *= 1099511628211ull; }
     char b[32];
     std::snprintf(b, sizeof b, "%016llx", (unsigned long long)h);

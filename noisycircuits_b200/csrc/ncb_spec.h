@@ -18,6 +18,8 @@ struct SpecOptions {
     int factor = 1;   // 1 (literal mode): one real coefficient is factored out of every rotation and the product is multiplied
                       // back in once per segment -- half the FP64 instructions of the symmetric rotations, none for x
     int ctas = 0;     // > 0: resident CTAs per SM the kernels are compiled for (launch bounds; 0: from registers and shared memory)
+    int ev_fast = 1;         // 1: in the event kernels a pass that lies entirely inside the range being run takes its fast list (the
+                             // whole-segment kernel's text) instead of the guarded operators
     int resident_fast = 1;   // 1: the resident kernels run whole segments that hold no jump event through the passes' fast lists
     int literal = 1;  // 1: gate coefficients are written into the source as exact literals (ptxas materialises them next to
                       // their use; the cubin then belongs to this circuit AND these angles); 0: they are read from the

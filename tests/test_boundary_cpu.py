@@ -121,7 +121,7 @@ def test_specialised_kernel_sources_compile_for_sm_100a(tmp_path, monkeypatch):
     src = prog.specialized_source()
     nseg = prog.query(4)
     # per segment: the whole-segment kernel and the kernel of the works that carry jump events
-    assert src.count('extern "C" __global__') == 2 * nseg and src.count("_ev(DevProgram") == nseg
+    assert src.count('extern "C" __global__') == 2 * nseg and src.count("_ev(const __grid_constant__ SpecCoef C, DevProgram") == nseg
     assert "spec_diag<" in src and "st_stream(dst" in src
     assert "switch" not in src and "sc." not in src             # no interpreter left in the generated code
     assert "C.c[" in src and "0x1p" not in src                  # coefficients come from the constant bank, not as literals
