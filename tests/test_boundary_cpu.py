@@ -284,3 +284,72 @@ def test_execute_argument_errors_match_the_reference(heron_noise):
             fn(n, instr, sq, tq, meas, [0], 10.0)
         with pytest.raises(ValueError, match="positive integer"):
             fn(n, instr, sq, tq, meas, [0], 0)
+
+
+def test_sweep_pipeline_never_touches_an_engine_in_flight(heron_noise, monkeypatch):
+    """RemoteExecutor.run_sweep / run_many (host logic, engine objects replaced by stand-ins): circuit i is launched before
+    circuit i - 1 is collected, preparations run on host threads into engine objects that are neither in flight nor being
+    prepared, results come back in order, and an exception leaves no run in flight."""
+    import threading
+    import time
+    from noisycircuits_b200 import solvers
+    sq, tq, _, _ = heron_noise
+    n = 5
+    lock = threading.Lock()
+    log = {"max_in_flight": 0, "in_flight": 0, "engines": 0, "updates": 0}
+
+    class FakeProgram:
+        def __init__(self, packed, mode, **opts):
+            with lock:
+                log["engines"] += 1
+            self.busy, self.preparing, self.packed = False, False, packed
+            time.sleep(0.002)
+
+        def update(self, packed):
+            assert not self.busy, "an engine was updated while its run was in flight"
+            assert not self.preparing, "two preparations in one engine"
+            self.preparing = True
+            time.sleep(0.002)
+            self.packed = packed
+            self.preparing = False
+            with lock:
+                log["updates"] += 1
+
+        def launch_mcwf(self, traj_count, **kw):
+            assert not self.busy and not self.preparing
+            self.busy = True
+            with lock:
+                log["in_flight"] += 1
+                log["max_in_flight"] = max(log["max_in_flight"], log["in_flight"])
+            if float(self.packed.theta[0]) == 666.0:
+                self.busy = False
+                with lock:
+                    log["in_flight"] -= 1
+                raise solvers._lib.NcbError(1, "boom")
+            return (self, float(self.packed.theta[0]))
+
+        def collect_mcwf(self, handle):
+            assert self.busy
+            self.busy = False
+            with lock:
+                log["in_flight"] -= 1
+            return np.full(1 << n, handle[1] * traj), {"events": 0}
+
+    traj = 10
+    monkeypatch.setattr(solvers, "Program", FakeProgram)
+    skeleton = [["rx", [q, q], 0.0] for q in range(n)]
+    thetas = np.zeros((23, n))
+    thetas[:, 0] = np.arange(23) + 1.0
+    ex = solvers.RemoteExecutor(n, sq, tq, 1)
+    out = ex.run_sweep(traj, skeleton, thetas)
+    assert [float(o[0]) for o in out] == [float(k + 1) for k in range(23)]                 # in order, divided by the trajectory count
+    assert log["max_in_flight"] == 2 and log["in_flight"] == 0                             # one running, one queued behind it
+    assert log["engines"] == ex.PREPARE_THREADS + 2 and log["updates"] == 23 - log["engines"]
+    lists = [[["rx", [q, q], float(k + 1) if q == 0 else 0.0] for q in range(n)] for k in range(9)]
+    assert [float(o[0]) for o in ex.run_many(traj, lists)] == [float(k + 1) for k in range(9)]
+    assert log["engines"] == ex.PREPARE_THREADS + 2                                          # the engine objects are kept between sweeps
+    thetas[7, 0] = 666.0
+    with pytest.raises(solvers._lib.NcbError):
+        ex.run_sweep(traj, skeleton, thetas)
+    assert log["in_flight"] == 0                                                            # nothing left in flight
+    assert len(ex.run_sweep(traj, skeleton, thetas[:5])) == 5                               # and the executor still works (fresh engines)
