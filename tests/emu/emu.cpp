@@ -6,6 +6,7 @@
 // geometry and the register-blocked index maps can be tested on machines without a GPU (pytest -m "not gpu").
 // CUDA-only pieces (cp.async, warp shuffles, launch configuration) are not covered here; the -m gpu tests are.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -243,6 +244,7 @@ void* emu_create(const ncb_circuit* c, int mode, int tile_bits, int reg_bits, in
         Emu* e = new Emu();
         CompileOptions opt;
         opt.tile_bits = tile_bits; opt.resident_bits = tile_bits; opt.reg_bits = reg_bits; opt.low_bits = low_bits; opt.fuse = fuse; opt.reorder = reorder;
+        if (const char* e = getenv("NCB_SPLIT_U")) opt.split_generic = atoi(e);      // (the engine reads the same switch)
         compile_program(view_of(c), mode, opt, e->P);
         return e;
     } catch (const std::exception& ex) { g_err = ex.what(); return nullptr; }

@@ -75,6 +75,24 @@ def test_eagle_replay_dense_two_qubit_and_non_unitary_base(eagle_noise, n, tile_
     assert stats["hard_events"] > 0
 
 
+def test_generic_products_hand_their_phases_to_the_tables(eagle_noise, monkeypatch):
+    """Fast lists: a generic one-bit product D1 . X . D2 leaves its phases in neighbouring phase tables and runs as the rx-like X
+    (CompileOptions::split_generic).  Same trajectories as with the switch off (and as the oracle), fewer generic operators."""
+    import re
+    sq, tq, _, _ = eagle_noise
+    n = 10
+    instr = circuits.eagle_layered(n, 3, circuits.coupled_pairs(tq, n), seed=5)
+    U = jumpy_uniforms(np.random.default_rng(4), 6, len(instr))
+    _st, on = check_replay(n, instr, sq, tq, U, tile_bits=9, reg_bits=4, low_bits=3, fuse=1)
+    states_on, _ = on.mcwf_states(U)
+    monkeypatch.setenv("NCB_SPLIT_U", "0")
+    _st, off = check_replay(n, instr, sq, tq, U, tile_bits=9, reg_bits=4, low_bits=3, fuse=1)
+    states_off, _ = off.mcwf_states(U)
+    count = lambda E: int(re.search(r"dense1:(\d+)", E.describe()).group(1))
+    assert count(on) < count(off)
+    assert np.abs(states_on - states_off).max() < 1e-12
+
+
 def test_non_adjacent_pairs_replay(golden, heron_noise):
     _z, meta = golden
     m = meta["far"]
