@@ -31,12 +31,20 @@ stats = {"program_hits": 0, "program_misses": 0, "noise_hits": 0, "noise_misses"
 
 def packed_digest(packed, mode: int, options: dict) -> str:
     """blake2b of everything a compiled program depends on: the packed circuit (ncb_circuit arrays), mode, options."""
+    # everything but the gate parameters is hashed once per gate skeleton (PackedCircuit.with_thetas hands the digest on): the
+    # Kraus pool is a few hundred KB, the parameters of a training loop's next circuit a few KB
+    static = getattr(packed, "_static_digest", None)
+    if static is None:
+        hs = hashlib.blake2b(digest_size=20)
+        hs.update(repr((int(packed.num_qubits), int(packed.num_instructions), int(packed.num_channels))).encode())
+        for a in (packed.opcode, packed.q0, packed.q1, packed.channel, packed.unitary_offset, packed.unitary_nq,
+                  packed.unitary_qubits, packed.unitary_pool, packed.channel_offset, packed.channel_count, packed.channel_dim, packed.kraus_pool):
+            hs.update(a.tobytes())
+        static = packed._static_digest = hs.digest()
     h = hashlib.blake2b(digest_size=20)
-    h.update(repr((int(packed.num_qubits), int(packed.num_instructions), int(packed.num_channels), int(mode),
-                   sorted((k, repr(v)) for k, v in options.items()))).encode())
-    for a in (packed.opcode, packed.q0, packed.q1, packed.theta, packed.channel, packed.unitary_offset, packed.unitary_nq,
-              packed.unitary_qubits, packed.unitary_pool, packed.channel_offset, packed.channel_count, packed.channel_dim, packed.kraus_pool):
-        h.update(a.tobytes())
+    h.update(static)
+    h.update(repr((int(mode), sorted((k, repr(v)) for k, v in options.items()))).encode())
+    h.update(packed.theta.tobytes())
     return h.hexdigest()
 
 

@@ -67,6 +67,7 @@ class RemoteExecutor:
         self.engine_options = engine_options
         self.last_stats = None
         self._cache, self._cache_digest = (None, None), None
+        self._skeleton = (None, None)
 
     # Generated kernels (ncb_options.specialize) cost a few seconds of compilation per new kernel set.  Without an explicit
     # specialize=... in the engine options: from SPECIALIZE_FROM trajectories per call the "parametric" kernels are used
@@ -90,14 +91,30 @@ class RemoteExecutor:
         key = (_fingerprint(instruction_list), str(opts["specialize"]), id(self.single_qubit_noise), id(self.two_qubit_noise))
         # (the cache may have recycled the object for another circuit meanwhile: its digest says what it holds now)
         if self._cache[0] != key or getattr(self._cache[1], "digest", None) != self._cache_digest:
-            packed = PackedCircuit(self.num_qubits, instruction_list, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
-            prog = cache.get_program(packed, _lib.MODE_MCWF, **opts)
+            prog = cache.get_program(self._pack(key[0]) or self._pack(key[0], instruction_list), _lib.MODE_MCWF, **opts)
             self._cache, self._cache_digest = (key, prog), prog.digest
         return self._cache[1]
+
+    def _pack(self, fingerprint, instruction_list=None):
+        """Packed circuit of an instruction list.  A training loop's next circuit is the last one's gate skeleton with other
+        parameters: then only the parameter array is replaced (``PackedCircuit.with_thetas``; no Python loop over the
+        instructions, no re-packing of the Kraus operators).  Without ``instruction_list``: None when the skeleton is new."""
+        skeleton = (tuple((name, qubits) for name, qubits, _p in fingerprint), id(self.single_qubit_noise), id(self.two_qubit_noise))
+        if instruction_list is None:
+            known, base = self._skeleton
+            if known != skeleton or any(name == "unitary" for name, _q, _p in fingerprint):
+                return None
+            thetas = np.zeros(base.theta.shape[0])
+            thetas[:len(fingerprint)] = [0.0 if p is None else float(p) for _n, _q, p in fingerprint]
+            return base.with_thetas(thetas)
+        packed = PackedCircuit(self.num_qubits, instruction_list, self.single_qubit_noise, self.two_qubit_noise, noisy=True)
+        self._skeleton = (skeleton, packed)
+        return packed
 
     def invalidate(self) -> None:
         """Forget the compiled program (after editing the noise dictionaries in place)."""
         self._cache, self._cache_digest = (None, None), None
+        self._skeleton = (None, None)
 
     def run_sum(self, instruction_list, traj_begin: int, traj_count: int, uniforms=None, device_probs=None,
                 accumulate=False, stream=0):

@@ -353,3 +353,32 @@ def test_sweep_pipeline_never_touches_an_engine_in_flight(heron_noise, monkeypat
         ex.run_sweep(traj, skeleton, thetas)
     assert log["in_flight"] == 0                                                            # nothing left in flight
     assert len(ex.run_sweep(traj, skeleton, thetas[:5])) == 5                               # and the executor still works (fresh engines)
+
+
+def test_next_parameter_set_reuses_the_packed_gate_skeleton(heron_noise):
+    """RemoteExecutor._program on the last circuit's gate skeleton with other parameters replaces the parameter array only;
+    the packed circuit (and with it the content key of the program cache) is what packing from scratch gives."""
+    from noisycircuits_b200 import cache
+    from noisycircuits_b200.solvers import RemoteExecutor, _fingerprint
+    sq, tq, _, _ = heron_noise
+    n = 6
+    pairs = circuits.coupled_pairs(tq, n, adjacent_only=True)
+    a, b = circuits.qnn_circuit(n, 2, pairs, seed=1), circuits.qnn_circuit(n, 2, pairs, seed=2)
+    ex = RemoteExecutor(n, sq, tq, 1)
+    assert ex._pack(_fingerprint(a)) is None                          # nothing known yet
+    ex._program(a)
+    reused = ex._pack(_fingerprint(b))
+    fresh = PackedCircuit(n, b, sq, tq)
+    assert reused is not None
+    for name in ("opcode", "q0", "q1", "theta", "channel", "unitary_offset", "unitary_nq", "unitary_qubits", "unitary_pool",
+                 "channel_offset", "channel_count", "channel_dim", "kraus_pool"):
+        assert getattr(reused, name).tobytes() == getattr(fresh, name).tobytes(), name
+    assert cache.packed_digest(reused, 0, {"specialize": False}) == cache.packed_digest(fresh, 0, {"specialize": False})
+    assert cache.packed_digest(reused, 0, {"specialize": False}) != cache.packed_digest(PackedCircuit(n, a, sq, tq), 0, {"specialize": False})
+    # another skeleton (one gate more), a unitary, or other noise dictionaries: packed from scratch
+    assert ex._pack(_fingerprint(b + [["x", [0, 0], 0]])) is None
+    assert ex._pack(_fingerprint(b[:-1] + [["unitary", [0], np.eye(2)]])) is None
+    ex2 = RemoteExecutor(n, dict(sq), tq, 1)
+    assert ex2._pack(_fingerprint(b)) is None
+    p1 = ex._program(b)
+    assert p1.packed.theta.tobytes() == fresh.theta.tobytes() and p1.describe() == Program(fresh).describe()
